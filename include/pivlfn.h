@@ -1,0 +1,119 @@
+/*
+ * pivlfn.h -- C ABI of the B200 (sm_100a) PIV-LiteFlowNet forward-pass kernels.
+ *
+ * Every entry point takes raw DEVICE pointers, plain ints/floats and a CUDA stream
+ * (cudaStream_t passed as void*), allocates nothing, and returns 0 on success,
+ * a negative PIVLFN_E* code on a validation error, or a positive cudaError_t.
+ * Tensors are fp32.  "NHWC view" = (ptr, C, ld): pixel p's channels start at
+ * ptr + p*ld floats, ld >= C, so a view can be a channel slice of a wider buffer
+ * (that is how torch.cat of the reference disappears).
+ *
+ * Each function names the reference code (file:line under abrosua/piv_liteflownet-pytorch)
+ * whose arithmetic it replaces.
+ */
+#ifndef PIVLFN_H
+#define PIVLFN_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIVLFN_OK 0
+#define PIVLFN_EINVAL (-1)      /* bad shape / stride / alignment argument         */
+#define PIVLFN_EUNSUPPORTED (-2) /* valid request this build has no kernel for       */
+#define PIVLFN_EDRIVER (-3)     /* CUDA driver entry point (tensor-map encode) unavailable */
+
+/* Library / device introspection. */
+int pivlfn_abi_version(void);
+/* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA paths usable). */
+int pivlfn_device_is_sm100(void);
+/* Number of kernels launched by this library since load (all entry points). */
+long long pivlfn_launch_count(void);
+
+/* ---- drop-in operator: FunctionCorrelation(tensorFirst, tensorSecond, intStride) ----------
+ * src/correlation.py:285-344 (_FunctionCorrelation.forward) with its two kernels
+ * kernel_Correlation_rearrange (:9-34) and kernel_Correlation_updateOutput (:36-104).
+ * first, second: [B,C,H,W] contiguous NCHW.  out: [B,49,ceil(H/s),ceil(W/s)] NCHW.
+ * out[b,(dy+3)*7+(dx+3),y,x] = (1/C) sum_c first[b,c,y*s,x*s] * second[b,c,y*s+dy*s,x*s+dx*s]. */
+int pivlfn_corr_nchw(const float* first, const float* second, float* out,
+                     int B, int C, int H, int W, int stride, void* stream);
+
+/* ---- model-internal operators (NHWC views) ---------------------------------------------- */
+
+/* src/models.py:321-323 (in-place per-channel mean subtraction of BOTH caller tensors) fused with
+ * the NCHW->NHWC pack.  img1,img2: [B,3,H,W] NCHW, modified in place.  out: [2B,H,W,4] (images of
+ * img1 first, then img2; 4th channel zero).  mean6: HOST pointer to 6 floats (3 per image). */
+int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, int B, int H, int W,
+                       const float* mean6, void* stream);
+
+/* src/models.py:336-343: bilinear 1/2 downsample with align_corners=False on even sizes
+ * == 2x2 mean.  in: [N,H,W,C] dense, out: [N,H/2,W/2,C] dense.  H, W even. */
+int pivlfn_avgpool2(const float* in, float* out, int N, int H, int W, int C, void* stream);
+
+/* torch.cat along channels (src/models.py:216,280) done as a strided slice copy: copies C channels of
+ * npix pixels from one NHWC view to another.  Views must be 16-byte aligned with ld % 4 == 0 when
+ * C % 4 == 0 (vector path); any C otherwise. */
+int pivlfn_copy_nhwc(const float* in, int in_ld, float* out, int out_ld, long long npix, int C, void* stream);
+
+/* torch.nn.Conv2d (+ LeakyReLU(0.1)) as used throughout src/models.py:70-106,123-126,154-163,
+ * 197-207,228-272.  Zero padding (KH/2, KW/2), stride 1 or 2, generic CUDA-core kernel.
+ * w: [KH*KW*Cin, CoutP] row-major, CoutP = Cout rounded up to a multiple of 4, zero padded.
+ * y = act(conv(x) + bias) (+ res).  res (optional) is an NHWC view with Cout channels
+ * (the "+ xflow" of src/models.py:186,216). */
+int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
+                     const float* w, const float* bias, float* y, int y_ld, int Cout,
+                     int KH, int KW, int stride, int lrelu,
+                     const float* res, int res_ld, void* stream);
+
+/* Same operator for 3x3 stride-1 convolutions on the tcgen05 tensor cores (implicit GEMM,
+ * TMA-fed, TMEM accumulators, fused bias + LeakyReLU).
+ * w_hi / w_lo: [Cout, 9, CinP] (CinP = Cin rounded up to 32) TF32 split of the weights
+ * (w ~= w_hi + w_lo); passes = 1 (plain TF32) or 3 (error-compensated 3xTF32 ~ fp32).
+ * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout % 16 == 0, 16 <= Cout <= 128. */
+int pivlfn_conv3x3_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
+                      const float* w_hi, const float* w_lo, const float* bias,
+                      float* y, int y_ld, int Cout, int lrelu, int passes, void* stream);
+
+/* torch.nn.ConvTranspose2d(C, C, 4, stride 2, padding 1, groups=C, bias=False):
+ * upConv_M (src/models.py:144-145, C=2) and upCorr_M (:151-152, C=49).
+ * in: NHWC view [N,H,W,C], w: [C,4,4], out: NHWC view [N,2H,2W,C]. */
+int pivlfn_deconv4x4s2_dw(const float* in, int in_ld, const float* w, float* out, int out_ld,
+                          int N, int H, int W, int C, void* stream);
+
+/* backwarp (src/models.py:20-35) as a standalone operator: out[p,c] = bilinear(in[.,c], p + scale*flow[p]),
+ * zeros outside.  flow: [N,H,W,2] dense (u,v). */
+int pivlfn_warp_nhwc(const float* in, int in_ld, const float* flow, float scale,
+                     float* out, int out_ld, int N, int H, int W, int C, void* stream);
+
+/* Matching cost volume (src/models.py:169-184): optional backwarp of f2 by scale*flow fused into the
+ * tile load (the warped features never reach HBM), 49-displacement correlation at stride 1 or 2
+ * (src/correlation.py:36-104), /C, then LeakyReLU(0.1).  flow may be NULL (level 6).
+ * out: NHWC view [N,ceil(H/s),ceil(W/s),49]. */
+int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld,
+                     const float* flow, float flow_scale, float* out, int out_ld,
+                     int N, int H, int W, int C, int stride, int lrelu, void* stream);
+
+/* Per-sample, per-channel spatial sums of a dense [N,H,W,2] flow in G deterministic partials
+ * (src/models.py:275, the .mean(2)).  partial: [N,G,2].  G = pivlfn_flow_mean_parts(). */
+int pivlfn_flow_mean_parts(void);
+int pivlfn_flow_mean(const float* flow, float* partial, int N, int H, int W, void* stream);
+
+/* Regularization inputs (src/models.py:275-277): rm = flow - mean(flow); brightness error
+ * sqrt(sum_c (img1 - backwarp(img2, scale*flow))^2).  Writes 3 channels (err, rm_u, rm_v) at out.
+ * img1,img2: [N,H,W,4] dense. */
+int pivlfn_reg_input(const float* img1, const float* img2, const float* flow, float scale,
+                     const float* partial, float* out, int out_ld, int N, int H, int W, void* stream);
+
+/* Regularization tail (src/models.py:281-302): d = exp(-x^2 - max(-x^2)); out_u = (sum_k wx_k d_k u_N(k) + bx)
+ * / sum_k d_k, same for v; N(k) = KxK zero-padded neighbourhood (F.unfold order).  dist: NHWC view with
+ * K*K channels.  flow_in/flow_out: [N,H,W,2] dense.  If out_nchw != NULL also writes
+ * final_scale * flow as [N,2,H,W] (src/models.py:370). */
+int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow_in,
+                    const float* wx, const float* bx, const float* wy, const float* by,
+                    float* flow_out, float* out_nchw, float final_scale,
+                    int K, int N, int H, int W, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIVLFN_H */

@@ -1,0 +1,223 @@
+// 49-displacement (+-3) cost volume, stride 1 or 2.
+//
+// Replaces src/correlation.py:285-344 (_FunctionCorrelation.forward) and its kernels
+// kernel_Correlation_rearrange (:9-34) + kernel_Correlation_updateOutput (:36-104).  The reference
+// first writes two zero-padded NHWC copies to HBM and then runs one 32-thread block per output pixel;
+// here the padding/rearrange is folded into the shared-memory tile load, each thread keeps its
+// displacement accumulators in registers, and nothing but the inputs and the 49-channel result
+// touches HBM.
+//
+//   out[b,(dy+3)*7+(dx+3),y,x] = (1/C) * sum_c f1[b,c,y*s,x*s] * f2[b,c,(y+dy)*s,(x+dx)*s]
+//
+// Two entry points: NCHW (the public FunctionCorrelation operator) and NHWC (model-internal, with the
+// backwarp of f2 and the LeakyReLU of src/models.py:171-184 fused in).
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// NCHW: CTA = 32 x 8 output pixels, one thread per pixel, 49 accumulators per thread.
+// ------------------------------------------------------------------------------------------------
+constexpr int NC_TX = 32, NC_TY = 8, NC_CK = 4;
+constexpr int NC_SW = NC_TX + 6, NC_SH = NC_TY + 6;
+
+__global__ void __launch_bounds__(NC_TX * NC_TY)
+corr_nchw_kernel(const float* __restrict__ f1, const float* __restrict__ f2, float* __restrict__ out,
+                 int C, int H, int W, int Ho, int Wo, int s) {
+    __shared__ float tile[NC_CK][NC_SH][NC_SW + 1];
+    const int b = blockIdx.z;
+    const int x0 = blockIdx.x * NC_TX, y0 = blockIdx.y * NC_TY;
+    const int tx = threadIdx.x % NC_TX, ty = threadIdx.x / NC_TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    const bool live = ox < Wo && oy < Ho;
+    const size_t plane = (size_t)H * W;
+    const float* f1b = f1 + (size_t)b * C * plane;
+    const float* f2b = f2 + (size_t)b * C * plane;
+
+    float acc[49];
+#pragma unroll
+    for (int i = 0; i < 49; ++i) acc[i] = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += NC_CK) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < NC_CK * NC_SH * NC_SW; idx += NC_TX * NC_TY) {
+            int i = idx % NC_SW;
+            int j = (idx / NC_SW) % NC_SH;
+            int cc = idx / (NC_SW * NC_SH);
+            int iy = (y0 + j - 3) * s, ix = (x0 + i - 3) * s;
+            float v = 0.f;
+            if (c0 + cc < C && iy >= 0 && iy < H && ix >= 0 && ix < W)
+                v = __ldg(f2b + (size_t)(c0 + cc) * plane + (size_t)iy * W + ix);
+            tile[cc][j][i] = v;
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int cc = 0; cc < NC_CK; ++cc) {
+                if (c0 + cc < C) {
+                    float a = __ldg(f1b + (size_t)(c0 + cc) * plane + (size_t)(oy * s) * W + ox * s);
+#pragma unroll
+                    for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+                        for (int dx = 0; dx < 7; ++dx)
+                            acc[dy * 7 + dx] = fmaf(a, tile[cc][ty + dy][tx + dx], acc[dy * 7 + dx]);
+                }
+            }
+        }
+    }
+    if (live) {
+        const float inv = 1.f / (float)C;
+        float* o = out + ((size_t)b * 49) * Ho * Wo + (size_t)oy * Wo + ox;
+#pragma unroll
+        for (int k = 0; k < 49; ++k) o[(size_t)k * Ho * Wo] = acc[k] * inv;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NHWC: CTA = 16 x 8 output pixels; 256 threads = 128 pixels x 2 halves of the displacement rows
+// (half 0: dy rows 0..3 = 28 displacements, half 1: rows 4..6 = 21).  Channels are staged 16 at a
+// time; the f2 tile (with +-3 halo, sampled every s pixels) is produced by bilinear backwarp when a
+// flow is given.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8 neighbouring
+// pixels are bank-conflict free.
+// ------------------------------------------------------------------------------------------------
+constexpr int NH_TX = 16, NH_TY = 8, NH_CK = 16, NH_PITCH = 20;
+constexpr int NH_SW = NH_TX + 6, NH_SH = NH_TY + 6;
+
+template <int ROWS>
+__device__ __forceinline__ void corr_accumulate(float (&acc)[28], const float* __restrict__ s1,
+                                                const float* __restrict__ s2row0) {
+    // s1: this pixel's 16 channels; s2row0: f2 tile pixel (ty+dy0, tx) -> walks ROWS rows x 7 cols
+#pragma unroll
+    for (int q = 0; q < NH_CK / 4; ++q) {
+        const float4 a = *reinterpret_cast<const float4*>(s1 + q * 4);
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const float4 v = *reinterpret_cast<const float4*>(s2row0 + (r * NH_SW + dx) * NH_PITCH + q * 4);
+                float t = acc[r * 7 + dx];
+                t = fmaf(a.x, v.x, t);
+                t = fmaf(a.y, v.y, t);
+                t = fmaf(a.z, v.z, t);
+                t = fmaf(a.w, v.w, t);
+                acc[r * 7 + dx] = t;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
+                 const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
+                 int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
+    __shared__ __align__(16) float s1[NH_TX * NH_TY * NH_PITCH];
+    __shared__ __align__(16) float s2[NH_SW * NH_SH * NH_PITCH];
+    const int n = blockIdx.z;
+    const int x0 = blockIdx.x * NH_TX, y0 = blockIdx.y * NH_TY;
+    const int tid = threadIdx.x;
+    const int pix = tid & 127, half = tid >> 7;
+    const int tx = pix % NH_TX, ty = pix / NH_TX;
+    const int ox = x0 + tx, oy = y0 + ty;
+    const bool live = ox < Wo && oy < Ho;
+    const size_t img = (size_t)n * H * W;
+
+    float acc[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+
+    for (int c0 = 0; c0 < C; c0 += NH_CK) {
+        __syncthreads();
+        // ---- f1 tile: 128 pixels x 4 quads ---------------------------------------------------------
+        for (int item = tid; item < NH_TX * NH_TY * (NH_CK / 4); item += 256) {
+            int q = item & 3, p = item >> 2;
+            int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
+            int c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < Wo && py < Ho && c < C) {
+                const float* src = f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c;
+                if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
+                else { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
+            }
+            *reinterpret_cast<float4*>(&s1[p * NH_PITCH + q * 4]) = v;
+        }
+        // ---- f2 tile (+halo), optionally backwarped --------------------------------------------------
+        for (int item = tid; item < NH_SW * NH_SH * (NH_CK / 4); item += 256) {
+            int q = item & 3, p = item >> 2;
+            int i = p % NH_SW, j = p / NH_SW;
+            int iy = (y0 + j - 3) * s, ix = (x0 + i - 3) * s;
+            int c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
+                const bool full = c + 3 < C;
+                if (flow == nullptr) {
+                    const float* src = f2 + (img + (size_t)iy * W + ix) * f2_ld + c;
+                    if (full) v = __ldg(reinterpret_cast<const float4*>(src));
+                    else { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
+                } else {
+                    const float2 fl = __ldg(reinterpret_cast<const float2*>(flow) + img + (size_t)iy * W + ix);
+                    const BilinearTaps t = make_taps((float)ix + fl.x * fscale, (float)iy + fl.y * fscale, H, W);
+                    const float wgt[4] = {t.w00, t.w01, t.w10, t.w11};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (wgt[k] != 0.f) {
+                            const float* src = f2 + (img + (size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * f2_ld + c;
+                            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (full) u = __ldg(reinterpret_cast<const float4*>(src));
+                            else { u.x = __ldg(src); if (c + 1 < C) u.y = __ldg(src + 1); if (c + 2 < C) u.z = __ldg(src + 2); }
+                            v.x = fmaf(wgt[k], u.x, v.x); v.y = fmaf(wgt[k], u.y, v.y);
+                            v.z = fmaf(wgt[k], u.z, v.z); v.w = fmaf(wgt[k], u.w, v.w);
+                        }
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(&s2[p * NH_PITCH + q * 4]) = v;
+        }
+        __syncthreads();
+        const float* a = &s1[pix * NH_PITCH];
+        if (half == 0) corr_accumulate<4>(acc, a, &s2[((ty + 0) * NH_SW + tx) * NH_PITCH]);
+        else           corr_accumulate<3>(acc, a, &s2[((ty + 4) * NH_SW + tx) * NH_PITCH]);
+    }
+    if (live) {
+        const float inv = 1.f / (float)C;
+        float* o = out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + half * 28;
+        const int cnt = half == 0 ? 28 : 21;
+#pragma unroll
+        for (int k = 0; k < 28; ++k) {
+            if (k < cnt) {
+                float v = acc[k] * inv;
+                o[k] = lrelu ? lrelu_f(v) : v;
+            }
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int pivlfn_corr_nchw(const float* first, const float* second, float* out,
+                                int B, int C, int H, int W, int stride, void* stream) {
+    if (!first || !second || !out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
+    if (B > 65535) return PIVLFN_EINVAL;
+    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
+    dim3 grid(cdiv(Wo, NC_TX), cdiv(Ho, NC_TY), B);
+    corr_nchw_kernel<<<grid, NC_TX * NC_TY, 0, (cudaStream_t)stream>>>(first, second, out, C, H, W, Ho, Wo, stride);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld,
+                                const float* flow, float flow_scale, float* out, int out_ld,
+                                int N, int H, int W, int C, int stride, int lrelu, void* stream) {
+    if (!f1 || !f2 || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
+    if (f1_ld < C || f2_ld < C || out_ld < 49 || N > 65535) return PIVLFN_EINVAL;
+    // float4 tile loads need 16-byte aligned pixel rows
+    if (((uintptr_t)f1 & 15) || ((uintptr_t)f2 & 15) || (f1_ld & 3) || (f2_ld & 3)) return PIVLFN_EINVAL;
+    if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
+    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
+    dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
+    corr_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
+                                                              C, H, W, Ho, Wo, stride, lrelu);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}

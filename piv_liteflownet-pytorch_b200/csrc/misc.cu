@@ -1,0 +1,367 @@
+// Memory-bound glue kernels of the LiteFlowNet forward pass (all NHWC fp32):
+// input prep, image pyramid, depthwise 2x up-convolution, standalone backwarp, flow mean,
+// regularisation inputs (mean removal + brightness error with the backwarp fused in) and the
+// regularisation tail (negative-square softmax + unfold + weighted sum in ONE kernel).
+#include "common.cuh"
+
+long long g_pivlfn_launches = 0;
+
+extern "C" int pivlfn_abi_version(void) { return 1; }
+extern "C" long long pivlfn_launch_count(void) { return g_pivlfn_launches; }
+extern "C" int pivlfn_device_is_sm100(void) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+    return major == 10;
+}
+
+namespace {
+
+constexpr int MEAN_PARTS = 32;
+
+// ---- src/models.py:321-323 + NCHW -> NHWC4 ------------------------------------------------------
+__global__ void prep_images_kernel(float* __restrict__ img1, float* __restrict__ img2, float4* __restrict__ out,
+                                   int B, int HW, float m10, float m11, float m12, float m20, float m21, float m22) {
+    const long long total = 2LL * B * HW;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int which = i >= (long long)B * HW;
+        const long long r = which ? i - (long long)B * HW : i;
+        const long long b = r / HW, p = r % HW;
+        float* src = (which ? img2 : img1) + b * 3 * HW + p;
+        float v0 = src[0] - (which ? m20 : m10);
+        float v1 = src[HW] - (which ? m21 : m11);
+        float v2 = src[2LL * HW] - (which ? m22 : m12);
+        src[0] = v0; src[HW] = v1; src[2LL * HW] = v2;   // the reference mutates its inputs in place
+        out[i] = make_float4(v0, v1, v2, 0.f);
+    }
+}
+
+// ---- src/models.py:336-343 -------------------------------------------------------------------------
+__global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C) {
+    const int Ho = H / 2, Wo = W / 2;
+    const long long total = (long long)N * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int ox = (int)(p % Wo);
+        long long t = p / Wo;
+        int oy = (int)(t % Ho);
+        long long n = t / Ho;
+        const float* s = in + ((n * H + 2 * oy) * W + 2 * ox) * C + c;
+        // same association as upsample_bilinear2d: 0.5*(0.5*a + 0.5*b) + 0.5*(0.5*c + 0.5*d)
+        float top = 0.5f * s[0] + 0.5f * s[C];
+        float bot = 0.5f * s[(long long)W * C] + 0.5f * s[(long long)W * C + C];
+        out[i] = 0.5f * top + 0.5f * bot;
+    }
+}
+
+// ---- ConvTranspose2d(C,C,4,s2,p1,groups=C,bias=False): src/models.py:144-145,151-152 ---------------
+// out[oy,ox,c] = sum over the (at most) 2x2 input pixels with ky = oy+1-2*iy, kx = ox+1-2*ix in [0,3].
+__global__ void deconv4x4s2_dw_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ w,
+                                      float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    const long long total = (long long)N * Ho * Wo * C;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int c = (int)(i % C);
+        long long p = i / C;
+        int ox = (int)(p % Wo);
+        long long t = p / Wo;
+        int oy = (int)(t % Ho);
+        long long n = t / Ho;
+        // oy even (2k): (iy,ky) in {(k,1),(k-1,3)};  oy odd (2k+1): {(k,2),(k+1,0)}
+        int iyA = oy >> 1, kyA = (oy & 1) ? 2 : 1;
+        int iyB = (oy & 1) ? iyA + 1 : iyA - 1, kyB = (oy & 1) ? 0 : 3;
+        int ixA = ox >> 1, kxA = (ox & 1) ? 2 : 1;
+        int ixB = (ox & 1) ? ixA + 1 : ixA - 1, kxB = (ox & 1) ? 0 : 3;
+        const float* wc = w + c * 16;
+        const float* base = in + n * H * W * in_ld + c;
+        float acc = 0.f;
+        const bool vyB = iyB >= 0 && iyB < H, vxB = ixB >= 0 && ixB < W;
+        // accumulate in the order of increasing (iy, ix) like a gather formulation of conv_transpose
+        int iy0 = iyA, ky0 = kyA, iy1 = iyB, ky1 = kyB; bool v0y = true, v1y = vyB;
+        if (iyB < iyA) { iy0 = iyB; ky0 = kyB; iy1 = iyA; ky1 = kyA; v0y = vyB; v1y = true; }
+        int ix0 = ixA, kx0 = kxA, ix1 = ixB, kx1 = kxB; bool v0x = true, v1x = vxB;
+        if (ixB < ixA) { ix0 = ixB; kx0 = kxB; ix1 = ixA; kx1 = kxA; v0x = vxB; v1x = true; }
+        if (v0y && v0x) acc = fmaf(base[((long long)iy0 * W + ix0) * in_ld], __ldg(wc + ky0 * 4 + kx0), acc);
+        if (v0y && v1x) acc = fmaf(base[((long long)iy0 * W + ix1) * in_ld], __ldg(wc + ky0 * 4 + kx1), acc);
+        if (v1y && v0x) acc = fmaf(base[((long long)iy1 * W + ix0) * in_ld], __ldg(wc + ky1 * 4 + kx0), acc);
+        if (v1y && v1x) acc = fmaf(base[((long long)iy1 * W + ix1) * in_ld], __ldg(wc + ky1 * 4 + kx1), acc);
+        out[p * out_ld + c] = acc;
+    }
+}
+
+// ---- channel-slice copy (the torch.cat of src/models.py:216,280) ------------------------------------------
+template <bool VEC>
+__global__ void copy_nhwc_kernel(const float* __restrict__ in, int in_ld, float* __restrict__ out, int out_ld,
+                                 long long npix, int C) {
+    const int Q = VEC ? C / 4 : C;
+    const long long total = npix * Q;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / Q;
+        const int q = (int)(i % Q);
+        if (VEC)
+            *reinterpret_cast<float4*>(out + p * out_ld + q * 4) =
+                __ldg(reinterpret_cast<const float4*>(in + p * in_ld + q * 4));
+        else
+            out[p * out_ld + q] = __ldg(in + p * in_ld + q);
+    }
+}
+
+// ---- backwarp, standalone (src/models.py:20-35) ---------------------------------------------------------
+__global__ void warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restrict__ flow, float scale,
+                                 float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
+    const int Q = (C + 3) / 4;
+    const long long total = (long long)N * H * W * Q;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        int q = (int)(i % Q);
+        long long p = i / Q;
+        int x = (int)(p % W);
+        long long t = p / W;
+        int y = (int)(t % H);
+        long long n = t / H;
+        const float2 fl = __ldg(flow + p);
+        const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
+        const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+        const int c = q * 4;
+        const int nc = min(4, C - c);
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (wgt[k] != 0.f) {
+                const float* s = in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c;
+                if (nc == 4) {
+                    float4 u = __ldg(reinterpret_cast<const float4*>(s));
+                    v[0] = fmaf(wgt[k], u.x, v[0]); v[1] = fmaf(wgt[k], u.y, v[1]);
+                    v[2] = fmaf(wgt[k], u.z, v[2]); v[3] = fmaf(wgt[k], u.w, v[3]);
+                } else {
+                    for (int j = 0; j < nc; ++j) v[j] = fmaf(wgt[k], __ldg(s + j), v[j]);
+                }
+            }
+        }
+        float* o = out + p * out_ld + c;
+        if (nc == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else for (int j = 0; j < nc; ++j) o[j] = v[j];
+    }
+}
+
+// ---- flow mean partials (src/models.py:275) --------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+flow_mean_kernel(const float2* __restrict__ flow, float* __restrict__ partial, int HW) {
+    const int n = blockIdx.y, part = blockIdx.x;
+    const long long per = ((long long)HW + MEAN_PARTS - 1) / MEAN_PARTS;
+    const long long beg = part * per, end = min((long long)HW, beg + per);
+    float su = 0.f, sv = 0.f;
+    for (long long i = beg + threadIdx.x; i < end; i += 256) {
+        float2 f = __ldg(flow + (long long)n * HW + i);
+        su += f.x; sv += f.y;
+    }
+    __shared__ float ru[8], rv[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        su += __shfl_xor_sync(0xffffffffu, su, o);
+        sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    }
+    if ((threadIdx.x & 31) == 0) { ru[threadIdx.x >> 5] = su; rv[threadIdx.x >> 5] = sv; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float a = 0.f, b = 0.f;
+        for (int i = 0; i < 8; ++i) { a += ru[i]; b += rv[i]; }
+        partial[((long long)n * MEAN_PARTS + part) * 2 + 0] = a;
+        partial[((long long)n * MEAN_PARTS + part) * 2 + 1] = b;
+    }
+}
+
+// ---- regularisation inputs (src/models.py:275-277) ---------------------------------------------------------
+__global__ void reg_input_kernel(const float4* __restrict__ img1, const float4* __restrict__ img2,
+                                 const float2* __restrict__ flow, float scale, const float* __restrict__ partial,
+                                 float* __restrict__ out, int out_ld, int N, int H, int W) {
+    const long long HW = (long long)H * W, total = (long long)N * HW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long n = p / HW;
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        float mu = 0.f, mv = 0.f;
+#pragma unroll 8
+        for (int i = 0; i < MEAN_PARTS; ++i) {
+            mu += __ldg(partial + (n * MEAN_PARTS + i) * 2);
+            mv += __ldg(partial + (n * MEAN_PARTS + i) * 2 + 1);
+        }
+        const float inv = 1.f / (float)HW;
+        mu *= inv; mv *= inv;
+        const float2 fl = __ldg(flow + p);
+        const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
+        const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+        float wr = 0.f, wg = 0.f, wb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (wgt[k] != 0.f) {
+                float4 u = __ldg(img2 + (n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1)));
+                wr = fmaf(wgt[k], u.x, wr); wg = fmaf(wgt[k], u.y, wg); wb = fmaf(wgt[k], u.z, wb);
+            }
+        }
+        const float4 a = __ldg(img1 + p);
+        const float dr = a.x - wr, dg = a.y - wg, db = a.z - wb;
+        float* o = out + p * out_ld;
+        o[0] = sqrtf(dr * dr + dg * dg + db * db);
+        o[1] = fl.x - mu;
+        o[2] = fl.y - mv;
+    }
+}
+
+// ---- regularisation tail (src/models.py:281-302), one kernel ---------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(128)
+reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __restrict__ flow,
+                const float* __restrict__ wx, const float* __restrict__ bx,
+                const float* __restrict__ wy, const float* __restrict__ by,
+                float2* __restrict__ flow_out, float* __restrict__ out_nchw, float final_scale,
+                int N, int H, int W) {
+    constexpr int KK = K * K, P = K / 2;
+    __shared__ float swx[KK], swy[KK];
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) { swx[i] = wx[i]; swy[i] = wy[i]; }
+    __syncthreads();
+    const float bxv = __ldg(bx), byv = __ldg(by);
+    const long long HW = (long long)H * W, total = (long long)N * HW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long n = p / HW;
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        const float* d = dist + p * dist_ld;
+        float ns[KK];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            float v = __ldg(d + k);
+            ns[k] = -(v * v);
+            mx = fmaxf(mx, ns[k]);
+        }
+        float sum = 0.f, au = 0.f, av = 0.f;
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const float e = expf(ns[k] - mx);
+            sum += e;
+            const int yy = y + k / K - P, xx = x + k % K - P;
+            float2 f = make_float2(0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
+            au = fmaf(swx[k], e * f.x, au);
+            av = fmaf(swy[k], e * f.y, av);
+        }
+        const float r = 1.f / sum;
+        const float u = (au + bxv) * r, v = (av + byv) * r;
+        flow_out[p] = make_float2(u, v);
+        if (out_nchw) {
+            const long long q = p - n * HW;
+            out_nchw[(n * 2 + 0) * HW + q] = u * final_scale;
+            out_nchw[(n * 2 + 1) * HW + q] = v * final_scale;
+        }
+    }
+}
+
+inline int grid_for(long long total, int block) {
+    long long g = (total + block - 1) / block;
+    const long long cap = 148LL * 32;       // a few waves of the 148 SMs, grid-stride beyond
+    return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, int B, int H, int W,
+                                  const float* mean6, void* stream) {
+    if (!img1 || !img2 || !out_nhwc4 || !mean6 || B <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if ((uintptr_t)out_nhwc4 & 15) return PIVLFN_EINVAL;
+    const long long total = 2LL * B * H * W;
+    prep_images_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        img1, img2, reinterpret_cast<float4*>(out_nhwc4), B, H * W,
+        mean6[0], mean6[1], mean6[2], mean6[3], mean6[4], mean6[5]);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_avgpool2(const float* in, float* out, int N, int H, int W, int C, void* stream) {
+    if (!in || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || (H & 1) || (W & 1)) return PIVLFN_EINVAL;
+    const long long total = (long long)N * (H / 2) * (W / 2) * C;
+    avgpool2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_deconv4x4s2_dw(const float* in, int in_ld, const float* w, float* out, int out_ld,
+                                     int N, int H, int W, int C, void* stream) {
+    if (!in || !w || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || in_ld < C || out_ld < C) return PIVLFN_EINVAL;
+    const long long total = (long long)N * 4 * H * W * C;
+    deconv4x4s2_dw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, w, out, out_ld, N, H, W, C);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_warp_nhwc(const float* in, int in_ld, const float* flow, float scale,
+                                float* out, int out_ld, int N, int H, int W, int C, void* stream) {
+    if (!in || !flow || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || in_ld < C || out_ld < C) return PIVLFN_EINVAL;
+    if (((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (in_ld & 3) || (out_ld & 3) || ((uintptr_t)flow & 7))
+        return PIVLFN_EINVAL;
+    const long long total = (long long)N * H * W * ((C + 3) / 4);
+    warp_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        in, in_ld, reinterpret_cast<const float2*>(flow), scale, out, out_ld, N, H, W, C);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_copy_nhwc(const float* in, int in_ld, float* out, int out_ld, long long npix, int C,
+                                void* stream) {
+    if (!in || !out || npix <= 0 || C <= 0 || in_ld < C || out_ld < C) return PIVLFN_EINVAL;
+    const bool vec = (C % 4 == 0) && !((uintptr_t)in & 15) && !((uintptr_t)out & 15) && !(in_ld & 3) && !(out_ld & 3);
+    if (vec)
+        copy_nhwc_kernel<true><<<grid_for(npix * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, npix, C);
+    else
+        copy_nhwc_kernel<false><<<grid_for(npix * C, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, out, out_ld, npix, C);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_flow_mean_parts(void) { return MEAN_PARTS; }
+
+extern "C" int pivlfn_flow_mean(const float* flow, float* partial, int N, int H, int W, void* stream) {
+    if (!flow || !partial || N <= 0 || H <= 0 || W <= 0 || N > 65535 || ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
+    flow_mean_kernel<<<dim3(MEAN_PARTS, N), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(flow), partial, H * W);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_reg_input(const float* img1, const float* img2, const float* flow, float scale,
+                                const float* partial, float* out, int out_ld, int N, int H, int W, void* stream) {
+    if (!img1 || !img2 || !flow || !partial || !out || N <= 0 || H <= 0 || W <= 0 || out_ld < 3) return PIVLFN_EINVAL;
+    if (((uintptr_t)img1 & 15) || ((uintptr_t)img2 & 15) || ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
+    const long long total = (long long)N * H * W;
+    reg_input_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(img1), reinterpret_cast<const float4*>(img2),
+        reinterpret_cast<const float2*>(flow), scale, partial, out, out_ld, N, H, W);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow_in,
+                               const float* wx, const float* bx, const float* wy, const float* by,
+                               float* flow_out, float* out_nchw, float final_scale,
+                               int K, int N, int H, int W, void* stream) {
+    if (!dist || !flow_in || !wx || !bx || !wy || !by || !flow_out || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (dist_ld < K * K || ((uintptr_t)flow_in & 7) || ((uintptr_t)flow_out & 7)) return PIVLFN_EINVAL;
+    const long long total = (long long)N * H * W;
+    const int g = grid_for(total, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    const float2* fi = reinterpret_cast<const float2*>(flow_in);
+    float2* fo = reinterpret_cast<float2*>(flow_out);
+    switch (K) {
+        case 3: reg_tail_kernel<3><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
+        case 5: reg_tail_kernel<5><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
+        case 7: reg_tail_kernel<7><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
+        default: return PIVLFN_EINVAL;
+    }
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}

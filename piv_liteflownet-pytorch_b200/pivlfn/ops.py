@@ -1,0 +1,164 @@
+"""Thin torch-tensor wrappers over the C ABI (include/pivlfn.h).
+
+PyTorch supplies device memory and the current stream; all arithmetic happens in libpivlfn.so.
+Every wrapper insists on CUDA fp32 tensors: there is no CPU or eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NotImplementedError("pivlfn operators run on CUDA tensors only (no CPU path)")
+        if t.dtype != torch.float32:
+            raise TypeError("pivlfn operators are fp32")
+
+
+@dataclass
+class View:
+    """C channels of a dense NHWC buffer [N,H,W,ld], starting at channel ``off``."""
+    base: torch.Tensor
+    off: int
+    C: int
+
+    @property
+    def ptr(self) -> int:
+        return self.base.data_ptr() + 4 * self.off
+
+    @property
+    def ld(self) -> int:
+        return self.base.shape[-1]
+
+    @property
+    def N(self):
+        return self.base.shape[0]
+
+    @property
+    def H(self):
+        return self.base.shape[1]
+
+    @property
+    def W(self):
+        return self.base.shape[2]
+
+    def torch(self) -> torch.Tensor:
+        return self.base[..., self.off:self.off + self.C]
+
+
+def view(t: torch.Tensor, off: int = 0, C: Optional[int] = None) -> View:
+    assert t.dim() == 4 and t.is_contiguous()
+    return View(t, off, t.shape[-1] - off if C is None else C)
+
+
+# ------------------------------------------------------------------------------------------------
+def corr_nchw(first: torch.Tensor, second: torch.Tensor, stride: int) -> torch.Tensor:
+    lib = _lib.load()
+    _need_cuda(first, second)
+    B, Cc, H, W = first.shape
+    out = torch.empty((B, 49, int(math.ceil(H / stride)), int(math.ceil(W / stride))),
+                      device=first.device, dtype=torch.float32)
+    _lib.check(lib.pivlfn_corr_nchw(first.data_ptr(), second.data_ptr(), out.data_ptr(),
+                                    B, Cc, H, W, int(stride), _stream()), "corr_nchw")
+    return out
+
+
+def prep_images(img1, img2, out, mean6):
+    lib = _lib.load()
+    _need_cuda(img1, img2, out)
+    B, _, H, W = img1.shape
+    arr = (C.c_float * 6)(*[float(m) for m in mean6])
+    _lib.check(lib.pivlfn_prep_images(img1.data_ptr(), img2.data_ptr(), out.data_ptr(), B, H, W, arr, _stream()),
+               "prep_images")
+
+
+def avgpool2(x: torch.Tensor, out: torch.Tensor):
+    lib = _lib.load()
+    N, H, W, Cc = x.shape
+    _lib.check(lib.pivlfn_avgpool2(x.data_ptr(), out.data_ptr(), N, H, W, Cc, _stream()), "avgpool2")
+
+
+def copy(src: View, dst: View, npix: int):
+    lib = _lib.load()
+    assert src.C == dst.C
+    _lib.check(lib.pivlfn_copy_nhwc(src.ptr, src.ld, dst.ptr, dst.ld, npix, src.C, _stream()), "copy_nhwc")
+
+
+def conv_simt(x: View, N, H, W, w, bias, y: View, KH, KW, stride, lrelu, res: Optional[View] = None):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_conv_simt(x.ptr, x.ld, N, H, W, x.C, w.data_ptr(),
+                                    bias.data_ptr() if bias is not None else None,
+                                    y.ptr, y.ld, y.C, KH, KW, stride, int(lrelu),
+                                    res.ptr if res is not None else None, res.ld if res is not None else 0,
+                                    _stream()), "conv_simt")
+
+
+def conv3x3_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, lrelu, passes):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_conv3x3_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),
+                                     w_lo.data_ptr() if w_lo is not None else None,
+                                     bias.data_ptr() if bias is not None else None,
+                                     y.ptr, y.ld, y.C, int(lrelu), int(passes), _stream()), "conv3x3_tc")
+
+
+def deconv4x4s2_dw(x: View, N, H, W, w, y: View):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_deconv4x4s2_dw(x.ptr, x.ld, w.data_ptr(), y.ptr, y.ld, N, H, W, x.C, _stream()),
+               "deconv4x4s2_dw")
+
+
+def warp(x: View, flow: torch.Tensor, scale: float, y: View, N, H, W):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_warp_nhwc(x.ptr, x.ld, flow.data_ptr(), float(scale), y.ptr, y.ld, N, H, W, x.C,
+                                    _stream()), "warp_nhwc")
+
+
+def corr_nhwc(f1: View, f2: View, flow: Optional[torch.Tensor], scale: float, out: View, N, H, W, stride, lrelu=True):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_corr_nhwc(f1.ptr, f1.ld, f2.ptr, f2.ld, flow.data_ptr() if flow is not None else None,
+                                    float(scale), out.ptr, out.ld, N, H, W, f1.C, int(stride), int(lrelu),
+                                    _stream()), "corr_nhwc")
+
+
+def flow_mean_parts() -> int:
+    return _lib.load().pivlfn_flow_mean_parts()
+
+
+def flow_mean(flow: torch.Tensor, partial: torch.Tensor):
+    lib = _lib.load()
+    N, H, W, _ = flow.shape
+    _lib.check(lib.pivlfn_flow_mean(flow.data_ptr(), partial.data_ptr(), N, H, W, _stream()), "flow_mean")
+
+
+def reg_input(img1, img2, flow, scale, partial, out: View):
+    lib = _lib.load()
+    N, H, W, _ = flow.shape
+    _lib.check(lib.pivlfn_reg_input(img1.data_ptr(), img2.data_ptr(), flow.data_ptr(), float(scale),
+                                    partial.data_ptr(), out.ptr, out.ld, N, H, W, _stream()), "reg_input")
+
+
+def reg_tail(dist: View, flow_in, wx, bx, wy, by, flow_out, out_nchw, final_scale, K):
+    lib = _lib.load()
+    N, H, W, _ = flow_in.shape
+    _lib.check(lib.pivlfn_reg_tail(dist.ptr, dist.ld, flow_in.data_ptr(), wx.data_ptr(), bx.data_ptr(),
+                                   wy.data_ptr(), by.data_ptr(), flow_out.data_ptr(),
+                                   out_nchw.data_ptr() if out_nchw is not None else None, float(final_scale),
+                                   K, N, H, W, _stream()), "reg_tail")
+
+
+def launch_count() -> int:
+    return int(_lib.load().pivlfn_launch_count())
