@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the PIV-LiteFlowNet-en forward pass (BASELINE.json metric: PIV pairs/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision 3xtf32|tf32|simt]
+
+One "step" = one forward pass over a batch of 64 synthetic 256x256 particle-image pairs (BASELINE.json
+configs[1]); under torchrun every rank owns its own 64 pairs (independent pairs shard with no data-path
+collective -> weak scaling), and the only collective is the max-over-ranks of the device time.
+
+  value      pairs/s, inputs already resident in HBM, timed with CUDA events on the launching stream
+  e2e        pairs/s through the drop-in API (src.models net(img1, img2)) with PINNED HOST inputs:
+             H2D of both image batches and D2H of the flow are inside the timed region
+  roofline   the dominant kernel (tcgen05 3x3 implicit-GEMM convolution, the level-1 128->128 layer of conv_R)
+             timed alone with CUDA events: algorithmic FLOPs / launch duration vs the measured bf16 peak
+  cpu_baseline  the CPU oracle (oracle/lfn_oracle.py, a restatement of the reference's forward) on this box's
+             host cores, on a bounded sample of the same workload (rank 0, N=1 only)
+
+`--impl reference` times the reference's CPU algorithm (the oracle port: the reference itself is Python
+that cannot travel to the GPU box and has no CPU path for its correlation) on the same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "piv_liteflownet-pytorch_b200"))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+BATCH, HH, WW = 64, 256, 256
+WORKLOAD = "PIV-LiteFlowNet-en fp32 forward, batch 64 of 256x256 synthetic particle pairs (BASELINE configs[1])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synthetic_batch(n, seed0):
+    """n distinct particle pairs: a small pool of generated pairs, tiled/rolled to distinct images (generation on the
+    host is O(particles) python; the pool keeps bench start-up short)."""
+    from pivlfn import synth
+    pool = [synth.particle_pair(HH, WW, seed0 + i, ("uniform", "rankine", "shear")[i % 3]) for i in range(8)]
+    a, b = [], []
+    for i in range(n):
+        i1, i2, _ = pool[i % 8]
+        sh = (i // 8) * 17
+        a.append(synth.to_rgb_tensor(np.roll(i1, sh, axis=1)))
+        b.append(synth.to_rgb_tensor(np.roll(i2, sh, axis=1)))
+    return torch.stack(a), torch.stack(b)
+
+
+def cpu_reference_rate(n_pairs, threads):
+    """Oracle forward on the host: pairs/s over ``n_pairs`` single-pair steps after one warm-up."""
+    from oracle import lfn_oracle as O
+    from pivlfn import synth
+    torch.set_num_threads(threads)
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b = synthetic_batch(1, 1000)
+    with torch.no_grad():
+        O.forward(sd, a, b, "piv")
+        t0 = time.perf_counter()
+        for _ in range(n_pairs):
+            O.forward(sd, a, b, "piv")
+        dt = time.perf_counter() - t0
+    return n_pairs / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # warm-up steps are single pairs too; every timed step is one 256x256 pair of the 64-pair workload
+    from oracle import lfn_oracle as O
+    from pivlfn import synth
+    torch.set_num_threads(threads)
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b = synthetic_batch(1, 1000)
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            O.forward(sd, a, b, "piv")
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(sd, a, b, "piv")
+        dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps of 1 pair 256x256 each (of the 64-pair batch), oracle port of the reference forward, torch fp32 CPU"
+    print(json.dumps({
+        "impl": "reference", "metric": "PIV pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def time_kernel(fn, iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def kernel_rooflines(eng, pk):
+    """Time the dominant kernels alone (CUDA events on the launching stream, working sets >> L2 at batch 64)."""
+    from pivlfn import ops
+    from pivlfn.model import SIMT
+    plan = eng.plan(BATCH, HH, WW)
+    d = plan.lv[1]
+    B, h, w = BATCH, HH, WW
+    out = {}
+    key = "NetE_R.0.conv_R.2"                      # 3x3 128 -> 128 at level 1: the largest single layer
+    cw = eng.w[key]
+    x, y = ops.view(d["t"][128][0]), ops.view(d["t"][128][1])
+    flops = 2.0 * B * h * w * 128 * 128 * 9
+    if eng.precision != SIMT and cw.w_hi is not None:
+        passes = 3 if eng.precision == "3xtf32" else 1
+        ms = time_kernel(lambda: ops.conv3x3_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, True, passes), 10)
+        name = f"conv3x3_tc_kernel (tcgen05 kind::tf32, {passes} pass)"
+    else:
+        ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
+        name = "conv_simt_kernel (fp32 FFMA)"
+    ach = flops / (ms * 1e-3) / 1e12
+    out["roofline"] = {"kernel": name, "layer": key + " 3x3 128->128 @256x256 x64", "bound": "tensor",
+                       "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
+                       "peak_source": pk["src"] + ", dense bf16 burst; kind::tf32 peak is half of it",
+                       "ms_per_launch": ms, "traffic": None}
+    # memory-bound: level-1 cost volume (stride 2, C=64, fused backwarp + LeakyReLU)
+    cm = 64
+    S_f1 = ops.view(d["Sbuf"], 0, cm)
+    ms = time_kernel(lambda: ops.corr_nhwc(S_f1, ops.view(d["f2"]), d["flowU"], 5.0, ops.view(d["corr"], 0, 49),
+                                           B, h, w, 2, True), 10)
+    byts = 4.0 * B * (2 * cm * h * w + 2 * h * w + 49 * (h // 2) * (w // 2))
+    ach = byts / (ms * 1e-3) / 1e9
+    out["roofline_corr"] = {"kernel": "corr_nhwc_kernel (level 1, s=2, fused backwarp)", "bound": "hbm", "achieved": ach,
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
+    ms = time_kernel(lambda: ops.reg_tail(ops.view(d["dist"], 0, 49), d["flowS"],
+                                          eng.raw["NetE_R.0.moduleScaleX.weight"], eng.raw["NetE_R.0.moduleScaleX.bias"],
+                                          eng.raw["NetE_R.0.moduleScaleY.weight"], eng.raw["NetE_R.0.moduleScaleY.bias"],
+                                          d["flowR"], None, 5.0, 7), 10)
+    byts = 4.0 * B * h * w * (49 + 4)
+    ach = byts / (ms * 1e-3) / 1e9
+    out["roofline_reg_tail"] = {"kernel": "reg_tail_kernel<7> (level 1)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+                                "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
+    ms = time_kernel(lambda: ops.warp(ops.view(d["f2"]), d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w), 10)
+    byts = 4.0 * B * h * w * (2 * cm + 2)
+    ach = byts / (ms * 1e-3) / 1e9
+    out["roofline_warp"] = {"kernel": "warp_nhwc_kernel (level 1, C=64)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+                            "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="pivlfn", choices=["pivlfn", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("PIVLFN_PRECISION", "3xtf32"))
+    ap.add_argument("--no-extra", action="store_true", help="skip the 1024x1024 and per-kernel side measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "pivlfn" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from pivlfn import ops, synth
+    from pivlfn.arch import CFGS, conv_flops_per_pixel
+    from src.models import piv_liteflownet
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    pk = peaks()
+
+    sd = synth.synthetic_state_dict("piv", 0)
+    net = piv_liteflownet(sd, 1).to(dev).eval()
+    net.precision = args.precision
+    eng = net.engine()
+    a, b = synthetic_batch(BATCH, 10_000 * (rank + 1))
+    a_pin, b_pin = a.pin_memory(), b.pin_memory()
+    plan = eng.plan(BATCH, HH, WW)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput ("value")
+    a_dev, b_dev = a.to(dev), b.to(dev)
+
+    def step_resident():
+        plan.in1.copy_(a_dev)            # fresh (un-normalised) inputs every step: the forward mutates them in place
+        plan.in2.copy_(b_dev)
+        plan.run_static()
+
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    launches = eng.launches - l0
+    from pivlfn import shard
+    total_pairs, ms = shard.gather_counts(BATCH * args.steps, ms_local)
+    value = total_pairs / (ms * 1e-3)
+
+    # ------------------------------------------------------------------ end to end through the drop-in API ("e2e")
+    out_host = torch.empty((BATCH, 2, HH, WW), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        x1 = a_pin.to(dev, non_blocking=True)
+        x2 = b_pin.to(dev, non_blocking=True)
+        with torch.no_grad():
+            flow = net(x1, x2)
+        out_host.copy_(flow, non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    _, ms_e2e = shard.gather_counts(BATCH * args.steps, e0.elapsed_time(e1))
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_value = total_pairs / (ms_e2e * 1e-3)
+    h2d = 2 * a.numel() * 4
+    d2h = out_host.numel() * 4
+
+    line = {
+        "metric": "PIV pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if args.precision != "tf32" else "tf32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "precision": args.precision, "global_batch": BATCH * world,
+                   "parallelism": f"pair-sharded x{world}, no data-path collective",
+                   "l2": "inputs larger than L2 (multi-GB working set per step)",
+                   "weights": "deterministic synthetic (pretrained blobs absent from the reference mount)"},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "api": "src.models.piv_liteflownet(...)(img1, img2) with pinned host tensors"},
+        "gpu_launches": int(launches), "clocks": clocks,
+        "conv_tflops_effective": conv_flops_per_pixel(CFGS["piv"]) * HH * WW * BATCH * world / (ms / args.steps * 1e-3) / 1e12,
+    }
+
+    if rank == 0 and not args.no_extra:
+        try:
+            line.update(kernel_rooflines(eng, pk))
+        except Exception as ex:  # a side measurement must not lose the headline
+            line["roofline"] = {"error": repr(ex)}
+    if not args.no_extra and world == 1:
+        # second headline shape: 1024x1024 (BASELINE configs[3] frame size), batch 4 resident in HBM
+        try:
+            del a_dev, b_dev
+            eng._plans.clear()
+            torch.cuda.empty_cache()
+            hh = 1024
+            from pivlfn import synth as S
+            i1, i2, _ = S.particle_pair(hh, hh, 5, "rankine")
+            xa = S.to_rgb_tensor(i1)[None].repeat(4, 1, 1, 1).to(dev)
+            xb = S.to_rgb_tensor(i2)[None].repeat(4, 1, 1, 1).to(dev)
+            p2 = eng.plan(4, hh, hh)
+
+            def step1024():
+                p2.in1.copy_(xa); p2.in2.copy_(xb); p2.run_static()
+            ms1024 = time_kernel(step1024, 5)
+            line["pairs_per_s_1024"] = {"value": 4 / (ms1024 * 1e-3), "batch": 4, "ms_per_step": ms1024,
+                                        "conv_tflops_effective": conv_flops_per_pixel(CFGS["piv"]) * hh * hh * 4 / (ms1024 * 1e-3) / 1e12}
+        except Exception as ex:
+            line["pairs_per_s_1024"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_reference_rate(3, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                                    "sample": f"3 single 256x256 pairs of the workload after 1 warm-up ({dt:.1f} s), oracle port, torch fp32"}
+        except Exception as ex:
+            line["cpu_baseline"] = {"error": repr(ex)}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

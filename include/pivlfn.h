@@ -113,6 +113,12 @@ int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow_in,
                     float* flow_out, float* out_nchw, float final_scale,
                     int K, int N, int H, int W, void* stream);
 
+/* F.interpolate(mode='bilinear', align_corners=False) of inference.py:46-49 (images up to a multiple of 32)
+ * and :57-61 (flow back to the input size, with u *= W/W' and v *= H/H' folded in as mul_even / mul_odd,
+ * applied to channels of even / odd index).  in: [NC,H,W], out: [NC,Ho,Wo], both dense NCHW planes. */
+int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, int H, int W, int Ho, int Wo,
+                                float mul_even, float mul_odd, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -262,6 +262,32 @@ reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __res
     }
 }
 
+
+// ---- F.interpolate(mode='bilinear', align_corners=False) on NCHW (inference.py:46-49,57-61) ------------------
+// src = (dst + 0.5) * (in / out) - 0.5 clamped at 0, second tap clamped at in-1; channels of even index are
+// multiplied by mul_even and odd ones by mul_odd (the u *= W/W', v *= H/H' of inference.py:60-61).
+__global__ void resize_bilinear_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int H, int W,
+                                            int Ho, int Wo, float mul_even, float mul_odd) {
+    const float ry = (float)H / (float)Ho, rx = (float)W / (float)Wo;
+    const long long total = (long long)NC * Ho * Wo;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ox = (int)(i % Wo);
+        const long long t = i / Wo;
+        const int oy = (int)(t % Ho);
+        const long long c = t / Ho;
+        const float sy = fmaxf(((float)oy + 0.5f) * ry - 0.5f, 0.f);
+        const float sx = fmaxf(((float)ox + 0.5f) * rx - 0.5f, 0.f);
+        const int y0 = min((int)sy, H - 1), x0 = min((int)sx, W - 1);
+        const int y1 = min(y0 + 1, H - 1), x1 = min(x0 + 1, W - 1);
+        const float ly = sy - (float)y0, lx = sx - (float)x0;
+        const float* p = in + c * (long long)H * W;
+        const float v = (1.f - ly) * ((1.f - lx) * __ldg(p + (long long)y0 * W + x0) + lx * __ldg(p + (long long)y0 * W + x1)) +
+                        ly * ((1.f - lx) * __ldg(p + (long long)y1 * W + x0) + lx * __ldg(p + (long long)y1 * W + x1));
+        out[i] = v * ((c & 1) ? mul_odd : mul_even);
+    }
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 32;       // a few waves of the 148 SMs, grid-stride beyond
@@ -362,6 +388,16 @@ extern "C" int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow
         case 7: reg_tail_kernel<7><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
         default: return PIVLFN_EINVAL;
     }
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, int H, int W, int Ho, int Wo,
+                                           float mul_even, float mul_odd, void* stream) {
+    if (!in || !out || NC <= 0 || H <= 0 || W <= 0 || Ho <= 0 || Wo <= 0) return PIVLFN_EINVAL;
+    const long long total = (long long)NC * Ho * Wo;
+    resize_bilinear_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, NC, H, W, Ho, Wo,
+                                                                                         mul_even, mul_odd);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }

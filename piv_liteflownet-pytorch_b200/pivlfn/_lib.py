@@ -27,6 +27,7 @@ PROTOTYPES = {
     "pivlfn_reg_input": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _p]),
     "pivlfn_reg_tail": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p]),
     "pivlfn_copy_nhwc": (_i, [_p, _i, _p, _i, _ll, _i, _p]),
+    "pivlfn_resize_bilinear_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
 }
 
 _lib = None
@@ -41,12 +42,13 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.isfile(LIB_PATH):
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("pivlfn_build", os.path.join(os.path.dirname(_HERE), "build.py"))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        mod.build()
+    # (re)build in-tree when the sources changed since the last build (no-op when the stamp matches; a box
+    # without nvcc uses the shipped library as is)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("pivlfn_build", os.path.join(os.path.dirname(_HERE), "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.build()
     if not os.path.isfile(LIB_PATH):
         raise PivlfnError("libpivlfn.so is missing: run `python piv_liteflownet-pytorch_b200/build.py` "
                           "(there is no CPU / eager fallback)")

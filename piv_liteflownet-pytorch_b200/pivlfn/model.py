@@ -1,0 +1,398 @@
+"""Forward pass of LiteFlowNet / LiteFlowNet2 (PIV and Hui variants) as a launch plan over the C ABI.
+
+``Engine`` owns (i) the weights repacked once into the kernels' layouts, (ii) one workspace of NHWC
+fp32 buffers per input shape and (iii) optionally a CUDA graph of the whole forward.  ``forward``
+replaces ``LiteFlowNet.forward`` (src/models.py:319-370) / ``LiteFlowNet2.forward`` (:660-716) of the
+reference: same inputs ([B,3,H,W] fp32 NCHW in [0,1], mean-subtracted IN PLACE like the reference),
+same output ([B,2,H',W'] fp32 NCHW flow in pixels).
+
+Data layout in HBM.  Every activation is NHWC fp32.  The reference's ``torch.cat`` calls disappear:
+each concatenated tensor is ONE buffer whose channel slices are written in place by their producers
+(``View`` = pointer + channel count + pixel pitch):
+
+    Sbuf[l] = [ f1 (Cm) | backwarp(f2) (Cm) | flow_M (2) | pad (2) ]       input of conv_S  (src/models.py:216)
+    Rbuf[l] = [ feat (Cr) | err (1) | flow_S - mean (2) | pad (1) ]        input of conv_R  (src/models.py:280)
+
+Rbuf's channel order differs from the reference's (err, rm, feat): the first conv_R weight is permuted
+at pack time instead, so that every slice stays 16-byte aligned.
+
+There is no CPU path: everything below launches kernels from libpivlfn.so.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, ops
+from .arch import (CFGS, CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END, ModelCfg,
+                   param_specs)
+from .ops import View, view
+
+# conv back-ends
+SIMT = "simt"          # exact fp32 FFMA on the CUDA cores
+TC_TF32 = "tf32"       # tcgen05 kind::tf32, one pass
+TC_3XTF32 = "3xtf32"   # tcgen05 kind::tf32, error-compensated three passes (fp32-equivalent)
+PRECISIONS = (SIMT, TC_TF32, TC_3XTF32)
+
+
+def _r4(c: int) -> int:
+    return (c + 3) & ~3
+
+
+def tf32_round(w: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest (ties away, like cvt.rna.tf32.f32) of fp32 to the 10-bit-mantissa TF32 grid."""
+    i = w.contiguous().view(torch.int32)
+    r = ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+    return torch.where(torch.isfinite(w), r, w)
+
+
+@dataclass
+class ConvW:
+    """One convolution's packed weights."""
+    cin: int
+    cout: int
+    kh: int
+    kw: int
+    stride: int
+    w_simt: torch.Tensor                    # [KH*KW*Cin, CoutP]
+    bias: Optional[torch.Tensor]
+    w_hi: Optional[torch.Tensor] = None     # [Cout, KH*KW, CinP32] TF32 split for the tcgen05 kernel
+    w_lo: Optional[torch.Tensor] = None
+
+
+def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_pad: int = 0,
+              in_perm: Optional[torch.Tensor] = None, tc: bool = True) -> ConvW:
+    """w: [Cout,Cin,KH,KW] (torch.nn.Conv2d layout) -> kernel layouts.  ``in_perm`` reorders input channels
+    (new channel j reads old channel in_perm[j]); ``cin_pad`` appends zero input channels."""
+    w = w.detach().to(torch.float32)
+    if in_perm is not None:
+        w = w[:, in_perm]
+    if cin_pad:
+        w = torch.cat([w, w.new_zeros(w.shape[0], cin_pad, w.shape[2], w.shape[3])], 1)
+    cout, cin, kh, kw = w.shape
+    coutp = _r4(cout)
+    ws = w.permute(2, 3, 1, 0).reshape(kh * kw * cin, cout)
+    if coutp != cout:
+        ws = torch.cat([ws, ws.new_zeros(ws.shape[0], coutp - cout)], 1)
+    cw = ConvW(cin, cout, kh, kw, stride, ws.contiguous(), None if b is None else b.detach().to(torch.float32).contiguous())
+    if tc and tc_eligible(cin, cout, kh, kw, stride):
+        cinp = (cin + 31) // 32 * 32
+        wt = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
+        if cinp != cin:
+            wt = torch.cat([wt, wt.new_zeros(cout, kh * kw, cinp - cin)], 2)
+        hi = tf32_round(wt)
+        lo = tf32_round(wt - hi)
+        cw.w_hi, cw.w_lo = hi.contiguous(), lo.contiguous()
+    return cw
+
+
+def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int) -> bool:
+    return kh == 3 and kw == 3 and stride == 1 and cout % 16 == 0 and 16 <= cout <= 128 and cin >= 16
+
+
+class Engine:
+    """Weights + workspaces + launch plan for one model."""
+
+    def __init__(self, cfg: ModelCfg, state_dict: Dict[str, torch.Tensor], device: torch.device,
+                 precision: str = None, use_graph: bool = None):
+        if device.type != "cuda":
+            raise NotImplementedError("pivlfn runs on CUDA devices only (no CPU path)")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.device = device
+        self.precision = precision or os.environ.get("PIVLFN_PRECISION", TC_3XTF32)
+        if self.precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {PRECISIONS}")
+        self.use_graph = (os.environ.get("PIVLFN_GRAPH", "1") != "0") if use_graph is None else use_graph
+        self.sf = cfg.scalefactor
+        self.w: Dict[str, ConvW] = {}
+        self.raw: Dict[str, torch.Tensor] = {}
+        self._plans: Dict[Tuple[int, int, int], "Plan"] = {}
+        self.launches = 0          # kernels launched (graph replays counted by their captured node count)
+        self._pack(state_dict)
+
+    # ---------------------------------------------------------------------------------------------
+    def _pack(self, sd: Dict[str, torch.Tensor]):
+        dev = self.device
+        cfg = self.cfg
+        specs = param_specs(cfg)
+        for k, shp in specs.items():
+            if k not in sd:
+                raise KeyError(f"missing parameter {k}")
+            if tuple(sd[k].shape) != tuple(shp):
+                raise RuntimeError(f"size mismatch for {k}: expected {tuple(shp)}, got {tuple(sd[k].shape)}")
+        g = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
+        use_tc = self.precision != SIMT
+
+        def conv(key, stride=1, cin_pad=0, in_perm=None):
+            self.w[key] = pack_conv(g(key + ".weight"), g(key + ".bias") if key + ".bias" in sd else None,
+                                    stride, cin_pad, in_perm, tc=use_tc)
+
+        for seq, idx, cin, cout, k, st in NETC:
+            conv(f"NetC.{seq}.{idx}", st, cin_pad=1 if cin == 3 else 0)
+        for e in range(cfg.n_ext):
+            conv(f"NetC_ext.{e}.conv_ext.0")
+        nh = len(cfg.head)
+        for i, lv in enumerate(cfg.levels):
+            for j in range(nh + 1):
+                conv(f"NetE_M.{i}.conv_M.{2 * j}")
+                conv(f"NetE_S.{i}.conv_S.{2 * j}")
+            for nm in ("upConv_M", "upCorr_M"):
+                key = f"NetE_M.{i}.{nm}.weight"
+                if key in sd:
+                    self.raw[key] = g(key).reshape(-1, 16).contiguous()
+            p = f"NetE_R.{i}"
+            if lv < 5:
+                conv(p + ".moduleFeat.0")
+            cr = 128 if lv < 5 else LEVEL_FEAT_CH[lv]
+            perm = torch.cat([torch.arange(3, 3 + cr), torch.arange(0, 3)]).to(dev)
+            conv(p + ".conv_R.0", in_perm=perm, cin_pad=1)
+            for j in range(1, len(CONV_R)):
+                conv(f"{p}.conv_R.{2 * j}")
+            conv(p + ".conv_dist_R.0")
+            if lv < 5:
+                conv(p + ".conv_dist_R.1")
+            for nm in ("moduleScaleX", "moduleScaleY"):
+                self.raw[f"{p}.{nm}.weight"] = g(f"{p}.{nm}.weight").reshape(-1).contiguous()
+                self.raw[f"{p}.{nm}.bias"] = g(f"{p}.{nm}.bias").reshape(-1).contiguous()
+
+    # ---------------------------------------------------------------------------------------------
+    def plan(self, B: int, H: int, W: int) -> "Plan":
+        key = (B, H, W)
+        p = self._plans.get(key)
+        if p is None:
+            p = Plan(self, B, H, W)
+            self._plans[key] = p
+        return p
+
+    def forward(self, img1: torch.Tensor, img2: torch.Tensor, return_levels: bool = False):
+        if not (img1.is_cuda and img2.is_cuda):
+            raise NotImplementedError("pivlfn: CUDA tensors required (there is no CPU path)")
+        assert img1.dtype == torch.float32 and img2.dtype == torch.float32
+        assert img1.dim() == 4 and img1.shape[1] == 3 and img1.shape == img2.shape
+        assert img1.is_contiguous() and img2.is_contiguous()
+        B, _, H, W = img1.shape
+        if H % 32 or W % 32:
+            raise RuntimeError(f"pivlfn: H and W must be multiples of 32 (got {H}x{W}); use estimate() which resizes "
+                               "like the reference (inference.py:39-49)")
+        return self.plan(B, H, W).run(img1, img2, return_levels)
+
+
+class Plan:
+    """Workspace and launch sequence for one (B, H, W)."""
+
+    def __init__(self, eng: Engine, B: int, H: int, W: int):
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        cfg = eng.cfg
+        dev = eng.device
+        E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
+        self.hw = {l: (H >> (l - 1), W >> (l - 1)) for l in range(1, 7)}
+        N2 = 2 * B
+        # static inputs (graph replays need fixed addresses)
+        self.in1, self.in2 = E(B, 3, H, W), E(B, 3, H, W)
+        self.img = {1: E(N2, H, W, 4)}
+        for l in range(2, 7):
+            self.img[l] = E(N2, *self.hw[l], 4)
+        # NetC intermediates and features
+        self.netc_out: List[torch.Tensor] = []
+        lvl = 1
+        for seq, idx, cin, cout, k, st in NETC:
+            if st == 2:
+                lvl += 1
+            self.netc_out.append(E(N2, *self.hw[lvl], cout))
+        self.feat = {l: self.netc_out[NETC_LEVEL_END[l]] for l in range(1, 7)}
+        self.lv: Dict[int, dict] = {}
+        nh = len(cfg.head)
+        for l in cfg.levels:
+            h, w = self.hw[l]
+            cm, cr = MATCH_FEAT_CH[l], (128 if l < 5 else LEVEL_FEAT_CH[l])
+            s = 2 if l < 4 else 1
+            d = dict(
+                f2=E(B, h, w, cm) if l <= 2 else None,
+                flowU=E(B, h, w, 2) if l != 6 else None,
+                corr=Z(B, (h + s - 1) // s, (w + s - 1) // s, 52),
+                corrU=Z(B, h, w, 52) if l < 4 else None,
+                Sbuf=Z(B, h, w, 2 * cm + 4),
+                Rbuf=Z(B, h, w, cr + 4),
+                flowM=E(B, h, w, 2), flowS=E(B, h, w, 2), flowR=E(B, h, w, 2),
+                partial=E(B, ops.flow_mean_parts(), 2),
+                dist=E(B, h, w, _r4(DIST_CH[l])), dist0=E(B, h, w, _r4(DIST_CH[l])) if l < 5 else None,
+            )
+            widths = sorted(set(cfg.head) | set(CONV_R))
+            d["t"] = {c: [E(B, h, w, c), E(B, h, w, c)] for c in widths}   # ping-pong per width
+            self.lv[l] = d
+        lo = cfg.lowest_level
+        self.out = E(B, 2, *self.hw[lo])
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_launches = 0
+        self._warm = 0
+
+    # ---------------------------------------------------------------------------------------------
+    def _conv(self, key: str, x: View, n: int, h: int, w: int, y: View, lrelu: bool = True,
+              res: Optional[View] = None):
+        eng = self.eng
+        cw = eng.w[key]
+        assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
+        if cw.w_hi is not None and res is None and eng.precision != SIMT:
+            ops.conv3x3_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, 3 if eng.precision == TC_3XTF32 else 1)
+        else:
+            ops.conv_simt(x, n, h, w, cw.w_simt, cw.bias, y, cw.kh, cw.kw, cw.stride, lrelu, res)
+
+    def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: View, out: View):
+        """conv_M / conv_S: 3x3 conv + LeakyReLU ..., then the KxK 32->2 flow head plus residual flow."""
+        B = self.B
+        h, w = self.hw[l]
+        t = self.lv[l]["t"]
+        used: Dict[int, int] = {}
+        for j in idxs[:-1]:
+            c = self.eng.w[f"{prefix}.{j}"].cout
+            k = used.get(c, 0)
+            used[c] = k ^ 1
+            y = view(t[c][k])
+            self._conv(f"{prefix}.{j}", x, B, h, w, y)
+            x = y
+        self._conv(f"{prefix}.{idxs[-1]}", x, B, h, w, out, lrelu=False, res=res)
+
+    def launch_all(self):
+        """Enqueue the whole forward on the current stream (inputs already in self.in1 / self.in2)."""
+        eng, cfg, B = self.eng, self.eng.cfg, self.B
+        N2 = 2 * B
+        H, W = self.H, self.W
+        ops.prep_images(self.in1, self.in2, self.img[1], cfg.mean)
+        for l in range(2, 7):
+            ops.avgpool2(self.img[l - 1], self.img[l])
+        # ---- NetC on both images at once (shared weights): batch 2B ----------------------------------------
+        x = view(self.img[1])
+        lvl = 1
+        for i, (seq, idx, cin, cout, k, st) in enumerate(NETC):
+            hi, wi = self.hw[lvl]
+            if st == 2:
+                lvl += 1
+            y = view(self.netc_out[i])
+            self._conv(f"NetC.{seq}.{idx}", x, N2, hi, wi, y)
+            x = y
+        nh = len(cfg.head)
+        head_idx = [2 * j for j in range(nh + 1)]
+        rconv_idx = [2 * j for j in range(len(CONV_R))]
+        xflow = None
+        for i in reversed(range(len(cfg.levels))):
+            l = cfg.levels[i]
+            d = self.lv[l]
+            h, w = self.hw[l]
+            cm = MATCH_FEAT_CH[l]
+            cr = 128 if l < 5 else LEVEL_FEAT_CH[l]
+            s = 2 if l < 4 else 1
+            scale = eng.sf[l]
+            feat = self.feat[l]                      # [2B,h,w,Cf]
+            feat1, feat2 = feat[:B], feat[B:]
+            S_f1, S_f2w, S_fl = view(d["Sbuf"], 0, cm), view(d["Sbuf"], cm, cm), view(d["Sbuf"], 2 * cm, 2)
+            if l <= 2:
+                # NetC_ext (src/models.py:353-355): list index idx = l-1 uses NetC_ext[idx-1] (wraps to [-1])
+                e = (l - 2) % cfg.n_ext
+                self._conv(f"NetC_ext.{e}.conv_ext.0", view(feat1), B, h, w, S_f1)
+                self._conv(f"NetC_ext.{e}.conv_ext.0", view(feat2), B, h, w, view(d["f2"]))
+                f2 = view(d["f2"])
+            else:
+                ops.copy(view(feat1), S_f1, B * h * w)
+                f2 = view(feat2)
+            # ---- Matching (src/models.py:165-187) ------------------------------------------------------------
+            if xflow is not None:
+                ops.deconv4x4s2_dw(view(xflow), B, h // 2, w // 2, eng.raw[f"NetE_M.{i}.upConv_M.weight"], view(d["flowU"]))
+                flowU = d["flowU"]
+            else:
+                flowU = None
+            ops.corr_nhwc(S_f1, f2, flowU, scale, view(d["corr"], 0, 49), B, h, w, s, lrelu=True)
+            if l < 4:
+                ops.deconv4x4s2_dw(view(d["corr"], 0, 49), B, (h + 1) // 2, (w + 1) // 2,
+                                   eng.raw[f"NetE_M.{i}.upCorr_M.weight"], view(d["corrU"], 0, 49))
+                cin = view(d["corrU"], 0, 49)
+            else:
+                cin = view(d["corr"], 0, 49)
+            self._chain(f"NetE_M.{i}.conv_M", head_idx, cin, l, view(flowU) if flowU is not None else None,
+                        view(d["flowM"]))
+            # ---- Subpixel (src/models.py:209-217) ------------------------------------------------------------
+            ops.warp(f2, d["flowM"], scale, S_f2w, B, h, w)
+            ops.copy(view(d["flowM"]), S_fl, B * h * w)
+            self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"], 0, 2 * cm + 2), l, view(d["flowM"]),
+                        view(d["flowS"]))
+            # ---- Regularization (src/models.py:274-303) ------------------------------------------------------
+            ops.flow_mean(d["flowS"], d["partial"])
+            ops.reg_input(self.img[l][:B], self.img[l][B:], d["flowS"], scale, d["partial"], view(d["Rbuf"], cr, 3))
+            if l < 5:
+                self._conv(f"NetE_R.{i}.moduleFeat.0", view(feat1), B, h, w, view(d["Rbuf"], 0, cr))
+            else:
+                ops.copy(view(feat1), view(d["Rbuf"], 0, cr), B * h * w)
+            x = view(d["Rbuf"], 0, cr + 4)
+            t = d["t"]
+            used: Dict[int, int] = {}
+            for j in rconv_idx:
+                c = eng.w[f"NetE_R.{i}.conv_R.{j}"].cout
+                k = used.get(c, 0)
+                used[c] = k ^ 1
+                y = view(t[c][k])
+                self._conv(f"NetE_R.{i}.conv_R.{j}", x, B, h, w, y)
+                x = y
+            dc = DIST_CH[l]
+            if l < 5:
+                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist0"], 0, dc), lrelu=False)
+                self._conv(f"NetE_R.{i}.conv_dist_R.1", view(d["dist0"], 0, dc), B, h, w, view(d["dist"], 0, dc), lrelu=False)
+            else:
+                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist"], 0, dc), lrelu=False)
+            p = f"NetE_R.{i}"
+            last = (l == cfg.lowest_level)
+            ops.reg_tail(view(d["dist"], 0, dc), d["flowS"], eng.raw[p + ".moduleScaleX.weight"],
+                         eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
+                         eng.raw[p + ".moduleScaleY.bias"], d["flowR"], self.out if last else None, eng.sf[1], KSIZE[l])
+            xflow = d["flowR"]
+
+    # ---------------------------------------------------------------------------------------------
+    def run_static(self):
+        """Run the forward on the static input buffers (self.in1/self.in2 -> self.out)."""
+        eng = self.eng
+        if not eng.use_graph:
+            c0 = ops.launch_count()
+            self.launch_all()
+            eng.launches += ops.launch_count() - c0
+            return
+        if self.graph is None:
+            if self._warm < 1:
+                # one eager run first: surfaces launch errors outside capture and warms lazy module loading
+                keep1, keep2 = self.in1.clone(), self.in2.clone()
+                c0 = ops.launch_count()
+                self.launch_all()
+                eng.launches += ops.launch_count() - c0
+                torch.cuda.current_stream().synchronize()
+                self._warm = 1
+                self.in1.copy_(keep1)
+                self.in2.copy_(keep2)
+            g = torch.cuda.CUDAGraph()
+            c0 = ops.launch_count()
+            with torch.cuda.graph(g):
+                self.launch_all()
+            self.graph_launches = ops.launch_count() - c0
+            self.graph = g
+        self.graph.replay()
+        eng.launches += self.graph_launches
+
+    def run(self, img1: torch.Tensor, img2: torch.Tensor, return_levels: bool = False, mutate_inputs: bool = True):
+        self.in1.copy_(img1)
+        self.in2.copy_(img2)
+        self.run_static()
+        if mutate_inputs:
+            # the reference subtracts the per-channel mean from the CALLER's tensors (src/models.py:321-323)
+            img1.copy_(self.in1)
+            img2.copy_(self.in2)
+        out = self.out.clone()
+        if not return_levels:
+            return out
+        levels = []
+        for i in reversed(range(len(self.eng.cfg.levels))):
+            d = self.lv[self.eng.cfg.levels[i]]
+            levels.append([d[k].permute(0, 3, 1, 2).contiguous() for k in ("flowM", "flowS", "flowR")])
+        return out, levels

@@ -160,5 +160,17 @@ def reg_tail(dist: View, flow_in, wx, bx, wy, by, flow_out, out_nchw, final_scal
                                    K, N, H, W, _stream()), "reg_tail")
 
 
+def resize_bilinear(x: torch.Tensor, Ho: int, Wo: int, mul_even: float = 1.0, mul_odd: float = 1.0) -> torch.Tensor:
+    """[B,C,H,W] -> [B,C,Ho,Wo], bilinear, align_corners=False (inference.py:46-49,57-61)."""
+    lib = _lib.load()
+    _need_cuda(x)
+    assert x.dim() == 4 and x.is_contiguous()
+    B, Cc, H, W = x.shape
+    out = torch.empty((B, Cc, Ho, Wo), device=x.device, dtype=torch.float32)
+    _lib.check(lib.pivlfn_resize_bilinear_nchw(x.data_ptr(), out.data_ptr(), B * Cc, H, W, Ho, Wo,
+                                               float(mul_even), float(mul_odd), _stream()), "resize_bilinear_nchw")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().pivlfn_launch_count())

@@ -64,6 +64,14 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(name, "flow absmax %.3f" % np.abs(out["flow"]).max(), {k: v.shape for k, v in out.items() if k.startswith("flow")})
 
+    # state_dict key order and shapes of the four reference models (the drop-in contract)
+    import json
+    keys = {}
+    for name, fn in (("piv", lambda: models.piv_liteflownet(None, 1)), ("hui", lambda: models.hui_liteflownet(None, 1)),
+                     ("piv2", lambda: models.piv_liteflownet(None, 2)), ("hui2", lambda: models.hui_liteflownet(None, 2))):
+        keys[name] = [[k, list(v.shape)] for k, v in fn().state_dict().items()]
+    json.dump(keys, open(os.path.join(HERE, "state_dict_keys.json"), "w"))
+
     # operator-level vectors from the reference's own backwarp (src/models.py:20-35)
     g = torch.Generator().manual_seed(7)
     inp = torch.randn(2, 5, 9, 13, generator=g)

@@ -1,0 +1,122 @@
+"""Whole-network parity on the B200 against the golden vectors of the unmodified reference (tests/golden) and
+the CPU oracle, through the drop-in API (src.models / inference.estimate), plus size-independent properties at
+the benchmark's full sizes.
+
+Tolerances (north_star): fp32-equivalent modes (`simt`, `3xtf32`): flow max-abs-diff <= 1e-2 px and mean <= 1e-3 px.
+Plain TF32 tensor-core mode (`tf32`) is reported separately with its own tolerance: max <= 0.25 px, mean <= 2e-2 px."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lfn_oracle as O
+from pivlfn import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+CASES = ["piv_b2_64x96", "piv_b1_128x128", "hui_b1_64x128", "piv2_b1_64x64", "hui2_b1_64x64"]
+TOL = {"simt": (1e-2, 1e-3), "3xtf32": (1e-2, 1e-3), "tf32": (0.25, 2e-2)}
+
+
+def _net(model, sd, precision):
+    from src.models import hui_liteflownet, piv_liteflownet
+    fac = {"piv": lambda: piv_liteflownet(sd, 1), "hui": lambda: hui_liteflownet(sd, 1),
+           "piv2": lambda: piv_liteflownet(sd, 2), "hui2": lambda: hui_liteflownet(sd, 2)}
+    net = fac[model]().to(DEV)
+    net.precision = precision
+    return net
+
+
+def _load(golden_dir, name):
+    d = np.load(os.path.join(golden_dir, name + ".npz"))
+    model = str(d["model"])
+    sd = synth.synthetic_state_dict(model, int(d["wseed"]))
+    a = torch.stack([synth.to_rgb_tensor(x) for x in d["img1_u8"]])
+    b = torch.stack([synth.to_rgb_tensor(x) for x in d["img2_u8"]])
+    return d, model, sd, a, b
+
+
+@pytest.mark.parametrize("precision", ["simt", "3xtf32", "tf32"])
+@pytest.mark.parametrize("name", CASES)
+def test_forward_matches_reference_golden(golden_dir, name, precision):
+    d, model, sd, a, b = _load(golden_dir, name)
+    net = _net(model, sd, precision).eval()
+    ad, bd = a.to(DEV), b.to(DEV)
+    with torch.no_grad():
+        flow = net(ad, bd)
+    assert flow.shape == d["flow"].shape and flow.dtype == torch.float32 and flow.is_cuda
+    diff = np.abs(flow.cpu().numpy() - d["flow"])
+    mx, mean = TOL[precision]
+    print(f"{name} {precision}: max {diff.max():.3e} mean {diff.mean():.3e}")
+    assert diff.max() <= mx and diff.mean() <= mean
+    # reference side effect: the caller's tensors are mean-subtracted in place (src/models.py:321-323)
+    assert np.allclose((ad.cpu() - a)[0, :, 0, 0].numpy(), d["img1_after"], atol=1e-6)
+    # training mode returns every level's [M, S, R] flows (src/models.py:365-367)
+    net.train()
+    with torch.no_grad():
+        levels = net(a.to(DEV), b.to(DEV))
+    net.eval()
+    nlv = len([k for k in d.files if k.endswith("_R")])
+    assert len(levels) >= nlv
+    for k in range(nlv):
+        for tag, t in zip("MSR", levels[k]):
+            g = d[f"lvl{k}_{tag}"]
+            assert t.shape == g.shape
+            assert np.abs(t.cpu().numpy() - g).max() <= mx, (k, tag)
+
+
+def test_graph_replay_equals_eager_and_is_deterministic(golden_dir):
+    d, model, sd, a, b = _load(golden_dir, "piv_b1_128x128")
+    from pivlfn.arch import CFGS
+    from pivlfn.model import Engine
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    e1 = Engine(CFGS[model], sdd, torch.device(DEV), "simt", use_graph=False)
+    e2 = Engine(CFGS[model], sdd, torch.device(DEV), "simt", use_graph=True)
+    o1 = e1.forward(a.to(DEV), b.to(DEV))
+    o2 = e2.forward(a.to(DEV), b.to(DEV))
+    o3 = e2.forward(a.to(DEV), b.to(DEV))
+    assert torch.equal(o1, o2) and torch.equal(o2, o3)
+    assert e1.launches > 100 and e2.launches >= 2 * e1.launches
+
+
+def test_estimate_non_multiple_of_32_vs_oracle():
+    from inference import estimate
+    sd = synth.synthetic_state_dict("hui", 12)
+    a, b, _ = synth.particle_batch(1, 50, 70, 901, "uniform")
+    ref = O.estimate(sd, a, b, "hui")
+    net = _net("hui", sd, "3xtf32")
+    a0 = a.to(DEV)
+    out = estimate(net, a0, b.to(DEV), tensor=True)
+    assert out.shape == (1, 2, 50, 70)
+    assert (out.cpu() - ref).abs().max().item() <= 1e-2
+    assert torch.equal(a0.cpu(), a)            # estimate does not mutate the caller's images (interpolate copies)
+    arr = estimate(net, a.to(DEV), b.to(DEV))
+    assert isinstance(arr, np.ndarray) and arr.shape == (50, 70, 2) and arr.dtype == np.float32
+
+
+def test_batch_independence_at_bench_size():
+    """Size-independent property at the benchmark shape (256x256): a batch equals its samples run one by one
+    (pairs are independent units -- the basis of pair sharding), and the flow tracks the known uniform
+    displacement direction with non-trivial magnitude."""
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b, _ = synth.particle_batch(3, 256, 256, 40, "uniform")
+    net = _net("piv", sd, "3xtf32")
+    with torch.no_grad():
+        full = net(a.to(DEV), b.to(DEV))
+        singles = torch.cat([net(a[i:i + 1].to(DEV), b[i:i + 1].to(DEV)) for i in range(3)])
+    assert torch.equal(full, singles)
+    assert full.abs().max().item() > 0.5 and torch.isfinite(full).all()
+
+
+def test_full_size_1024_runs_and_matches_simt():
+    """1024x1024 (cfg4 shape): the tensor-core path agrees with the exact-fp32 CUDA-core path of this repo
+    within the fp32-parity tolerance (the CPU oracle would take minutes at this size)."""
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b, _ = synth.particle_batch(1, 1024, 1024, 77, "rankine")
+    with torch.no_grad():
+        o3 = _net("piv", sd, "3xtf32")(a.to(DEV), b.to(DEV))
+        os_ = _net("piv", sd, "simt")(a.to(DEV), b.to(DEV))
+    diff = (o3 - os_).abs()
+    print(f"1024^2 3xtf32 vs simt: max {diff.max().item():.3e} mean {diff.mean().item():.3e}")
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
