@@ -1,7 +1,369 @@
-// placeholder: replaced by the tcgen05 implicit-GEMM kernel
+// 3x3 stride-1 convolution (+ bias + LeakyReLU) as an implicit GEMM on the 5th-generation tensor cores:
+//   D[128 pixels x Cout] += A[128 pixels x 32 ch] * B[32 ch x Cout]     per (filter tap, 32-channel chunk)
+// tcgen05.mma kind::tf32 with the accumulator in TMEM, operands staged in shared memory by TMA
+// (cp.async.bulk.tensor, 128B swizzle), mbarrier producer/consumer pipeline, warp-specialised:
+//
+//   warp 0        TMA producer: per stage one 4-D box of the NHWC activations at the tap's (dy,dx) offset
+//                 (zero padding = TMA out-of-bounds fill, so no im2col buffer and no border code) and one box of
+//                 the packed weights [Cout][tap][CinP]
+//   warp 1        TMEM allocation + MMA issue (one elected lane)
+//   warps 2..5    3xTF32 mode: split every landed A tile in shared memory into hi = rna_tf32(a) (in place) and
+//                 lo = a - hi (second buffer);  all modes: epilogue TMEM -> registers -> bias + LeakyReLU -> NHWC store
+//
+// passes == 1: plain TF32 (D = A*Bhi).  passes == 3: error-compensated 3xTF32 (D = Ahi*Bhi + Alo*Bhi + Ahi*Blo),
+// which reproduces fp32 convolution to ~1e-6 relative.  Replaces torch.nn.Conv2d(k=3,s=1,p=1)+LeakyReLU(0.1) of
+// src/models.py:77-106 (NetC), :154-160 (conv_M), :197-204 (conv_S), :236-250 (conv_R).
+#include <cuda.h>
 #include "common.cuh"
+
+namespace {
+
+constexpr int TILE_M = 128;          // output pixels per CTA (UMMA M)
+constexpr int KC = 32;               // channels per stage: 32 fp32 = one 128-byte swizzle row
+constexpr int A_BYTES = TILE_M * KC * 4;   // 16 KB
+constexpr int NTHREADS = 192;
+constexpr int EPI_WARP0 = 2;
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (ignored for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct ConvTcArgs {
+    const float* bias;
+    float* y;
+    int y_ld;
+    int N, H, W, Cin, Cout;
+    int bw, bh, bn;          // spatial / batch extent of the 128-pixel tile (bw * bh * bn == 128)
+    int tiles_x, tiles_y;
+    int lrelu;
+};
+
+// PASSES = 1 (TF32) or 3 (3xTF32).  TCOLS = TMEM columns (power of two >= Cout).
+template <int PASSES, int STAGES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                  const __grid_constant__ CUtensorMap tmBlo, const ConvTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stage][A | Alo (3-pass) | Bhi | Blo (3-pass)], every tile 1024-byte aligned
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int b_bytes = a.Cout * KC * 4;
+    const int stage_bytes = (PASSES == 3 ? 2 : 1) * (A_BYTES + b_bytes);
+    __shared__ __align__(8) uint64_t full_bar[STAGES], ready_bar[STAGES], empty_bar[STAGES], accum_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = (a.Cin + KC - 1) / KC;
+    const int niter = 9 * nchunk;
+
+    // tile coordinates
+    const int tx = blockIdx.x % a.tiles_x;
+    const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
+    const int tn = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int x0 = tx * a.bw, y0 = ty * a.bh, n0 = tn * a.bn;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&ready_bar[s], 4);      // one arrival per split warp
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(&accum_bar, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmBhi);
+        if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+    }
+    if (warp == 1) {
+        // TMEM: Cout fp32 accumulator columns (power of two >= 32)
+        const uint32_t ncols = a.Cout <= 32 ? 32u : (a.Cout <= 64 ? 64u : 128u);
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= EPI_WARP0) {
+        for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.Cout; i += 128) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                const int tap = it / nchunk, ch = it - tap * nchunk;
+                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* st = smem + (size_t)stage * stage_bytes;
+                uint8_t* sA = st;
+                uint8_t* sBhi = st + (PASSES == 3 ? 2 : 1) * A_BYTES;
+                mbar_expect_tx(&full_bar[stage], A_BYTES + (PASSES == 3 ? 2 : 1) * b_bytes);
+                tma_load_4d(sA, &tmA, &full_bar[stage], ch * KC, x0 + dx, y0 + dy, n0);
+                tma_load_3d(sBhi, &tmBhi, &full_bar[stage], ch * KC, tap, 0);
+                if (PASSES == 3) tma_load_3d(sBhi + b_bytes, &tmBlo, &full_bar[stage], ch * KC, tap, 0);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(a.Cout);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc = 0;
+            for (int it = 0; it < niter; ++it) {
+                const int tap = it / nchunk, ch = it - tap * nchunk;
+                const int kleft = a.Cin - ch * KC;
+                const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;      // K = 8 per tf32 MMA
+                mbar_wait(PASSES == 3 ? &ready_bar[stage] : &full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint32_t sBhi = sA + (PASSES == 3 ? 2 : 1) * A_BYTES;
+                const uint64_t dA = make_smem_desc(sA), dBhi = make_smem_desc(sBhi);
+                for (int k = 0; k < nk; ++k) {
+                    const uint64_t koff = (uint64_t)(k * 2);      // 32 bytes >> 4
+                    umma_tf32(tmem_base, dA + koff, dBhi + koff, idesc, acc);
+                    acc = 1;
+                    if (PASSES == 3) {
+                        const uint64_t dAlo = make_smem_desc(sA + A_BYTES), dBlo = make_smem_desc(sBhi + b_bytes);
+                        umma_tf32(tmem_base, dAlo + koff, dBhi + koff, idesc, 1);
+                        umma_tf32(tmem_base, dA + koff, dBlo + koff, idesc, 1);
+                    }
+                }
+                umma_commit(&empty_bar[stage]);                    // frees the smem slot when these MMAs retire
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(&accum_bar);                               // accumulator complete
+        }
+    } else {
+        // ============================ split warps + epilogue ============================
+        const int et = threadIdx.x - EPI_WARP0 * 32;               // 0..127
+        if (PASSES == 3) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < niter; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                float4* pa = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes);
+                float4* pl = reinterpret_cast<float4*>(smem + (size_t)stage * stage_bytes + A_BYTES);
+#pragma unroll
+                for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                    const int idx = et + i * 128;
+                    float4 v = pa[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    pa[idx] = h;
+                    pl[idx] = l;
+                }
+                fence_proxy_async();            // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ready_bar[stage]);
+                if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+        // ---- epilogue: thread = one accumulator row (pixel); TMEM lane quarter = warp % 4 ----------------------
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int px = row % a.bw, py = (row / a.bw) % a.bh, pn = row / (a.bw * a.bh);
+        const int x = x0 + px, yy = y0 + py, n = n0 + pn;
+        const bool live = x < a.W && yy < a.H && n < a.N;
+        float* dst = a.y + (((size_t)n * a.H + yy) * a.W + x) * a.y_ld;
+        for (int c0 = 0; c0 < a.Cout; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            if (live) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o;
+                    o.x = __uint_as_float(v[j + 0]) + bias_s[c0 + j + 0];
+                    o.y = __uint_as_float(v[j + 1]) + bias_s[c0 + j + 1];
+                    o.z = __uint_as_float(v[j + 2]) + bias_s[c0 + j + 2];
+                    o.w = __uint_as_float(v[j + 3]) + bias_s[c0 + j + 3];
+                    if (a.lrelu) { o.x = lrelu_f(o.x); o.y = lrelu_f(o.y); o.z = lrelu_f(o.z); o.w = lrelu_f(o.w); }
+                    *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        const uint32_t ncols = a.Cout <= 32 ? 32u : (a.Cout <= 64 ? 64u : 128u);
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+template <int PASSES, int STAGES>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const ConvTcArgs& a, int grid,
+           cudaStream_t st) {
+    const int stage_bytes = (PASSES == 3 ? 2 : 1) * (A_BYTES + a.Cout * KC * 4);
+    const int smem = STAGES * stage_bytes + 1024;
+    auto kern = conv3x3_tc_kernel<PASSES, STAGES>;
+    static int configured = 0;
+    if (configured < smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return (int)e;
+        configured = 200 * 1024;
+    }
+    kern<<<grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, a);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+}  // namespace
+
 extern "C" int pivlfn_conv3x3_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                                  const float* w_hi, const float* w_lo, const float* bias,
                                  float* y, int y_ld, int Cout, int lrelu, int passes, void* stream) {
-    return PIVLFN_EUNSUPPORTED;
+    if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return PIVLFN_EINVAL;
+    if (passes != 1 && passes != 3) return PIVLFN_EINVAL;
+    if (passes == 3 && !w_lo) return PIVLFN_EINVAL;
+    if (Cout % 32 != 0 || Cout < 32 || Cout > 128) return PIVLFN_EUNSUPPORTED;
+    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < Cout) return PIVLFN_EINVAL;
+    if (((uintptr_t)w_hi & 15) || (w_lo && ((uintptr_t)w_lo & 15))) return PIVLFN_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+
+    ConvTcArgs a;
+    a.bias = bias; a.y = y; a.y_ld = y_ld; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.lrelu = lrelu;
+    a.bw = pow2_ceil(W < 16 ? W : 16);
+    int rem = TILE_M / a.bw;
+    a.bh = pow2_ceil(H < rem ? H : rem);
+    a.bn = TILE_M / (a.bw * a.bh);
+    a.tiles_x = cdiv(W, a.bw);
+    a.tiles_y = cdiv(H, a.bh);
+    const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
+    if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
+
+    CUtensorMap tmA, tmBhi, tmBlo;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    }
+    const int CinP = (Cin + KC - 1) / KC * KC;
+    for (int i = 0; i < (passes == 3 ? 2 : 1); ++i) {
+        cuuint64_t dims[3] = {(cuuint64_t)CinP, 9, (cuuint64_t)Cout};
+        cuuint64_t strides[2] = {(cuuint64_t)CinP * 4, (cuuint64_t)9 * CinP * 4};
+        cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)Cout};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(i == 0 ? &tmBhi : &tmBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(i == 0 ? w_hi : w_lo),
+                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    }
+    if (passes != 3) tmBlo = tmBhi;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (passes == 3) return launch<3, 3>(tmA, tmBhi, tmBlo, a, (int)grid, st);
+    return launch<1, 6>(tmA, tmBhi, tmBlo, a, (int)grid, st);
 }
