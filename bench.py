@@ -175,8 +175,8 @@ def kernel_rooflines(eng, pk):
     flops = 2.0 * B * h * w * 128 * 128 * 9
     if eng.precision != SIMT and cw.w_hi is not None:
         passes = 3 if eng.precision == "3xtf32" else 1
-        ms = time_kernel(lambda: ops.conv3x3_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, True, passes), 10)
-        name = f"conv3x3_tc_kernel (tcgen05 kind::tf32, {passes} pass)"
+        ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes), 10)
+        name = f"conv_tc_kernel (tcgen05 kind::tf32, {passes} pass)"
     else:
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
         name = "conv_simt_kernel (fp32 FFMA)"

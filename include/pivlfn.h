@@ -42,8 +42,9 @@ int pivlfn_corr_nchw(const float* first, const float* second, float* out,
 
 /* src/models.py:321-323 (in-place per-channel mean subtraction of BOTH caller tensors) fused with
  * the NCHW->NHWC pack.  img1,img2: [B,3,H,W] NCHW, modified in place.  out: [2B,H,W,4] (images of
- * img1 first, then img2; 4th channel zero).  mean6: HOST pointer to 6 floats (3 per image). */
-int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, int B, int H, int W,
+ * img1 first, then img2; 4th channel zero).  out_pad (optional): [2B,H,W+8,4] copy with a 4-pixel border left
+ * and right that the caller zeroed once (input of pivlfn_conv_stem_tc).  mean6: HOST pointer to 6 floats. */
+int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, float* out_pad, int B, int H, int W,
                        const float* mean6, void* stream);
 
 /* src/models.py:336-343: bilinear 1/2 downsample with align_corners=False on even sizes
@@ -65,14 +66,23 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
                      int KH, int KW, int stride, int lrelu,
                      const float* res, int res_ld, void* stream);
 
-/* Same operator for 3x3 stride-1 convolutions on the tcgen05 tensor cores (implicit GEMM,
- * TMA-fed, TMEM accumulators, fused bias + LeakyReLU).
- * w_hi / w_lo: [Cout, 9, CinP] (CinP = Cin rounded up to 32) TF32 split of the weights
- * (w ~= w_hi + w_lo); passes = 1 (plain TF32) or 3 (error-compensated 3xTF32 ~ fp32).
- * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout % 16 == 0, 16 <= Cout <= 128. */
-int pivlfn_conv3x3_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
-                      const float* w_hi, const float* w_lo, const float* bias,
-                      float* y, int y_ld, int Cout, int lrelu, int passes, void* stream);
+/* Same operator for every stride-1 convolution (KH, KW odd, <= 7) on the tcgen05 tensor cores: implicit GEMM,
+ * TMA-fed (zero padding = TMA out-of-bounds fill), TMEM accumulators, fused bias + LeakyReLU (+ residual).
+ * w_hi / w_lo: [CoutP, KH*KW, CinP] (CoutP = Cout rounded up to 16, CinP = Cin rounded up to 32, zero padded):
+ * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32) or 3 (error-compensated 3xTF32 ~ fp32).
+ * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
+int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
+                   const float* w_hi, const float* w_lo, const float* bias,
+                   float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                   const float* res, int res_ld, int passes, void* stream);
+
+/* NetC.conv1 (src/models.py:70-73): 7x7, 3 -> 32, stride 1, on the tensor cores.  img_pad: [N,H,W+8,4], the
+ * zero-bordered NHWC4 image written by pivlfn_prep_images (pixel x at column x+4).  One GEMM-K row of 32 floats
+ * per filter row = the 8 pixels x-3..x+4, fetched through an overlapping-window tensor map.
+ * w_hi / w_lo: [32, 7, 32] with column kx*4 + c (kx = 7 and c = 3 are zero). */
+int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
+                        const float* w_hi, const float* w_lo, const float* bias,
+                        float* y, int y_ld, int lrelu, int passes, void* stream);
 
 /* torch.nn.ConvTranspose2d(C, C, 4, stride 2, padding 1, groups=C, bias=False):
  * upConv_M (src/models.py:144-145, C=2) and upCorr_M (:151-152, C=49).

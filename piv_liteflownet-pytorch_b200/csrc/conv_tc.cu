@@ -104,33 +104,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct ConvTcArgs {
     const float* bias;
+    const float* res;        // optional residual view (added after the activation), Cout channels
     float* y;
-    int y_ld;
-    int N, H, W, Cin, Cout;
+    int y_ld, res_ld;
+    int N, H, W, Cin;
+    int Cout, CoutP;         // real output channels / MMA N (multiple of 16, zero-padded weights)
+    int KW, ntaps, ox, oy;   // tap t reads the input at (x + t % KW + ox, y + t / KW + oy)
     int bw, bh, bn;          // spatial / batch extent of the 128-pixel tile (bw * bh * bn == 128)
     int tiles_x, tiles_y;
-    int lrelu;
+    int lrelu, stages, vec_store;
 };
 
-// PASSES = 1 (TF32) or 3 (3xTF32).  TCOLS = TMEM columns (power of two >= Cout).
-template <int PASSES, int STAGES>
+constexpr int MAX_STAGES = 8;
+
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : 256u)); }
+
+// PASSES = 1 (TF32) or 3 (3xTF32).
+template <int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
-conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                  const __grid_constant__ CUtensorMap tmBlo, const ConvTcArgs a) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, const ConvTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stage][A | Alo (3-pass) | Bhi | Blo (3-pass)], every tile 1024-byte aligned
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_bytes = a.Cout * KC * 4;
+    const int b_bytes = a.CoutP * KC * 4;
     const int stage_bytes = (PASSES == 3 ? 2 : 1) * (A_BYTES + b_bytes);
-    __shared__ __align__(8) uint64_t full_bar[STAGES], ready_bar[STAGES], empty_bar[STAGES], accum_bar;
+    const int STAGES = a.stages;
+    __shared__ __align__(8) uint64_t full_bar[MAX_STAGES], ready_bar[MAX_STAGES], empty_bar[MAX_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.Cin + KC - 1) / KC;
-    const int niter = 9 * nchunk;
+    const int niter = a.ntaps * nchunk;
+    const uint32_t ncols = tmem_cols_for(PASSES == 3 ? 2 * a.CoutP : a.CoutP);
 
     // tile coordinates
     const int tx = blockIdx.x % a.tiles_x;
@@ -151,13 +170,12 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (PASSES == 3) tma_prefetch_desc(&tmBlo);
     }
     if (warp == 1) {
-        // TMEM: Cout fp32 accumulator columns (power of two >= 32)
-        const uint32_t ncols = a.Cout <= 32 ? 32u : (a.Cout <= 64 ? 64u : 128u);
+        // TMEM: fp32 accumulator columns (main, plus the low-order correction accumulator in 3xTF32 mode)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= EPI_WARP0) {
-        for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.Cout; i += 128) bias_s[i] = a.bias ? a.bias[i] : 0.f;
+        for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.CoutP; i += 128) bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -171,7 +189,7 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
                 const int tap = it / nchunk, ch = it - tap * nchunk;
-                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                const int dy = tap / a.KW + a.oy, dx = tap % a.KW + a.ox;
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 uint8_t* st = smem + (size_t)stage * stage_bytes;
                 uint8_t* sA = st;
@@ -186,10 +204,11 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_tf32(a.Cout);
+            const uint32_t idesc = make_idesc_tf32(a.CoutP);
+            const uint32_t tmem_corr = tmem_base + (uint32_t)a.CoutP;      // 3xTF32: low-order terms accumulate separately
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t acc = 0;
+            uint32_t acc = 0, acc_corr = 0;
             for (int it = 0; it < niter; ++it) {
                 const int tap = it / nchunk, ch = it - tap * nchunk;
                 const int kleft = a.Cin - ch * KC;
@@ -199,20 +218,21 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint32_t sA = smem_u32(smem + (size_t)stage * stage_bytes);
                 const uint32_t sBhi = sA + (PASSES == 3 ? 2 : 1) * A_BYTES;
                 const uint64_t dA = make_smem_desc(sA), dBhi = make_smem_desc(sBhi);
+                const uint64_t dAlo = make_smem_desc(sA + A_BYTES), dBlo = make_smem_desc(sBhi + b_bytes);
                 for (int k = 0; k < nk; ++k) {
                     const uint64_t koff = (uint64_t)(k * 2);      // 32 bytes >> 4
                     umma_tf32(tmem_base, dA + koff, dBhi + koff, idesc, acc);
                     acc = 1;
                     if (PASSES == 3) {
-                        const uint64_t dAlo = make_smem_desc(sA + A_BYTES), dBlo = make_smem_desc(sBhi + b_bytes);
-                        umma_tf32(tmem_base, dAlo + koff, dBhi + koff, idesc, 1);
-                        umma_tf32(tmem_base, dA + koff, dBlo + koff, idesc, 1);
+                        umma_tf32(tmem_corr, dAlo + koff, dBhi + koff, idesc, acc_corr);
+                        umma_tf32(tmem_corr, dA + koff, dBlo + koff, idesc, 1);
+                        acc_corr = 1;
                     }
                 }
                 umma_commit(&empty_bar[stage]);                    // frees the smem slot when these MMAs retire
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            umma_commit(&accum_bar);                               // accumulator complete
+            umma_commit(&accum_bar);                               // accumulators complete
         }
     } else {
         // ============================ split warps + epilogue ============================
@@ -251,20 +271,38 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int px = row % a.bw, py = (row / a.bw) % a.bh, pn = row / (a.bw * a.bh);
         const int x = x0 + px, yy = y0 + py, n = n0 + pn;
         const bool live = x < a.W && yy < a.H && n < a.N;
-        float* dst = a.y + (((size_t)n * a.H + yy) * a.W + x) * a.y_ld;
-        for (int c0 = 0; c0 < a.Cout; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            if (live) {
+        const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
+        float* dst = a.y + pix * a.y_ld;
+        const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)c0, v);
+            if (PASSES == 3) {
+                uint32_t u[16];
+                tmem_ld16(trow + (uint32_t)(a.CoutP + c0), u);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o;
-                    o.x = __uint_as_float(v[j + 0]) + bias_s[c0 + j + 0];
-                    o.y = __uint_as_float(v[j + 1]) + bias_s[c0 + j + 1];
-                    o.z = __uint_as_float(v[j + 2]) + bias_s[c0 + j + 2];
-                    o.w = __uint_as_float(v[j + 3]) + bias_s[c0 + j + 3];
-                    if (a.lrelu) { o.x = lrelu_f(o.x); o.y = lrelu_f(o.y); o.z = lrelu_f(o.z); o.w = lrelu_f(o.w); }
-                    *reinterpret_cast<float4*>(dst + c0 + j) = o;
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            if (live) {
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(v[j]) + bias_s[c0 + j];
+                    if (a.lrelu) t = lrelu_f(t);
+                    o[j] = t;
+                }
+                if (a.vec_store && c0 + 16 <= a.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
+                        *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
                 }
             }
         }
@@ -272,7 +310,6 @@ conv3x3_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
-        const uint32_t ncols = a.Cout <= 32 ? 32u : (a.Cout <= 64 ? 64u : 128u);
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
     }
 }
@@ -298,45 +335,75 @@ EncodeTiledFn get_encode() {
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-template <int PASSES, int STAGES>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const ConvTcArgs& a, int grid,
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int PASSES>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, ConvTcArgs& a, int grid,
            cudaStream_t st) {
-    const int stage_bytes = (PASSES == 3 ? 2 : 1) * (A_BYTES + a.Cout * KC * 4);
-    const int smem = STAGES * stage_bytes + 1024;
-    auto kern = conv3x3_tc_kernel<PASSES, STAGES>;
-    static int configured = 0;
-    if (configured < smem) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const int stage_bytes = (PASSES == 3 ? 2 : 1) * (A_BYTES + a.CoutP * KC * 4);
+    int stages = (SMEM_BUDGET - 1024) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    const int niter = a.ntaps * ((a.Cin + KC - 1) / KC);
+    if (stages > niter) stages = niter;
+    if (stages < 2 && niter >= 2) return PIVLFN_EUNSUPPORTED;
+    a.stages = stages;
+    const int smem = stages * stage_bytes + 1024;
+    auto kern = conv_tc_kernel<PASSES>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
         if (e != cudaSuccess) return (int)e;
-        configured = 200 * 1024;
+        configured = true;
     }
     kern<<<grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, a);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
 
+// weights [CoutP][ntaps][CinP] -> box (32 channels, 1 tap, CoutP rows)
+int encode_weights(EncodeTiledFn enc, CUtensorMap* tm, const float* w, int CinP, int ntaps, int CoutP) {
+    cuuint64_t dims[3] = {(cuuint64_t)CinP, (cuuint64_t)ntaps, (cuuint64_t)CoutP};
+    cuuint64_t strides[2] = {(cuuint64_t)CinP * 4, (cuuint64_t)ntaps * CinP * 4};
+    cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)CoutP};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PIVLFN_OK : PIVLFN_EINVAL;
+}
+
+void choose_tile(ConvTcArgs& a) {
+    a.bw = pow2_ceil(a.W < 16 ? a.W : 16);
+    const int rem = TILE_M / a.bw;
+    a.bh = pow2_ceil(a.H < rem ? a.H : rem);
+    a.bn = TILE_M / (a.bw * a.bh);
+    a.tiles_x = cdiv(a.W, a.bw);
+    a.tiles_y = cdiv(a.H, a.bh);
+}
+
 }  // namespace
 
-extern "C" int pivlfn_conv3x3_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
-                                 const float* w_hi, const float* w_lo, const float* bias,
-                                 float* y, int y_ld, int Cout, int lrelu, int passes, void* stream) {
-    if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return PIVLFN_EINVAL;
+extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
+                              const float* w_hi, const float* w_lo, const float* bias,
+                              float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                              const float* res, int res_ld, int passes, void* stream) {
+    if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
     if (passes != 1 && passes != 3) return PIVLFN_EINVAL;
     if (passes == 3 && !w_lo) return PIVLFN_EINVAL;
-    if (Cout % 32 != 0 || Cout < 32 || Cout > 128) return PIVLFN_EUNSUPPORTED;
-    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < Cout) return PIVLFN_EINVAL;
+    if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
+    if (Cout > 128) return PIVLFN_EUNSUPPORTED;
+    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 3) || y_ld < Cout) return PIVLFN_EINVAL;
+    if (res && res_ld < Cout) return PIVLFN_EINVAL;
     if (((uintptr_t)w_hi & 15) || (w_lo && ((uintptr_t)w_lo & 15))) return PIVLFN_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
 
     ConvTcArgs a;
-    a.bias = bias; a.y = y; a.y_ld = y_ld; a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.lrelu = lrelu;
-    a.bw = pow2_ceil(W < 16 ? W : 16);
-    int rem = TILE_M / a.bw;
-    a.bh = pow2_ceil(H < rem ? H : rem);
-    a.bn = TILE_M / (a.bw * a.bh);
-    a.tiles_x = cdiv(W, a.bw);
-    a.tiles_y = cdiv(H, a.bh);
+    a.bias = bias; a.res = res; a.res_ld = res_ld; a.y = y; a.y_ld = y_ld;
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.CoutP = (Cout + 15) & ~15; a.lrelu = lrelu;
+    a.KW = KW; a.ntaps = KH * KW; a.ox = -(KW / 2); a.oy = -(KH / 2);
+    a.vec_store = (!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0;
+    choose_tile(a);
     const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
     if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
 
@@ -352,18 +419,49 @@ extern "C" int pivlfn_conv3x3_tc(const float* x, int x_ld, int N, int H, int W, 
         if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
     }
     const int CinP = (Cin + KC - 1) / KC * KC;
-    for (int i = 0; i < (passes == 3 ? 2 : 1); ++i) {
-        cuuint64_t dims[3] = {(cuuint64_t)CinP, 9, (cuuint64_t)Cout};
-        cuuint64_t strides[2] = {(cuuint64_t)CinP * 4, (cuuint64_t)9 * CinP * 4};
-        cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)Cout};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(i == 0 ? &tmBhi : &tmBlo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(i == 0 ? w_hi : w_lo),
-                         dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-    }
-    if (passes != 3) tmBlo = tmBhi;
+    if (encode_weights(enc, &tmBhi, w_hi, CinP, a.ntaps, a.CoutP)) return PIVLFN_EINVAL;
+    if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, a.ntaps, a.CoutP)) return PIVLFN_EINVAL; }
+    else tmBlo = tmBhi;
     cudaStream_t st = (cudaStream_t)stream;
-    if (passes == 3) return launch<3, 3>(tmA, tmBhi, tmBlo, a, (int)grid, st);
-    return launch<1, 6>(tmA, tmBhi, tmBlo, a, (int)grid, st);
+    return passes == 3 ? launch<3>(tmA, tmBhi, tmBlo, a, (int)grid, st) : launch<1>(tmA, tmBhi, tmBlo, a, (int)grid, st);
+}
+
+// NetC.conv1 (src/models.py:70-73): 7x7, 3 -> 32, stride 1, pad 3 on the zero-bordered NHWC4 image buffer
+// img_pad [N, H, W+8, 4] (pixel x of the image at column x+4).  One GEMM-K row per filter row: the 8 pixels
+// x-3..x+4 of input row y+ky-3 are 32 contiguous floats in memory, fetched through a tensor map whose pixel
+// stride (16 B) is smaller than its box row (128 B), i.e. overlapping windows -- no im2col buffer.
+// Weights: [32][7][32] with column index kx*4 + c (kx = 7 and c = 3 zero).
+extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
+                                   const float* w_hi, const float* w_lo, const float* bias,
+                                   float* y, int y_ld, int lrelu, int passes, void* stream) {
+    if (!img_pad || !w_hi || !y || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (passes != 1 && passes != 3) return PIVLFN_EINVAL;
+    if (passes == 3 && !w_lo) return PIVLFN_EINVAL;
+    if (((uintptr_t)img_pad & 15) || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < 32) return PIVLFN_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+    ConvTcArgs a;
+    a.bias = bias; a.res = nullptr; a.res_ld = 0; a.y = y; a.y_ld = y_ld;
+    a.N = N; a.H = H; a.W = W; a.Cin = 32; a.Cout = 32; a.CoutP = 32; a.lrelu = lrelu;
+    a.KW = 1; a.ntaps = 7; a.ox = 1; a.oy = -3; a.vec_store = 1;
+    choose_tile(a);
+    const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
+    if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    {
+        const cuuint64_t Wp = (cuuint64_t)W + 8;
+        cuuint64_t dims[4] = {32, (cuuint64_t)W + 1, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {16, Wp * 16, (cuuint64_t)H * Wp * 16};
+        cuuint32_t box[4] = {32, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img_pad), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
+    }
+    if (encode_weights(enc, &tmBhi, w_hi, 32, 7, 32)) return PIVLFN_EINVAL;
+    if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
+    else tmBlo = tmBhi;
+    cudaStream_t st = (cudaStream_t)stream;
+    return passes == 3 ? launch<3>(tmA, tmBhi, tmBlo, a, (int)grid, st) : launch<1>(tmA, tmBhi, tmBlo, a, (int)grid, st);
 }

@@ -21,6 +21,7 @@ constexpr int MEAN_PARTS = 32;
 
 // ---- src/models.py:321-323 + NCHW -> NHWC4 ------------------------------------------------------
 __global__ void prep_images_kernel(float* __restrict__ img1, float* __restrict__ img2, float4* __restrict__ out,
+                                   float4* __restrict__ out_pad, int W,
                                    int B, int HW, float m10, float m11, float m12, float m20, float m21, float m22) {
     const long long total = 2LL * B * HW;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -34,6 +35,10 @@ __global__ void prep_images_kernel(float* __restrict__ img1, float* __restrict__
         float v2 = src[2LL * HW] - (which ? m22 : m12);
         src[0] = v0; src[HW] = v1; src[2LL * HW] = v2;   // the reference mutates its inputs in place
         out[i] = make_float4(v0, v1, v2, 0.f);
+        if (out_pad) {
+            const long long row = i / W;          // (image, y) row index; rows of the padded copy are W+8 pixels
+            out_pad[row * (W + 8) + 4 + (i - row * W)] = make_float4(v0, v1, v2, 0.f);
+        }
     }
 }
 
@@ -296,13 +301,13 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
-extern "C" int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, int B, int H, int W,
+extern "C" int pivlfn_prep_images(float* img1, float* img2, float* out_nhwc4, float* out_pad, int B, int H, int W,
                                   const float* mean6, void* stream) {
     if (!img1 || !img2 || !out_nhwc4 || !mean6 || B <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
-    if ((uintptr_t)out_nhwc4 & 15) return PIVLFN_EINVAL;
+    if (((uintptr_t)out_nhwc4 & 15) || ((uintptr_t)out_pad & 15)) return PIVLFN_EINVAL;
     const long long total = 2LL * B * H * W;
     prep_images_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        img1, img2, reinterpret_cast<float4*>(out_nhwc4), B, H * W,
+        img1, img2, reinterpret_cast<float4*>(out_nhwc4), reinterpret_cast<float4*>(out_pad), W, B, H * W,
         mean6[0], mean6[1], mean6[2], mean6[3], mean6[4], mean6[5]);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();

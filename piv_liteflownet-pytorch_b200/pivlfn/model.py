@@ -61,8 +61,9 @@ class ConvW:
     stride: int
     w_simt: torch.Tensor                    # [KH*KW*Cin, CoutP]
     bias: Optional[torch.Tensor]
-    w_hi: Optional[torch.Tensor] = None     # [Cout, KH*KW, CinP32] TF32 split for the tcgen05 kernel
+    w_hi: Optional[torch.Tensor] = None     # [CoutP16, KH*KW, CinP32] TF32 split for the tcgen05 kernel
     w_lo: Optional[torch.Tensor] = None
+    stem: bool = False                      # 7x7 3->32 packed as [32, 7, 32] for pivlfn_conv_stem_tc
 
 
 def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_pad: int = 0,
@@ -82,17 +83,33 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
     cw = ConvW(cin, cout, kh, kw, stride, ws.contiguous(), None if b is None else b.detach().to(torch.float32).contiguous())
     if tc and tc_eligible(cin, cout, kh, kw, stride):
         cinp = (cin + 31) // 32 * 32
+        coutp = (cout + 15) // 16 * 16
         wt = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
-        if cinp != cin:
-            wt = torch.cat([wt, wt.new_zeros(cout, kh * kw, cinp - cin)], 2)
-        hi = tf32_round(wt)
-        lo = tf32_round(wt - hi)
-        cw.w_hi, cw.w_lo = hi.contiguous(), lo.contiguous()
+        wt = torch.nn.functional.pad(wt, (0, cinp - cin, 0, 0, 0, coutp - cout))
+        cw.w_hi, cw.w_lo = _split_tf32(wt)
     return cw
 
 
+def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
+    """NetC.conv1 [32,3,7,7] -> [32, 7 (ky), 32 (kx*4 + c)] for the overlapping-window tensor-core stem."""
+    w = w.detach().to(torch.float32)
+    cw = pack_conv(w, b, 1, cin_pad=1, tc=False)
+    wt = torch.zeros(32, 7, 8, 4, device=w.device)
+    wt[:, :, :7, :3] = w.permute(0, 2, 3, 1)           # [cout, ky, kx, c]
+    cw.w_hi, cw.w_lo = _split_tf32(wt.reshape(32, 7, 32))
+    cw.stem = True
+    return cw
+
+
+def _split_tf32(wt: torch.Tensor):
+    hi = tf32_round(wt)
+    lo = tf32_round(wt - hi)
+    return hi.contiguous(), lo.contiguous()
+
+
 def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int) -> bool:
-    return kh == 3 and kw == 3 and stride == 1 and cout % 16 == 0 and 16 <= cout <= 128 and cin >= 16
+    """Stride-1 convolutions with at least 8 input channels run on the tensor cores (any odd kernel up to 7x7)."""
+    return stride == 1 and cout <= 128 and cin >= 8 and kh <= 7 and kw <= 7
 
 
 class Engine:
@@ -134,7 +151,10 @@ class Engine:
                                     stride, cin_pad, in_perm, tc=use_tc)
 
         for seq, idx, cin, cout, k, st in NETC:
-            conv(f"NetC.{seq}.{idx}", st, cin_pad=1 if cin == 3 else 0)
+            if cin == 3 and use_tc:
+                self.w[f"NetC.{seq}.{idx}"] = pack_stem(g(f"NetC.{seq}.{idx}.weight"), g(f"NetC.{seq}.{idx}.bias"))
+            else:
+                conv(f"NetC.{seq}.{idx}", st, cin_pad=1 if cin == 3 else 0)
         for e in range(cfg.n_ext):
             conv(f"NetC_ext.{e}.conv_ext.0")
         nh = len(cfg.head)
@@ -197,6 +217,7 @@ class Plan:
         # static inputs (graph replays need fixed addresses)
         self.in1, self.in2 = E(B, 3, H, W), E(B, 3, H, W)
         self.img = {1: E(N2, H, W, 4)}
+        self.img_pad = Z(N2, H, W + 8, 4) if eng.precision != SIMT else None     # zero border written once
         for l in range(2, 7):
             self.img[l] = E(N2, *self.hw[l], 4)
         # NetC intermediates and features
@@ -239,8 +260,11 @@ class Plan:
         eng = self.eng
         cw = eng.w[key]
         assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
-        if cw.w_hi is not None and res is None and eng.precision != SIMT:
-            ops.conv3x3_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, 3 if eng.precision == TC_3XTF32 else 1)
+        passes = 3 if eng.precision == TC_3XTF32 else 1
+        if cw.stem and eng.precision != SIMT:
+            ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes)
+        elif cw.w_hi is not None and eng.precision != SIMT:
+            ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res)
         else:
             ops.conv_simt(x, n, h, w, cw.w_simt, cw.bias, y, cw.kh, cw.kw, cw.stride, lrelu, res)
 
@@ -264,7 +288,7 @@ class Plan:
         eng, cfg, B = self.eng, self.eng.cfg, self.B
         N2 = 2 * B
         H, W = self.H, self.W
-        ops.prep_images(self.in1, self.in2, self.img[1], cfg.mean)
+        ops.prep_images(self.in1, self.in2, self.img[1], cfg.mean, self.img_pad)
         for l in range(2, 7):
             ops.avgpool2(self.img[l - 1], self.img[l])
         # ---- NetC on both images at once (shared weights): batch 2B ----------------------------------------

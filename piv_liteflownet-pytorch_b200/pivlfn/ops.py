@@ -77,12 +77,13 @@ def corr_nchw(first: torch.Tensor, second: torch.Tensor, stride: int) -> torch.T
     return out
 
 
-def prep_images(img1, img2, out, mean6):
+def prep_images(img1, img2, out, mean6, out_pad=None):
     lib = _lib.load()
-    _need_cuda(img1, img2, out)
+    _need_cuda(img1, img2, out, out_pad)
     B, _, H, W = img1.shape
     arr = (C.c_float * 6)(*[float(m) for m in mean6])
-    _lib.check(lib.pivlfn_prep_images(img1.data_ptr(), img2.data_ptr(), out.data_ptr(), B, H, W, arr, _stream()),
+    _lib.check(lib.pivlfn_prep_images(img1.data_ptr(), img2.data_ptr(), out.data_ptr(),
+                                      out_pad.data_ptr() if out_pad is not None else None, B, H, W, arr, _stream()),
                "prep_images")
 
 
@@ -107,12 +108,22 @@ def conv_simt(x: View, N, H, W, w, bias, y: View, KH, KW, stride, lrelu, res: Op
                                     _stream()), "conv_simt")
 
 
-def conv3x3_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, lrelu, passes):
+def conv_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, KH, KW, lrelu, passes, res: Optional[View] = None):
     lib = _lib.load()
-    _lib.check(lib.pivlfn_conv3x3_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),
-                                     w_lo.data_ptr() if w_lo is not None else None,
-                                     bias.data_ptr() if bias is not None else None,
-                                     y.ptr, y.ld, y.C, int(lrelu), int(passes), _stream()), "conv3x3_tc")
+    _lib.check(lib.pivlfn_conv_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),
+                                  w_lo.data_ptr() if w_lo is not None else None,
+                                  bias.data_ptr() if bias is not None else None,
+                                  y.ptr, y.ld, y.C, KH, KW, int(lrelu),
+                                  res.ptr if res is not None else None, res.ld if res is not None else 0,
+                                  int(passes), _stream()), "conv_tc")
+
+
+def conv_stem_tc(img_pad: torch.Tensor, N, H, W, w_hi, w_lo, bias, y: View, lrelu, passes):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_conv_stem_tc(img_pad.data_ptr(), N, H, W, w_hi.data_ptr(),
+                                       w_lo.data_ptr() if w_lo is not None else None,
+                                       bias.data_ptr() if bias is not None else None,
+                                       y.ptr, y.ld, int(lrelu), int(passes), _stream()), "conv_stem_tc")
 
 
 def deconv4x4s2_dw(x: View, N, H, W, w, y: View):

@@ -98,16 +98,28 @@ def test_pack_conv_layouts(cin, cout, kh, kw, stride):
     cw = pack_conv(w, b, stride)
     assert (_conv_from_simt_pack(x.permute(0, 2, 3, 1), cw) - ref).abs().max() < 1e-3
     if cw.w_hi is not None:
-        cinp = cw.w_hi.shape[2]
-        assert cinp % 32 == 0 and cw.w_hi.shape == (cout, 9, cinp)
-        wsum = (cw.w_hi + cw.w_lo)[:, :, :cin].reshape(cout, 3, 3, cin).permute(0, 3, 1, 2)
+        coutp, cinp = cw.w_hi.shape[0], cw.w_hi.shape[2]
+        assert cinp % 32 == 0 and coutp % 16 == 0 and cw.w_hi.shape == (coutp, kh * kw, cinp)
+        wsum = (cw.w_hi + cw.w_lo)[:cout, :, :cin].reshape(cout, kh, kw, cin).permute(0, 3, 1, 2)
         assert (wsum - w).abs().max() <= w.abs().max() * 2 ** -20
         assert cw.w_hi[:, :, cin:].abs().max() == 0 if cinp > cin else True
+        assert cw.w_hi[cout:].abs().max() == 0 if coutp > cout else True
     # input-channel permutation + padding (how Rbuf's channel order is absorbed into the weights)
     perm = torch.cat([torch.arange(3, cin), torch.arange(0, 3)]) if cin > 3 else torch.arange(cin)
     cw2 = pack_conv(w, b, stride, cin_pad=1, in_perm=perm)
     xp = torch.cat([x[:, perm], torch.full((1, 1, 9, 10), 7.0)], 1)     # garbage in the pad channel is ignored
     assert (_conv_from_simt_pack(xp.permute(0, 2, 3, 1), cw2) - ref).abs().max() < 1e-3
+
+
+def test_pack_stem_layout():
+    from pivlfn.model import pack_stem
+    g = torch.Generator().manual_seed(3)
+    w, b = torch.randn(32, 3, 7, 7, generator=g), torch.randn(32, generator=g)
+    cw = pack_stem(w, b)
+    assert cw.stem and cw.w_hi.shape == (32, 7, 32) and cw.cin == 4
+    full = (cw.w_hi + cw.w_lo).reshape(32, 7, 8, 4)
+    assert (full[:, :, :7, :3].permute(0, 3, 1, 2) - w).abs().max() <= w.abs().max() * 2 ** -20
+    assert full[:, :, 7].abs().max() == 0 and full[..., 3].abs().max() == 0
 
 
 def test_pair_and_frame_ranges():

@@ -23,7 +23,7 @@ def _net(model, sd, precision):
     from src.models import hui_liteflownet, piv_liteflownet
     fac = {"piv": lambda: piv_liteflownet(sd, 1), "hui": lambda: hui_liteflownet(sd, 1),
            "piv2": lambda: piv_liteflownet(sd, 2), "hui2": lambda: hui_liteflownet(sd, 2)}
-    net = fac[model]().to(DEV)
+    net = fac[model]().to(DEV).eval()      # like the reference, a fresh module is in training mode
     net.precision = precision
     return net
 
