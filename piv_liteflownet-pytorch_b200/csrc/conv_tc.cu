@@ -14,6 +14,7 @@
 // which reproduces fp32 convolution to ~1e-6 relative.  Replaces torch.nn.Conv2d(k=3,s=1,p=1)+LeakyReLU(0.1) of
 // src/models.py:77-106 (NetC), :154-160 (conv_M), :197-204 (conv_S), :236-250 (conv_R).
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -314,6 +315,239 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// =================================================================================================================
+// Halo-resident variant (W >= 8, at least 3 taps).  The per-tap kernel above re-fetches a shifted 16 KB activation
+// tile for every filter tap; here each 32-channel chunk of the input is fetched ONCE as a halo tile
+//     [16 + KH - 1 rows][16 pixels (x0 - KW/2 ...)][32 ch]   (pixel pitch 128 B, row pitch 2048 B, 128B swizzle)
+// and every tap's A operand is a shifted window INTO that tile: rows of one 8-row core group are the 8 pixels of one
+// output row (tile = 8 wide x 16 tall), consecutive groups are 2048 B apart (SBO), and the window start
+// (ky * 16 + kx) * 128 B is not 1024-byte aligned, which the descriptor's base-offset field (= kx) accounts for.
+// Shared-memory traffic per tap drops from 48 KB (A + B) to the weights only, the 3xTF32 split runs once per chunk
+// instead of once per tap, and the weights stream through their own mbarrier ring.
+// =================================================================================================================
+constexpr int HALO_W = 16;                 // pixels per halo row (8 outputs + up to 6 halo + pad to a multiple of 8)
+constexpr int HT_W = 8, HT_H = 16;         // output tile
+
+__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr, uint32_t base_off) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((HALO_W * 128) >> 4) << 32;     // next 8-pixel group = next halo row
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(base_off & 7) << 49;            // swizzle phase of the (unaligned) start address
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct ConvHaloArgs {
+    const float* bias;
+    const float* res;
+    float* y;
+    int y_ld, res_ld;
+    int N, H, W, Cin;
+    int Cout, CoutP;
+    int KH, KW;
+    int tiles_x, tiles_y;
+    int lrelu, vec_store;
+    int nA, nB;              // activation buffers (1 or 2), weight ring depth
+    int bo_mode;             // 1: base_offset = kx (default); 0: base_offset = 0 (experiment)
+};
+
+template <int PASSES>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                    const __grid_constant__ CUtensorMap tmBlo, const ConvHaloArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int halo_rows = HT_H + a.KH - 1;
+    const int halo_bytes = halo_rows * HALO_W * 128;                    // multiple of 2048
+    const int a_buf = (PASSES == 3 ? 2 : 1) * halo_bytes;               // [hi | lo]
+    const int b_bytes = a.CoutP * KC * 4;
+    const int b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;                // [hi | lo]
+    uint8_t* smemB = smem + (size_t)a.nA * a_buf;
+    __shared__ __align__(8) uint64_t a_full[2], a_ready[2], a_empty[2], b_full[MAX_STAGES], b_empty[MAX_STAGES], accum_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = (a.Cin + KC - 1) / KC;
+    const int ntaps = a.KH * a.KW;
+    const uint32_t ncols = tmem_cols_for(PASSES == 3 ? 2 * a.CoutP : a.CoutP);
+    const int tx = blockIdx.x % a.tiles_x;
+    const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
+    const int n = blockIdx.x / (a.tiles_x * a.tiles_y);
+    const int x0 = tx * HT_W, y0 = ty * HT_H;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        mbar_init(&accum_bar, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmBhi);
+        if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= EPI_WARP0) {
+        for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.CoutP; i += 128) bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            auto load_A = [&](int c) {
+                const int buf = c % a.nA;
+                const uint32_t use = (uint32_t)(c / a.nA);
+                mbar_wait(&a_empty[buf], (use & 1) ^ 1);
+                mbar_expect_tx(&a_full[buf], halo_bytes);
+                tma_load_4d(smem + (size_t)buf * a_buf, &tmA, &a_full[buf], c * KC, x0 - a.KW / 2, y0 - a.KH / 2, n);
+            };
+            load_A(0);
+            for (int c = 0; c < nchunk; ++c) {
+                bool next_issued = (c + 1 >= nchunk);
+                for (int t = 0; t < ntaps; ++t) {
+                    mbar_wait(&b_empty[bs], bphase ^ 1);
+                    uint8_t* sB = smemB + (size_t)bs * b_stage;
+                    mbar_expect_tx(&b_full[bs], b_stage);
+                    tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
+                    if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
+                    if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                    // once nB weight tiles of this chunk are in flight the previous chunk has fully retired, so the
+                    // other activation buffer is free: prefetch the next chunk's halo now (never blocks)
+                    if (!next_issued && t + 1 >= a.nB) { load_A(c + 1); next_issued = true; }
+                }
+                if (!next_issued) load_A(c + 1);
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc_tf32(a.CoutP);
+            const uint32_t tmem_corr = tmem_base + (uint32_t)a.CoutP;
+            int bs = 0;
+            uint32_t bphase = 0;
+            uint32_t acc = 0, acc_corr = 0;
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c % a.nA;
+                const uint32_t use = (uint32_t)(c / a.nA);
+                const int kleft = a.Cin - c * KC;
+                const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
+                mbar_wait(PASSES == 3 ? &a_ready[buf] : &a_full[buf], use & 1);
+                tc_fence_after();
+                const uint32_t sAhi = smem_u32(smem + (size_t)buf * a_buf);
+                const uint32_t sAlo = sAhi + halo_bytes;
+                for (int t = 0; t < ntaps; ++t) {
+                    const int ky = t / a.KW, kx = t - ky * a.KW;
+                    const uint32_t woff = (uint32_t)((ky * HALO_W + kx) * 128);
+                    const uint32_t bo = a.bo_mode ? (uint32_t)kx : 0u;
+                    mbar_wait(&b_full[bs], bphase);
+                    tc_fence_after();
+                    const uint32_t sBhi = smem_u32(smemB + (size_t)bs * b_stage);
+                    const uint64_t dA = make_smem_desc_halo(sAhi + woff, bo), dAlo = make_smem_desc_halo(sAlo + woff, bo);
+                    const uint64_t dBhi = make_smem_desc(sBhi), dBlo = make_smem_desc(sBhi + b_bytes);
+                    for (int k = 0; k < nk; ++k) {
+                        const uint64_t koff = (uint64_t)(k * 2);
+                        umma_tf32(tmem_base, dA + koff, dBhi + koff, idesc, acc);
+                        acc = 1;
+                        if (PASSES == 3) {
+                            umma_tf32(tmem_corr, dAlo + koff, dBhi + koff, idesc, acc_corr);
+                            umma_tf32(tmem_corr, dA + koff, dBlo + koff, idesc, 1);
+                            acc_corr = 1;
+                        }
+                    }
+                    umma_commit(&b_empty[bs]);
+                    if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                }
+                umma_commit(&a_empty[buf]);
+            }
+            umma_commit(&accum_bar);
+        }
+    } else {
+        // ============================ split warps + epilogue ============================
+        const int et = threadIdx.x - EPI_WARP0 * 32;
+        if (PASSES == 3) {
+            const int nvec = halo_bytes / 16;
+            for (int c = 0; c < nchunk; ++c) {
+                const int buf = c % a.nA;
+                const uint32_t use = (uint32_t)(c / a.nA);
+                mbar_wait(&a_full[buf], use & 1);
+                float4* pa = reinterpret_cast<float4*>(smem + (size_t)buf * a_buf);
+                float4* pl = reinterpret_cast<float4*>(smem + (size_t)buf * a_buf + halo_bytes);
+#pragma unroll 4
+                for (int idx = et; idx < nvec; idx += 128) {
+                    float4 v = pa[idx];
+                    float4 h, l;
+                    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                    pa[idx] = h;
+                    pl[idx] = l;
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_ready[buf]);
+            }
+        }
+        mbar_wait(&accum_bar, 0);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int x = x0 + (row & (HT_W - 1)), yy = y0 + row / HT_W;
+        const bool live = x < a.W && yy < a.H;
+        const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
+        float* dst = a.y + pix * a.y_ld;
+        const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
+            uint32_t v[16];
+            tmem_ld16(trow + (uint32_t)c0, v);
+            if (PASSES == 3) {
+                uint32_t u[16];
+                tmem_ld16(trow + (uint32_t)(a.CoutP + c0), u);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
+            if (live) {
+                float o[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float t = __uint_as_float(v[j]) + bias_s[c0 + j];
+                    if (a.lrelu) t = lrelu_f(t);
+                    o[j] = t;
+                }
+                if (a.vec_store && c0 + 16 <= a.Cout) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                        if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
+                        *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -336,6 +570,7 @@ EncodeTiledFn get_encode() {
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int HALO_SMEM_BUDGET = 224 * 1024;
 
 template <int PASSES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, ConvTcArgs& a, int grid,
@@ -398,16 +633,70 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
 
+    const int CoutP = (Cout + 15) & ~15;
+    const int CinP = (Cin + KC - 1) / KC * KC;
+    const int vec_store = (!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    if (encode_weights(enc, &tmBhi, w_hi, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
+    if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
+    else tmBlo = tmBhi;
+
+    static int use_halo = -1, bo_mode = 1;
+    if (use_halo < 0) {
+        const char* e = getenv("PIVLFN_TC_HALO");
+        use_halo = (e && e[0] == '0') ? 0 : 1;
+        const char* b = getenv("PIVLFN_TC_BO");
+        bo_mode = (b && b[0] == '0') ? 0 : 1;
+    }
+    if (use_halo && W >= HT_W && KH * KW >= 3) {
+        // ---- halo-resident path -------------------------------------------------------------------------------
+        ConvHaloArgs h;
+        h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
+        h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
+        h.tiles_x = cdiv(W, HT_W); h.tiles_y = cdiv(H, HT_H); h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode;
+        const int nchunk = CinP / KC;
+        const int halo_rows = HT_H + KH - 1;
+        const int a_buf = (passes == 3 ? 2 : 1) * halo_rows * HALO_W * 128;
+        const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;
+        h.nA = nchunk > 1 ? 2 : 1;
+        int nB = (HALO_SMEM_BUDGET - 1024 - h.nA * a_buf) / b_stage;
+        if (nB > MAX_STAGES) nB = MAX_STAGES;
+        if (nB > nchunk * KH * KW) nB = nchunk * KH * KW;
+        if (nB >= 2 || nchunk * KH * KW == 1) {
+            h.nB = nB;
+            const long long grid = (long long)h.tiles_x * h.tiles_y * N;
+            if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
+            cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+            cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
+            cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)HALO_W, (cuuint32_t)halo_rows, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+            const int smem = h.nA * a_buf + nB * b_stage + 1024;
+            static bool cfg1 = false, cfg3 = false;
+            if (passes == 3) {
+                if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
+                conv_tc_halo_kernel<3><<<(int)grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+            } else {
+                if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
+                conv_tc_halo_kernel<1><<<(int)grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+            }
+            PIVLFN_LAUNCHED();
+            return pivlfn_last_error();
+        }
+    }
+
     ConvTcArgs a;
     a.bias = bias; a.res = res; a.res_ld = res_ld; a.y = y; a.y_ld = y_ld;
-    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.CoutP = (Cout + 15) & ~15; a.lrelu = lrelu;
+    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.CoutP = CoutP; a.lrelu = lrelu;
     a.KW = KW; a.ntaps = KH * KW; a.ox = -(KW / 2); a.oy = -(KH / 2);
-    a.vec_store = (!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0;
+    a.vec_store = vec_store;
     choose_tile(a);
     const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
     if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
-
-    CUtensorMap tmA, tmBhi, tmBlo;
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
@@ -418,11 +707,6 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
     }
-    const int CinP = (Cin + KC - 1) / KC * KC;
-    if (encode_weights(enc, &tmBhi, w_hi, CinP, a.ntaps, a.CoutP)) return PIVLFN_EINVAL;
-    if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, a.ntaps, a.CoutP)) return PIVLFN_EINVAL; }
-    else tmBlo = tmBhi;
-    cudaStream_t st = (cudaStream_t)stream;
     return passes == 3 ? launch<3>(tmA, tmBhi, tmBlo, a, (int)grid, st) : launch<1>(tmA, tmBhi, tmBlo, a, (int)grid, st);
 }
 
