@@ -321,7 +321,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 //     [16 + KH - 1 rows][16 pixels (x0 - KW/2 ...)][32 ch]   (pixel pitch 128 B, row pitch 2048 B, 128B swizzle)
 // and every tap's A operand is a shifted window INTO that tile: rows of one 8-row core group are the 8 pixels of one
 // output row (tile = 8 wide x 16 tall), consecutive groups are 2048 B apart (SBO), and the window start
-// (ky * 16 + kx) * 128 B is not 1024-byte aligned, which the descriptor's base-offset field (= kx) accounts for.
+// (ky * 16 + kx) * 128 B is not 1024-byte aligned; measured on B200 the swizzle XOR uses absolute shared-memory
+// address bits (the same rule TMA used when it wrote the tile), so the descriptor's base-offset field stays 0.
 // Shared-memory traffic per tap drops from 48 KB (A + B) to the weights only, the 3xTF32 split runs once per chunk
 // instead of once per tap, and the weights stream through their own mbarrier ring.
 // =================================================================================================================
@@ -350,7 +351,9 @@ struct ConvHaloArgs {
     int tiles_x, tiles_y;
     int lrelu, vec_store;
     int nA, nB;              // activation buffers (1 or 2), weight ring depth
-    int bo_mode;             // 1: base_offset = kx (default); 0: base_offset = 0 (experiment)
+    int bo_mode;             // 0 (default): descriptor base_offset = 0 -- measured on B200: the 128B swizzle is applied
+                             // to absolute shared-memory address bits, so an unaligned window start needs no
+                             // correction; 1: base_offset = kx (gives wrong results; kept as an experiment switch)
 };
 
 template <int PASSES>
@@ -642,12 +645,12 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    static int use_halo = -1, bo_mode = 1;
+    static int use_halo = -1, bo_mode = 0;
     if (use_halo < 0) {
         const char* e = getenv("PIVLFN_TC_HALO");
         use_halo = (e && e[0] == '0') ? 0 : 1;
         const char* b = getenv("PIVLFN_TC_BO");
-        bo_mode = (b && b[0] == '0') ? 0 : 1;
+        bo_mode = (b && b[0] == '1') ? 1 : 0;
     }
     if (use_halo && W >= HT_W && KH * KW >= 3) {
         // ---- halo-resident path -------------------------------------------------------------------------------

@@ -174,7 +174,7 @@ def test_conv_tc_vs_torch(case, passes, tol):
     assert y[..., cout:].abs().max().item() == 0          # never writes outside its channel slice
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (1, 2e-2)])
 @pytest.mark.parametrize("hw", [(16, 16), (40, 56), (8, 8)])
 def test_conv_stem_tc_vs_torch(hw, passes, tol):
     """NetC.conv1 (7x7, 3 -> 32) through the overlapping-window tensor map on the zero-bordered image."""
