@@ -28,6 +28,19 @@ constexpr int EPI_WARP0 = 2;
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a fully active warp (elect.sync): the compiler then knows the guarded region runs on a single thread
+// and emits tcgen05 / TMA instructions directly instead of a per-active-lane serialisation loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -185,7 +198,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
             for (int it = 0; it < niter; ++it) {
@@ -204,7 +217,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(a.CoutP);
             const uint32_t tmem_corr = tmem_base + (uint32_t)a.CoutP;      // 3xTF32: low-order terms accumulate separately
             int stage = 0;
@@ -404,7 +417,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         // ================================ TMA producer ================================
-        if (lane == 0) {
+        if (elect_one()) {
             int bs = 0;
             uint32_t bphase = 0;
             auto load_A = [&](int c) {
@@ -433,7 +446,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(a.CoutP);
             const uint32_t tmem_corr = tmem_base + (uint32_t)a.CoutP;
             int bs = 0;
