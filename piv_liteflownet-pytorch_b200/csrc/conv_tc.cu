@@ -143,7 +143,9 @@ struct ConvTcArgs {
 
 constexpr int MAX_STAGES = 8;
 
-__device__ __forceinline__ uint32_t tmem_cols_for(int n) { return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : 256u)); }
+__device__ __forceinline__ uint32_t tmem_cols_for(int n) {
+    return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u)));
+}
 
 // PASSES = 1 (TF32) or 3 (3xTF32).
 template <int PASSES>
@@ -331,24 +333,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // =================================================================================================================
 // Halo-resident variant (W >= 8, at least 3 taps).  The per-tap kernel above re-fetches a shifted 16 KB activation
 // tile for every filter tap; here each 32-channel chunk of the input is fetched ONCE as a halo tile
-//     [16 + KH - 1 rows][16 pixels (x0 - KW/2 ...)][32 ch]   (pixel pitch 128 B, row pitch 2048 B, 128B swizzle)
-// and every tap's A operand is a shifted window INTO that tile: rows of one 8-row core group are the 8 pixels of one
-// output row (tile = 8 wide x 16 tall), consecutive groups are 2048 B apart (SBO), and the window start
-// (ky * 16 + kx) * 128 B is not 1024-byte aligned; measured on B200 the swizzle XOR uses absolute shared-memory
-// address bits (the same rule TMA used when it wrote the tile), so the descriptor's base-offset field stays 0.
-// Shared-memory traffic per tap drops from 48 KB (A + B) to the weights only, the 3xTF32 split runs once per chunk
-// instead of once per tap, and the weights stream through their own mbarrier ring.
+//     [16*NT + KH - 1 rows][8 + KW - 1 pixels][32 ch]     (pixel pitch 128 B, dense rows, 128B swizzle)
+// and every tap's A operand is a shifted window INTO that tile: the 8 rows of one core group are the 8 pixels of one
+// output row (tile = 8 wide x 16 tall), consecutive groups are one halo row apart (SBO = pitch * 128 B).  The window
+// start (ky * pitch + kx) * 128 B is not 1024-byte aligned; measured on B200 the swizzle XOR uses absolute
+// shared-memory address bits (the same rule TMA used when it wrote the tile), so the descriptor's base-offset field
+// stays 0 and any pitch works.  One CTA computes NT vertically stacked tiles (NT accumulator sets in TMEM) so that
+// every streamed weight tile is used for NT * 128 pixels -- the weights re-streamed from L2 by every CTA were the
+// bottleneck of the per-tap kernel.  3xTF32: buffers rotate raw(c+1) / hi(c) / lo(c) through three equal slots.
 // =================================================================================================================
-constexpr int HALO_W = 16;                 // pixels per halo row (8 outputs + up to 6 halo + pad to a multiple of 8)
-constexpr int HT_W = 8, HT_H = 16;         // output tile
+constexpr int HT_W = 8, HT_H = 16;         // output tile (UMMA M = 128 rows = 16 rows of 8 pixels)
+constexpr int MAX_NT = 4;
 
-__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr, uint32_t base_off) {
+__device__ __forceinline__ uint64_t make_smem_desc_halo(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((HALO_W * 128) >> 4) << 32;     // next 8-pixel group = next halo row
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;          // next 8-pixel group = next halo row
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)(base_off & 7) << 49;            // swizzle phase of the (unaligned) start address
+    d |= (uint64_t)(base_off & 7) << 49;
     d |= (uint64_t)2 << 61;
     return d;
 }
@@ -363,11 +366,15 @@ struct ConvHaloArgs {
     int KH, KW;
     int tiles_x, tiles_y;
     int lrelu, vec_store;
-    int nA, nB;              // activation buffers (1 or 2), weight ring depth
-    int bo_mode;             // 0 (default): descriptor base_offset = 0 -- measured on B200: the 128B swizzle is applied
-                             // to absolute shared-memory address bits, so an unaligned window start needs no
-                             // correction; 1: base_offset = kx (gives wrong results; kept as an experiment switch)
+    int NT;                  // vertically stacked 8x16 tiles per CTA
+    int nBuf, nB;            // activation buffer slots, weight ring depth
+    int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
+                             // B200, kept as an experiment switch
 };
+
+// buffer slot of chunk c's activations (hi after the split) and of its low-order part
+__device__ __forceinline__ int slot_x(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf; }
+__device__ __forceinline__ int slot_l(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1; }
 
 template <int PASSES>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -375,27 +382,27 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const __grid_constant__ CUtensorMap tmBlo, const ConvHaloArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int halo_rows = HT_H + a.KH - 1;
-    const int halo_bytes = halo_rows * HALO_W * 128;                    // multiple of 2048
-    const int a_buf = (PASSES == 3 ? 2 : 1) * halo_bytes;               // [hi | lo]
+    const int pitch = HT_W + a.KW - 1;
+    const int halo_rows = HT_H * a.NT + a.KH - 1;
+    const int halo_bytes = halo_rows * pitch * 128;
+    const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int b_bytes = a.CoutP * KC * 4;
     const int b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;                // [hi | lo]
-    uint8_t* smemB = smem + (size_t)a.nA * a_buf;
-    __shared__ __align__(8) uint64_t a_full[2], a_ready[2], a_empty[2], b_full[MAX_STAGES], b_empty[MAX_STAGES], accum_bar;
+    uint8_t* smemB = smem + (size_t)a.nBuf * slot_bytes;
+    __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES], accum_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.Cin + KC - 1) / KC;
     const int ntaps = a.KH * a.KW;
-    const uint32_t ncols = tmem_cols_for(PASSES == 3 ? 2 * a.CoutP : a.CoutP);
+    const uint32_t ncols = tmem_cols_for((PASSES == 3 ? 2 : 1) * a.NT * a.CoutP);
     const int tx = blockIdx.x % a.tiles_x;
     const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
     const int n = blockIdx.x / (a.tiles_x * a.tiles_y);
-    const int x0 = tx * HT_W, y0 = ty * HT_H;
+    const int x0 = tx * HT_W, y0 = ty * HT_H * a.NT;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], 1); }
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         mbar_init(&accum_bar, 1);
         fence_barrier_init();
@@ -406,9 +413,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    if (warp >= EPI_WARP0) {
-        for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.CoutP; i += 128) bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -421,15 +425,18 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int bs = 0;
             uint32_t bphase = 0;
             auto load_A = [&](int c) {
-                const int buf = c % a.nA;
-                const uint32_t use = (uint32_t)(c / a.nA);
-                mbar_wait(&a_empty[buf], (use & 1) ^ 1);
-                mbar_expect_tx(&a_full[buf], halo_bytes);
-                tma_load_4d(smem + (size_t)buf * a_buf, &tmA, &a_full[buf], c * KC, x0 - a.KW / 2, y0 - a.KH / 2, n);
+                // slot_x(c) was last read by chunk c-2's MMAs (as its hi or its lo slot): wait until chunk c-2 retired
+                if (c >= 2) mbar_wait(&chunk_done[(c - 2) & 1], (uint32_t)(((c - 2) >> 1) & 1));
+                mbar_expect_tx(&a_full[c & 1], halo_bytes);
+                tma_load_4d(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes, &tmA, &a_full[c & 1], c * KC, x0 - a.KW / 2,
+                            y0 - a.KH / 2, n);
             };
             load_A(0);
+            if (nchunk > 1 && a.nBuf != 3) load_A(1);          // 1-pass: both slots free at start
             for (int c = 0; c < nchunk; ++c) {
-                bool next_issued = (c + 1 >= nchunk);
+                // 3xTF32: raw(c+1) goes into the slot that chunk c does not use -> can be issued right away
+                bool next_issued = (c + 1 >= nchunk) || (a.nBuf != 3 && c == 0);
+                if (!next_issued && a.nBuf == 3 && c == 0) { load_A(1); next_issued = true; }
                 for (int t = 0; t < ntaps; ++t) {
                     mbar_wait(&b_empty[bs], bphase ^ 1);
                     uint8_t* sB = smemB + (size_t)bs * b_stage;
@@ -437,8 +444,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                     if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
                     if (++bs == a.nB) { bs = 0; bphase ^= 1; }
-                    // once nB weight tiles of this chunk are in flight the previous chunk has fully retired, so the
-                    // other activation buffer is free: prefetch the next chunk's halo now (never blocks)
+                    // once nB weight tiles of this chunk are in flight the previous chunk has fully retired, so its
+                    // slot(s) are free: prefetch the next chunk's halo now (the waits inside never block)
                     if (!next_issued && t + 1 >= a.nB) { load_A(c + 1); next_issued = true; }
                 }
                 if (!next_issued) load_A(c + 1);
@@ -448,42 +455,46 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         // ================================ MMA issuer ==================================
         if (elect_one()) {
             const uint32_t idesc = make_idesc_tf32(a.CoutP);
-            const uint32_t tmem_corr = tmem_base + (uint32_t)a.CoutP;
+            const uint32_t sbo = (uint32_t)(pitch * 128);
+            const uint32_t tile_step = (uint32_t)(HT_H * pitch * 128);
             int bs = 0;
             uint32_t bphase = 0;
-            uint32_t acc = 0, acc_corr = 0;
+            uint32_t acc = 0;
             for (int c = 0; c < nchunk; ++c) {
-                const int buf = c % a.nA;
-                const uint32_t use = (uint32_t)(c / a.nA);
+                const uint32_t par = (uint32_t)((c >> 1) & 1);
                 const int kleft = a.Cin - c * KC;
                 const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
-                mbar_wait(PASSES == 3 ? &a_ready[buf] : &a_full[buf], use & 1);
+                mbar_wait(PASSES == 3 ? &a_ready[c & 1] : &a_full[c & 1], par);
                 tc_fence_after();
-                const uint32_t sAhi = smem_u32(smem + (size_t)buf * a_buf);
-                const uint32_t sAlo = sAhi + halo_bytes;
+                const uint32_t sAhi = smem_u32(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes);
+                const uint32_t sAlo = smem_u32(smem + (size_t)slot_l(c, a.nBuf) * slot_bytes);
                 for (int t = 0; t < ntaps; ++t) {
                     const int ky = t / a.KW, kx = t - ky * a.KW;
-                    const uint32_t woff = (uint32_t)((ky * HALO_W + kx) * 128);
+                    const uint32_t woff = (uint32_t)((ky * pitch + kx) * 128);
                     const uint32_t bo = a.bo_mode ? (uint32_t)kx : 0u;
                     mbar_wait(&b_full[bs], bphase);
                     tc_fence_after();
                     const uint32_t sBhi = smem_u32(smemB + (size_t)bs * b_stage);
-                    const uint64_t dA = make_smem_desc_halo(sAhi + woff, bo), dAlo = make_smem_desc_halo(sAlo + woff, bo);
                     const uint64_t dBhi = make_smem_desc(sBhi), dBlo = make_smem_desc(sBhi + b_bytes);
-                    for (int k = 0; k < nk; ++k) {
-                        const uint64_t koff = (uint64_t)(k * 2);
-                        umma_tf32(tmem_base, dA + koff, dBhi + koff, idesc, acc);
-                        acc = 1;
-                        if (PASSES == 3) {
-                            umma_tf32(tmem_corr, dAlo + koff, dBhi + koff, idesc, acc_corr);
-                            umma_tf32(tmem_corr, dA + koff, dBlo + koff, idesc, 1);
-                            acc_corr = 1;
+                    for (int i = 0; i < a.NT; ++i) {
+                        const uint64_t dA = make_smem_desc_halo(sAhi + woff + i * tile_step, sbo, bo);
+                        const uint64_t dAlo = make_smem_desc_halo(sAlo + woff + i * tile_step, sbo, bo);
+                        const uint32_t t_main = tmem_base + (uint32_t)(i * a.CoutP);
+                        const uint32_t t_corr = tmem_base + (uint32_t)((a.NT + i) * a.CoutP);
+                        for (int k = 0; k < nk; ++k) {
+                            const uint64_t koff = (uint64_t)(k * 2);
+                            umma_tf32(t_main, dA + koff, dBhi + koff, idesc, acc | (uint32_t)(k > 0));
+                            if (PASSES == 3) {
+                                umma_tf32(t_corr, dAlo + koff, dBhi + koff, idesc, acc | (uint32_t)(k > 0));
+                                umma_tf32(t_corr, dA + koff, dBlo + koff, idesc, 1);
+                            }
                         }
                     }
+                    acc = 1;
                     umma_commit(&b_empty[bs]);
                     if (++bs == a.nB) { bs = 0; bphase ^= 1; }
                 }
-                umma_commit(&a_empty[buf]);
+                umma_commit(&chunk_done[c & 1]);
             }
             umma_commit(&accum_bar);
         }
@@ -493,11 +504,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (PASSES == 3) {
             const int nvec = halo_bytes / 16;
             for (int c = 0; c < nchunk; ++c) {
-                const int buf = c % a.nA;
-                const uint32_t use = (uint32_t)(c / a.nA);
-                mbar_wait(&a_full[buf], use & 1);
-                float4* pa = reinterpret_cast<float4*>(smem + (size_t)buf * a_buf);
-                float4* pl = reinterpret_cast<float4*>(smem + (size_t)buf * a_buf + halo_bytes);
+                // the lo slot of chunk c was in use by chunk c-1's MMAs
+                if (c >= 1) mbar_wait(&chunk_done[(c - 1) & 1], (uint32_t)(((c - 1) >> 1) & 1));
+                mbar_wait(&a_full[c & 1], (uint32_t)((c >> 1) & 1));
+                float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes);
+                float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(c, a.nBuf) * slot_bytes);
 #pragma unroll 4
                 for (int idx = et; idx < nvec; idx += 128) {
                     float4 v = pa[idx];
@@ -512,47 +523,50 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 fence_proxy_async();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[buf]);
+                if (lane == 0) mbar_arrive(&a_ready[c & 1]);
             }
         }
         mbar_wait(&accum_bar, 0);
         tc_fence_after();
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int x = x0 + (row & (HT_W - 1)), yy = y0 + row / HT_W;
-        const bool live = x < a.W && yy < a.H;
-        const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
-        float* dst = a.y + pix * a.y_ld;
-        const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
+        const int x = x0 + (row & (HT_W - 1));
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld16(trow + (uint32_t)c0, v);
-            if (PASSES == 3) {
-                uint32_t u[16];
-                tmem_ld16(trow + (uint32_t)(a.CoutP + c0), u);
+        for (int i = 0; i < a.NT; ++i) {
+            const int yy = y0 + i * HT_H + row / HT_W;
+            const bool live = x < a.W && yy < a.H;
+            const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
+            float* dst = a.y + pix * a.y_ld;
+            const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
+            for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(trow + (uint32_t)(i * a.CoutP + c0), v);
+                if (PASSES == 3) {
+                    uint32_t u[16];
+                    tmem_ld16(trow + (uint32_t)((a.NT + i) * a.CoutP + c0), u);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-            }
-            if (live) {
-                float o[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    float t = __uint_as_float(v[j]) + bias_s[c0 + j];
-                    if (a.lrelu) t = lrelu_f(t);
-                    o[j] = t;
+                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
                 }
-                if (a.vec_store && c0 + 16 <= a.Cout) {
+                if (live) {
+                    float o[16];
 #pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                        if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
-                        *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                    for (int j = 0; j < 16; ++j) {
+                        float t = __uint_as_float(v[j]) + ((a.bias && c0 + j < a.Cout) ? __ldg(a.bias + c0 + j) : 0.f);
+                        if (a.lrelu) t = lrelu_f(t);
+                        o[j] = t;
                     }
-                } else {
+                    if (a.vec_store && c0 + 16 <= a.Cout) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j)
-                        if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                        for (int j = 0; j < 16; j += 4) {
+                            float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                            if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
+                            *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                    }
                 }
             }
         }
@@ -586,7 +600,7 @@ EncodeTiledFn get_encode() {
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 constexpr int SMEM_BUDGET = 200 * 1024;
-constexpr int HALO_SMEM_BUDGET = 224 * 1024;
+constexpr int HALO_SMEM_BUDGET = 227 * 1024 - 512;   // 227 KB per CTA minus the static barriers
 
 template <int PASSES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, ConvTcArgs& a, int grid,
@@ -658,40 +672,51 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    static int use_halo = -1, bo_mode = 0;
+    static int use_halo = -1, bo_mode = 0, nt_limit = 0;
     if (use_halo < 0) {
         const char* e = getenv("PIVLFN_TC_HALO");
         use_halo = (e && e[0] == '0') ? 0 : 1;
         const char* b = getenv("PIVLFN_TC_BO");
         bo_mode = (b && b[0] == '1') ? 1 : 0;
+        const char* t = getenv("PIVLFN_TC_NT");
+        nt_limit = t ? atoi(t) : 0;
     }
     if (use_halo && W >= HT_W && KH * KW >= 3) {
         // ---- halo-resident path -------------------------------------------------------------------------------
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
-        h.tiles_x = cdiv(W, HT_W); h.tiles_y = cdiv(H, HT_H); h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode;
+        h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode;
         const int nchunk = CinP / KC;
-        const int halo_rows = HT_H + KH - 1;
-        const int a_buf = (passes == 3 ? 2 : 1) * halo_rows * HALO_W * 128;
+        const int pitch = HT_W + KW - 1;
         const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;
-        h.nA = nchunk > 1 ? 2 : 1;
-        int nB = (HALO_SMEM_BUDGET - 1024 - h.nA * a_buf) / b_stage;
-        if (nB > MAX_STAGES) nB = MAX_STAGES;
-        if (nB > nchunk * KH * KW) nB = nchunk * KH * KW;
-        if (nB >= 2 || nchunk * KH * KW == 1) {
-            h.nB = nB;
+        const int ntile_total = nchunk * KH * KW;
+        // NT stacked tiles per CTA: bounded by TMEM (512 columns), by the image height and by shared memory
+        int NT = nt_limit > 0 ? nt_limit : MAX_NT;
+        while (NT > 1 && ((passes == 3 ? 2 : 1) * NT * CoutP > 512 || HT_H * (NT - 1) >= H)) --NT;
+        for (; NT >= 1; --NT) {
+            if (NT == 3) continue;
+            const int halo_rows = HT_H * NT + KH - 1;
+            const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
+            const int nBuf = passes == 3 ? (nchunk > 1 ? 3 : 2) : (nchunk > 1 ? 2 : 1);
+            int nB = (HALO_SMEM_BUDGET - 1024 - nBuf * slot) / b_stage;
+            if (nB > MAX_STAGES) nB = MAX_STAGES;
+            if (nB > ntile_total) nB = ntile_total;
+            const int need = ntile_total >= 3 ? (passes == 3 ? 2 : 3) : 1;
+            if (nB < need || halo_rows > 256) continue;
+            h.NT = NT; h.nBuf = nBuf; h.nB = nB;
+            h.tiles_x = cdiv(W, HT_W); h.tiles_y = cdiv(H, HT_H * NT);
             const long long grid = (long long)h.tiles_x * h.tiles_y * N;
             if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
             cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
-            cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)HALO_W, (cuuint32_t)halo_rows, 1};
+            cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)pitch, (cuuint32_t)halo_rows, 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            const int smem = h.nA * a_buf + nB * b_stage + 1024;
+            const int smem = nBuf * slot + nB * b_stage + 1024;
             static bool cfg1 = false, cfg3 = false;
             if (passes == 3) {
                 if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
