@@ -600,7 +600,8 @@ EncodeTiledFn get_encode() {
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
 constexpr int SMEM_BUDGET = 200 * 1024;
-constexpr int HALO_SMEM_BUDGET = 227 * 1024 - 512;   // 227 KB per CTA minus the static barriers
+constexpr int HALO_SMEM_BUDGET = 226 * 1024;   // 227 KB opt-in per CTA minus the static part (padded to 1 KB by the
+                                               // 1024-byte alignment of the dynamic array, which also makes align-up slack unnecessary)
 
 template <int PASSES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, ConvTcArgs& a, int grid,
@@ -699,7 +700,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
             const int halo_rows = HT_H * NT + KH - 1;
             const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
             const int nBuf = passes == 3 ? (nchunk > 1 ? 3 : 2) : (nchunk > 1 ? 2 : 1);
-            int nB = (HALO_SMEM_BUDGET - 1024 - nBuf * slot) / b_stage;
+            int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
             if (nB > MAX_STAGES) nB = MAX_STAGES;
             if (nB > ntile_total) nB = ntile_total;
             const int need = ntile_total >= 3 ? (passes == 3 ? 2 : 3) : 1;
@@ -716,7 +717,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            const int smem = nBuf * slot + nB * b_stage + 1024;
+            const int smem = nBuf * slot + nB * b_stage;
             static bool cfg1 = false, cfg3 = false;
             if (passes == 3) {
                 if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
