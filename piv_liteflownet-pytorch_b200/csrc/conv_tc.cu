@@ -364,10 +364,12 @@ struct ConvHaloArgs {
     int N, H, W, Cin;
     int Cout, CoutP;
     int KH, KW;
-    int tiles_x, tiles_y;
+    int tiles_x, tiles_y, total;   // work items = N * tiles_y * tiles_x groups of NT stacked 8x16 tiles
     int lrelu, vec_store;
-    int NT;                  // vertically stacked 8x16 tiles per CTA
+    int NT;                  // vertically stacked 8x16 tiles per work item
     int nBuf, nB;            // activation buffer slots, weight ring depth
+    int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
+    int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
                              // B200, kept as an experiment switch
 };
@@ -376,8 +378,12 @@ struct ConvHaloArgs {
 __device__ __forceinline__ int slot_x(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf; }
 __device__ __forceinline__ int slot_l(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1; }
 
+constexpr int HALO_THREADS = 384;      // warp 0 TMA, 1 MMA, 4-7 epilogue (TMEM lane quarter = warp % 4), 8-11 split
+
+// Persistent: one CTA per SM loops over work items; all roles walk the same global (item, chunk, tap) sequence so
+// the mbarrier phases simply keep counting across items.
 template <int PASSES>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                     const __grid_constant__ CUtensorMap tmBlo, const ConvHaloArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -389,22 +395,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int b_bytes = a.CoutP * KC * 4;
     const int b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;                // [hi | lo]
     uint8_t* smemB = smem + (size_t)a.nBuf * slot_bytes;
-    __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES], accum_bar;
+    __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
+        acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.Cin + KC - 1) / KC;
     const int ntaps = a.KH * a.KW;
-    const uint32_t ncols = tmem_cols_for((PASSES == 3 ? 2 : 1) * a.NT * a.CoutP);
-    const int tx = blockIdx.x % a.tiles_x;
-    const int ty = (blockIdx.x / a.tiles_x) % a.tiles_y;
-    const int n = blockIdx.x / (a.tiles_x * a.tiles_y);
-    const int x0 = tx * HT_W, y0 = ty * HT_H * a.NT;
+    const int set_cols = ((PASSES == 3 && a.corr) ? 2 : 1) * a.NT * a.CoutP;
+    const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
+    const int G = gridDim.x;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], 1);
+            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+        }
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        mbar_init(&accum_bar, 1);
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmBhi);
@@ -424,31 +431,40 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (elect_one()) {
             int bs = 0;
             uint32_t bphase = 0;
-            auto load_A = [&](int c) {
-                // slot_x(c) was last read by chunk c-2's MMAs (as its hi or its lo slot): wait until chunk c-2 retired
-                if (c >= 2) mbar_wait(&chunk_done[(c - 2) & 1], (uint32_t)(((c - 2) >> 1) & 1));
-                mbar_expect_tx(&a_full[c & 1], halo_bytes);
-                tma_load_4d(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes, &tmA, &a_full[c & 1], c * KC, x0 - a.KW / 2,
-                            y0 - a.KH / 2, n);
+            int gc = 0;                                   // global chunk counter
+            auto load_A = [&](int g, int w, int c) {
+                const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
+                // slot_x(g) was last read by global chunk g-2's MMAs (as its hi or its lo slot)
+                if (g >= 2) mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1));
+                mbar_expect_tx(&a_full[g & 1], halo_bytes);
+                tma_load_4d(smem + (size_t)slot_x(g, a.nBuf) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
+                            tx * HT_W - a.KW / 2, ty * HT_H * a.NT - a.KH / 2, n);
             };
-            load_A(0);
-            if (nchunk > 1 && a.nBuf != 3) load_A(1);          // 1-pass: both slots free at start
-            for (int c = 0; c < nchunk; ++c) {
-                // 3xTF32: raw(c+1) goes into the slot that chunk c does not use -> can be issued right away
-                bool next_issued = (c + 1 >= nchunk) || (a.nBuf != 3 && c == 0);
-                if (!next_issued && a.nBuf == 3 && c == 0) { load_A(1); next_issued = true; }
-                for (int t = 0; t < ntaps; ++t) {
-                    mbar_wait(&b_empty[bs], bphase ^ 1);
-                    uint8_t* sB = smemB + (size_t)bs * b_stage;
-                    mbar_expect_tx(&b_full[bs], b_stage);
-                    tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
-                    if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
-                    if (++bs == a.nB) { bs = 0; bphase ^= 1; }
-                    // once nB weight tiles of this chunk are in flight the previous chunk has fully retired, so its
-                    // slot(s) are free: prefetch the next chunk's halo now (the waits inside never block)
-                    if (!next_issued && t + 1 >= a.nB) { load_A(c + 1); next_issued = true; }
+            // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
+            auto next_of = [&](int w, int c, int& w2, int& c2) { c2 = c + 1; w2 = w; if (c2 == nchunk) { c2 = 0; w2 = w + G; } };
+            bool pre = false;                             // is chunk gc already issued?
+            for (int w = blockIdx.x; w < a.total; w += G) {
+                for (int c = 0; c < nchunk; ++c, ++gc) {
+                    if (!pre) load_A(gc, w, c);
+                    pre = false;
+                    int w2, c2;
+                    next_of(w, c, w2, c2);
+                    const bool has_next = w2 < a.total;
+                    // with >= 3 slots (or 2 slots in 1-pass mode) the next chunk's slot is free as soon as chunk gc-1
+                    // retired; issue it after nB weight tiles (by then chunk gc-1 has certainly retired)
+                    bool next_issued = !has_next || a.nBuf < 2;
+                    if (!next_issued && gc == 0) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                    for (int t = 0; t < ntaps; ++t) {
+                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                        uint8_t* sB = smemB + (size_t)bs * b_stage;
+                        mbar_expect_tx(&b_full[bs], b_stage);
+                        tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
+                        if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
+                        if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                        if (!next_issued && t + 1 >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                    }
+                    if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
-                if (!next_issued) load_A(c + 1);
             }
         }
     } else if (warp == 1) {
@@ -459,116 +475,139 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t tile_step = (uint32_t)(HT_H * pitch * 128);
             int bs = 0;
             uint32_t bphase = 0;
-            uint32_t acc = 0;
-            for (int c = 0; c < nchunk; ++c) {
-                const uint32_t par = (uint32_t)((c >> 1) & 1);
-                const int kleft = a.Cin - c * KC;
-                const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
-                mbar_wait(PASSES == 3 ? &a_ready[c & 1] : &a_full[c & 1], par);
+            int gc = 0, wl = 0;
+            for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+                const int as = wl % a.nsets;
+                const uint32_t use = (uint32_t)(wl / a.nsets);
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);             // epilogue drained this accumulator set
                 tc_fence_after();
-                const uint32_t sAhi = smem_u32(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes);
-                const uint32_t sAlo = smem_u32(smem + (size_t)slot_l(c, a.nBuf) * slot_bytes);
-                for (int t = 0; t < ntaps; ++t) {
-                    const int ky = t / a.KW, kx = t - ky * a.KW;
-                    const uint32_t woff = (uint32_t)((ky * pitch + kx) * 128);
-                    const uint32_t bo = a.bo_mode ? (uint32_t)kx : 0u;
-                    mbar_wait(&b_full[bs], bphase);
+                const uint32_t tset = tmem_base + (uint32_t)(as * set_cols);
+                uint32_t acc = 0;
+                for (int c = 0; c < nchunk; ++c, ++gc) {
+                    const uint32_t par = (uint32_t)((gc >> 1) & 1);
+                    const int kleft = a.Cin - c * KC;
+                    const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
+                    mbar_wait(PASSES == 3 ? &a_ready[gc & 1] : &a_full[gc & 1], par);
                     tc_fence_after();
-                    const uint32_t sBhi = smem_u32(smemB + (size_t)bs * b_stage);
-                    const uint64_t dBhi = make_smem_desc(sBhi), dBlo = make_smem_desc(sBhi + b_bytes);
-                    for (int i = 0; i < a.NT; ++i) {
-                        const uint64_t dA = make_smem_desc_halo(sAhi + woff + i * tile_step, sbo, bo);
-                        const uint64_t dAlo = make_smem_desc_halo(sAlo + woff + i * tile_step, sbo, bo);
-                        const uint32_t t_main = tmem_base + (uint32_t)(i * a.CoutP);
-                        const uint32_t t_corr = tmem_base + (uint32_t)((a.NT + i) * a.CoutP);
-                        for (int k = 0; k < nk; ++k) {
-                            const uint64_t koff = (uint64_t)(k * 2);
-                            umma_tf32(t_main, dA + koff, dBhi + koff, idesc, acc | (uint32_t)(k > 0));
-                            if (PASSES == 3) {
-                                umma_tf32(t_corr, dAlo + koff, dBhi + koff, idesc, acc | (uint32_t)(k > 0));
-                                umma_tf32(t_corr, dA + koff, dBlo + koff, idesc, 1);
+                    const uint32_t sAhi = smem_u32(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
+                    const uint32_t sAlo = smem_u32(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
+                    for (int t = 0; t < ntaps; ++t) {
+                        const int ky = t / a.KW, kx = t - ky * a.KW;
+                        const uint32_t woff = (uint32_t)((ky * pitch + kx) * 128);
+                        const uint32_t bo = a.bo_mode ? (uint32_t)kx : 0u;
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        const uint32_t sBhi = smem_u32(smemB + (size_t)bs * b_stage);
+                        const uint64_t dBhi = make_smem_desc(sBhi), dBlo = make_smem_desc(sBhi + b_bytes);
+                        for (int i = 0; i < a.NT; ++i) {
+                            const uint64_t dA = make_smem_desc_halo(sAhi + woff + i * tile_step, sbo, bo);
+                            const uint64_t dAlo = make_smem_desc_halo(sAlo + woff + i * tile_step, sbo, bo);
+                            const uint32_t t_main = tset + (uint32_t)(i * a.CoutP);
+                            const uint32_t t_corr = a.corr ? tset + (uint32_t)((a.NT + i) * a.CoutP) : t_main;
+                            for (int k = 0; k < nk; ++k) {
+                                const uint64_t koff = (uint64_t)(k * 2);
+                                const uint32_t first = acc | (uint32_t)(k > 0);
+                                umma_tf32(t_main, dA + koff, dBhi + koff, idesc, first);
+                                if (PASSES == 3) {
+                                    umma_tf32(t_corr, dAlo + koff, dBhi + koff, idesc, a.corr ? first : 1u);
+                                    umma_tf32(t_corr, dA + koff, dBlo + koff, idesc, 1);
+                                }
                             }
                         }
+                        acc = 1;
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == a.nB) { bs = 0; bphase ^= 1; }
                     }
-                    acc = 1;
-                    umma_commit(&b_empty[bs]);
-                    if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                    umma_commit(&chunk_done[gc & 1]);
                 }
-                umma_commit(&chunk_done[c & 1]);
+                umma_commit(&acc_full[as]);
             }
-            umma_commit(&accum_bar);
         }
-    } else {
-        // ============================ split warps + epilogue ============================
-        const int et = threadIdx.x - EPI_WARP0 * 32;
+    } else if (warp >= 8) {
+        // ================================ 3xTF32 split warps ============================
         if (PASSES == 3) {
+            const int et = threadIdx.x - 8 * 32;
             const int nvec = halo_bytes / 16;
-            for (int c = 0; c < nchunk; ++c) {
-                // the lo slot of chunk c was in use by chunk c-1's MMAs
-                if (c >= 1) mbar_wait(&chunk_done[(c - 1) & 1], (uint32_t)(((c - 1) >> 1) & 1));
-                mbar_wait(&a_full[c & 1], (uint32_t)((c >> 1) & 1));
-                float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(c, a.nBuf) * slot_bytes);
-                float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(c, a.nBuf) * slot_bytes);
+            int gc = 0;
+            for (int w = blockIdx.x; w < a.total; w += G) {
+                for (int c = 0; c < nchunk; ++c, ++gc) {
+                    // the lo slot of chunk gc was in use by chunk gc-1's MMAs
+                    if (gc >= 1) mbar_wait(&chunk_done[(gc - 1) & 1], (uint32_t)(((gc - 1) >> 1) & 1));
+                    mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1));
+                    float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
+                    float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
 #pragma unroll 4
-                for (int idx = et; idx < nvec; idx += 128) {
-                    float4 v = pa[idx];
-                    float4 h, l;
-                    h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-                    h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-                    h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-                    h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-                    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                    pa[idx] = h;
-                    pl[idx] = l;
+                    for (int idx = et; idx < nvec; idx += 128) {
+                        float4 v = pa[idx];
+                        float4 h, l;
+                        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                        pa[idx] = h;
+                        pl[idx] = l;
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&a_ready[gc & 1]);
                 }
-                fence_proxy_async();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&a_ready[c & 1]);
             }
         }
-        mbar_wait(&accum_bar, 0);
-        tc_fence_after();
+    } else if (warp >= 4) {
+        // ================================ epilogue warps ================================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int x = x0 + (row & (HT_W - 1));
-        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int i = 0; i < a.NT; ++i) {
-            const int yy = y0 + i * HT_H + row / HT_W;
-            const bool live = x < a.W && yy < a.H;
-            const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
-            float* dst = a.y + pix * a.y_ld;
-            const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
-            for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(trow + (uint32_t)(i * a.CoutP + c0), v);
-                if (PASSES == 3) {
-                    uint32_t u[16];
-                    tmem_ld16(trow + (uint32_t)((a.NT + i) * a.CoutP + c0), u);
+        int wl = 0;
+        for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+            const int as = wl % a.nsets;
+            const uint32_t use = (uint32_t)(wl / a.nsets);
+            const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
+            const int x = tx * HT_W + (row & (HT_W - 1));
+            mbar_wait(&acc_full[as], use & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
+            for (int i = 0; i < a.NT; ++i) {
+                const int yy = (ty * a.NT + i) * HT_H + row / HT_W;
+                const bool live = x < a.W && yy < a.H;
+                const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
+                float* dst = a.y + pix * a.y_ld;
+                const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
+                for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
+                    uint32_t v[16];
+                    tmem_ld16(trow + (uint32_t)(i * a.CoutP + c0), v);
+                    if (PASSES == 3 && a.corr) {
+                        uint32_t u[16];
+                        tmem_ld16(trow + (uint32_t)((a.NT + i) * a.CoutP + c0), u);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
-                }
-                if (live) {
-                    float o[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float t = __uint_as_float(v[j]) + ((a.bias && c0 + j < a.Cout) ? __ldg(a.bias + c0 + j) : 0.f);
-                        if (a.lrelu) t = lrelu_f(t);
-                        o[j] = t;
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
                     }
-                    if (a.vec_store && c0 + 16 <= a.Cout) {
+                    if (live) {
+                        float o[16];
 #pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                            if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
-                            *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                        for (int j = 0; j < 16; ++j) {
+                            float t = __uint_as_float(v[j]) + ((a.bias && c0 + j < a.Cout) ? __ldg(a.bias + c0 + j) : 0.f);
+                            if (a.lrelu) t = lrelu_f(t);
+                            o[j] = t;
                         }
-                    } else {
+                        if (a.vec_store && c0 + 16 <= a.Cout) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                            for (int j = 0; j < 16; j += 4) {
+                                float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                                if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
+                                *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                        }
                     }
                 }
             }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
     }
     tc_fence_before();
@@ -595,6 +634,16 @@ EncodeTiledFn get_encode() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     return fn;
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
 }
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
@@ -673,7 +722,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    static int use_halo = -1, bo_mode = 0, nt_limit = 0;
+    static int use_halo = -1, bo_mode = 0, nt_limit = 0, corr_mode = 1;
     if (use_halo < 0) {
         const char* e = getenv("PIVLFN_TC_HALO");
         use_halo = (e && e[0] == '0') ? 0 : 1;
@@ -681,6 +730,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         bo_mode = (b && b[0] == '1') ? 1 : 0;
         const char* t = getenv("PIVLFN_TC_NT");
         nt_limit = t ? atoi(t) : 0;
+        const char* cm = getenv("PIVLFN_TC_CORR");
+        corr_mode = (cm && cm[0] == '0') ? 0 : 1;
     }
     if (use_halo && W >= HT_W && KH * KW >= 3) {
         // ---- halo-resident path -------------------------------------------------------------------------------
@@ -692,23 +743,30 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         const int pitch = HT_W + KW - 1;
         const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;
         const int ntile_total = nchunk * KH * KW;
-        // NT stacked tiles per CTA: bounded by TMEM (512 columns), by the image height and by shared memory
-        int NT = nt_limit > 0 ? nt_limit : MAX_NT;
-        while (NT > 1 && ((passes == 3 ? 2 : 1) * NT * CoutP > 512 || HT_H * (NT - 1) >= H)) --NT;
+        // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the
+        // epilogue overlaps the next item's MMAs), by the image height and by shared memory
+        const int corr = (passes == 3 && corr_mode) ? 1 : 0;
+        const int acc_mult = corr ? 2 : 1;
+        int NT = nt_limit > 0 ? nt_limit : (CoutP <= 32 ? 1 : 2);
+        if (NT > MAX_NT) NT = MAX_NT;
+        while (NT > 1 && (acc_mult * NT * CoutP > 512 || HT_H * (NT - 1) >= H)) --NT;
         for (; NT >= 1; --NT) {
             if (NT == 3) continue;
             const int halo_rows = HT_H * NT + KH - 1;
             const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
-            const int nBuf = passes == 3 ? (nchunk > 1 ? 3 : 2) : (nchunk > 1 ? 2 : 1);
+            const int nBuf = passes == 3 ? 3 : 2;
             int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
             if (nB > MAX_STAGES) nB = MAX_STAGES;
-            if (nB > ntile_total) nB = ntile_total;
-            const int need = ntile_total >= 3 ? (passes == 3 ? 2 : 3) : 1;
+            const int need = passes == 3 ? 2 : 3;
             if (nB < need || halo_rows > 256) continue;
+            h.corr = corr;
+            h.nsets = (2 * acc_mult * NT * CoutP <= 512) ? 2 : 1;
             h.NT = NT; h.nBuf = nBuf; h.nB = nB;
             h.tiles_x = cdiv(W, HT_W); h.tiles_y = cdiv(H, HT_H * NT);
-            const long long grid = (long long)h.tiles_x * h.tiles_y * N;
-            if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
+            const long long total = (long long)h.tiles_x * h.tiles_y * N;
+            if (total > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
+            h.total = (int)total;
+            const long long grid = total < num_sms() ? total : num_sms();
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
             cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
             cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)pitch, (cuuint32_t)halo_rows, 1};
@@ -721,10 +779,10 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
             static bool cfg1 = false, cfg3 = false;
             if (passes == 3) {
                 if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
-                conv_tc_halo_kernel<3><<<(int)grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+                conv_tc_halo_kernel<3><<<(int)grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
             } else {
                 if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
-                conv_tc_halo_kernel<1><<<(int)grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+                conv_tc_halo_kernel<1><<<(int)grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
             }
             PIVLFN_LAUNCHED();
             return pivlfn_last_error();
