@@ -102,6 +102,20 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
         "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Same instruction with the two shared-memory descriptors given as (low word, constant high word): the issuing thread
+// only has to produce two 32-bit values per MMA.
+__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -372,7 +386,11 @@ struct ConvHaloArgs {
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
                              // B200, kept as an experiment switch
+    long long* dbg;          // optional: CTA 0 writes per-role wait-cycle totals (tools/profile_conv.py --trace)
 };
+
+#define DBG_T0() long long _t0 = a.dbg ? clock64() : 0
+#define DBG_ADD(var) do { if (a.dbg) var += clock64() - _t0; } while (0)
 
 // buffer slot of chunk c's activations (hi after the split) and of its low-order part
 __device__ __forceinline__ int slot_x(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf; }
@@ -407,11 +425,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int G = gridDim.x;
 
     if (threadIdx.x == 0) {
+        const uint32_t n_iss = a.NT >= 2 ? 2u : 1u;           // MMA-issuing threads, each commits to the barriers
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], 1);
-            mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4);
+            mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], n_iss);
+            mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 4);
         }
-        for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmBhi);
@@ -432,10 +451,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int bs = 0;
             uint32_t bphase = 0;
             int gc = 0;                                   // global chunk counter
+            long long p_b = 0, p_a = 0;
             auto load_A = [&](int g, int w, int c) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
                 // slot_x(g) was last read by global chunk g-2's MMAs (as its hi or its lo slot)
-                if (g >= 2) mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1));
+                if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
                 mbar_expect_tx(&a_full[g & 1], halo_bytes);
                 tma_load_4d(smem + (size_t)slot_x(g, a.nBuf) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
                             tx * HT_W - a.KW / 2, ty * HT_H * a.NT - a.KH / 2, n);
@@ -455,7 +475,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     bool next_issued = !has_next || a.nBuf < 2;
                     if (!next_issued && gc == 0) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
                     for (int t = 0; t < ntaps; ++t) {
-                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                        { DBG_T0(); mbar_wait(&b_empty[bs], bphase ^ 1); DBG_ADD(p_b); }
                         uint8_t* sB = smemB + (size_t)bs * b_stage;
                         mbar_expect_tx(&b_full[bs], b_stage);
                         tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
@@ -466,20 +486,37 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
             }
+            if (a.dbg && blockIdx.x == 0) { a.dbg[5] = p_b; a.dbg[6] = p_a; }
         }
-    } else if (warp == 1) {
-        // ================================ MMA issuer ==================================
+    } else if (warp == 1 || warp == 2) {
+        // ================================ MMA issuers =================================
+        // Two issuing threads (warps 1 and 2): issuer j feeds the stacked tiles i = j, j+2, ... (own TMEM accumulators),
+        // because ONE thread cannot issue tf32 MMAs (64 cycles each at N = 128) fast enough.
         if (elect_one()) {
+            const int issuer = warp - 1;
+            const int n_issuers = a.NT >= 2 ? 2 : 1;
+            if (issuer < n_issuers) {
+            // Issue-rate matters: one thread feeds the tensor core, and every scalar instruction between two
+            // tcgen05.mma is on the critical path (measured ~100 cycles per MMA with naive 64-bit descriptor math,
+            // vs a 64-cycle MMA).  All descriptors are therefore (constant high word, 32-bit low word) pairs and the
+            // per-MMA work is one or two 32-bit adds.
             const uint32_t idesc = make_idesc_tf32(a.CoutP);
-            const uint32_t sbo = (uint32_t)(pitch * 128);
-            const uint32_t tile_step = (uint32_t)(HT_H * pitch * 128);
+            const uint32_t hiA = (uint32_t)(make_smem_desc_halo(0, (uint32_t)(pitch * 128), 0) >> 32);
+            const uint32_t hiB = (uint32_t)(make_smem_desc(0) >> 32);
+            const uint32_t lbo_bits = 1u << 16;
+            const uint32_t tile16 = (uint32_t)(HT_H * pitch * 8);       // one stacked tile further, in 16-byte units
+            const uint32_t blo16 = (uint32_t)(b_bytes >> 4);
+            const uint32_t corr_off = a.corr ? (uint32_t)(a.NT * a.CoutP) : 0u;
+            const uint32_t pitch8 = (uint32_t)(pitch * 8);
             int bs = 0;
             uint32_t bphase = 0;
             int gc = 0, wl = 0;
+            long long w_acc = 0, w_a = 0, w_b = 0;
+            const long long t_begin = a.dbg ? clock64() : 0;
             for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
                 const int as = wl % a.nsets;
                 const uint32_t use = (uint32_t)(wl / a.nsets);
-                mbar_wait(&acc_empty[as], (use & 1) ^ 1);             // epilogue drained this accumulator set
+                { DBG_T0(); mbar_wait(&acc_empty[as], (use & 1) ^ 1); DBG_ADD(w_acc); }   // epilogue drained this set
                 tc_fence_after();
                 const uint32_t tset = tmem_base + (uint32_t)(as * set_cols);
                 uint32_t acc = 0;
@@ -487,32 +524,33 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t par = (uint32_t)((gc >> 1) & 1);
                     const int kleft = a.Cin - c * KC;
                     const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
-                    mbar_wait(PASSES == 3 ? &a_ready[gc & 1] : &a_full[gc & 1], par);
+                    { DBG_T0(); mbar_wait(PASSES == 3 ? &a_ready[gc & 1] : &a_full[gc & 1], par); DBG_ADD(w_a); }
                     tc_fence_after();
-                    const uint32_t sAhi = smem_u32(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
-                    const uint32_t sAlo = smem_u32(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
+                    const uint32_t aHi16 = (smem_u32(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
+                    const uint32_t aLo16 = (smem_u32(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
+                    uint32_t row16 = 0;                               // (ky * pitch) * 8
+                    int kx = 0;
                     for (int t = 0; t < ntaps; ++t) {
-                        const int ky = t / a.KW, kx = t - ky * a.KW;
-                        const uint32_t woff = (uint32_t)((ky * pitch + kx) * 128);
-                        const uint32_t bo = a.bo_mode ? (uint32_t)kx : 0u;
-                        mbar_wait(&b_full[bs], bphase);
+                        const uint32_t woff16 = row16 + (uint32_t)(kx * 8);
+                        if (++kx == a.KW) { kx = 0; row16 += pitch8; }
+                        { DBG_T0(); mbar_wait(&b_full[bs], bphase); DBG_ADD(w_b); }
                         tc_fence_after();
-                        const uint32_t sBhi = smem_u32(smemB + (size_t)bs * b_stage);
-                        const uint64_t dBhi = make_smem_desc(sBhi), dBlo = make_smem_desc(sBhi + b_bytes);
-                        for (int i = 0; i < a.NT; ++i) {
-                            const uint64_t dA = make_smem_desc_halo(sAhi + woff + i * tile_step, sbo, bo);
-                            const uint64_t dAlo = make_smem_desc_halo(sAlo + woff + i * tile_step, sbo, bo);
-                            const uint32_t t_main = tset + (uint32_t)(i * a.CoutP);
-                            const uint32_t t_corr = a.corr ? tset + (uint32_t)((a.NT + i) * a.CoutP) : t_main;
-                            for (int k = 0; k < nk; ++k) {
-                                const uint64_t koff = (uint64_t)(k * 2);
-                                const uint32_t first = acc | (uint32_t)(k > 0);
-                                umma_tf32(t_main, dA + koff, dBhi + koff, idesc, first);
-                                if (PASSES == 3) {
-                                    umma_tf32(t_corr, dAlo + koff, dBhi + koff, idesc, a.corr ? first : 1u);
-                                    umma_tf32(t_corr, dA + koff, dBlo + koff, idesc, 1);
+                        const uint32_t bHi16 = (smem_u32(smemB + (size_t)bs * b_stage) >> 4) | lbo_bits;
+                        uint32_t a_hi = aHi16 + woff16 + issuer * tile16, a_lo = aLo16 + woff16 + issuer * tile16;
+                        uint32_t t_main = tset + (uint32_t)(issuer * a.CoutP);
+                        for (int i = issuer; i < a.NT; i += n_issuers) {
+#pragma unroll
+                            for (int k = 0; k < KC / 8; ++k) {
+                                if (k < nk) {
+                                    const uint32_t first = acc | (uint32_t)(k > 0);
+                                    umma_tf32_lohi(t_main, a_hi + 2 * k, hiA, bHi16 + 2 * k, hiB, idesc, first);
+                                    if (PASSES == 3) {
+                                        umma_tf32_lohi(t_main + corr_off, a_lo + 2 * k, hiA, bHi16 + 2 * k, hiB, idesc, a.corr ? first : 1u);
+                                        umma_tf32_lohi(t_main + corr_off, a_hi + 2 * k, hiA, bHi16 + blo16 + 2 * k, hiB, idesc, 1);
+                                    }
                                 }
                             }
+                            a_hi += n_issuers * tile16; a_lo += n_issuers * tile16; t_main += (uint32_t)(n_issuers * a.CoutP);
                         }
                         acc = 1;
                         umma_commit(&b_empty[bs]);
@@ -522,6 +560,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
                 umma_commit(&acc_full[as]);
             }
+            if (a.dbg && blockIdx.x == 0 && issuer == 0) {
+                a.dbg[0] = clock64() - t_begin; a.dbg[1] = w_acc; a.dbg[2] = w_a; a.dbg[3] = w_b; a.dbg[4] = wl;
+            }
+            }
         }
     } else if (warp >= 8) {
         // ================================ 3xTF32 split warps ============================
@@ -529,11 +571,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int et = threadIdx.x - 8 * 32;
             const int nvec = halo_bytes / 16;
             int gc = 0;
+            long long s_w1 = 0, s_w2 = 0, s_busy = 0;
             for (int w = blockIdx.x; w < a.total; w += G) {
                 for (int c = 0; c < nchunk; ++c, ++gc) {
                     // the lo slot of chunk gc was in use by chunk gc-1's MMAs
-                    if (gc >= 1) mbar_wait(&chunk_done[(gc - 1) & 1], (uint32_t)(((gc - 1) >> 1) & 1));
-                    mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1));
+                    { DBG_T0(); if (gc >= 1) mbar_wait(&chunk_done[(gc - 1) & 1], (uint32_t)(((gc - 1) >> 1) & 1)); DBG_ADD(s_w1); }
+                    { DBG_T0(); mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1)); DBG_ADD(s_w2); }
+                    const long long s_t0 = a.dbg ? clock64() : 0;
                     float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
                     float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
 #pragma unroll 4
@@ -551,20 +595,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&a_ready[gc & 1]);
+                    if (a.dbg) s_busy += clock64() - s_t0;
                 }
             }
+            if (a.dbg && blockIdx.x == 0 && threadIdx.x == 8 * 32) { a.dbg[9] = s_w1; a.dbg[10] = s_w2; a.dbg[11] = s_busy; }
         }
     } else if (warp >= 4) {
         // ================================ epilogue warps ================================
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int wl = 0;
+        long long e_wait = 0, e_busy = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
             const int as = wl % a.nsets;
             const uint32_t use = (uint32_t)(wl / a.nsets);
             const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
             const int x = tx * HT_W + (row & (HT_W - 1));
-            mbar_wait(&acc_full[as], use & 1);
+            { DBG_T0(); mbar_wait(&acc_full[as], use & 1); DBG_ADD(e_wait); }
+            const long long e_t0 = a.dbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
             for (int i = 0; i < a.NT; ++i) {
@@ -608,7 +656,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[as]);
+            if (a.dbg) e_busy += clock64() - e_t0;
         }
+        if (a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { a.dbg[7] = e_wait; a.dbg[8] = e_busy; }
     }
     tc_fence_before();
     __syncthreads();
@@ -698,6 +748,11 @@ void choose_tile(ConvTcArgs& a) {
 
 }  // namespace
 
+static long long* g_conv_tc_dbg = nullptr;
+/* Debug hook (not part of the public header): device buffer of >= 16 int64 that CTA 0 of the persistent conv kernel
+ * fills with per-role wait-cycle totals; NULL switches the instrumentation off. */
+extern "C" void pivlfn_debug_set_conv_trace(long long* dev_buf) { g_conv_tc_dbg = dev_buf; }
+
 extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                               const float* w_hi, const float* w_lo, const float* bias,
                               float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
@@ -738,7 +793,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
-        h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode;
+        h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode; h.dbg = g_conv_tc_dbg;
         const int nchunk = CinP / KC;
         const int pitch = HT_W + KW - 1;
         const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;

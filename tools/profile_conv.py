@@ -24,6 +24,15 @@ cw = pack_conv(w, b, 1)
 x = torch.randn(B, H, H, (cin + 3) & ~3, generator=g).to(dev)
 y = torch.empty(B, H, H, (cout + 3) & ~3, device=dev)
 passes = 3 if prec == "3xtf32" else 1
+trace = "--trace" in sys.argv
+if trace:
+    import ctypes
+    from pivlfn import _lib
+    dbg = torch.zeros(16, dtype=torch.int64, device=dev)
+    fn = _lib.load().pivlfn_debug_set_conv_trace
+    fn.argtypes = [ctypes.c_void_p]
+    fn.restype = None
+    fn(dbg.data_ptr())
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(4):
     if i == 1:
@@ -33,3 +42,9 @@ e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
 print(f"{prec} conv {cin}->{cout} {k}x{k} @ {B}x{H}x{H}: {ms:.3f} ms, {2.0 * B * H * H * cin * cout * k * k / ms / 1e9:.1f} TFLOP/s")
+if trace:
+    torch.cuda.synchronize()
+    t = dbg.cpu().tolist()
+    names = ["mma_total", "mma_wait_acc_empty", "mma_wait_A", "mma_wait_B", "items", "prod_wait_b_empty", "prod_wait_slot",
+             "epi_wait_acc_full", "epi_busy", "split_wait_prev_chunk", "split_wait_raw", "split_busy"]
+    print("  trace (CTA 0, cycles): " + ", ".join(f"{n}={v}" for n, v in zip(names, t)))

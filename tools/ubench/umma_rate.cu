@@ -10,11 +10,11 @@ __device__ __forceinline__ bool elect_one() {
     asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo = 1024) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)(sbo >> 4) << 32;
     d |= (uint64_t)1 << 46;
     d |= (uint64_t)2 << 61;
     return d;
@@ -30,6 +30,8 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 }
 
 // mode 0: one accumulator; 1: alternate two accumulators; 2: A fixed, B varies (different smem tiles)
+// mode 3: A with SBO = 1280 (halo pitch 10); 4: SBO = 1280 and start + 128 B; 5: SBO = 1024, start + 128 B;
+// mode 6: like 4 but a different window start for every MMA (tap shifts)
 template <int KIND>
 __global__ void __launch_bounds__(64, 1) bench(int N, int iters, int mode, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -53,14 +55,16 @@ __global__ void __launch_bounds__(64, 1) bench(int N, int iters, int mode, long 
     if (warp == 1 && elect_one()) {
         const uint32_t fmt = KIND == 0 ? 2u : 1u;
         const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
-        const uint32_t sA = smem_u32(smem), sB = sA + 16384;
+        const uint32_t sA = smem_u32(smem), sB = sA + 24576;
         long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 uint32_t d = tmem + ((mode == 1 && (k & 1)) ? 256u : 0u);
                 uint32_t sb = sB + ((mode == 2) ? (uint32_t)(k * 8192 % 32768) : 0u);
-                umma<KIND>(d, make_desc(sA) + k * 2, make_desc(sb) + k * 2, idesc, 1);
+                uint32_t sa = sA + ((mode == 4 || mode == 5) ? 128u : 0u) + (mode == 6 ? (uint32_t)(((it + k) % 3) * 128 + ((it / 3) % 3) * 1280) : 0u);
+                uint32_t sbo = (mode == 3 || mode == 4 || mode == 6) ? 1280u : 1024u;
+                umma<KIND>(d, make_desc(sa, sbo) + k * 2, make_desc(sb) + k * 2, idesc, 1);
             }
         }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
@@ -83,10 +87,10 @@ int main() {
     cudaFuncSetAttribute(bench<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(bench<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     const int iters = 2000;
-    for (int kind = 0; kind < 2; ++kind)
-        for (int mode = 0; mode < 3; ++mode)
-            for (int N : {16, 32, 64, 128, 256}) {
-                for (int grid : {1, 148}) {
+    for (int kind = 0; kind < 1; ++kind)
+        for (int mode = 0; mode < 7; ++mode)
+            for (int N : {16, 64, 128}) {
+                for (int grid : {148}) {
                     if (kind == 0) bench<0><<<grid, 64, 64 * 1024>>>(N, iters, mode, d);
                     else bench<1><<<grid, 64, 64 * 1024>>>(N, iters, mode, d);
                     cudaError_t e = cudaDeviceSynchronize();
