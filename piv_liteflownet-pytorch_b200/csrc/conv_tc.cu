@@ -386,6 +386,8 @@ struct ConvHaloArgs {
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
                              // B200, kept as an experiment switch
+    int split_trunc;         // 3xTF32 split: 0 = hi = rna_tf32(a) written back, lo = a - hi; 1 = leave a in place (the
+                             // tensor core reads only its top 19 bits) and write lo = a - trunc_tf32(a)
     long long* dbg;          // optional: CTA 0 writes per-role wait-cycle totals (tools/profile_conv.py --trace)
 };
 
@@ -396,7 +398,8 @@ struct ConvHaloArgs {
 __device__ __forceinline__ int slot_x(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf; }
 __device__ __forceinline__ int slot_l(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1; }
 
-constexpr int HALO_THREADS = 384;      // warp 0 TMA, 1 MMA, 4-7 epilogue (TMEM lane quarter = warp % 4), 8-11 split
+constexpr int HALO_THREADS = 512;      // warp 0 TMA, 1-2 MMA issue, 4-7 epilogue (TMEM lane quarter = warp % 4), 8-15 split
+constexpr int SPLIT_THREADS = 256;
 
 // Persistent: one CTA per SM loops over work items; all roles walk the same global (item, chunk, tap) sequence so
 // the mbarrier phases simply keep counting across items.
@@ -416,10 +419,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
         acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[128];          // fits in the 1 KB the static part is padded to anyway
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.Cin + KC - 1) / KC;
     const int ntaps = a.KH * a.KW;
+    if (threadIdx.x >= 128 && threadIdx.x < 256) {
+        const int i = threadIdx.x - 128;
+        bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+    }
     const int set_cols = ((PASSES == 3 && a.corr) ? 2 : 1) * a.NT * a.CoutP;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
     const int G = gridDim.x;
@@ -427,7 +435,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 0) {
         const uint32_t n_iss = a.NT >= 2 ? 2u : 1u;           // MMA-issuing threads, each commits to the barriers
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], 4); mbar_init(&chunk_done[i], n_iss);
+            mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], SPLIT_THREADS / 32); mbar_init(&chunk_done[i], n_iss);
             mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 4);
         }
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
@@ -580,17 +588,30 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const long long s_t0 = a.dbg ? clock64() : 0;
                     float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
                     float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
+                    if (a.split_trunc) {
 #pragma unroll 4
-                    for (int idx = et; idx < nvec; idx += 128) {
-                        float4 v = pa[idx];
-                        float4 h, l;
-                        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-                        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-                        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-                        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-                        l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                        pa[idx] = h;
-                        pl[idx] = l;
+                        for (int idx = et; idx < nvec; idx += SPLIT_THREADS) {
+                            const float4 v = pa[idx];
+                            float4 l;
+                            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
+                            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
+                            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                            pl[idx] = l;
+                        }
+                    } else {
+#pragma unroll 4
+                        for (int idx = et; idx < nvec; idx += SPLIT_THREADS) {
+                            float4 v = pa[idx];
+                            float4 h, l;
+                            h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
+                            h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
+                            h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
+                            h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
+                            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+                            pa[idx] = h;
+                            pl[idx] = l;
+                        }
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -634,7 +655,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         float o[16];
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            float t = __uint_as_float(v[j]) + ((a.bias && c0 + j < a.Cout) ? __ldg(a.bias + c0 + j) : 0.f);
+                            float t = __uint_as_float(v[j]) + bias_s[c0 + j];
                             if (a.lrelu) t = lrelu_f(t);
                             o[j] = t;
                         }
@@ -777,7 +798,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    static int use_halo = -1, bo_mode = 0, nt_limit = 0, corr_mode = 1;
+    static int use_halo = -1, bo_mode = 0, nt_limit = 0, corr_mode = 1, split_trunc = 0;
     if (use_halo < 0) {
         const char* e = getenv("PIVLFN_TC_HALO");
         use_halo = (e && e[0] == '0') ? 0 : 1;
@@ -787,6 +808,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         nt_limit = t ? atoi(t) : 0;
         const char* cm = getenv("PIVLFN_TC_CORR");
         corr_mode = (cm && cm[0] == '0') ? 0 : 1;
+        const char* sm = getenv("PIVLFN_TC_SPLIT_TRUNC");
+        split_trunc = (sm && sm[0] == '1') ? 1 : 0;
     }
     if (use_halo && W >= HT_W && KH * KW >= 3) {
         // ---- halo-resident path -------------------------------------------------------------------------------
@@ -794,6 +817,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode; h.dbg = g_conv_tc_dbg;
+        h.split_trunc = split_trunc;
         const int nchunk = CinP / KC;
         const int pitch = HT_W + KW - 1;
         const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;
@@ -802,7 +826,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         // epilogue overlaps the next item's MMAs), by the image height and by shared memory
         const int corr = (passes == 3 && corr_mode) ? 1 : 0;
         const int acc_mult = corr ? 2 : 1;
-        int NT = nt_limit > 0 ? nt_limit : (CoutP <= 32 ? 1 : 2);
+        int NT = nt_limit > 0 ? nt_limit : 2;
         if (NT > MAX_NT) NT = MAX_NT;
         while (NT > 1 && (acc_mult * NT * CoutP > 512 || HT_H * (NT - 1) >= H)) --NT;
         for (; NT >= 1; --NT) {
