@@ -142,6 +142,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 struct ConvTcArgs {
     const float* bias;
     const float* res;        // optional residual view (added after the activation), Cout channels
@@ -386,8 +396,10 @@ struct ConvHaloArgs {
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
                              // B200, kept as an experiment switch
-    int split_trunc;         // 3xTF32 split: 0 = hi = rna_tf32(a) written back, lo = a - hi; 1 = leave a in place (the
-                             // tensor core reads only its top 19 bits) and write lo = a - trunc_tf32(a)
+    int x_shift;             // x coordinate of tap column 0 relative to the output pixel (normally -(KW/2); +1 for the stem)
+    int split_trunc;         // 3xTF32 split: 1 (default) = leave a in place (measured: the tensor core reads only the top
+                             // 19 bits of an fp32 operand, i.e. truncates) and write lo = a - trunc_tf32(a);
+                             // 0 = hi = rna_tf32(a) written back, lo = a - hi
     long long* dbg;          // optional: CTA 0 writes per-role wait-cycle totals (tools/profile_conv.py --trace)
 };
 
@@ -466,7 +478,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
                 mbar_expect_tx(&a_full[g & 1], halo_bytes);
                 tma_load_4d(smem + (size_t)slot_x(g, a.nBuf) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
-                            tx * HT_W - a.KW / 2, ty * HT_H * a.NT - a.KH / 2, n);
+                            tx * HT_W + a.x_shift, ty * HT_H * a.NT - a.KH / 2, n);
             };
             // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
             auto next_of = [&](int w, int c, int& w2, int& c2) { c2 = c + 1; w2 = w; if (c2 == nchunk) { c2 = 0; w2 = w + G; } };
@@ -588,29 +600,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const long long s_t0 = a.dbg ? clock64() : 0;
                     float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
                     float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
-                    if (a.split_trunc) {
-#pragma unroll 4
-                        for (int idx = et; idx < nvec; idx += SPLIT_THREADS) {
-                            const float4 v = pa[idx];
-                            float4 l;
-                            l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
-                            l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
-                            l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
-                            l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-                            pl[idx] = l;
-                        }
-                    } else {
-#pragma unroll 4
-                        for (int idx = et; idx < nvec; idx += SPLIT_THREADS) {
-                            float4 v = pa[idx];
-                            float4 h, l;
-                            h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xFFFFE000u);
-                            h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xFFFFE000u);
-                            h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xFFFFE000u);
-                            h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xFFFFE000u);
-                            l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-                            pa[idx] = h;
-                            pl[idx] = l;
+                    // all loads of a batch are issued before the first use (latency-bound otherwise: the MMAs wait
+                    // for this between two chunks)
+                    constexpr int SB = 6;
+                    for (int base = et; base < nvec; base += SB * SPLIT_THREADS) {
+                        float4 v[SB];
+#pragma unroll
+                        for (int j = 0; j < SB; ++j)
+                            if (base + j * SPLIT_THREADS < nvec) v[j] = pa[base + j * SPLIT_THREADS];
+#pragma unroll
+                        for (int j = 0; j < SB; ++j) {
+                            const int idx = base + j * SPLIT_THREADS;
+                            if (idx < nvec) {
+                                float4 h, l;
+                                if (a.split_trunc) {
+                                    h.x = __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+                                    h.y = __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+                                    h.z = __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+                                    h.w = __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+                                } else {
+                                    h.x = __uint_as_float((__float_as_uint(v[j].x) + 0x1000u) & 0xFFFFE000u);
+                                    h.y = __uint_as_float((__float_as_uint(v[j].y) + 0x1000u) & 0xFFFFE000u);
+                                    h.z = __uint_as_float((__float_as_uint(v[j].z) + 0x1000u) & 0xFFFFE000u);
+                                    h.w = __uint_as_float((__float_as_uint(v[j].w) + 0x1000u) & 0xFFFFE000u);
+                                    pa[idx] = h;
+                                }
+                                l.x = v[j].x - h.x; l.y = v[j].y - h.y; l.z = v[j].z - h.z; l.w = v[j].w - h.w;
+                                pl[idx] = l;
+                            }
                         }
                     }
                     fence_proxy_async();
@@ -642,34 +659,45 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
                 float* dst = a.y + pix * a.y_ld;
                 const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
-                for (int c0 = 0; c0 < a.CoutP; c0 += 16) {
-                    uint32_t v[16];
-                    tmem_ld16(trow + (uint32_t)(i * a.CoutP + c0), v);
-                    if (PASSES == 3 && a.corr) {
-                        uint32_t u[16];
-                        tmem_ld16(trow + (uint32_t)((a.NT + i) * a.CoutP + c0), u);
+                // two 16-column TMEM loads in flight per wait: (main, corr) of the same columns in 3xTF32+corr mode,
+                // otherwise two consecutive column groups
+                const bool dual = (PASSES == 3 && a.corr);
+                const int cstep = dual ? 16 : 32;
+                for (int c0 = 0; c0 < a.CoutP; c0 += cstep) {
+                    uint32_t v[16], u[16];
+                    const bool second = dual || (c0 + 16 < a.CoutP);
+                    tmem_ld16_nowait(trow + (uint32_t)(i * a.CoutP + c0), v);
+                    if (second)
+                        tmem_ld16_nowait(trow + (uint32_t)(dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16), u);
+                    tmem_ld_wait();
+                    if (dual) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
                     }
-                    if (live) {
-                        float o[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            float t = __uint_as_float(v[j]) + bias_s[c0 + j];
-                            if (a.lrelu) t = lrelu_f(t);
-                            o[j] = t;
-                        }
-                        if (a.vec_store && c0 + 16 <= a.Cout) {
+                    for (int half = 0; half < 2; ++half) {
+                        if (half == 1 && (dual || !second)) break;
+                        const int cb = c0 + half * 16;
+                        if (live) {
+                            float o[16];
 #pragma unroll
-                            for (int j = 0; j < 16; j += 4) {
-                                float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                                if (rsd) { w4.x += rsd[c0 + j]; w4.y += rsd[c0 + j + 1]; w4.z += rsd[c0 + j + 2]; w4.w += rsd[c0 + j + 3]; }
-                                *reinterpret_cast<float4*>(dst + c0 + j) = w4;
+                            for (int j = 0; j < 16; ++j) {
+                                float t = __uint_as_float(half ? u[j] : v[j]) + bias_s[cb + j];
+                                if (a.lrelu) t = lrelu_f(t);
+                                o[j] = t;
                             }
-                        } else {
+                            if (a.vec_store && cb + 16 <= a.Cout) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                if (c0 + j < a.Cout) dst[c0 + j] = o[j] + (rsd ? rsd[c0 + j] : 0.f);
+                                for (int j = 0; j < 16; j += 4) {
+                                    float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                                    if (rsd) { w4.x += rsd[cb + j]; w4.y += rsd[cb + j + 1]; w4.z += rsd[cb + j + 2]; w4.w += rsd[cb + j + 3]; }
+                                    *reinterpret_cast<float4*>(dst + cb + j) = w4;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j)
+                                    if (cb + j < a.Cout) dst[cb + j] = o[j] + (rsd ? rsd[cb + j] : 0.f);
+                            }
                         }
                     }
                 }
@@ -767,6 +795,76 @@ void choose_tile(ConvTcArgs& a) {
     a.tiles_y = cdiv(a.H, a.bh);
 }
 
+// Environment switches of the halo kernel (experiments; defaults are the measured best).
+struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc; };
+const HaloEnv& halo_env() {
+    static HaloEnv e = {-1, 0, 0, 1, 0};
+    if (e.use_halo < 0) {
+        const char* v = getenv("PIVLFN_TC_HALO");
+        e.use_halo = (v && v[0] == '0') ? 0 : 1;
+        v = getenv("PIVLFN_TC_BO");
+        e.bo_mode = (v && v[0] == '1') ? 1 : 0;
+        v = getenv("PIVLFN_TC_NT");
+        e.nt_limit = v ? atoi(v) : 0;
+        v = getenv("PIVLFN_TC_CORR");
+        e.corr_mode = (v && v[0] == '0') ? 0 : 1;
+        v = getenv("PIVLFN_TC_SPLIT_TRUNC");
+        e.split_trunc = (v && v[0] == '0') ? 0 : 1;
+    }
+    return e;
+}
+
+// Choose NT / buffers / ring depth for the halo kernel; fills h and returns the dynamic shared memory size, or 0 when
+// no configuration fits (caller falls back to the per-tap kernel).
+int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
+    const HaloEnv& env = halo_env();
+    const int pitch = HT_W + h.KW - 1;
+    const int b_stage = (passes == 3 ? 2 : 1) * h.CoutP * KC * 4;
+    const int corr = (passes == 3 && env.corr_mode) ? 1 : 0;
+    const int acc_mult = corr ? 2 : 1;
+    // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the epilogue
+    // overlaps the next item's MMAs), by the image height and by shared memory
+    int NT = env.nt_limit > 0 ? env.nt_limit : 2;
+    if (NT > MAX_NT) NT = MAX_NT;
+    while (NT > 1 && (acc_mult * NT * h.CoutP > 512 || HT_H * (NT - 1) >= h.H)) --NT;
+    for (; NT >= 1; --NT) {
+        if (NT == 3) continue;
+        const int halo_rows = HT_H * NT + h.KH - 1;
+        const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
+        const int nBuf = passes == 3 ? 3 : 2;
+        int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
+        if (nB > MAX_STAGES) nB = MAX_STAGES;
+        const int need = passes == 3 ? 2 : 3;
+        if (nB < need || halo_rows > 256) continue;
+        h.corr = corr;
+        h.nsets = (2 * acc_mult * NT * h.CoutP <= 512) ? 2 : 1;
+        h.NT = NT; h.nBuf = nBuf; h.nB = nB;
+        h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
+        const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
+        if (total > 0x7FFFFFFFLL) return 0;
+        h.total = (int)total;
+        h.bo_mode = env.bo_mode; h.split_trunc = env.split_trunc;
+        *halo_rows_out = halo_rows;
+        return nBuf * slot + nB * b_stage;
+    }
+    return 0;
+}
+
+int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const ConvHaloArgs& h, int passes,
+                int smem, cudaStream_t st) {
+    const int grid = h.total < num_sms() ? h.total : num_sms();
+    static bool cfg1 = false, cfg3 = false;
+    if (passes == 3) {
+        if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
+        conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+    } else {
+        if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
+        conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+    }
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
 }  // namespace
 
 static long long* g_conv_tc_dbg = nullptr;
@@ -798,73 +896,24 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    static int use_halo = -1, bo_mode = 0, nt_limit = 0, corr_mode = 1, split_trunc = 0;
-    if (use_halo < 0) {
-        const char* e = getenv("PIVLFN_TC_HALO");
-        use_halo = (e && e[0] == '0') ? 0 : 1;
-        const char* b = getenv("PIVLFN_TC_BO");
-        bo_mode = (b && b[0] == '1') ? 1 : 0;
-        const char* t = getenv("PIVLFN_TC_NT");
-        nt_limit = t ? atoi(t) : 0;
-        const char* cm = getenv("PIVLFN_TC_CORR");
-        corr_mode = (cm && cm[0] == '0') ? 0 : 1;
-        const char* sm = getenv("PIVLFN_TC_SPLIT_TRUNC");
-        split_trunc = (sm && sm[0] == '1') ? 1 : 0;
-    }
-    if (use_halo && W >= HT_W && KH * KW >= 3) {
-        // ---- halo-resident path -------------------------------------------------------------------------------
+    if (halo_env().use_halo && W >= HT_W && KH * KW >= 3) {
+        // ---- halo-resident persistent path --------------------------------------------------------------------
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
-        h.lrelu = lrelu; h.vec_store = vec_store; h.bo_mode = bo_mode; h.dbg = g_conv_tc_dbg;
-        h.split_trunc = split_trunc;
-        const int nchunk = CinP / KC;
-        const int pitch = HT_W + KW - 1;
-        const int b_stage = (passes == 3 ? 2 : 1) * CoutP * KC * 4;
-        const int ntile_total = nchunk * KH * KW;
-        // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the
-        // epilogue overlaps the next item's MMAs), by the image height and by shared memory
-        const int corr = (passes == 3 && corr_mode) ? 1 : 0;
-        const int acc_mult = corr ? 2 : 1;
-        int NT = nt_limit > 0 ? nt_limit : 2;
-        if (NT > MAX_NT) NT = MAX_NT;
-        while (NT > 1 && (acc_mult * NT * CoutP > 512 || HT_H * (NT - 1) >= H)) --NT;
-        for (; NT >= 1; --NT) {
-            if (NT == 3) continue;
-            const int halo_rows = HT_H * NT + KH - 1;
-            const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
-            const int nBuf = passes == 3 ? 3 : 2;
-            int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
-            if (nB > MAX_STAGES) nB = MAX_STAGES;
-            const int need = passes == 3 ? 2 : 3;
-            if (nB < need || halo_rows > 256) continue;
-            h.corr = corr;
-            h.nsets = (2 * acc_mult * NT * CoutP <= 512) ? 2 : 1;
-            h.NT = NT; h.nBuf = nBuf; h.nB = nB;
-            h.tiles_x = cdiv(W, HT_W); h.tiles_y = cdiv(H, HT_H * NT);
-            const long long total = (long long)h.tiles_x * h.tiles_y * N;
-            if (total > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
-            h.total = (int)total;
-            const long long grid = total < num_sms() ? total : num_sms();
+        h.lrelu = lrelu; h.vec_store = vec_store; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
+        int halo_rows = 0;
+        const int smem = halo_configure(h, passes, &halo_rows);
+        if (smem > 0) {
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
             cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
-            cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)pitch, (cuuint32_t)halo_rows, 1};
+            cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(HT_W + KW - 1), (cuuint32_t)halo_rows, 1};
             cuuint32_t estr[4] = {1, 1, 1, 1};
             CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            const int smem = nBuf * slot + nB * b_stage;
-            static bool cfg1 = false, cfg3 = false;
-            if (passes == 3) {
-                if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
-                conv_tc_halo_kernel<3><<<(int)grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
-            } else {
-                if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
-                conv_tc_halo_kernel<1><<<(int)grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
-            }
-            PIVLFN_LAUNCHED();
-            return pivlfn_last_error();
+            return halo_launch(tmA, tmBhi, tmBlo, h, passes, smem, st);
         }
     }
 
@@ -903,6 +952,32 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
     if (((uintptr_t)img_pad & 15) || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < 32) return PIVLFN_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
+    if (halo_env().use_halo && W >= HT_W) {
+        // one GEMM-K "chunk" of 32 floats = 8 pixels x 4 channels; 7 taps = the 7 filter rows; window column 0 is pixel
+        // x - 3 = padded column x + 1
+        ConvHaloArgs h;
+        h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
+        h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
+        h.lrelu = lrelu; h.vec_store = 1; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
+        int halo_rows = 0;
+        const int smem = halo_configure(h, passes, &halo_rows);
+        if (smem > 0) {
+            CUtensorMap tA, tBhi, tBlo;
+            const cuuint64_t Wp = (cuuint64_t)W + 8;
+            cuuint64_t dims[4] = {32, (cuuint64_t)W + 1, (cuuint64_t)H, (cuuint64_t)N};
+            cuuint64_t strides[3] = {16, Wp * 16, (cuuint64_t)H * Wp * 16};
+            cuuint32_t box[4] = {32, (cuuint32_t)HT_W, (cuuint32_t)halo_rows, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img_pad), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
+            if (encode_weights(enc, &tBhi, w_hi, 32, 7, 32)) return PIVLFN_EINVAL;
+            if (passes == 3) { if (encode_weights(enc, &tBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
+            else tBlo = tBhi;
+            return halo_launch(tA, tBhi, tBlo, h, passes, smem, (cudaStream_t)stream);
+        }
+    }
     ConvTcArgs a;
     a.bias = bias; a.res = nullptr; a.res_ld = 0; a.y = y; a.y_ld = y_ld;
     a.N = N; a.H = H; a.W = W; a.Cin = 32; a.Cout = 32; a.CoutP = 32; a.lrelu = lrelu;
