@@ -150,6 +150,11 @@ __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[1
           "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
 }
+// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(float* p, const float* o) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
+                 "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct ConvTcArgs {
@@ -686,7 +691,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 if (a.lrelu) t = lrelu_f(t);
                                 o[j] = t;
                             }
-                            if (a.vec_store && cb + 16 <= a.Cout) {
+                            if (a.vec_store == 2 && cb + 16 <= a.Cout && !rsd) {
+                                st_global_v8(dst + cb, o);
+                                st_global_v8(dst + cb + 8, o + 8);
+                            } else if (a.vec_store && cb + 16 <= a.Cout) {
 #pragma unroll
                                 for (int j = 0; j < 16; j += 4) {
                                     float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -889,14 +897,15 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
 
     const int CoutP = (Cout + 15) & ~15;
     const int CinP = (Cin + KC - 1) / KC * KC;
-    const int vec_store = (!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0;
+    // 2: 32-byte aligned rows -> 256-bit stores; 1: 16-byte aligned -> 128-bit stores; 0: scalar stores
+    const int vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7) && !(Cout & 7)) ? 2 : ((!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0);
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tmA, tmBhi, tmBlo;
     if (encode_weights(enc, &tmBhi, w_hi, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
 
-    if (halo_env().use_halo && W >= HT_W && KH * KW >= 3) {
+    if (halo_env().use_halo && W >= HT_W) {
         // ---- halo-resident persistent path --------------------------------------------------------------------
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
@@ -958,7 +967,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         ConvHaloArgs h;
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
-        h.lrelu = lrelu; h.vec_store = 1; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
+        h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {

@@ -64,37 +64,56 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict_
 
 // ---- ConvTranspose2d(C,C,4,s2,p1,groups=C,bias=False): src/models.py:144-145,151-152 ---------------
 // out[oy,ox,c] = sum over the (at most) 2x2 input pixels with ky = oy+1-2*iy, kx = ox+1-2*ix in [0,3].
+// One thread = one output pixel x V consecutive channels (V = 4: float4 traffic; V = 1: any layout).
+// Accumulation order: increasing (iy, ix), like a gather formulation of conv_transpose.
+template <int V>
 __global__ void deconv4x4s2_dw_kernel(const float* __restrict__ in, int in_ld, const float* __restrict__ w,
                                       float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
     const int Ho = 2 * H, Wo = 2 * W;
-    const long long total = (long long)N * Ho * Wo * C;
+    const int G = (C + V - 1) / V;
+    const long long total = (long long)N * Ho * Wo * G;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
-        int c = (int)(i % C);
-        long long p = i / C;
-        int ox = (int)(p % Wo);
-        long long t = p / Wo;
-        int oy = (int)(t % Ho);
-        long long n = t / Ho;
-        // oy even (2k): (iy,ky) in {(k,1),(k-1,3)};  oy odd (2k+1): {(k,2),(k+1,0)}
-        int iyA = oy >> 1, kyA = (oy & 1) ? 2 : 1;
-        int iyB = (oy & 1) ? iyA + 1 : iyA - 1, kyB = (oy & 1) ? 0 : 3;
-        int ixA = ox >> 1, kxA = (ox & 1) ? 2 : 1;
-        int ixB = (ox & 1) ? ixA + 1 : ixA - 1, kxB = (ox & 1) ? 0 : 3;
-        const float* wc = w + c * 16;
+        const int g = (int)(i % G);
+        const long long p = i / G;
+        const int ox = (int)(p % Wo);
+        const long long t = p / Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        // oy even (2k): (iy,ky) in {(k-1,3),(k,1)};  oy odd (2k+1): {(k,2),(k+1,0)}   (listed in increasing iy)
+        const int iy0 = (oy & 1) ? (oy >> 1) : (oy >> 1) - 1, ky0 = (oy & 1) ? 2 : 3;
+        const int iy1 = iy0 + 1, ky1 = (oy & 1) ? 0 : 1;
+        const int ix0 = (ox & 1) ? (ox >> 1) : (ox >> 1) - 1, kx0 = (ox & 1) ? 2 : 3;
+        const int ix1 = ix0 + 1, kx1 = (ox & 1) ? 0 : 1;
+        const bool vy0 = iy0 >= 0, vy1 = iy1 < H, vx0 = ix0 >= 0, vx1 = ix1 < W;
+        const int c = g * V;
         const float* base = in + n * H * W * in_ld + c;
-        float acc = 0.f;
-        const bool vyB = iyB >= 0 && iyB < H, vxB = ixB >= 0 && ixB < W;
-        // accumulate in the order of increasing (iy, ix) like a gather formulation of conv_transpose
-        int iy0 = iyA, ky0 = kyA, iy1 = iyB, ky1 = kyB; bool v0y = true, v1y = vyB;
-        if (iyB < iyA) { iy0 = iyB; ky0 = kyB; iy1 = iyA; ky1 = kyA; v0y = vyB; v1y = true; }
-        int ix0 = ixA, kx0 = kxA, ix1 = ixB, kx1 = kxB; bool v0x = true, v1x = vxB;
-        if (ixB < ixA) { ix0 = ixB; kx0 = kxB; ix1 = ixA; kx1 = kxA; v0x = vxB; v1x = true; }
-        if (v0y && v0x) acc = fmaf(base[((long long)iy0 * W + ix0) * in_ld], __ldg(wc + ky0 * 4 + kx0), acc);
-        if (v0y && v1x) acc = fmaf(base[((long long)iy0 * W + ix1) * in_ld], __ldg(wc + ky0 * 4 + kx1), acc);
-        if (v1y && v0x) acc = fmaf(base[((long long)iy1 * W + ix0) * in_ld], __ldg(wc + ky1 * 4 + kx0), acc);
-        if (v1y && v1x) acc = fmaf(base[((long long)iy1 * W + ix1) * in_ld], __ldg(wc + ky1 * 4 + kx1), acc);
-        out[p * out_ld + c] = acc;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.f;
+        const int iys[2] = {iy0, iy1}, kys[2] = {ky0, ky1}, ixs[2] = {ix0, ix1}, kxs[2] = {kx0, kx1};
+        const bool vys[2] = {vy0, vy1}, vxs[2] = {vx0, vx1};
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                if (vys[a] && vxs[b]) {
+                    const float* src = base + ((long long)iys[a] * W + ixs[b]) * in_ld;
+                    float v[V];
+                    if (V == 4) {
+                        const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                    } else {
+                        v[0] = __ldg(src);
+                    }
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        if (c + j < C) acc[j] = fmaf(v[j], __ldg(w + (c + j) * 16 + kys[a] * 4 + kxs[b]), acc[j]);
+                }
+            }
+        float* o = out + p * out_ld + c;
+        if (V == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        else o[0] = acc[0];
     }
 }
 
@@ -324,8 +343,16 @@ extern "C" int pivlfn_avgpool2(const float* in, float* out, int N, int H, int W,
 extern "C" int pivlfn_deconv4x4s2_dw(const float* in, int in_ld, const float* w, float* out, int out_ld,
                                      int N, int H, int W, int C, void* stream) {
     if (!in || !w || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || in_ld < C || out_ld < C) return PIVLFN_EINVAL;
-    const long long total = (long long)N * 4 * H * W * C;
-    deconv4x4s2_dw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, w, out, out_ld, N, H, W, C);
+    // float4 path: both views 16-byte aligned with room for the channel count rounded up to 4 (pad channels get 0)
+    const bool vec = !((uintptr_t)in & 15) && !((uintptr_t)out & 15) && !(in_ld & 3) && !(out_ld & 3) &&
+                     in_ld >= ((C + 3) & ~3) && out_ld >= ((C + 3) & ~3);
+    if (vec) {
+        const long long total = (long long)N * 4 * H * W * ((C + 3) / 4);
+        deconv4x4s2_dw_kernel<4><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, w, out, out_ld, N, H, W, C);
+    } else {
+        const long long total = (long long)N * 4 * H * W * C;
+        deconv4x4s2_dw_kernel<1><<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, in_ld, w, out, out_ld, N, H, W, C);
+    }
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
