@@ -74,14 +74,22 @@ corr_nchw_kernel(const float* __restrict__ f1, const float* __restrict__ f2, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// NHWC: CTA = 16 x 8 output pixels; 256 threads = 128 pixels x 2 halves of the displacement rows
-// (half 0: dy rows 0..3 = 28 displacements, half 1: rows 4..6 = 21).  Channels are staged 16 at a
-// time; the f2 tile (with +-3 halo, sampled every s pixels) is produced by bilinear backwarp when a
-// flow is given.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8 neighbouring
-// pixels are bank-conflict free.
+// NHWC: CTA = 16 x 8 output pixels, 384 threads, warp-specialised and double-buffered:
+//   warps 0..7  : compute -- 128 pixels x 2 halves of the displacement rows (half 0: dy rows 0..3 = 28
+//                 displacements, half 1: rows 4..6 = 21), accumulators in registers;
+//   warps 8..11 : loaders -- stage the next 16-channel chunk of the f1 tile and of the f2 tile (+-3 halo, sampled
+//                 every s pixels) into the other shared-memory buffer while the compute warps work.
+// The backwarp of f2 (src/models.py:171) is folded into the tile load: the bilinear taps of every tile pixel are
+// computed ONCE per CTA (they do not depend on the channel chunk), so the per-chunk gathers are independent loads
+// with no flow -> address dependency.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8
+// neighbouring pixels are bank-conflict free.
 // ------------------------------------------------------------------------------------------------
 constexpr int NH_TX = 16, NH_TY = 8, NH_CK = 16, NH_PITCH = 20;
 constexpr int NH_SW = NH_TX + 6, NH_SH = NH_TY + 6;
+constexpr int NH_NPIX2 = NH_SW * NH_SH;                 // 308 tile pixels of f2
+constexpr int NH_THREADS = 384;              // 256 compute + 128 loader threads
+constexpr int NH_S1 = NH_TX * NH_TY * NH_PITCH, NH_S2 = NH_NPIX2 * NH_PITCH;
+constexpr int NH_SMEM = (2 * (NH_S1 + NH_S2)) * 4 + NH_NPIX2 * (16 + 8);
 
 template <int ROWS>
 __device__ __forceinline__ void corr_accumulate(float (&acc)[28], const float* __restrict__ s1,
@@ -106,78 +114,113 @@ __device__ __forceinline__ void corr_accumulate(float (&acc)[28], const float* _
     }
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ float4 ld_quad(const float* src, int c, int C) {
+    if (c + 3 < C) return __ldg(reinterpret_cast<const float4*>(src));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    v.x = __ldg(src);
+    if (c + 1 < C) v.y = __ldg(src + 1);
+    if (c + 2 < C) v.z = __ldg(src + 2);
+    return v;
+}
+
+__global__ void __launch_bounds__(NH_THREADS, 2)
 corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
                  const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
                  int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
-    __shared__ __align__(16) float s1[NH_TX * NH_TY * NH_PITCH];
-    __shared__ __align__(16) float s2[NH_SW * NH_SH * NH_PITCH];
+    extern __shared__ __align__(16) float smem_f[];
+    float* s1 = smem_f;                                  // [2][NH_S1]
+    float* s2 = smem_f + 2 * NH_S1;                      // [2][NH_S2]
+    float4* tapw = reinterpret_cast<float4*>(smem_f + 2 * (NH_S1 + NH_S2));      // [308] bilinear weights
+    int2* tapxy = reinterpret_cast<int2*>(tapw + NH_NPIX2);                       // [308] top-left tap (x0, y0)
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * NH_TX, y0 = blockIdx.y * NH_TY;
     const int tid = threadIdx.x;
-    const int pix = tid & 127, half = tid >> 7;
-    const int tx = pix % NH_TX, ty = pix / NH_TX;
-    const int ox = x0 + tx, oy = y0 + ty;
-    const bool live = ox < Wo && oy < Ho;
     const size_t img = (size_t)n * H * W;
+    const int nch = (C + NH_CK - 1) / NH_CK;
 
+    // ---- bilinear taps of the 308 f2-tile pixels, once per CTA -----------------------------------------------
+    if (tid < NH_NPIX2) {
+        const int i = tid % NH_SW, j = tid / NH_SW;
+        const int iy = (y0 + j - 3) * s, ix = (x0 + i - 3) * s;
+        float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+        int2 xy = make_int2(0, 0);
+        if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            float fx = 0.f, fy = 0.f;
+            if (flow != nullptr) {
+                const float2 fl = __ldg(reinterpret_cast<const float2*>(flow) + img + (size_t)iy * W + ix);
+                fx = fl.x * fscale; fy = fl.y * fscale;
+            }
+            const BilinearTaps t = make_taps((float)ix + fx, (float)iy + fy, H, W);
+            wv = make_float4(t.w00, t.w01, t.w10, t.w11);
+            xy = make_int2(t.x0, t.y0);
+        }
+        tapw[tid] = wv;
+        tapxy[tid] = xy;
+    }
+    __syncthreads();
+
+    auto stage = [&](int ch, int buf, int lt, int nlt) {
+        const int c0 = ch * NH_CK;
+        float* d1 = s1 + buf * NH_S1;
+        float* d2 = s2 + buf * NH_S2;
+        // f1 tile: 128 pixels x 4 quads
+        for (int item = lt; item < NH_TX * NH_TY * (NH_CK / 4); item += nlt) {
+            const int q = item & 3, p = item >> 2;
+            const int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
+            const int c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < Wo && py < Ho && c < C) v = ld_quad(f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c, c, C);
+            *reinterpret_cast<float4*>(&d1[p * NH_PITCH + q * 4]) = v;
+        }
+        // f2 tile (+halo), backwarped through the precomputed taps
+        for (int item = lt; item < NH_NPIX2 * (NH_CK / 4); item += nlt) {
+            const int q = item & 3, p = item >> 2;
+            const int c = c0 + q * 4;
+            const float4 wv = tapw[p];
+            const int2 xy = tapxy[p];
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C) {
+                const float wgt[4] = {wv.x, wv.y, wv.z, wv.w};
+                float4 u[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (wgt[k] != 0.f)
+                        u[k] = ld_quad(f2 + (img + (size_t)(xy.y + (k >> 1)) * W + (xy.x + (k & 1))) * f2_ld + c, c, C);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v.x = fmaf(wgt[k], u[k].x, v.x); v.y = fmaf(wgt[k], u[k].y, v.y);
+                    v.z = fmaf(wgt[k], u[k].z, v.z); v.w = fmaf(wgt[k], u[k].w, v.w);
+                }
+            }
+            *reinterpret_cast<float4*>(&d2[p * NH_PITCH + q * 4]) = v;
+        }
+    };
+
+    const bool is_loader = tid >= 256;
+    const int pix = tid & 127, half = (tid >> 7) & 1;
+    const int tx = pix % NH_TX, ty = pix / NH_TX;
     float acc[28];
 #pragma unroll
     for (int i = 0; i < 28; ++i) acc[i] = 0.f;
 
-    for (int c0 = 0; c0 < C; c0 += NH_CK) {
-        __syncthreads();
-        // ---- f1 tile: 128 pixels x 4 quads ---------------------------------------------------------
-        for (int item = tid; item < NH_TX * NH_TY * (NH_CK / 4); item += 256) {
-            int q = item & 3, p = item >> 2;
-            int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
-            int c = c0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < Wo && py < Ho && c < C) {
-                const float* src = f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c;
-                if (c + 3 < C) v = __ldg(reinterpret_cast<const float4*>(src));
-                else { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
-            }
-            *reinterpret_cast<float4*>(&s1[p * NH_PITCH + q * 4]) = v;
-        }
-        // ---- f2 tile (+halo), optionally backwarped --------------------------------------------------
-        for (int item = tid; item < NH_SW * NH_SH * (NH_CK / 4); item += 256) {
-            int q = item & 3, p = item >> 2;
-            int i = p % NH_SW, j = p / NH_SW;
-            int iy = (y0 + j - 3) * s, ix = (x0 + i - 3) * s;
-            int c = c0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (iy >= 0 && iy < H && ix >= 0 && ix < W && c < C) {
-                const bool full = c + 3 < C;
-                if (flow == nullptr) {
-                    const float* src = f2 + (img + (size_t)iy * W + ix) * f2_ld + c;
-                    if (full) v = __ldg(reinterpret_cast<const float4*>(src));
-                    else { v.x = __ldg(src); if (c + 1 < C) v.y = __ldg(src + 1); if (c + 2 < C) v.z = __ldg(src + 2); }
-                } else {
-                    const float2 fl = __ldg(reinterpret_cast<const float2*>(flow) + img + (size_t)iy * W + ix);
-                    const BilinearTaps t = make_taps((float)ix + fl.x * fscale, (float)iy + fl.y * fscale, H, W);
-                    const float wgt[4] = {t.w00, t.w01, t.w10, t.w11};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (wgt[k] != 0.f) {
-                            const float* src = f2 + (img + (size_t)(t.y0 + (k >> 1)) * W + (t.x0 + (k & 1))) * f2_ld + c;
-                            float4 u = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (full) u = __ldg(reinterpret_cast<const float4*>(src));
-                            else { u.x = __ldg(src); if (c + 1 < C) u.y = __ldg(src + 1); if (c + 2 < C) u.z = __ldg(src + 2); }
-                            v.x = fmaf(wgt[k], u.x, v.x); v.y = fmaf(wgt[k], u.y, v.y);
-                            v.z = fmaf(wgt[k], u.z, v.z); v.w = fmaf(wgt[k], u.w, v.w);
-                        }
-                    }
-                }
-            }
-            *reinterpret_cast<float4*>(&s2[p * NH_PITCH + q * 4]) = v;
+    stage(0, 0, tid, NH_THREADS);                        // everybody stages the first chunk
+    __syncthreads();
+    for (int ch = 0; ch < nch; ++ch) {
+        const int buf = ch & 1;
+        if (is_loader) {
+            if (ch + 1 < nch) stage(ch + 1, buf ^ 1, tid - 256, NH_THREADS - 256);
+        } else {
+            const float* a = s1 + buf * NH_S1 + pix * NH_PITCH;
+            const float* b = s2 + buf * NH_S2;
+            if (half == 0) corr_accumulate<4>(acc, a, b + ((ty + 0) * NH_SW + tx) * NH_PITCH);
+            else           corr_accumulate<3>(acc, a, b + ((ty + 4) * NH_SW + tx) * NH_PITCH);
         }
         __syncthreads();
-        const float* a = &s1[pix * NH_PITCH];
-        if (half == 0) corr_accumulate<4>(acc, a, &s2[((ty + 0) * NH_SW + tx) * NH_PITCH]);
-        else           corr_accumulate<3>(acc, a, &s2[((ty + 4) * NH_SW + tx) * NH_PITCH]);
     }
-    if (live) {
+    const int ox = x0 + tx, oy = y0 + ty;
+    if (!is_loader && ox < Wo && oy < Ho) {
         const float inv = 1.f / (float)C;
         float* o = out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + half * 28;
         const int cnt = half == 0 ? 28 : 21;
@@ -216,8 +259,14 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
     if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
     const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
     dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
-    corr_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
-                                                              C, H, W, Ho, Wo, stride, lrelu);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(corr_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    corr_nhwc_kernel<<<grid, NH_THREADS, NH_SMEM, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
+                                                                          C, H, W, Ho, Wo, stride, lrelu);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }

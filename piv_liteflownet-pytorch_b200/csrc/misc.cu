@@ -136,40 +136,58 @@ __global__ void copy_nhwc_kernel(const float* __restrict__ in, int in_ld, float*
 }
 
 // ---- backwarp, standalone (src/models.py:20-35) ---------------------------------------------------------
-__global__ void warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restrict__ flow, float scale,
-                                 float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
+// One block = one 8x8 pixel patch x all channel quads (a 2-D patch keeps the bilinear taps of neighbouring pixels
+// in L1: every fetched 128-byte line is used by ~4 pixels instead of ~2 with a 1-D row segment).
+__global__ void __launch_bounds__(256)
+warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restrict__ flow, float scale,
+                 float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
     const int Q = (C + 3) / 4;
-    const long long total = (long long)N * H * W * Q;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-         i += (long long)gridDim.x * blockDim.x) {
-        int q = (int)(i % Q);
-        long long p = i / Q;
-        int x = (int)(p % W);
-        long long t = p / W;
-        int y = (int)(t % H);
-        long long n = t / H;
-        const float2 fl = __ldg(flow + p);
-        const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
-        const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
-        const int c = q * 4;
-        const int nc = min(4, C - c);
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+    const int tiles_x = (W + 7) / 8, tiles_y = (H + 7) / 8;
+    const long long ntiles = (long long)N * tiles_y * tiles_x;
+    const int items = 64 * Q;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tx = (int)(tile % tiles_x);
+        const long long t2 = tile / tiles_x;
+        const int ty = (int)(t2 % tiles_y);
+        const long long n = t2 / tiles_y;
+        for (int it = threadIdx.x; it < items; it += 256) {
+            const int q = it % Q, pp = it / Q;
+            const int x = tx * 8 + (pp & 7), y = ty * 8 + (pp >> 3);
+            if (x >= W || y >= H) continue;
+            const long long p = (n * H + y) * W + x;
+            const float2 fl = __ldg(flow + p);
+            const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
+            const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+            const int c = q * 4;
+            const int nc = min(4, C - c);
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nc == 4) {
+                float4 u[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (wgt[k] != 0.f) {
-                const float* s = in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c;
-                if (nc == 4) {
-                    float4 u = __ldg(reinterpret_cast<const float4*>(s));
-                    v[0] = fmaf(wgt[k], u.x, v[0]); v[1] = fmaf(wgt[k], u.y, v[1]);
-                    v[2] = fmaf(wgt[k], u.z, v[2]); v[3] = fmaf(wgt[k], u.w, v[3]);
-                } else {
-                    for (int j = 0; j < nc; ++j) v[j] = fmaf(wgt[k], __ldg(s + j), v[j]);
+                for (int k = 0; k < 4; ++k) {
+                    u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (wgt[k] != 0.f)
+                        u[k] = __ldg(reinterpret_cast<const float4*>(
+                            in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c));
                 }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[0] = fmaf(wgt[k], u[k].x, v[0]); v[1] = fmaf(wgt[k], u[k].y, v[1]);
+                    v[2] = fmaf(wgt[k], u[k].z, v[2]); v[3] = fmaf(wgt[k], u[k].w, v[3]);
+                }
+                *reinterpret_cast<float4*>(out + p * out_ld + c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (wgt[k] != 0.f) {
+                        const float* sp = in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c;
+                        for (int j = 0; j < nc; ++j) v[j] = fmaf(wgt[k], __ldg(sp + j), v[j]);
+                    }
+                }
+                float* o = out + p * out_ld + c;
+                for (int j = 0; j < nc; ++j) o[j] = v[j];
             }
         }
-        float* o = out + p * out_ld + c;
-        if (nc == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-        else for (int j = 0; j < nc; ++j) o[j] = v[j];
     }
 }
 
@@ -238,54 +256,80 @@ __global__ void reg_input_kernel(const float4* __restrict__ img1, const float4* 
 }
 
 // ---- regularisation tail (src/models.py:281-302), one kernel ---------------------------------------------------
+// Block = 128 consecutive pixels.  Their K*K distance rows are contiguous in memory (pixel pitch dist_ld), so they are
+// staged into shared memory with coalesced float4 loads (one thread reading its own 200-byte row directly would touch
+// a different sector per lane); the row pitch in shared memory is odd, so lanes reading the same k hit distinct banks.
 template <int K>
 __global__ void __launch_bounds__(128)
 reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __restrict__ flow,
                 const float* __restrict__ wx, const float* __restrict__ bx,
                 const float* __restrict__ wy, const float* __restrict__ by,
                 float2* __restrict__ flow_out, float* __restrict__ out_nchw, float final_scale,
-                int N, int H, int W) {
+                int N, int H, int W, int vec) {
     constexpr int KK = K * K, P = K / 2;
+    constexpr int SP = ((KK + 3) & ~3) + 1;              // odd pitch >= the padded channel count
     __shared__ float swx[KK], swy[KK];
+    __shared__ float sd[128 * SP];
     for (int i = threadIdx.x; i < KK; i += blockDim.x) { swx[i] = wx[i]; swy[i] = wy[i]; }
-    __syncthreads();
     const float bxv = __ldg(bx), byv = __ldg(by);
     const long long HW = (long long)H * W, total = (long long)N * HW;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
-         p += (long long)gridDim.x * blockDim.x) {
-        const long long n = p / HW;
-        const int x = (int)(p % W), y = (int)((p / W) % H);
-        const float* d = dist + p * dist_ld;
-        float ns[KK];
-        float mx = -INFINITY;
-#pragma unroll
-        for (int k = 0; k < KK; ++k) {
-            float v = __ldg(d + k);
-            ns[k] = -(v * v);
-            mx = fmaxf(mx, ns[k]);
+    for (long long p0 = (long long)blockIdx.x * 128; p0 < total; p0 += (long long)gridDim.x * 128) {
+        const int np = (int)min(128LL, total - p0);
+        __syncthreads();
+        if (vec) {
+            const int q4 = dist_ld >> 2;                 // float4 per pixel row (pad channels included)
+            const float4* src = reinterpret_cast<const float4*>(dist + p0 * dist_ld);
+            for (int i = threadIdx.x; i < np * q4; i += 128) {
+                const float4 v = __ldg(src + i);
+                const int pp = i / q4, k = (i - pp * q4) * 4;
+                float* d = &sd[pp * SP + k];
+                if (k < KK) d[0] = v.x;
+                if (k + 1 < KK) d[1] = v.y;
+                if (k + 2 < KK) d[2] = v.z;
+                if (k + 3 < KK) d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < np * KK; i += 128) {
+                const int pp = i / KK, k = i - pp * KK;
+                sd[pp * SP + k] = __ldg(dist + (p0 + pp) * dist_ld + k);
+            }
         }
-        float sum = 0.f, au = 0.f, av = 0.f;
+        __syncthreads();
+        if ((int)threadIdx.x < np) {
+            const long long p = p0 + threadIdx.x;
+            const long long n = p / HW;
+            const int x = (int)(p % W), y = (int)((p / W) % H);
+            const float* d = &sd[threadIdx.x * SP];
+            float ns[KK];
+            float mx = -INFINITY;
 #pragma unroll
-        for (int k = 0; k < KK; ++k) {
-            const float e = expf(ns[k] - mx);
-            sum += e;
-            const int yy = y + k / K - P, xx = x + k % K - P;
-            float2 f = make_float2(0.f, 0.f);
-            if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
-            au = fmaf(swx[k], e * f.x, au);
-            av = fmaf(swy[k], e * f.y, av);
-        }
-        const float r = 1.f / sum;
-        const float u = (au + bxv) * r, v = (av + byv) * r;
-        flow_out[p] = make_float2(u, v);
-        if (out_nchw) {
-            const long long q = p - n * HW;
-            out_nchw[(n * 2 + 0) * HW + q] = u * final_scale;
-            out_nchw[(n * 2 + 1) * HW + q] = v * final_scale;
+            for (int k = 0; k < KK; ++k) {
+                const float v = d[k];
+                ns[k] = -(v * v);
+                mx = fmaxf(mx, ns[k]);
+            }
+            float sum = 0.f, au = 0.f, av = 0.f;
+#pragma unroll
+            for (int k = 0; k < KK; ++k) {
+                const float e = expf(ns[k] - mx);
+                sum += e;
+                const int yy = y + k / K - P, xx = x + k % K - P;
+                float2 f = make_float2(0.f, 0.f);
+                if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
+                au = fmaf(swx[k], e * f.x, au);
+                av = fmaf(swy[k], e * f.y, av);
+            }
+            const float r = 1.f / sum;
+            const float u = (au + bxv) * r, v = (av + byv) * r;
+            flow_out[p] = make_float2(u, v);
+            if (out_nchw) {
+                const long long q = p - n * HW;
+                out_nchw[(n * 2 + 0) * HW + q] = u * final_scale;
+                out_nchw[(n * 2 + 1) * HW + q] = v * final_scale;
+            }
         }
     }
 }
-
 
 // ---- F.interpolate(mode='bilinear', align_corners=False) on NCHW (inference.py:46-49,57-61) ------------------
 // src = (dst + 0.5) * (in / out) - 0.5 clamped at 0, second tap clamped at in-1; channels of even index are
@@ -362,8 +406,8 @@ extern "C" int pivlfn_warp_nhwc(const float* in, int in_ld, const float* flow, f
     if (!in || !flow || !out || N <= 0 || H <= 0 || W <= 0 || C <= 0 || in_ld < C || out_ld < C) return PIVLFN_EINVAL;
     if (((uintptr_t)in & 15) || ((uintptr_t)out & 15) || (in_ld & 3) || (out_ld & 3) || ((uintptr_t)flow & 7))
         return PIVLFN_EINVAL;
-    const long long total = (long long)N * H * W * ((C + 3) / 4);
-    warp_nhwc_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+    const long long ntiles = (long long)N * ((H + 7) / 8) * ((W + 7) / 8);
+    warp_nhwc_kernel<<<(int)(ntiles < 148LL * 64 ? ntiles : 148LL * 64), 256, 0, (cudaStream_t)stream>>>(
         in, in_ld, reinterpret_cast<const float2*>(flow), scale, out, out_ld, N, H, W, C);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
@@ -414,10 +458,12 @@ extern "C" int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow
     cudaStream_t st = (cudaStream_t)stream;
     const float2* fi = reinterpret_cast<const float2*>(flow_in);
     float2* fo = reinterpret_cast<float2*>(flow_out);
+    // coalesced float4 staging needs 16-byte aligned rows that hold the channel count rounded up to 4
+    const int vec = (!((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3)) ? 1 : 0;
     switch (K) {
-        case 3: reg_tail_kernel<3><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
-        case 5: reg_tail_kernel<5><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
-        case 7: reg_tail_kernel<7><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W); break;
+        case 3: reg_tail_kernel<3><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
+        case 5: reg_tail_kernel<5><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
+        case 7: reg_tail_kernel<7><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
         default: return PIVLFN_EINVAL;
     }
     PIVLFN_LAUNCHED();
