@@ -74,22 +74,20 @@ corr_nchw_kernel(const float* __restrict__ f1, const float* __restrict__ f2, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// NHWC: CTA = 16 x 8 output pixels, 384 threads, warp-specialised and double-buffered:
-//   warps 0..7  : compute -- 128 pixels x 2 halves of the displacement rows (half 0: dy rows 0..3 = 28
-//                 displacements, half 1: rows 4..6 = 21), accumulators in registers;
-//   warps 8..11 : loaders -- stage the next 16-channel chunk of the f1 tile and of the f2 tile (+-3 halo, sampled
-//                 every s pixels) into the other shared-memory buffer while the compute warps work.
-// The backwarp of f2 (src/models.py:171) is folded into the tile load: the bilinear taps of every tile pixel are
-// computed ONCE per CTA (they do not depend on the channel chunk), so the per-chunk gathers are independent loads
-// with no flow -> address dependency.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8
+// NHWC: CTA = 16 x 8 output pixels, 256 threads = 128 pixels x 2 halves of the displacement rows (half 0: dy rows
+// 0..3 = 28 displacements, half 1: rows 4..6 = 21), accumulators in registers.  Channels are staged 16 at a time into
+// shared memory: the f1 tile and the f2 tile (+-3 halo, sampled every s pixels).  The backwarp of f2
+// (src/models.py:171) is folded into the tile load: the bilinear taps of every tile pixel are computed ONCE per CTA
+// (they do not depend on the channel chunk), so the per-chunk gathers are independent loads with no flow -> address
+// dependency and are issued twelve at a time per thread.  Two CTAs per SM overlap one CTA's load phase with the
+// other's compute phase.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8
 // neighbouring pixels are bank-conflict free.
 // ------------------------------------------------------------------------------------------------
 constexpr int NH_TX = 16, NH_TY = 8, NH_CK = 16, NH_PITCH = 20;
 constexpr int NH_SW = NH_TX + 6, NH_SH = NH_TY + 6;
 constexpr int NH_NPIX2 = NH_SW * NH_SH;                 // 308 tile pixels of f2
-constexpr int NH_THREADS = 384;              // 256 compute + 128 loader threads
+constexpr int NH_THREADS = 256;
 constexpr int NH_S1 = NH_TX * NH_TY * NH_PITCH, NH_S2 = NH_NPIX2 * NH_PITCH;
-constexpr int NH_SMEM = (2 * (NH_S1 + NH_S2)) * 4 + NH_NPIX2 * (16 + 8);
 
 template <int ROWS>
 __device__ __forceinline__ void corr_accumulate(float (&acc)[28], const float* __restrict__ s1,
@@ -127,11 +125,10 @@ __global__ void __launch_bounds__(NH_THREADS, 2)
 corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
                  const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
                  int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
-    extern __shared__ __align__(16) float smem_f[];
-    float* s1 = smem_f;                                  // [2][NH_S1]
-    float* s2 = smem_f + 2 * NH_S1;                      // [2][NH_S2]
-    float4* tapw = reinterpret_cast<float4*>(smem_f + 2 * (NH_S1 + NH_S2));      // [308] bilinear weights
-    int2* tapxy = reinterpret_cast<int2*>(tapw + NH_NPIX2);                       // [308] top-left tap (x0, y0)
+    __shared__ __align__(16) float s1[NH_S1];
+    __shared__ __align__(16) float s2[NH_S2];
+    __shared__ float4 tapw[NH_NPIX2];                    // bilinear weights of the tile pixels
+    __shared__ int2 tapxy[NH_NPIX2];                     // top-left tap (x0, y0)
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * NH_TX, y0 = blockIdx.y * NH_TY;
     const int tid = threadIdx.x;
@@ -139,8 +136,8 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
     const int nch = (C + NH_CK - 1) / NH_CK;
 
     // ---- bilinear taps of the 308 f2-tile pixels, once per CTA -----------------------------------------------
-    if (tid < NH_NPIX2) {
-        const int i = tid % NH_SW, j = tid / NH_SW;
+    for (int p = tid; p < NH_NPIX2; p += NH_THREADS) {
+        const int i = p % NH_SW, j = p / NH_SW;
         const int iy = (y0 + j - 3) * s, ix = (x0 + i - 3) * s;
         float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
         int2 xy = make_int2(0, 0);
@@ -154,73 +151,75 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             wv = make_float4(t.w00, t.w01, t.w10, t.w11);
             xy = make_int2(t.x0, t.y0);
         }
-        tapw[tid] = wv;
-        tapxy[tid] = xy;
+        tapw[p] = wv;
+        tapxy[p] = xy;
     }
-    __syncthreads();
 
-    auto stage = [&](int ch, int buf, int lt, int nlt) {
-        const int c0 = ch * NH_CK;
-        float* d1 = s1 + buf * NH_S1;
-        float* d2 = s2 + buf * NH_S2;
-        // f1 tile: 128 pixels x 4 quads
-        for (int item = lt; item < NH_TX * NH_TY * (NH_CK / 4); item += nlt) {
-            const int q = item & 3, p = item >> 2;
-            const int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
-            const int c = c0 + q * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < Wo && py < Ho && c < C) v = ld_quad(f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c, c, C);
-            *reinterpret_cast<float4*>(&d1[p * NH_PITCH + q * 4]) = v;
-        }
-        // f2 tile (+halo), backwarped through the precomputed taps
-        for (int item = lt; item < NH_NPIX2 * (NH_CK / 4); item += nlt) {
-            const int q = item & 3, p = item >> 2;
-            const int c = c0 + q * 4;
-            const float4 wv = tapw[p];
-            const int2 xy = tapxy[p];
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (c < C) {
-                const float wgt[4] = {wv.x, wv.y, wv.z, wv.w};
-                float4 u[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (wgt[k] != 0.f)
-                        u[k] = ld_quad(f2 + (img + (size_t)(xy.y + (k >> 1)) * W + (xy.x + (k & 1))) * f2_ld + c, c, C);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v.x = fmaf(wgt[k], u[k].x, v.x); v.y = fmaf(wgt[k], u[k].y, v.y);
-                    v.z = fmaf(wgt[k], u[k].z, v.z); v.w = fmaf(wgt[k], u[k].w, v.w);
-                }
-            }
-            *reinterpret_cast<float4*>(&d2[p * NH_PITCH + q * 4]) = v;
-        }
-    };
-
-    const bool is_loader = tid >= 256;
-    const int pix = tid & 127, half = (tid >> 7) & 1;
+    const int pix = tid & 127, half = tid >> 7;
     const int tx = pix % NH_TX, ty = pix / NH_TX;
     float acc[28];
 #pragma unroll
     for (int i = 0; i < 28; ++i) acc[i] = 0.f;
 
-    stage(0, 0, tid, NH_THREADS);                        // everybody stages the first chunk
-    __syncthreads();
     for (int ch = 0; ch < nch; ++ch) {
-        const int buf = ch & 1;
-        if (is_loader) {
-            if (ch + 1 < nch) stage(ch + 1, buf ^ 1, tid - 256, NH_THREADS - 256);
-        } else {
-            const float* a = s1 + buf * NH_S1 + pix * NH_PITCH;
-            const float* b = s2 + buf * NH_S2;
-            if (half == 0) corr_accumulate<4>(acc, a, b + ((ty + 0) * NH_SW + tx) * NH_PITCH);
-            else           corr_accumulate<3>(acc, a, b + ((ty + 4) * NH_SW + tx) * NH_PITCH);
+        const int c0 = ch * NH_CK;
+        __syncthreads();                                  // previous chunk consumed (and tap table visible)
+        // ---- f1 tile: 128 pixels x 4 quads = 2 items per thread ----------------------------------------------
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int item = tid + k * NH_THREADS;
+            const int q = item & 3, p = item >> 2;
+            const int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
+            const int c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (px < Wo && py < Ho && c < C) v = ld_quad(f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c, c, C);
+            *reinterpret_cast<float4*>(&s1[p * NH_PITCH + q * 4]) = v;
+        }
+        // ---- f2 tile (+halo): 1232 items, three at a time (12 independent gathers in flight per thread) --------
+        constexpr int UNR = 3;
+        for (int base = tid; base < NH_NPIX2 * 4; base += UNR * NH_THREADS) {
+            float4 u[UNR][4];
+            float4 wv[UNR];
+            bool ok[UNR];
+#pragma unroll
+            for (int e = 0; e < UNR; ++e) {
+                const int item = base + e * NH_THREADS;
+                ok[e] = item < NH_NPIX2 * 4;
+                const int q = item & 3, p = ok[e] ? (item >> 2) : 0;
+                const int c = c0 + q * 4;
+                wv[e] = tapw[p];
+                const int2 xy = tapxy[p];
+                const float wgt[4] = {wv[e].x, wv[e].y, wv[e].z, wv[e].w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    u[e][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ok[e] && c < C && wgt[k] != 0.f)
+                        u[e][k] = ld_quad(f2 + (img + (size_t)(xy.y + (k >> 1)) * W + (xy.x + (k & 1))) * f2_ld + c, c, C);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < UNR; ++e) {
+                if (ok[e]) {
+                    const int item = base + e * NH_THREADS;
+                    const int q = item & 3, p = item >> 2;
+                    const float wgt[4] = {wv[e].x, wv[e].y, wv[e].z, wv[e].w};
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v.x = fmaf(wgt[k], u[e][k].x, v.x); v.y = fmaf(wgt[k], u[e][k].y, v.y);
+                        v.z = fmaf(wgt[k], u[e][k].z, v.z); v.w = fmaf(wgt[k], u[e][k].w, v.w);
+                    }
+                    *reinterpret_cast<float4*>(&s2[p * NH_PITCH + q * 4]) = v;
+                }
+            }
         }
         __syncthreads();
+        const float* a = &s1[pix * NH_PITCH];
+        if (half == 0) corr_accumulate<4>(acc, a, &s2[((ty + 0) * NH_SW + tx) * NH_PITCH]);
+        else           corr_accumulate<3>(acc, a, &s2[((ty + 4) * NH_SW + tx) * NH_PITCH]);
     }
     const int ox = x0 + tx, oy = y0 + ty;
-    if (!is_loader && ox < Wo && oy < Ho) {
+    if (ox < Wo && oy < Ho) {
         const float inv = 1.f / (float)C;
         float* o = out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + half * 28;
         const int cnt = half == 0 ? 28 : 21;
@@ -259,13 +258,7 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
     if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
     const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
     dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(corr_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NH_SMEM);
-        if (e != cudaSuccess) return (int)e;
-        configured = true;
-    }
-    corr_nhwc_kernel<<<grid, NH_THREADS, NH_SMEM, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
+    corr_nhwc_kernel<<<grid, NH_THREADS, 0, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
                                                                           C, H, W, Ho, Wo, stride, lrelu);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();

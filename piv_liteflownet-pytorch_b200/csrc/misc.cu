@@ -277,16 +277,28 @@ reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __res
         const int np = (int)min(128LL, total - p0);
         __syncthreads();
         if (vec) {
+            // all float4 loads of a thread are issued before the first shared-memory store (13 in flight for K = 7)
             const int q4 = dist_ld >> 2;                 // float4 per pixel row (pad channels included)
             const float4* src = reinterpret_cast<const float4*>(dist + p0 * dist_ld);
-            for (int i = threadIdx.x; i < np * q4; i += 128) {
-                const float4 v = __ldg(src + i);
-                const int pp = i / q4, k = (i - pp * q4) * 4;
-                float* d = &sd[pp * SP + k];
-                if (k < KK) d[0] = v.x;
-                if (k + 1 < KK) d[1] = v.y;
-                if (k + 2 < KK) d[2] = v.z;
-                if (k + 3 < KK) d[3] = v.w;
+            const int nvec = np * q4;
+            constexpr int MAXV = (((KK + 3) & ~3) / 4) + 1;     // enough for dist_ld up to round4(KK) + 4
+            float4 v[MAXV];
+#pragma unroll
+            for (int j = 0; j < MAXV; ++j) {
+                const int i = threadIdx.x + j * 128;
+                if (i < nvec) v[j] = __ldg(src + i);
+            }
+#pragma unroll
+            for (int j = 0; j < MAXV; ++j) {
+                const int i = threadIdx.x + j * 128;
+                if (i < nvec) {
+                    const int pp = i / q4, k = (i - pp * q4) * 4;
+                    float* d = &sd[pp * SP + k];
+                    if (k < KK) d[0] = v[j].x;
+                    if (k + 1 < KK) d[1] = v[j].y;
+                    if (k + 2 < KK) d[2] = v[j].z;
+                    if (k + 3 < KK) d[3] = v[j].w;
+                }
             }
         } else {
             for (int i = threadIdx.x; i < np * KK; i += 128) {
@@ -300,18 +312,17 @@ reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __res
             const long long n = p / HW;
             const int x = (int)(p % W), y = (int)((p / W) % H);
             const float* d = &sd[threadIdx.x * SP];
-            float ns[KK];
             float mx = -INFINITY;
 #pragma unroll
             for (int k = 0; k < KK; ++k) {
                 const float v = d[k];
-                ns[k] = -(v * v);
-                mx = fmaxf(mx, ns[k]);
+                mx = fmaxf(mx, -(v * v));
             }
             float sum = 0.f, au = 0.f, av = 0.f;
 #pragma unroll
             for (int k = 0; k < KK; ++k) {
-                const float e = expf(ns[k] - mx);
+                const float dv = d[k];
+                const float e = expf(-(dv * dv) - mx);
                 sum += e;
                 const int yy = y + k / K - P, xx = x + k % K - P;
                 float2 f = make_float2(0.f, 0.f);
@@ -459,7 +470,8 @@ extern "C" int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow
     const float2* fi = reinterpret_cast<const float2*>(flow_in);
     float2* fo = reinterpret_cast<float2*>(flow_out);
     // coalesced float4 staging needs 16-byte aligned rows that hold the channel count rounded up to 4
-    const int vec = (!((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3)) ? 1 : 0;
+    const int vec = (!((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3) &&
+                     dist_ld <= ((K * K + 3) & ~3) + 4) ? 1 : 0;
     switch (K) {
         case 3: reg_tail_kernel<3><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
         case 5: reg_tail_kernel<5><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
