@@ -256,82 +256,94 @@ __global__ void reg_input_kernel(const float4* __restrict__ img1, const float4* 
 }
 
 // ---- regularisation tail (src/models.py:281-302), one kernel ---------------------------------------------------
-// Block = 128 consecutive pixels.  Their K*K distance rows are contiguous in memory (pixel pitch dist_ld), so they are
-// staged into shared memory with coalesced float4 loads (one thread reading its own 200-byte row directly would touch
-// a different sector per lane); the row pitch in shared memory is odd, so lanes reading the same k hit distinct banks.
+// d_k = exp(-x_k^2 - max_j(-x_j^2));  u_out = (sum_k wx_k d_k u_N(k) + bx) / sum_k d_k, same for v.
+//
+// Bulk variant (aligned rows): persistent blocks of 128 threads walk tiles of 128 consecutive pixels.  A tile's K*K
+// distance rows are ONE contiguous block of 128 * dist_ld floats, fetched with a single cp.async.bulk (1-D TMA copy,
+// no registers) into one of two shared-memory buffers while the previous tile is being computed.  Every thread then
+// reads its own row as float4 (pitch dist_ld = 52 / 28 / 12 floats: the 8 lanes of a quarter-warp hit disjoint banks).
+__device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
 template <int K>
-__global__ void __launch_bounds__(128)
-reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __restrict__ flow,
-                const float* __restrict__ wx, const float* __restrict__ bx,
-                const float* __restrict__ wy, const float* __restrict__ by,
-                float2* __restrict__ flow_out, float* __restrict__ out_nchw, float final_scale,
-                int N, int H, int W, int vec) {
+__device__ __forceinline__ void reg_tail_pixel(const float* __restrict__ d, const float2* __restrict__ flow, long long n,
+                                               int x, int y, int H, int W, const float* swx, const float* swy, float bxv,
+                                               float byv, float& u, float& v) {
     constexpr int KK = K * K, P = K / 2;
-    constexpr int SP = ((KK + 3) & ~3) + 1;              // odd pitch >= the padded channel count
+    float mx = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) mx = fmaxf(mx, -(d[k] * d[k]));
+    float sum = 0.f, au = 0.f, av = 0.f;
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+        const float e = expf(-(d[k] * d[k]) - mx);
+        sum += e;
+        const int yy = y + k / K - P, xx = x + k % K - P;
+        float2 f = make_float2(0.f, 0.f);
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
+        au = fmaf(swx[k], e * f.x, au);
+        av = fmaf(swy[k], e * f.y, av);
+    }
+    const float r = 1.f / sum;
+    u = (au + bxv) * r;
+    v = (av + byv) * r;
+}
+
+template <int K>
+__global__ void __launch_bounds__(128, 4)
+reg_tail_bulk_kernel(const float* __restrict__ dist, int dist_ld, const float2* __restrict__ flow,
+                     const float* __restrict__ wx, const float* __restrict__ bx,
+                     const float* __restrict__ wy, const float* __restrict__ by,
+                     float2* __restrict__ flow_out, float* __restrict__ out_nchw, float final_scale,
+                     int N, int H, int W) {
+    constexpr int KK = K * K;
+    extern __shared__ __align__(128) float sbuf[];       // [2][128 * dist_ld]
     __shared__ float swx[KK], swy[KK];
-    __shared__ float sd[128 * SP];
-    for (int i = threadIdx.x; i < KK; i += blockDim.x) { swx[i] = wx[i]; swy[i] = wy[i]; }
+    __shared__ __align__(8) unsigned long long bar[2];
+    for (int i = threadIdx.x; i < KK; i += 128) { swx[i] = wx[i]; swy[i] = wy[i]; }
     const float bxv = __ldg(bx), byv = __ldg(by);
     const long long HW = (long long)H * W, total = (long long)N * HW;
-    for (long long p0 = (long long)blockIdx.x * 128; p0 < total; p0 += (long long)gridDim.x * 128) {
-        const int np = (int)min(128LL, total - p0);
-        __syncthreads();
-        if (vec) {
-            // all float4 loads of a thread are issued before the first shared-memory store (13 in flight for K = 7)
-            const int q4 = dist_ld >> 2;                 // float4 per pixel row (pad channels included)
-            const float4* src = reinterpret_cast<const float4*>(dist + p0 * dist_ld);
-            const int nvec = np * q4;
-            constexpr int MAXV = (((KK + 3) & ~3) / 4) + 1;     // enough for dist_ld up to round4(KK) + 4
-            float4 v[MAXV];
-#pragma unroll
-            for (int j = 0; j < MAXV; ++j) {
-                const int i = threadIdx.x + j * 128;
-                if (i < nvec) v[j] = __ldg(src + i);
-            }
-#pragma unroll
-            for (int j = 0; j < MAXV; ++j) {
-                const int i = threadIdx.x + j * 128;
-                if (i < nvec) {
-                    const int pp = i / q4, k = (i - pp * q4) * 4;
-                    float* d = &sd[pp * SP + k];
-                    if (k < KK) d[0] = v[j].x;
-                    if (k + 1 < KK) d[1] = v[j].y;
-                    if (k + 2 < KK) d[2] = v[j].z;
-                    if (k + 3 < KK) d[3] = v[j].w;
-                }
-            }
-        } else {
-            for (int i = threadIdx.x; i < np * KK; i += 128) {
-                const int pp = i / KK, k = i - pp * KK;
-                sd[pp * SP + k] = __ldg(dist + (p0 + pp) * dist_ld + k);
-            }
-        }
-        __syncthreads();
-        if ((int)threadIdx.x < np) {
-            const long long p = p0 + threadIdx.x;
+    const long long ntiles = (total + 127) / 128;
+    const int tile_floats = 128 * dist_ld;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr_u32(&bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](long long tile, int buf) {
+        const long long p0 = tile * 128;
+        const unsigned bytes = (unsigned)(min(128LL, total - p0) * dist_ld * 4);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(&bar[buf])), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_addr_u32(sbuf + buf * tile_floats)), "l"(dist + p0 * dist_ld), "r"(bytes),
+                       "r"(smem_addr_u32(&bar[buf])) : "memory");
+    };
+    if (threadIdx.x == 0 && (long long)blockIdx.x < ntiles) issue(blockIdx.x, 0);
+    int it = 0;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        const long long next = tile + gridDim.x;
+        if (threadIdx.x == 0 && next < ntiles) issue(next, buf ^ 1);      // buf^1 was released by the barrier below
+        const unsigned parity = (unsigned)((it >> 1) & 1);
+        unsigned done;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_addr_u32(&bar[buf])), "r"(parity) : "memory");
+        } while (!done);
+        const long long p = tile * 128 + threadIdx.x;
+        if (p < total) {
             const long long n = p / HW;
             const int x = (int)(p % W), y = (int)((p / W) % H);
-            const float* d = &sd[threadIdx.x * SP];
-            float mx = -INFINITY;
+            // own row -> registers through float4 shared loads
+            const float4* row = reinterpret_cast<const float4*>(sbuf + buf * tile_floats + threadIdx.x * dist_ld);
+            float d[(KK + 3) & ~3];
 #pragma unroll
-            for (int k = 0; k < KK; ++k) {
-                const float v = d[k];
-                mx = fmaxf(mx, -(v * v));
+            for (int j = 0; j < ((KK + 3) >> 2); ++j) {
+                const float4 q = row[j];
+                d[4 * j] = q.x; d[4 * j + 1] = q.y; d[4 * j + 2] = q.z; d[4 * j + 3] = q.w;
             }
-            float sum = 0.f, au = 0.f, av = 0.f;
-#pragma unroll
-            for (int k = 0; k < KK; ++k) {
-                const float dv = d[k];
-                const float e = expf(-(dv * dv) - mx);
-                sum += e;
-                const int yy = y + k / K - P, xx = x + k % K - P;
-                float2 f = make_float2(0.f, 0.f);
-                if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
-                au = fmaf(swx[k], e * f.x, au);
-                av = fmaf(swy[k], e * f.y, av);
-            }
-            const float r = 1.f / sum;
-            const float u = (au + bxv) * r, v = (av + byv) * r;
+            float u, v;
+            reg_tail_pixel<K>(d, flow, n, x, y, H, W, swx, swy, bxv, byv, u, v);
             flow_out[p] = make_float2(u, v);
             if (out_nchw) {
                 const long long q = p - n * HW;
@@ -339,7 +351,64 @@ reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __res
                 out_nchw[(n * 2 + 1) * HW + q] = v * final_scale;
             }
         }
+        __syncthreads();                                  // everybody is done with buf before it is refilled
     }
+}
+
+// Generic variant (any alignment / pitch): one thread per pixel reading its row directly.
+template <int K>
+__global__ void __launch_bounds__(128)
+reg_tail_kernel(const float* __restrict__ dist, int dist_ld, const float2* __restrict__ flow,
+                const float* __restrict__ wx, const float* __restrict__ bx,
+                const float* __restrict__ wy, const float* __restrict__ by,
+                float2* __restrict__ flow_out, float* __restrict__ out_nchw, float final_scale,
+                int N, int H, int W) {
+    constexpr int KK = K * K;
+    __shared__ float swx[KK], swy[KK];
+    for (int i = threadIdx.x; i < KK; i += blockDim.x) { swx[i] = wx[i]; swy[i] = wy[i]; }
+    __syncthreads();
+    const float bxv = __ldg(bx), byv = __ldg(by);
+    const long long HW = (long long)H * W, total = (long long)N * HW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const long long n = p / HW;
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        float d[KK];
+#pragma unroll
+        for (int k = 0; k < KK; ++k) d[k] = __ldg(dist + p * dist_ld + k);
+        float u, v;
+        reg_tail_pixel<K>(d, flow, n, x, y, H, W, swx, swy, bxv, byv, u, v);
+        flow_out[p] = make_float2(u, v);
+        if (out_nchw) {
+            const long long q = p - n * HW;
+            out_nchw[(n * 2 + 0) * HW + q] = u * final_scale;
+            out_nchw[(n * 2 + 1) * HW + q] = v * final_scale;
+        }
+    }
+}
+
+template <int K>
+int launch_reg_tail(const float* dist, int dist_ld, const float2* fi, const float* wx, const float* bx, const float* wy,
+                    const float* by, float2* fo, float* out_nchw, float final_scale, int N, int H, int W, cudaStream_t st) {
+    const long long total = (long long)N * H * W;
+    const bool bulk = !((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3) && dist_ld <= 64;
+    if (bulk) {
+        const int smem = 2 * 128 * dist_ld * 4;
+        static bool configured = false;
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(reg_tail_bulk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 64 * 4);
+            if (e != cudaSuccess) return (int)e;
+            configured = true;
+        }
+        const long long ntiles = (total + 127) / 128;
+        const int grid = (int)(ntiles < 148LL * 4 ? ntiles : 148LL * 4);
+        reg_tail_bulk_kernel<K><<<grid, 128, smem, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W);
+    } else {
+        long long g = (total + 127) / 128;
+        if (g > 148LL * 32) g = 148LL * 32;
+        reg_tail_kernel<K><<<(int)g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W);
+    }
+    return 0;
 }
 
 // ---- F.interpolate(mode='bilinear', align_corners=False) on NCHW (inference.py:46-49,57-61) ------------------
@@ -464,20 +533,17 @@ extern "C" int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow
                                int K, int N, int H, int W, void* stream) {
     if (!dist || !flow_in || !wx || !bx || !wy || !by || !flow_out || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
     if (dist_ld < K * K || ((uintptr_t)flow_in & 7) || ((uintptr_t)flow_out & 7)) return PIVLFN_EINVAL;
-    const long long total = (long long)N * H * W;
-    const int g = grid_for(total, 128);
     cudaStream_t st = (cudaStream_t)stream;
     const float2* fi = reinterpret_cast<const float2*>(flow_in);
     float2* fo = reinterpret_cast<float2*>(flow_out);
-    // coalesced float4 staging needs 16-byte aligned rows that hold the channel count rounded up to 4
-    const int vec = (!((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3) &&
-                     dist_ld <= ((K * K + 3) & ~3) + 4) ? 1 : 0;
+    int rc = 0;
     switch (K) {
-        case 3: reg_tail_kernel<3><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
-        case 5: reg_tail_kernel<5><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
-        case 7: reg_tail_kernel<7><<<g, 128, 0, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, vec); break;
+        case 3: rc = launch_reg_tail<3>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, st); break;
+        case 5: rc = launch_reg_tail<5>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, st); break;
+        case 7: rc = launch_reg_tail<7>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W, st); break;
         default: return PIVLFN_EINVAL;
     }
+    if (rc) return rc;
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
