@@ -181,10 +181,19 @@ def kernel_rooflines(eng, pk):
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
         name = "conv_simt_kernel (fp32 FFMA)"
     ach = flops / (ms * 1e-3) / 1e12
+    # DRAM traffic of this exact launch from the committed `ncu --set full` capture (profiles/), if there is one
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_ncu_traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(eng.precision, {}).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
     out["roofline"] = {"kernel": name, "layer": key + " 3x3 128->128 @256x256 x64", "bound": "tensor",
                        "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
                        "peak_source": pk["src"] + ", dense bf16 burst; kind::tf32 peak is half of it",
-                       "ms_per_launch": ms, "traffic": None}
+                       "ms_per_launch": ms, "traffic": traffic, "flops_per_launch": flops,
+                       "algorithmic_bytes_per_launch": 4.0 * B * h * w * (128 + 128)}
     # memory-bound: level-1 cost volume (stride 2, C=64, fused backwarp + LeakyReLU)
     cm = 64
     S_f1 = ops.view(d["Sbuf"], 0, cm)
