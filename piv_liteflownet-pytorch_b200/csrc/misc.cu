@@ -150,64 +150,42 @@ warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restri
         const long long t2 = tile / tiles_x;
         const int ty = (int)(t2 % tiles_y);
         const long long n = t2 / tiles_y;
-        // two items per thread and iteration: both flow loads, then all eight tap loads, then the blends (the chain
-        // flow -> tap address -> tap value is latency-bound otherwise)
-        for (int it0 = threadIdx.x; it0 < items; it0 += 512) {
-            long long pix[2];
-            int cq[2];
-            bool ok[2];
-            float2 fl[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int it = it0 + e * 256;
-                const int q = it % Q, pp = it / Q;
-                const int x = tx * 8 + (pp & 7), y = ty * 8 + (pp >> 3);
-                ok[e] = it < items && x < W && y < H;
-                pix[e] = ok[e] ? (n * H + y) * W + x : 0;
-                cq[e] = q * 4;
-                fl[e] = ok[e] ? __ldg(flow + pix[e]) : make_float2(0.f, 0.f);
-            }
-            float4 u[2][4];
-            float wgt[2][4];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int x = (int)(pix[e] % W), y = (int)((pix[e] / W) % H);
-                const BilinearTaps tp = make_taps((float)x + fl[e].x * scale, (float)y + fl[e].y * scale, H, W);
-                wgt[e][0] = tp.w00; wgt[e][1] = tp.w01; wgt[e][2] = tp.w10; wgt[e][3] = tp.w11;
-                const int c = cq[e];
+        for (int it = threadIdx.x; it < items; it += 256) {
+            const int q = it % Q, pp = it / Q;
+            const int x = tx * 8 + (pp & 7), y = ty * 8 + (pp >> 3);
+            if (x >= W || y >= H) continue;
+            const long long p = (n * H + y) * W + x;
+            const float2 fl = __ldg(flow + p);
+            const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
+            const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+            const int c = q * 4;
+            const int nc = min(4, C - c);
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (nc == 4) {
+                float4 u[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    u[e][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok[e] && wgt[e][k] != 0.f) {
+                    u[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (wgt[k] != 0.f)
+                        u[k] = __ldg(reinterpret_cast<const float4*>(
+                            in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c));
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    v[0] = fmaf(wgt[k], u[k].x, v[0]); v[1] = fmaf(wgt[k], u[k].y, v[1]);
+                    v[2] = fmaf(wgt[k], u[k].z, v[2]); v[3] = fmaf(wgt[k], u[k].w, v[3]);
+                }
+                *reinterpret_cast<float4*>(out + p * out_ld + c) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (wgt[k] != 0.f) {
                         const float* sp = in + ((n * H + (tp.y0 + (k >> 1))) * W + (tp.x0 + (k & 1))) * in_ld + c;
-                        if (c + 3 < C) {
-                            u[e][k] = __ldg(reinterpret_cast<const float4*>(sp));
-                        } else {
-                            u[e][k].x = __ldg(sp);
-                            if (c + 1 < C) u[e][k].y = __ldg(sp + 1);
-                            if (c + 2 < C) u[e][k].z = __ldg(sp + 2);
-                        }
+                        for (int j = 0; j < nc; ++j) v[j] = fmaf(wgt[k], __ldg(sp + j), v[j]);
                     }
                 }
-            }
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                if (!ok[e]) continue;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    v.x = fmaf(wgt[e][k], u[e][k].x, v.x); v.y = fmaf(wgt[e][k], u[e][k].y, v.y);
-                    v.z = fmaf(wgt[e][k], u[e][k].z, v.z); v.w = fmaf(wgt[e][k], u[e][k].w, v.w);
-                }
-                const int c = cq[e];
-                float* o = out + pix[e] * out_ld + c;
-                if (c + 3 < C) {
-                    *reinterpret_cast<float4*>(o) = v;
-                } else {
-                    o[0] = v.x;
-                    if (c + 1 < C) o[1] = v.y;
-                    if (c + 2 < C) o[2] = v.z;
-                }
+                float* o = out + p * out_ld + c;
+                for (int j = 0; j < nc; ++j) o[j] = v[j];
             }
         }
     }
