@@ -1,0 +1,518 @@
+"""One very large PIV frame tiled by rows across GPUs (BASELINE.json configs[4]).
+
+The reference has no tiling at all ("1024 x 1024 takes too much memory!", inference.py:227).  Here rank r of P owns
+rows [r*H/P, (r+1)*H/P) of the frame at every pyramid level and runs the SAME kernels as the single-GPU plan on a local
+buffer that carries E halo rows above and below its slab:
+
+* after an operator with vertical reach r the outermost r halo rows of its output are stale; validity is tracked
+  statically per tensor and halo rows are re-fetched from the row neighbours (NCCL send/recv of contiguous NHWC row
+  blocks over NVLink) only when the next consumer needs more valid rows than are left -- a chain of 3x3 convolutions
+  exchanges once every ~E layers, not once per layer;
+* beyond the true frame edge the halo rows are kept at zero (the zero padding of conv / correlation / backwarp / unfold);
+* the only global coupling of the network, the per-sample flow mean of the regularisation (src/models.py:275), is a
+  2-float all-reduce per level;
+* coarse levels whose slabs would be thinner than the halo are replicated on every rank (all-gather of a few rows).
+
+The backwarp reach is data dependent; ``warp_reach`` rows are provisioned and the bound is verified after the run.
+``LoopbackGroup`` runs P ranks in lock-step inside one process (tests on a single GPU); ``DistGroup`` uses
+torch.distributed (one process per GPU, backend nccl).  Batch size is 1 (left / right camera pairs are independent
+units and go through pair sharding).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable, Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
+from .model import SIMT, TC_3XTF32, Engine
+from .ops import View, view
+
+
+class TT:
+    """Tensor handle of the tiled plan: an NHWC buffer [N, rows, W, C] at pyramid level ``level``.
+    ``tiled``: rows = own + 2E (local slab + halos) else the full frame (replicated level).
+    ``valid``: number of halo rows on each side that currently hold exact data (E after an exchange)."""
+
+    def __init__(self, t: torch.Tensor, level: int, tiled: bool, name: str):
+        self.t, self.level, self.tiled, self.name = t, level, tiled, name
+        self.valid = 0
+
+
+@dataclass
+class Step:
+    kind: str                   # "op" | "exchange" | "allreduce" | "allgather" | "zero"
+    fn: Optional[Callable] = None
+    tt: Optional[TT] = None
+    src: Optional[torch.Tensor] = None
+    dst: Optional[torch.Tensor] = None
+
+
+class TiledPlan:
+    def __init__(self, eng: Engine, H: int, W: int, rank: int, world: int, halo: int = 16, warp_reach: int = 8):
+        if H % (32 * world) or W % 32:
+            raise ValueError("tiled mode: H must be a multiple of 32*world and W of 32")
+        if halo % 2 or halo < 8 or warp_reach + 6 > halo:
+            raise ValueError("halo must be even, >= 8 and >= warp_reach + 6 (stride-2 cost volume reach)")
+        self.eng, self.H, self.W, self.rank, self.world = eng, H, W, rank, world
+        self.E, self.wr = halo, warp_reach
+        self.own = {l: (H // world) >> (l - 1) for l in range(1, 7)}
+        self.Hl = {l: H >> (l - 1) for l in range(1, 7)}
+        self.Wl = {l: W >> (l - 1) for l in range(1, 7)}
+        # levels whose slab is at least one halo thick are tiled; coarser levels are replicated
+        self.Lt = max([l for l in range(1, 7) if self.own[l] >= halo and self.own[l] % 2 == 0] or [0])
+        if self.Lt < eng.cfg.lowest_level:
+            raise ValueError("frame too small to tile at this world size / halo")
+        self.top, self.bottom = rank == 0, rank == world - 1
+        self.steps: List[Step] = []
+        self.handles: List[TT] = []
+        dev = eng.device
+        self._E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        self._Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
+        self._build()
+
+    # ---- geometry -------------------------------------------------------------------------------------------------
+    def is_tiled(self, l: int) -> bool:
+        return l <= self.Lt
+
+    def rows(self, l: int) -> int:
+        return self.own[l] + 2 * self.E if self.is_tiled(l) else self.Hl[l]
+
+    def new(self, name: str, l: int, C: int, N: int = 1, zero: bool = False) -> TT:
+        t = (self._Z if zero else self._E)(N, self.rows(l), self.Wl[l], C)
+        h = TT(t, l, self.is_tiled(l), name)
+        if not h.tiled:
+            h.valid = 1 << 30
+        self.handles.append(h)
+        return h
+
+    # ---- step recording -------------------------------------------------------------------------------------------
+    def _need(self, tt: TT, need: int):
+        """Make sure ``need`` halo rows of tt are exact before the next operator reads them."""
+        if tt.tiled and tt.valid < need:
+            assert need <= self.E, (tt.name, need)
+            self.steps.append(Step("exchange", tt=tt))
+            for h in self.handles:                    # channel slices share buffers: whole rows travel
+                if h.t.data_ptr() == tt.t.data_ptr() and h.valid >= 0:
+                    h.valid = self.E
+            tt.valid = self.E
+
+    def _op(self, fn: Callable, out: TT, valid: int):
+        self.steps.append(Step("op", fn=fn))
+        if out.tiled:
+            out.valid = max(0, min(valid, self.E))
+            self.steps.append(Step("zero", tt=out))        # recorded on every rank (identical step lists); no-op inside
+
+    def alias(self, tt: TT, name: str) -> TT:
+        """A second handle on the same buffer (another channel slice) with its own validity."""
+        h = TT(tt.t, tt.level, tt.tiled, name)
+        h.valid = tt.valid
+        self.handles.append(h)
+        return h
+
+    @staticmethod
+    def _img(tt: TT, n: int, r0: int = 0, nr: Optional[int] = None) -> torch.Tensor:
+        """Rows [r0, r0+nr) of image n as a dense [1, nr, W, C] tensor (contiguous because N == 1)."""
+        nr = tt.t.shape[1] - r0 if nr is None else nr
+        return tt.t[n:n + 1, r0:r0 + nr]
+
+    # ---- operators (same-level) -----------------------------------------------------------------------------------
+    def conv(self, key: str, x: TT, xo: int, xc: int, y: TT, yo: int, lrelu: bool = True, res: Optional[TT] = None,
+             stem_pad: Optional[TT] = None):
+        eng = self.eng
+        cw = eng.w[key]
+        r = cw.kh // 2
+        self._need(x, r)
+        if res is not None:
+            self._need(res, 0)
+        N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
+        passes = 3 if eng.precision == TC_3XTF32 else 1
+
+        def run():
+            for n in range(N):
+                xv = view(self._img(x, n), xo, xc)
+                yv = view(self._img(y, n), yo, cw.cout)
+                rv = view(self._img(res, n), 0, cw.cout) if res is not None else None
+                if cw.stem and eng.precision != SIMT:
+                    ops.conv_stem_tc(self._img(stem_pad, n), 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, lrelu, passes)
+                elif cw.w_hi is not None and eng.precision != SIMT:
+                    ops.conv_tc(xv, 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, cw.kh, cw.kw, lrelu, passes, rv)
+                else:
+                    ops.conv_simt(xv, 1, hh, ww, cw.w_simt, cw.bias, yv, cw.kh, cw.kw, 1, lrelu, rv)
+        v = x.valid - r
+        if res is not None:
+            v = min(v, res.valid)
+        self._op(run, y, v)
+
+    def copy(self, x: TT, xo: int, C: int, y: TT, yo: int):
+        def run():
+            for n in range(x.t.shape[0]):
+                a, b = self._img(x, n), self._img(y, n)
+                ops.copy(view(a, xo, C), view(b, yo, C), a.shape[1] * a.shape[2])
+        self._op(run, y, x.valid)
+
+    def warp(self, f2: TT, C: int, flow: TT, scale: float, y: TT, yo: int):
+        self._need(f2, self.wr)
+        self._need(flow, 0)
+
+        def run():
+            a, fl, b = self._img(f2, 0), self._img(flow, 0), self._img(y, 0)
+            ops.warp(view(a, 0, C), fl, scale, view(b, yo, C), 1, a.shape[1], a.shape[2])
+        self._op(run, y, min(flow.valid, f2.valid - self.wr))
+
+    # ---- the plan -------------------------------------------------------------------------------------------------
+    def _down_views(self, x: TT, y: TT, n: int, pad_rows: int):
+        """Input / output row windows of a stride-2 operator from level l (x) to level l+1 (y).
+        Returns (x tensor, y tensor, rows of y to all-gather or None)."""
+        E = self.E
+        if x.tiled and y.tiled:
+            # local output row j <-> local input row 2j - E (+ tap): input window from row 0, output from row E/2
+            hin = x.t.shape[1]
+            return self._img(x, n), self._img(y, n, E // 2, hin // 2), None
+        if not x.tiled:
+            return self._img(x, n), self._img(y, n), None
+        raise AssertionError("tiled -> replicated goes through _down_gather")
+
+    def down(self, kind: str, x: TT, y: TT, key: Optional[str] = None, C: int = 4):
+        """Stride-2 operator across levels: 'pool' (2x2 mean, src/models.py:336-343) or 'conv' (3x3 s2 NetC conv)."""
+        eng = self.eng
+        N = x.t.shape[0]
+        E = self.E
+        if x.tiled and not y.tiled:
+            # boundary: compute the owned rows of the coarser level (+1 junk row each side) and all-gather them
+            self._need(x, 2)
+            own2 = self.own[y.level]
+            tmp = self._E(N, own2 + 2, self.Wl[y.level], y.t.shape[3])
+
+            def run():
+                for n in range(N):
+                    xin = self._img(x, n, E - 2, 2 * own2 + 4)
+                    self._down_call(kind, key, xin, tmp[n:n + 1], C)
+            self.steps.append(Step("op", fn=run))
+            self.steps.append(Step("allgather", src=tmp, dst=y.t))
+            return
+        if kind == "conv":
+            self._need(x, 1)
+
+        def run2():
+            for n in range(N):
+                a, b, _ = self._down_views(x, y, n, 1)
+                self._down_call(kind, key, a, b, C)
+        v = (x.valid - 1) // 2 if kind == "conv" else x.valid // 2
+        self._op(run2, y, min(v, E // 2) if y.tiled else v)
+
+    def _down_call(self, kind, key, a: torch.Tensor, b: torch.Tensor, C: int):
+        if kind == "pool":
+            ops.avgpool2(a, b)
+        else:
+            cw = self.eng.w[key]
+            ops.conv_simt(view(a, 0, cw.cin), 1, a.shape[1], a.shape[2], cw.w_simt, cw.bias, view(b, 0, cw.cout), 3, 3, 2, True)
+
+    def up(self, x: TT, C: int, w: torch.Tensor, y: TT, yo: int = 0, xo: int = 0):
+        """Depthwise ConvTranspose 4x4 s2 from level l+1 (x) to level l (y) (src/models.py:144-145,151-152)."""
+        E = self.E
+        self._need(x, 1)
+        if x.tiled and y.tiled:
+            j0, i0 = E // 2, 0
+            hin = min(x.t.shape[1] - j0, (y.t.shape[1] - i0) // 2)
+            v = max(0, min(2 * (x.valid - 1), E - 2))
+        elif not x.tiled and y.tiled:
+            R0 = self.rank * self.own[y.level]
+            j0 = max(0, (R0 - E) // 2)
+            i0 = 2 * j0 - R0 + E
+            hin = min(x.t.shape[1] - j0, (y.t.shape[1] - i0) // 2)
+            v = E - 2
+        else:
+            j0, i0, hin, v = 0, 0, x.t.shape[1], 1 << 30
+
+        def run():
+            a = self._img(x, 0, j0, hin)
+            b = self._img(y, 0, i0, 2 * hin)
+            ops.deconv4x4s2_dw(view(a, xo, C), 1, hin, a.shape[2], w, view(b, yo, C))
+        self._op(run, y, v)
+
+    def _build(self):
+        eng, cfg, E = self.eng, self.eng.cfg, self.E
+        tc = eng.precision != SIMT
+        # ---- inputs: every rank is handed its slab of both mean-free images incl. halo rows (zero outside the frame)
+        self.in1 = self._E(1, 3, self.rows(1), self.W)
+        self.in2 = self._E(1, 3, self.rows(1), self.W)
+        img: Dict[int, TT] = {1: self.new("img1", 1, 4, N=2)}
+        img_pad = None
+        if tc:
+            img_pad = TT(self._Z(2, self.rows(1), self.W + 8, 4), 1, True, "img_pad")
+            img_pad.valid = E
+
+        def prep():
+            ops.prep_images(self.in1, self.in2, img[1].t, (0.0,) * 6, img_pad.t if img_pad is not None else None)
+        self.steps.append(Step("op", fn=prep))
+        img[1].valid = E                                           # inputs arrive with exact halos
+        for l in range(2, 7):
+            img[l] = self.new(f"img{l}", l, 4, N=2)
+            self.down("pool", img[l - 1], img[l])
+        # ---- NetC on both images ------------------------------------------------------------------------------------
+        feats: Dict[int, TT] = {}
+        x, lvl = img[1], 1
+        for i, (seq, idx, cin, cout, k, st) in enumerate(NETC):
+            key = f"NetC.{seq}.{idx}"
+            if st == 2:
+                lvl += 1
+                y = self.new(key, lvl, cout, N=2)
+                self.down("conv", x, y, key)
+            else:
+                y = self.new(key, lvl, cout, N=2)
+                self.conv(key, x, 0, x.t.shape[3], y, 0, stem_pad=img_pad)
+            x = y
+            if NETC_LEVEL_END[lvl] == i:
+                feats[lvl] = y
+        nh = len(cfg.head)
+        head_idx = [2 * j for j in range(nh + 1)]
+        xflow: Optional[TT] = None
+        self.flows: Dict[int, TT] = {}
+        for i in reversed(range(len(cfg.levels))):
+            l = cfg.levels[i]
+            cm = MATCH_FEAT_CH[l]
+            cr = 128 if l < 5 else LEVEL_FEAT_CH[l]
+            s = 2 if l < 4 else 1
+            scale = eng.sf[l]
+            feat = feats[l]
+            f1 = TT(feat.t[0:1], l, feat.tiled, f"feat1_{l}"); f1.valid = feat.valid
+            f2r = TT(feat.t[1:2], l, feat.tiled, f"feat2_{l}"); f2r.valid = feat.valid
+            self.handles += [f1, f2r]
+            im1 = TT(img[l].t[0:1], l, img[l].tiled, f"im1_{l}"); im1.valid = img[l].valid
+            im2 = TT(img[l].t[1:2], l, img[l].tiled, f"im2_{l}"); im2.valid = img[l].valid
+            self.handles += [im1, im2]
+            Sbuf = self.new(f"Sbuf{l}", l, 2 * cm + 4, zero=True)
+            S_f2w, S_fl = self.alias(Sbuf, f"S_f2w{l}"), self.alias(Sbuf, f"S_fl{l}")
+            if l <= 2:
+                e = (l - 2) % cfg.n_ext
+                self.conv(f"NetC_ext.{e}.conv_ext.0", f1, 0, LEVEL_FEAT_CH[l], Sbuf, 0)
+                f2 = self.new(f"f2e{l}", l, cm)
+                self.conv(f"NetC_ext.{e}.conv_ext.0", f2r, 0, LEVEL_FEAT_CH[l], f2, 0)
+            else:
+                self.copy(f1, 0, cm, Sbuf, 0)
+                f2 = f2r
+            # ---- Matching ------------------------------------------------------------------------------------
+            flowU = None
+            if xflow is not None:
+                flowU = self.new(f"flowU{l}", l, 2)
+                self.up(xflow, 2, eng.raw[f"NetE_M.{i}.upConv_M.weight"], flowU)
+            corr_rows = (self.rows(l) + s - 1) // s
+            corr = TT(self._Z(1, corr_rows, (self.Wl[l] + s - 1) // s, 52), l, self.is_tiled(l), f"corr{l}")
+            self.handles.append(corr)
+            self._need(Sbuf, 0)
+            self._need(f2, 3 * s + (self.wr if flowU is not None else 0))
+            if flowU is not None:
+                self._need(flowU, 3 * s)
+
+            def run_corr(Sbuf=Sbuf, f2=f2, flowU=flowU, corr=corr, cm=cm, s=s, scale=scale):
+                a, b = self._img(Sbuf, 0), self._img(f2, 0)
+                ops.corr_nhwc(view(a, 0, cm), view(b, 0, cm), self._img(flowU, 0) if flowU is not None else None, scale,
+                              view(corr.t, 0, 49), 1, a.shape[1], a.shape[2], s, True)
+            self.steps.append(Step("op", fn=run_corr))
+            vin = min(Sbuf.valid, f2.valid - 3 * s - (self.wr if flowU is not None else 0),
+                      flowU.valid - 3 * s if flowU is not None else 1 << 30)
+            if s == 2:
+                corrU = self.new(f"corrU{l}", l, 52, zero=True)
+
+                def run_upc(corr=corr, corrU=corrU, i=i):
+                    ops.deconv4x4s2_dw(view(corr.t, 0, 49), 1, corr.t.shape[1], corr.t.shape[2],
+                                       eng.raw[f"NetE_M.{i}.upCorr_M.weight"], view(corrU.t, 0, 49))
+                # half-resolution cost volume rows 2 apart: valid rows shrink by 2 through the 4x4 up-convolution
+                self._op(run_upc, corrU, vin - 2)
+                cin = corrU
+            else:
+                corr.valid = max(0, min(vin, E)) if corr.tiled else 1 << 30
+                if corr.tiled:
+                    self.steps.append(Step("zero", tt=corr))
+                cin = corr
+            flowM = self.new(f"flowM{l}", l, 2)
+            self._chain(f"NetE_M.{i}.conv_M", head_idx, cin, 49, l, flowU, flowM)
+            # ---- Subpixel ------------------------------------------------------------------------------------
+            self.warp(f2, cm, flowM, scale, S_f2w, cm)
+            self.copy(flowM, 0, 2, S_fl, 2 * cm)
+            Sall = self.alias(Sbuf, f"Sall{l}")
+            Sall.valid = min(Sbuf.valid, S_f2w.valid, S_fl.valid)
+            flowS = self.new(f"flowS{l}", l, 2)
+            self._chain(f"NetE_S.{i}.conv_S", head_idx, Sall, 2 * cm + 2, l, flowM, flowS)
+            # ---- Regularization ------------------------------------------------------------------------------
+            partial = self._E(1, ops.flow_mean_parts(), 2)
+            r0, nr = (E, self.own[l]) if flowS.tiled else (0, self.Hl[l])
+            frac = float(self.rows(l)) / float(self.Hl[l])     # reg_input divides by the LOCAL pixel count
+
+            def run_mean(flowS=flowS, partial=partial, r0=r0, nr=nr):
+                ops.flow_mean(self._img(flowS, 0, r0, nr).contiguous(), partial)
+            self.steps.append(Step("op", fn=run_mean))
+            if flowS.tiled:
+                self.steps.append(Step("allreduce", src=partial))
+                self.steps.append(Step("op", fn=lambda partial=partial, frac=frac: partial.mul_(frac)))
+            Rbuf = self.new(f"Rbuf{l}", l, cr + 4, zero=True)
+            R_in = self.alias(Rbuf, f"R_in{l}")
+            self._need(im2, self.wr)
+            self._need(im1, 0)
+            self._need(flowS, 0)
+
+            def run_ri(im1=im1, im2=im2, flowS=flowS, partial=partial, Rbuf=Rbuf, cr=cr, scale=scale):
+                ops.reg_input(self._img(im1, 0), self._img(im2, 0), self._img(flowS, 0), scale, partial,
+                              view(self._img(Rbuf, 0), cr, 3))
+            self._op(run_ri, R_in, min(im1.valid, flowS.valid, im2.valid - self.wr))
+            if l < 5:
+                self.conv(f"NetE_R.{i}.moduleFeat.0", f1, 0, LEVEL_FEAT_CH[l], Rbuf, 0)
+            else:
+                self.copy(f1, 0, cr, Rbuf, 0)
+            Rall = self.alias(Rbuf, f"Rall{l}")
+            Rall.valid = min(Rbuf.valid, R_in.valid)
+            x = Rall
+            xc = cr + 4
+            for j in range(len(CONV_R)):
+                key = f"NetE_R.{i}.conv_R.{2 * j}"
+                y = self.new(key, l, eng.w[key].cout)
+                self.conv(key, x, 0, xc, y, 0)
+                x, xc = y, eng.w[key].cout
+            dc = DIST_CH[l]
+            dist = self.new(f"dist{l}", l, (dc + 3) & ~3)
+            if l < 5:
+                dist0 = self.new(f"dist0{l}", l, (dc + 3) & ~3)
+                self.conv(f"NetE_R.{i}.conv_dist_R.0", x, 0, xc, dist0, 0, lrelu=False)
+                self.conv(f"NetE_R.{i}.conv_dist_R.1", dist0, 0, dc, dist, 0, lrelu=False)
+            else:
+                self.conv(f"NetE_R.{i}.conv_dist_R.0", x, 0, xc, dist, 0, lrelu=False)
+            flowR = self.new(f"flowR{l}", l, 2)
+            K = KSIZE[l]
+            last = l == cfg.lowest_level
+            if last:
+                self.out_local = self._E(1, 2, self.rows(l), self.Wl[l])
+            self._need(flowS, K // 2)
+            self._need(dist, 0)
+            p = f"NetE_R.{i}"
+
+            def run_tail(dist=dist, flowS=flowS, flowR=flowR, dc=dc, K=K, last=last, p=p):
+                ops.reg_tail(view(self._img(dist, 0), 0, dc), self._img(flowS, 0), eng.raw[p + ".moduleScaleX.weight"],
+                             eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
+                             eng.raw[p + ".moduleScaleY.bias"], self._img(flowR, 0), self.out_local if last else None,
+                             eng.sf[1], K)
+            self._op(run_tail, flowR, min(dist.valid, flowS.valid - K // 2))
+            self.flows[l] = flowS
+            xflow = flowR
+
+    def _chain(self, prefix: str, idxs: List[int], x: TT, xc: int, l: int, res: Optional[TT], out: TT):
+        for j in idxs[:-1]:
+            key = f"{prefix}.{j}"
+            y = self.new(key, l, self.eng.w[key].cout)
+            self.conv(key, x, 0, xc, y, 0)
+            x, xc = y, self.eng.w[key].cout
+        self.conv(f"{prefix}.{idxs[-1]}", x, 0, xc, out, 0, lrelu=False, res=res)
+
+    # ---- execution ------------------------------------------------------------------------------------------------
+    def load_inputs(self, img1: torch.Tensor, img2: torch.Tensor):
+        """img1, img2: the full [1,3,H,W] images in [0,1] (any device); this rank's slab + halo rows are cut out here and
+        the per-channel mean is subtracted (src/models.py:321-323); rows outside the frame stay zero, which is the zero
+        padding the first convolution sees."""
+        E, own = self.E, self.own[1]
+        R0 = self.rank * own
+        mean = self.eng.cfg.mean
+        for dst, src, m in ((self.in1, img1, mean[:3]), (self.in2, img2, mean[3:])):
+            dst.zero_()
+            g0, g1 = max(0, R0 - E), min(self.H, R0 + own + E)
+            mm = torch.tensor(m, device=dst.device, dtype=torch.float32).view(1, 3, 1, 1)
+            dst[:, :, g0 - (R0 - E):g1 - (R0 - E)] = src[:, :, g0:g1].to(dst.device) - mm
+
+    def owned_output(self) -> torch.Tensor:
+        l = self.eng.cfg.lowest_level
+        return self.out_local[:, :, self.E:self.E + self.own[l]]
+
+    def check_warp_reach(self):
+        """The provisioned backwarp reach must cover the largest vertical displacement that was actually sampled."""
+        for l, f in self.flows.items():
+            if f.tiled:
+                m = float(f.t[..., 1].abs().max()) * self.eng.sf[l]
+                if m + 1.0 > self.wr:
+                    raise RuntimeError(f"tiled mode: vertical displacement {m:.2f} px at level {l} exceeds warp_reach={self.wr}")
+
+
+def _zero_outside(tt: TT, plan: TiledPlan):
+    E, own = plan.E, plan.own[tt.level]
+    if plan.top:
+        tt.t[:, :E].zero_()
+    if plan.bottom:
+        tt.t[:, E + own:].zero_()
+
+
+class LoopbackGroup:
+    """P ranks run in lock-step inside ONE process on one device (tests): communication steps are tensor copies."""
+
+    def __init__(self, plans: List[TiledPlan]):
+        self.plans = plans
+        n = len(plans[0].steps)
+        assert all(len(p.steps) == n for p in plans), "ranks must record identical step sequences"
+
+    def run(self):
+        P = len(self.plans)
+        for k in range(len(self.plans[0].steps)):
+            kind = self.plans[0].steps[k].kind
+            assert all(p.steps[k].kind == kind for p in self.plans)
+            if kind == "op":
+                for p in self.plans:
+                    p.steps[k].fn()
+            elif kind == "zero":
+                for p in self.plans:
+                    _zero_outside(p.steps[k].tt, p)
+            elif kind == "exchange":
+                for r, p in enumerate(self.plans):
+                    tt, E, own = p.steps[k].tt, p.E, p.own[p.steps[k].tt.level]
+                    if r > 0:
+                        up = self.plans[r - 1].steps[k].tt
+                        tt.t[:, :E].copy_(up.t[:, own:own + E])
+                    if r < P - 1:
+                        dn = self.plans[r + 1].steps[k].tt
+                        tt.t[:, E + own:].copy_(dn.t[:, E:2 * E])
+            elif kind == "allreduce":
+                tot = sum(p.steps[k].src for p in self.plans)
+                for p in self.plans:
+                    p.steps[k].src.copy_(tot)
+            elif kind == "allgather":
+                for p in self.plans:
+                    dst = p.steps[k].dst
+                    o2 = dst.shape[1] // P
+                    for r, q in enumerate(self.plans):
+                        dst[:, r * o2:(r + 1) * o2].copy_(q.steps[k].src[:, 1:1 + o2])
+
+
+class DistGroup:
+    """One process per GPU: NCCL send/recv of halo row blocks with the row neighbours, all-reduce, all-gather."""
+
+    def __init__(self, plan: TiledPlan):
+        import torch.distributed as dist
+        self.plan, self.dist = plan, dist
+
+    def run(self):
+        dist, p = self.dist, self.plan
+        E = p.E
+        for st in p.steps:
+            if st.kind == "op":
+                st.fn()
+            elif st.kind == "zero":
+                _zero_outside(st.tt, p)
+            elif st.kind == "exchange":
+                t, own = st.tt.t, p.own[st.tt.level]
+                reqs = []
+                bufs = []
+                for n in range(t.shape[0]):
+                    if p.rank > 0:
+                        reqs.append(dist.P2POp(dist.isend, t[n, E:2 * E], p.rank - 1))
+                        reqs.append(dist.P2POp(dist.irecv, t[n, :E], p.rank - 1))
+                    if p.rank < p.world - 1:
+                        reqs.append(dist.P2POp(dist.isend, t[n, own:own + E], p.rank + 1))
+                        reqs.append(dist.P2POp(dist.irecv, t[n, E + own:], p.rank + 1))
+                if reqs:
+                    for w in dist.batch_isend_irecv(reqs):
+                        w.wait()
+            elif st.kind == "allreduce":
+                dist.all_reduce(st.src)
+            elif st.kind == "allgather":
+                o2 = st.dst.shape[1] // p.world
+                for n in range(st.src.shape[0]):
+                    piece = st.src[n, 1:1 + o2].contiguous()
+                    dist.all_gather_into_tensor(st.dst[n], piece)
