@@ -23,7 +23,7 @@ def test_tiled_equals_single_gpu(model, H, W, P, precision):
     a = synth.to_rgb_tensor(i1)[None].to(DEV)
     b = synth.to_rgb_tensor(i2)[None].to(DEV)
     ref = eng.forward(a.clone(), b.clone())
-    plans = [TiledPlan(eng, H, W, r, P, halo=16, warp_reach=10) for r in range(P)]
+    plans = [TiledPlan(eng, H, W, r, P, halo=24, warp_reach=16) for r in range(P)]
     assert 1 <= plans[0].Lt <= 6
     for p in plans:
         p.load_inputs(a, b)
