@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PIV-LiteFlowNet-en forward pass (BASELINE.json metric: PIV pairs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision 3xtf32|tf32|simt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision 3xtf32|tf32c|tf32|simt]
 
 One "step" = one forward pass over a batch of 64 synthetic 256x256 particle-image pairs (BASELINE.json
 configs[1]); under torchrun every rank owns its own 64 pairs (independent pairs shard with no data-path
@@ -174,9 +174,11 @@ def kernel_rooflines(eng, pk):
     x, y = ops.view(d["t"][128][0]), ops.view(d["t"][128][1])
     flops = 2.0 * B * h * w * 128 * 128 * 9
     if eng.precision != SIMT and cw.w_hi is not None:
-        passes = 3 if eng.precision == "3xtf32" else 1
-        ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes), 10)
-        name = f"conv_tc_kernel (tcgen05 kind::tf32, {passes} pass)"
+        from pivlfn.model import PASSES
+        passes = PASSES.get(eng.precision, 1)
+        ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes, None,
+                                             cw.w_c16 if passes == 2 else None), 10)
+        name = f"conv_tc_halo_kernel<{passes}> (tcgen05 kind::tf32" + (" + kind::f16 bf16 corrections)" if passes == 2 else f", {passes} pass)")
     else:
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
         name = "conv_simt_kernel (fp32 FFMA)"

@@ -69,10 +69,12 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
 /* Same operator for every stride-1 convolution (KH, KW odd, <= 7) on the tcgen05 tensor cores: implicit GEMM,
  * TMA-fed (zero padding = TMA out-of-bounds fill), TMEM accumulators, fused bias + LeakyReLU (+ residual).
  * w_hi / w_lo: [CoutP, KH*KW, CinP] (CoutP = Cout rounded up to 16, CinP = Cin rounded up to 32, zero padded):
- * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32) or 3 (error-compensated 3xTF32 ~ fp32).
+ * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32), 3 (error-compensated 3xTF32 ~ fp32) or
+ * 2 (TF32 main product + the two low-order products in bf16: same accuracy class, 2/3 of the tensor-core work).
+ * w_c16 (passes == 2 only, else NULL): bf16 pack [bf16(w) | bf16(w - w_hi)], each [CoutP, KH*KW, CinP].
  * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
 int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
-                   const float* w_hi, const float* w_lo, const float* bias,
+                   const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                    float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
                    const float* res, int res_ld, int passes, void* stream);
 
@@ -81,7 +83,7 @@ int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
  * per filter row = the 8 pixels x-3..x+4, fetched through an overlapping-window tensor map.
  * w_hi / w_lo: [32, 7, 32] with column kx*4 + c (kx = 7 and c = 3 are zero). */
 int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
-                        const float* w_hi, const float* w_lo, const float* bias,
+                        const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                         float* y, int y_ld, int lrelu, int passes, void* stream);
 
 /* torch.nn.ConvTranspose2d(C, C, 4, stride 2, padding 1, groups=C, bias=False):

@@ -116,6 +116,29 @@ __device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
         "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulate: the 3xTF32 correction terms at twice the
+// tf32 rate (mode PASSES == 2)
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// two fp32 -> packed bf16x2 (round to nearest even), low half = first value
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -423,7 +446,12 @@ constexpr int SPLIT_THREADS = 256;
 template <int PASSES>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                    const __grid_constant__ CUtensorMap tmBlo, const ConvHaloArgs a) {
+                    const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmB16,
+                    const __grid_constant__ CUtensorMap tmBlo16, const ConvHaloArgs a) {
+    // PASSES: 1 = plain TF32; 3 = 3xTF32 (all three products in tf32); 2 = TF32 main product + the two low-order
+    // products in bf16 (kind::f16, K = 16: half the MMA instructions of the tf32 corrections, same fp32 accuracy class
+    // because the corrections are ~2^-11 of the result and bf16 keeps 8 bits of them)
+    constexpr bool SPLIT = PASSES >= 2;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int pitch = HT_W + a.KW - 1;
@@ -431,7 +459,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int halo_bytes = halo_rows * pitch * 128;
     const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int b_bytes = a.CoutP * KC * 4;
-    const int b_stage = (PASSES == 3 ? 2 : 1) * b_bytes;                // [hi | lo]
+    const int b_stage = (SPLIT ? 2 : 1) * b_bytes;                      // [hi | lo]  or  [hi | bf16(w) | bf16(w_lo)]
     uint8_t* smemB = smem + (size_t)a.nBuf * slot_bytes;
     __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
         acc_full[2], acc_empty[2];
@@ -445,7 +473,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int i = threadIdx.x - 128;
         bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
     }
-    const int set_cols = ((PASSES == 3 && a.corr) ? 2 : 1) * a.NT * a.CoutP;
+    const int set_cols = ((SPLIT && a.corr) ? 2 : 1) * a.NT * a.CoutP;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
     const int G = gridDim.x;
 
@@ -460,6 +488,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmBhi);
         if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+        if (PASSES == 2) { tma_prefetch_desc(&tmB16); tma_prefetch_desc(&tmBlo16); }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
@@ -505,6 +534,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mbar_expect_tx(&b_full[bs], b_stage);
                         tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
+                        if (PASSES == 2) {
+                            tma_load_3d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, t, 0);
+                            tma_load_3d(sB + b_bytes + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
+                        }
                         if (++bs == a.nB) { bs = 0; bphase ^= 1; }
                         if (!next_issued && t + 1 >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
                     }
@@ -533,6 +566,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t blo16 = (uint32_t)(b_bytes >> 4);
             const uint32_t corr_off = a.corr ? (uint32_t)(a.NT * a.CoutP) : 0u;
             const uint32_t pitch8 = (uint32_t)(pitch * 8);
+            // bf16 operand descriptors (mode 2): 64-byte rows, SWIZZLE_64B (layout type 4), 8-row group stride = pitch * 64 B
+            const uint32_t hiA16 = (uint32_t)((((uint64_t)((pitch * 64) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
+            const uint32_t hiB16 = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
+            const uint32_t idesc16 = make_idesc_bf16(a.CoutP);
+            const uint32_t half16 = (uint32_t)(halo_rows * pitch * 64) >> 4;       // bf16(a_lo) tile behind bf16(a)
             int bs = 0;
             uint32_t bphase = 0;
             int gc = 0, wl = 0;
@@ -549,10 +587,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const uint32_t par = (uint32_t)((gc >> 1) & 1);
                     const int kleft = a.Cin - c * KC;
                     const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
-                    { DBG_T0(); mbar_wait(PASSES == 3 ? &a_ready[gc & 1] : &a_full[gc & 1], par); DBG_ADD(w_a); }
+                    { DBG_T0(); mbar_wait(SPLIT ? &a_ready[gc & 1] : &a_full[gc & 1], par); DBG_ADD(w_a); }
                     tc_fence_after();
                     const uint32_t aHi16 = (smem_u32(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
                     const uint32_t aLo16 = (smem_u32(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
+                    const uint32_t p16_base = aLo16;                 // mode 2: the "lo" slot holds the two bf16 tiles
                     uint32_t row16 = 0;                               // (ky * pitch) * 8
                     int kx = 0;
                     for (int t = 0; t < ntaps; ++t) {
@@ -575,6 +614,22 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     }
                                 }
                             }
+                            if (PASSES == 2) {
+                                // bf16 tiles: 64-byte rows (32 channels), 64B swizzle; [bf16(a) | bf16(a_lo)] in the pair slot,
+                                // [bf16(w) | bf16(w_lo)] behind the fp32 weights of the stage
+                                const uint32_t pa16 = p16_base + woff16 / 2 + (uint32_t)i * (tile16 / 2);
+                                const uint32_t b16 = bHi16 + blo16;
+#pragma unroll
+                                for (int kk = 0; kk < KC / 16; ++kk) {
+                                    if (2 * kk < nk) {
+                                        const uint32_t firstc = a.corr ? (acc | (uint32_t)(kk > 0)) : 1u;
+                                        // a_lo * w
+                                        umma_bf16_lohi(t_main + corr_off, pa16 + half16 + 2 * kk, hiA16, b16 + 2 * kk, hiB16, idesc16, firstc);
+                                        // a * w_lo
+                                        umma_bf16_lohi(t_main + corr_off, pa16 + 2 * kk, hiA16, b16 + blo16 / 2 + 2 * kk, hiB16, idesc16, 1);
+                                    }
+                                }
+                            }
                             a_hi += n_issuers * tile16; a_lo += n_issuers * tile16; t_main += (uint32_t)(n_issuers * a.CoutP);
                         }
                         acc = 1;
@@ -592,7 +647,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 8) {
         // ================================ 3xTF32 split warps ============================
-        if (PASSES == 3) {
+        if (SPLIT) {
             const int et = threadIdx.x - 8 * 32;
             const int nvec = halo_bytes / 16;
             int gc = 0;
@@ -608,6 +663,43 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // all loads of a batch are issued before the first use (latency-bound otherwise: the MMAs wait
                     // for this between two chunks)
                     constexpr int SB = 6;
+                    if (PASSES == 2) {
+                        // bf16(a) and bf16(a - trunc_tf32(a)) into the pair slot, 64-byte rows with the 64B swizzle applied
+                        // by hand (absolute shared-memory address bits [7:8] -> [4:5], the rule TMA / UMMA use)
+                        const uint32_t pair_abs = smem_u32(pl);
+                        const uint32_t half_b = (uint32_t)(halo_rows * pitch * 64);
+                        uint8_t* pair = reinterpret_cast<uint8_t*>(pl);
+                        for (int base = et; base < nvec; base += SB * SPLIT_THREADS) {
+                            float4 v[SB];
+#pragma unroll
+                            for (int j = 0; j < SB; ++j)
+                                if (base + j * SPLIT_THREADS < nvec) v[j] = pa[base + j * SPLIT_THREADS];
+#pragma unroll
+                            for (int j = 0; j < SB; ++j) {
+                                const int idx = base + j * SPLIT_THREADS;
+                                if (idx < nvec) {
+                                    // which (pixel, channel quad) this 16-byte chunk of the 128B-swizzled fp32 tile holds
+                                    const uint32_t abs16 = (smem_u32(pa) >> 4) + (uint32_t)idx;
+                                    const uint32_t lc = (abs16 & 7u) ^ ((abs16 >> 3) & 7u);
+                                    const uint32_t pix = (uint32_t)idx >> 3;
+                                    float4 l;
+                                    l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
+                                    l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
+                                    l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
+                                    l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
+                                    const uint32_t off = pix * 64u + lc * 8u;
+                                    uint32_t ad = pair_abs + off;
+                                    ad ^= ((ad >> 7) & 3u) << 4;
+                                    *reinterpret_cast<uint2*>(pair + (ad - pair_abs)) =
+                                        make_uint2(pack_bf16(v[j].x, v[j].y), pack_bf16(v[j].z, v[j].w));
+                                    uint32_t ad2 = pair_abs + half_b + off;
+                                    ad2 ^= ((ad2 >> 7) & 3u) << 4;
+                                    *reinterpret_cast<uint2*>(pair + (ad2 - pair_abs)) =
+                                        make_uint2(pack_bf16(l.x, l.y), pack_bf16(l.z, l.w));
+                                }
+                            }
+                        }
+                    } else
                     for (int base = et; base < nvec; base += SB * SPLIT_THREADS) {
                         float4 v[SB];
 #pragma unroll
@@ -666,7 +758,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
                 // two 16-column TMEM loads in flight per wait: (main, corr) of the same columns in 3xTF32+corr mode,
                 // otherwise two consecutive column groups
-                const bool dual = (PASSES == 3 && a.corr);
+                const bool dual = (SPLIT && a.corr);
                 const int cstep = dual ? 16 : 32;
                 for (int c0 = 0; c0 < a.CoutP; c0 += cstep) {
                     uint32_t v[16], u[16];
@@ -794,6 +886,18 @@ int encode_weights(EncodeTiledFn enc, CUtensorMap* tm, const float* w, int CinP,
     return r == CUDA_SUCCESS ? PIVLFN_OK : PIVLFN_EINVAL;
 }
 
+// bf16 weights [CoutP][ntaps][CinP] -> box (32 channels = 64 bytes, 1 tap, CoutP rows), 64B swizzle
+int encode_weights_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* w, int CinP, int ntaps, int CoutP) {
+    cuuint64_t dims[3] = {(cuuint64_t)CinP, (cuuint64_t)ntaps, (cuuint64_t)CoutP};
+    cuuint64_t strides[2] = {(cuuint64_t)CinP * 2, (cuuint64_t)ntaps * CinP * 2};
+    cuuint32_t box[3] = {(cuuint32_t)KC, 1, (cuuint32_t)CoutP};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PIVLFN_OK : PIVLFN_EINVAL;
+}
+
 void choose_tile(ConvTcArgs& a) {
     a.bw = pow2_ceil(a.W < 16 ? a.W : 16);
     const int rem = TILE_M / a.bw;
@@ -827,8 +931,8 @@ const HaloEnv& halo_env() {
 int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
     const HaloEnv& env = halo_env();
     const int pitch = HT_W + h.KW - 1;
-    const int b_stage = (passes == 3 ? 2 : 1) * h.CoutP * KC * 4;
-    const int corr = (passes == 3 && env.corr_mode) ? 1 : 0;
+    const int b_stage = (passes >= 2 ? 2 : 1) * h.CoutP * KC * 4;
+    const int corr = (passes >= 2 && env.corr_mode) ? 1 : 0;
     const int acc_mult = corr ? 2 : 1;
     // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the epilogue
     // overlaps the next item's MMAs), by the image height and by shared memory
@@ -839,10 +943,10 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         if (NT == 3) continue;
         const int halo_rows = HT_H * NT + h.KH - 1;
         const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
-        const int nBuf = passes == 3 ? 3 : 2;
+        const int nBuf = passes >= 2 ? 3 : 2;
         int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
         if (nB > MAX_STAGES) nB = MAX_STAGES;
-        const int need = passes == 3 ? 2 : 3;
+        const int need = passes >= 2 ? 2 : 3;
         if (nB < need || halo_rows > 256) continue;
         h.corr = corr;
         h.nsets = (2 * acc_mult * NT * h.CoutP <= 512) ? 2 : 1;
@@ -858,16 +962,20 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
     return 0;
 }
 
-int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const ConvHaloArgs& h, int passes,
-                int smem, cudaStream_t st) {
+int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmB16,
+                const CUtensorMap& tmBlo16, const ConvHaloArgs& h, int passes, int smem, cudaStream_t st) {
     const int grid = h.total < num_sms() ? h.total : num_sms();
-    static bool cfg1 = false, cfg3 = false;
+    static bool cfg1 = false, cfg2 = false, cfg3 = false;
+    cudaError_t e = cudaSuccess;
     if (passes == 3) {
-        if (!cfg3) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
-        conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+        if (!cfg3) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
+        conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+    } else if (passes == 2) {
+        if (!cfg2) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg2 = true; }
+        conv_tc_halo_kernel<2><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
     } else {
-        if (!cfg1) { cudaError_t e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
-        conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, h);
+        if (!cfg1) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
+        conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
     }
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
@@ -881,12 +989,13 @@ static long long* g_conv_tc_dbg = nullptr;
 extern "C" void pivlfn_debug_set_conv_trace(long long* dev_buf) { g_conv_tc_dbg = dev_buf; }
 
 extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
-                              const float* w_hi, const float* w_lo, const float* bias,
+                              const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                               float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
                               const float* res, int res_ld, int passes, void* stream) {
     if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
-    if (passes != 1 && passes != 3) return PIVLFN_EINVAL;
-    if (passes == 3 && !w_lo) return PIVLFN_EINVAL;
+    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
+    if (passes == 2 && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
     if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
     if (Cout > 128) return PIVLFN_EUNSUPPORTED;
     if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 3) || y_ld < Cout) return PIVLFN_EINVAL;
@@ -902,8 +1011,15 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tmA, tmBhi, tmBlo;
     if (encode_weights(enc, &tmBhi, w_hi, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
-    if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
+    if (passes >= 2) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
+    CUtensorMap tmB16 = tmBhi, tmBlo16 = tmBhi;
+    if (passes == 2) {
+        // w_c16 = [bf16(w) | bf16(w - tf32(w))], each [CoutP][taps][CinP]
+        const size_t half = (size_t)CoutP * KH * KW * CinP * 2;
+        if (encode_weights_bf16(enc, &tmB16, w_c16, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
+        if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
+    }
 
     if (halo_env().use_halo && W >= HT_W) {
         // ---- halo-resident persistent path --------------------------------------------------------------------
@@ -922,9 +1038,10 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            return halo_launch(tmA, tmBhi, tmBlo, h, passes, smem, st);
+            return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, st);
         }
     }
+    if (passes == 2) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
 
     ConvTcArgs a;
     a.bias = bias; a.res = res; a.res_ld = res_ld; a.y = y; a.y_ld = y_ld;
@@ -953,11 +1070,12 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
 // stride (16 B) is smaller than its box row (128 B), i.e. overlapping windows -- no im2col buffer.
 // Weights: [32][7][32] with column index kx*4 + c (kx = 7 and c = 3 zero).
 extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
-                                   const float* w_hi, const float* w_lo, const float* bias,
+                                   const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                                    float* y, int y_ld, int lrelu, int passes, void* stream) {
     if (!img_pad || !w_hi || !y || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
-    if (passes != 1 && passes != 3) return PIVLFN_EINVAL;
-    if (passes == 3 && !w_lo) return PIVLFN_EINVAL;
+    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
+    if (passes == 2 && !w_c16) return PIVLFN_EINVAL;
     if (((uintptr_t)img_pad & 15) || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < 32) return PIVLFN_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
@@ -982,9 +1100,14 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
             if (encode_weights(enc, &tBhi, w_hi, 32, 7, 32)) return PIVLFN_EINVAL;
-            if (passes == 3) { if (encode_weights(enc, &tBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
+            if (passes >= 2) { if (encode_weights(enc, &tBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
             else tBlo = tBhi;
-            return halo_launch(tA, tBhi, tBlo, h, passes, smem, (cudaStream_t)stream);
+            CUtensorMap tB16 = tBhi, tBlo16 = tBhi;
+            if (passes == 2) {
+                if (encode_weights_bf16(enc, &tB16, w_c16, 32, 7, 32)) return PIVLFN_EINVAL;
+                if (encode_weights_bf16(enc, &tBlo16, (const char*)w_c16 + (size_t)32 * 7 * 32 * 2, 32, 7, 32)) return PIVLFN_EINVAL;
+            }
+            return halo_launch(tA, tBhi, tBlo, tB16, tBlo16, h, passes, smem, (cudaStream_t)stream);
         }
     }
     ConvTcArgs a;
@@ -1006,6 +1129,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
     }
+    if (passes == 2) passes = 3;
     if (encode_weights(enc, &tmBhi, w_hi, 32, 7, 32)) return PIVLFN_EINVAL;
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;

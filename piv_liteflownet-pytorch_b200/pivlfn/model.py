@@ -37,7 +37,9 @@ from .ops import View, view
 SIMT = "simt"          # exact fp32 FFMA on the CUDA cores
 TC_TF32 = "tf32"       # tcgen05 kind::tf32, one pass
 TC_3XTF32 = "3xtf32"   # tcgen05 kind::tf32, error-compensated three passes (fp32-equivalent)
-PRECISIONS = (SIMT, TC_TF32, TC_3XTF32)
+TC_TF32C = "tf32c"     # tf32 main product + the two low-order products in bf16 (fp32-equivalent, 2/3 of the MMA work)
+PRECISIONS = (SIMT, TC_TF32, TC_3XTF32, TC_TF32C)
+PASSES = {TC_TF32: 1, TC_3XTF32: 3, TC_TF32C: 2}
 
 
 def _r4(c: int) -> int:
@@ -63,6 +65,7 @@ class ConvW:
     bias: Optional[torch.Tensor]
     w_hi: Optional[torch.Tensor] = None     # [CoutP16, KH*KW, CinP32] TF32 split for the tcgen05 kernel
     w_lo: Optional[torch.Tensor] = None
+    w_c16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] bf16: bf16(w), bf16(w - w_hi)  (precision tf32c)
     stem: bool = False                      # 7x7 3->32 packed as [32, 7, 32] for pivlfn_conv_stem_tc
 
 
@@ -87,7 +90,12 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         wt = w.permute(0, 2, 3, 1).reshape(cout, kh * kw, cin)
         wt = torch.nn.functional.pad(wt, (0, cinp - cin, 0, 0, 0, coutp - cout))
         cw.w_hi, cw.w_lo = _split_tf32(wt)
+        cw.w_c16 = _pack_c16(wt, cw.w_hi)
     return cw
+
+
+def _pack_c16(wt: torch.Tensor, w_hi: torch.Tensor) -> torch.Tensor:
+    return torch.stack([wt.to(torch.bfloat16), (wt - w_hi).to(torch.bfloat16)]).contiguous()
 
 
 def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
@@ -97,6 +105,7 @@ def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
     wt = torch.zeros(32, 7, 8, 4, device=w.device)
     wt[:, :, :7, :3] = w.permute(0, 2, 3, 1)           # [cout, ky, kx, c]
     cw.w_hi, cw.w_lo = _split_tf32(wt.reshape(32, 7, 32))
+    cw.w_c16 = _pack_c16(wt.reshape(32, 7, 32), cw.w_hi)
     cw.stem = True
     return cw
 
@@ -260,11 +269,12 @@ class Plan:
         eng = self.eng
         cw = eng.w[key]
         assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
-        passes = 3 if eng.precision == TC_3XTF32 else 1
+        passes = PASSES.get(eng.precision, 1)
+        c16 = cw.w_c16 if passes == 2 else None
         if cw.stem and eng.precision != SIMT:
-            ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes)
+            ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes, c16)
         elif cw.w_hi is not None and eng.precision != SIMT:
-            ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res)
+            ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res, c16)
         else:
             ops.conv_simt(x, n, h, w, cw.w_simt, cw.bias, y, cw.kh, cw.kw, cw.stride, lrelu, res)
 

@@ -27,7 +27,7 @@ import torch
 
 from . import ops
 from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
-from .model import SIMT, TC_3XTF32, Engine
+from .model import PASSES, SIMT, Engine
 from .ops import View, view
 
 
@@ -128,7 +128,8 @@ class TiledPlan:
         if res is not None:
             self._need(res, 0)
         N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
-        passes = 3 if eng.precision == TC_3XTF32 else 1
+        passes = PASSES.get(eng.precision, 1)
+        c16 = cw.w_c16 if passes == 2 else None
 
         def run():
             for n in range(N):
@@ -136,9 +137,9 @@ class TiledPlan:
                 yv = view(self._img(y, n), yo, cw.cout)
                 rv = view(self._img(res, n), 0, cw.cout) if res is not None else None
                 if cw.stem and eng.precision != SIMT:
-                    ops.conv_stem_tc(self._img(stem_pad, n), 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, lrelu, passes)
+                    ops.conv_stem_tc(self._img(stem_pad, n), 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, lrelu, passes, c16)
                 elif cw.w_hi is not None and eng.precision != SIMT:
-                    ops.conv_tc(xv, 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, cw.kh, cw.kw, lrelu, passes, rv)
+                    ops.conv_tc(xv, 1, hh, ww, cw.w_hi, cw.w_lo, cw.bias, yv, cw.kh, cw.kw, lrelu, passes, rv, c16)
                 else:
                     ops.conv_simt(xv, 1, hh, ww, cw.w_simt, cw.bias, yv, cw.kh, cw.kw, 1, lrelu, rv)
         v = x.valid - r

@@ -18,7 +18,7 @@ from pivlfn import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 CASES = ["piv_b2_64x96", "piv_b1_128x128", "hui_b1_64x128", "piv2_b1_64x64", "hui2_b1_64x64"]
-TOL = {"simt": (1e-2, 1e-3), "3xtf32": (1e-2, 1e-3)}          # absolute, px
+TOL = {"simt": (1e-2, 1e-3), "3xtf32": (1e-2, 1e-3), "tf32c": (1e-2, 1e-3)}          # absolute, px
 TOL_TF32_REL = (3e-2, 5e-3)                                     # relative to |flow|max of the case
 
 
@@ -49,7 +49,7 @@ def _load(golden_dir, name):
     return d, model, sd, a, b
 
 
-@pytest.mark.parametrize("precision", ["simt", "3xtf32", "tf32"])
+@pytest.mark.parametrize("precision", ["simt", "3xtf32", "tf32c", "tf32"])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_reference_golden(golden_dir, name, precision):
     d, model, sd, a, b = _load(golden_dir, name)

@@ -23,7 +23,7 @@ b = torch.randn(cout, generator=g).to(dev)
 cw = pack_conv(w, b, 1)
 x = torch.randn(B, H, H, (cin + 3) & ~3, generator=g).to(dev)
 y = torch.empty(B, H, H, (cout + 3) & ~3, device=dev)
-passes = 3 if prec == "3xtf32" else 1
+passes = {"3xtf32": 3, "tf32c": 2}.get(prec, 1)
 trace = "--trace" in sys.argv
 if trace:
     import ctypes
@@ -37,7 +37,8 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for i in range(4):
     if i == 1:
         e0.record()
-    ops.conv_tc(ops.view(x, 0, cin), B, H, H, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), k, k, True, passes)
+    ops.conv_tc(ops.view(x, 0, cin), B, H, H, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), k, k, True, passes, None,
+                cw.w_c16 if passes == 2 else None)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
