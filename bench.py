@@ -10,6 +10,8 @@ collective -> weak scaling), and the only collective is the max-over-ranks of th
   value      pairs/s, inputs already resident in HBM, timed with CUDA events on the launching stream
   e2e        pairs/s through the drop-in API (src.models net(img1, img2)) with PINNED HOST inputs:
              H2D of both image batches and D2H of the flow are inside the timed region
+  precision  tf32c (default): fp32-equivalent -- tf32 main product + bf16 low-order products on the tensor cores;
+             3xtf32: the same with all three products in tf32; tf32: one pass (reported separately); simt: fp32 FFMA
   roofline   the dominant kernel (tcgen05 3x3 implicit-GEMM convolution, the level-1 128->128 layer of conv_R)
              timed alone with CUDA events: algorithmic FLOPs / launch duration vs the measured bf16 peak
   cpu_baseline  the CPU oracle (oracle/lfn_oracle.py, a restatement of the reference's forward) on this box's
@@ -227,7 +229,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pivlfn", choices=["pivlfn", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PIVLFN_PRECISION", "3xtf32"))
+    ap.add_argument("--precision", default=os.environ.get("PIVLFN_PRECISION", "tf32c"))
     ap.add_argument("--no-extra", action="store_true", help="skip the 1024x1024 and per-kernel side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "pivlfn" else args.warmup

@@ -131,7 +131,7 @@ class Engine:
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device
-        self.precision = precision or os.environ.get("PIVLFN_PRECISION", TC_3XTF32)
+        self.precision = precision or os.environ.get("PIVLFN_PRECISION", TC_TF32C)
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.use_graph = (os.environ.get("PIVLFN_GRAPH", "1") != "0") if use_graph is None else use_graph
