@@ -435,8 +435,14 @@ struct ConvHaloArgs {
 #define DBG_ADD(var) do { if (a.dbg) var += clock64() - _t0; } while (0)
 
 // buffer slot of chunk c's activations (hi after the split) and of its low-order part
-__device__ __forceinline__ int slot_x(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf; }
-__device__ __forceinline__ int slot_l(int c, int nbuf) { return nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1; }
+// nbuf == 4: two (x, lo) pairs, plain double buffering -- the split of chunk c+1 overlaps the MMAs of chunk c;
+// nbuf == 3: rotation raw(c+1) / x(c) / lo(c) when shared memory has no room for a fourth slot (N = 128)
+__device__ __forceinline__ int slot_x(int c, int nbuf) {
+    return nbuf == 4 ? 2 * (c & 1) : (nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf);
+}
+__device__ __forceinline__ int slot_l(int c, int nbuf) {
+    return nbuf == 4 ? 2 * (c & 1) + 1 : (nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1);
+}
 
 constexpr int HALO_THREADS = 512;      // warp 0 TMA, 1-2 MMA issue, 4-7 epilogue (TMEM lane quarter = warp % 4), 8-15 split
 constexpr int SPLIT_THREADS = 256;
@@ -654,8 +660,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             long long s_w1 = 0, s_w2 = 0, s_busy = 0;
             for (int w = blockIdx.x; w < a.total; w += G) {
                 for (int c = 0; c < nchunk; ++c, ++gc) {
-                    // the lo slot of chunk gc was in use by chunk gc-1's MMAs
-                    { DBG_T0(); if (gc >= 1) mbar_wait(&chunk_done[(gc - 1) & 1], (uint32_t)(((gc - 1) >> 1) & 1)); DBG_ADD(s_w1); }
+                    // the lo slot of chunk gc was last in use by chunk gc-1's MMAs (3 slots) or chunk gc-2's (4 slots)
+                    {
+                        DBG_T0();
+                        const int dep = gc - (a.nBuf == 4 ? 2 : 1);
+                        if (dep >= 0) mbar_wait(&chunk_done[dep & 1], (uint32_t)((dep >> 1) & 1));
+                        DBG_ADD(s_w1);
+                    }
                     { DBG_T0(); mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1)); DBG_ADD(s_w2); }
                     const long long s_t0 = a.dbg ? clock64() : 0;
                     float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
@@ -669,33 +680,39 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t pair_abs = smem_u32(pl);
                         const uint32_t half_b = (uint32_t)(halo_rows * pitch * 64);
                         uint8_t* pair = reinterpret_cast<uint8_t*>(pl);
-                        for (int base = et; base < nvec; base += SB * SPLIT_THREADS) {
-                            float4 v[SB];
+                        // one thread = two adjacent 16-byte chunks of a row = 8 consecutive channels -> one 16-byte bf16 store
+                        const int npair = nvec >> 1;
+                        constexpr int SP2 = 4;
+                        for (int base = et; base < npair; base += SP2 * SPLIT_THREADS) {
+                            float4 v0[SP2], v1[SP2];
 #pragma unroll
-                            for (int j = 0; j < SB; ++j)
-                                if (base + j * SPLIT_THREADS < nvec) v[j] = pa[base + j * SPLIT_THREADS];
+                            for (int j = 0; j < SP2; ++j) {
+                                const int q = base + j * SPLIT_THREADS;
+                                if (q < npair) { v0[j] = pa[2 * q]; v1[j] = pa[2 * q + 1]; }
+                            }
 #pragma unroll
-                            for (int j = 0; j < SB; ++j) {
-                                const int idx = base + j * SPLIT_THREADS;
-                                if (idx < nvec) {
-                                    // which (pixel, channel quad) this 16-byte chunk of the 128B-swizzled fp32 tile holds
-                                    const uint32_t abs16 = (smem_u32(pa) >> 4) + (uint32_t)idx;
-                                    const uint32_t lc = (abs16 & 7u) ^ ((abs16 >> 3) & 7u);
-                                    const uint32_t pix = (uint32_t)idx >> 3;
-                                    float4 l;
-                                    l.x = v[j].x - __uint_as_float(__float_as_uint(v[j].x) & 0xFFFFE000u);
-                                    l.y = v[j].y - __uint_as_float(__float_as_uint(v[j].y) & 0xFFFFE000u);
-                                    l.z = v[j].z - __uint_as_float(__float_as_uint(v[j].z) & 0xFFFFE000u);
-                                    l.w = v[j].w - __uint_as_float(__float_as_uint(v[j].w) & 0xFFFFE000u);
-                                    const uint32_t off = pix * 64u + lc * 8u;
+                            for (int j = 0; j < SP2; ++j) {
+                                const int q = base + j * SPLIT_THREADS;
+                                if (q < npair) {
+                                    const uint32_t abs16 = (smem_u32(pa) >> 4) + (uint32_t)(2 * q);
+                                    const uint32_t lc0 = (abs16 & 7u) ^ ((abs16 >> 3) & 7u);   // logical chunk of v0 (v1: lc0 ^ 1)
+                                    const uint32_t pix = (uint32_t)q >> 2;
+                                    const float4 a0 = (lc0 & 1u) ? v1[j] : v0[j];             // channels 8L .. 8L+3
+                                    const float4 a1 = (lc0 & 1u) ? v0[j] : v1[j];             // channels 8L+4 .. 8L+7
+                                    uint4 h, l;
+                                    h.x = pack_bf16(a0.x, a0.y); h.y = pack_bf16(a0.z, a0.w);
+                                    h.z = pack_bf16(a1.x, a1.y); h.w = pack_bf16(a1.z, a1.w);
+#define PIVLFN_LO(f) ((f) - __uint_as_float(__float_as_uint(f) & 0xFFFFE000u))
+                                    l.x = pack_bf16(PIVLFN_LO(a0.x), PIVLFN_LO(a0.y)); l.y = pack_bf16(PIVLFN_LO(a0.z), PIVLFN_LO(a0.w));
+                                    l.z = pack_bf16(PIVLFN_LO(a1.x), PIVLFN_LO(a1.y)); l.w = pack_bf16(PIVLFN_LO(a1.z), PIVLFN_LO(a1.w));
+#undef PIVLFN_LO
+                                    const uint32_t off = pix * 64u + (lc0 >> 1) * 16u;
                                     uint32_t ad = pair_abs + off;
                                     ad ^= ((ad >> 7) & 3u) << 4;
-                                    *reinterpret_cast<uint2*>(pair + (ad - pair_abs)) =
-                                        make_uint2(pack_bf16(v[j].x, v[j].y), pack_bf16(v[j].z, v[j].w));
+                                    *reinterpret_cast<uint4*>(pair + (ad - pair_abs)) = h;
                                     uint32_t ad2 = pair_abs + half_b + off;
                                     ad2 ^= ((ad2 >> 7) & 3u) << 4;
-                                    *reinterpret_cast<uint2*>(pair + (ad2 - pair_abs)) =
-                                        make_uint2(pack_bf16(l.x, l.y), pack_bf16(l.z, l.w));
+                                    *reinterpret_cast<uint4*>(pair + (ad2 - pair_abs)) = l;
                                 }
                             }
                         }
@@ -943,7 +960,10 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         if (NT == 3) continue;
         const int halo_rows = HT_H * NT + h.KH - 1;
         const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
-        const int nBuf = passes >= 2 ? 3 : 2;
+        int nBuf = passes >= 2 ? 3 : 2;
+        // a fourth slot (double-buffered (x, lo) pairs: no split bubble between chunks) when it still leaves a 3-deep
+        // weight ring
+        if (passes >= 2 && (HALO_SMEM_BUDGET - 4 * slot) / b_stage >= 3) nBuf = 4;
         int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
         if (nB > MAX_STAGES) nB = MAX_STAGES;
         const int need = passes >= 2 ? 2 : 3;
