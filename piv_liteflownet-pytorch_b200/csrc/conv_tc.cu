@@ -444,7 +444,7 @@ __device__ __forceinline__ int slot_l(int c, int nbuf) {
     return nbuf == 4 ? 2 * (c & 1) + 1 : (nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1);
 }
 
-constexpr int HALO_THREADS = 512;      // warp 0 TMA, 1-2 MMA issue, 4-7 epilogue (TMEM lane quarter = warp % 4), 8-15 split
+constexpr int HALO_THREADS = 640;      // warp 0 TMA, 1-2 MMA issue, 4-7 + 16-19 epilogue (TMEM lane quarter = warp % 4), 8-15 split
 constexpr int SPLIT_THREADS = 256;
 
 // Persistent: one CTA per SM loops over work items; all roles walk the same global (item, chunk, tap) sequence so
@@ -487,7 +487,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t n_iss = a.NT >= 2 ? 2u : 1u;           // MMA-issuing threads, each commits to the barriers
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], 1); mbar_init(&a_ready[i], SPLIT_THREADS / 32); mbar_init(&chunk_done[i], n_iss);
-            mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 4);
+            mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 8);
         }
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
         fence_barrier_init();
@@ -651,7 +651,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 8 && warp < 16) {
         // ================================ 3xTF32 split warps ============================
         if (SPLIT) {
             const int et = threadIdx.x - 8 * 32;
@@ -754,6 +754,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
     } else if (warp >= 4) {
         // ================================ epilogue warps ================================
+        // two warps per TMEM lane quarter (warps 4-7: first half of the output channels, 16-19: second half)
+        const int egrp = warp >= 16 ? 1 : 0;
+        const bool halves = (a.CoutP % 32) == 0;                        // both halves must be multiples of 16 columns
+        const int chalf = halves ? a.CoutP / 2 : a.CoutP;
+        const int cbeg = halves ? egrp * chalf : 0;
+        const int cend = halves ? cbeg + chalf : (egrp == 0 ? a.CoutP : 0);
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int wl = 0;
@@ -777,9 +783,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 // otherwise two consecutive column groups
                 const bool dual = (SPLIT && a.corr);
                 const int cstep = dual ? 16 : 32;
-                for (int c0 = 0; c0 < a.CoutP; c0 += cstep) {
+                for (int c0 = cbeg; c0 < cend; c0 += cstep) {
                     uint32_t v[16], u[16];
-                    const bool second = dual || (c0 + 16 < a.CoutP);
+                    const bool second = dual || (c0 + 16 < cend);
                     tmem_ld16_nowait(trow + (uint32_t)(i * a.CoutP + c0), v);
                     if (second)
                         tmem_ld16_nowait(trow + (uint32_t)(dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16), u);
