@@ -66,7 +66,7 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
                      int KH, int KW, int stride, int lrelu,
                      const float* res, int res_ld, void* stream);
 
-/* Same operator for every stride-1 convolution (KH, KW odd, <= 7) on the tcgen05 tensor cores: implicit GEMM,
+/* Same operator for every convolution with odd KH, KW <= 7 and stride 1 or 2 on the tcgen05 tensor cores: implicit GEMM,
  * TMA-fed (zero padding = TMA out-of-bounds fill), TMEM accumulators, fused bias + LeakyReLU (+ residual).
  * w_hi / w_lo: [CoutP, KH*KW, CinP] (CoutP = Cout rounded up to 16, CinP = Cin rounded up to 32, zero padded):
  * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32), 3 (error-compensated 3xTF32 ~ fp32) or
@@ -75,7 +75,7 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
  * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
 int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
-                   float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                   float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                    const float* res, int res_ld, int passes, void* stream);
 
 /* NetC.conv1 (src/models.py:70-73): 7x7, 3 -> 32, stride 1, on the tensor cores.  img_pad: [N,H,W+8,4], the

@@ -191,6 +191,8 @@ struct ConvTcArgs {
     int bw, bh, bn;          // spatial / batch extent of the 128-pixel tile (bw * bh * bn == 128)
     int tiles_x, tiles_y;
     int lrelu, stages, vec_store;
+    int sx;                  // convolution stride (1 or 2): H, W above are the OUTPUT size, the tensor map walks the
+                             // input with element stride sx so that a tap's box holds exactly the sampled pixels
 };
 
 constexpr int MAX_STAGES = 8;
@@ -263,7 +265,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint8_t* sA = st;
                 uint8_t* sBhi = st + (PASSES == 3 ? 2 : 1) * A_BYTES;
                 mbar_expect_tx(&full_bar[stage], A_BYTES + (PASSES == 3 ? 2 : 1) * b_bytes);
-                tma_load_4d(sA, &tmA, &full_bar[stage], ch * KC, x0 + dx, y0 + dy, n0);
+                tma_load_4d(sA, &tmA, &full_bar[stage], ch * KC, x0 * a.sx + dx, y0 * a.sx + dy, n0);
                 tma_load_3d(sBhi, &tmBhi, &full_bar[stage], ch * KC, tap, 0);
                 if (PASSES == 3) tma_load_3d(sBhi + b_bytes, &tmBlo, &full_bar[stage], ch * KC, tap, 0);
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1016,13 +1018,14 @@ extern "C" void pivlfn_debug_set_conv_trace(long long* dev_buf) { g_conv_tc_dbg 
 
 extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                               const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
-                              float* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                              float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                               const float* res, int res_ld, int passes, void* stream) {
     if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
     if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
     if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
     if (passes == 2 && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
     if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
     if (Cout > 128) return PIVLFN_EUNSUPPORTED;
     if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 3) || y_ld < Cout) return PIVLFN_EINVAL;
     if (res && res_ld < Cout) return PIVLFN_EINVAL;
@@ -1047,7 +1050,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
     }
 
-    if (halo_env().use_halo && W >= HT_W) {
+    if (halo_env().use_halo && W >= HT_W && stride == 1) {
         // ---- halo-resident persistent path --------------------------------------------------------------------
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
@@ -1069,10 +1072,12 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     }
     if (passes == 2) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
 
+    // ---- per-tap kernel: tiny levels, and stride-2 convolutions (the tap's box is fetched with TMA element stride 2) ----
     ConvTcArgs a;
     a.bias = bias; a.res = res; a.res_ld = res_ld; a.y = y; a.y_ld = y_ld;
-    a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.CoutP = CoutP; a.lrelu = lrelu;
-    a.KW = KW; a.ntaps = KH * KW; a.ox = -(KW / 2); a.oy = -(KH / 2);
+    const int Ho = (H + 2 * (KH / 2) - KH) / stride + 1, Wo = (W + 2 * (KW / 2) - KW) / stride + 1;
+    a.N = N; a.H = Ho; a.W = Wo; a.Cin = Cin; a.Cout = Cout; a.CoutP = CoutP; a.lrelu = lrelu;
+    a.KW = KW; a.ntaps = KH * KW; a.ox = -(KW / 2); a.oy = -(KH / 2); a.sx = stride;
     a.vec_store = vec_store;
     choose_tile(a);
     const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
@@ -1080,8 +1085,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     {
         cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
-        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bn};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(a.bw * stride), (cuuint32_t)(a.bh * stride), (cuuint32_t)a.bn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
         CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1139,7 +1144,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
     ConvTcArgs a;
     a.bias = bias; a.res = nullptr; a.res_ld = 0; a.y = y; a.y_ld = y_ld;
     a.N = N; a.H = H; a.W = W; a.Cin = 32; a.Cout = 32; a.CoutP = 32; a.lrelu = lrelu;
-    a.KW = 1; a.ntaps = 7; a.ox = 1; a.oy = -3; a.vec_store = 1;
+    a.KW = 1; a.ntaps = 7; a.ox = 1; a.oy = -3; a.vec_store = 1; a.sx = 1;
     choose_tile(a);
     const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
     if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;

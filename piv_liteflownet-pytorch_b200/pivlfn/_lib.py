@@ -18,7 +18,7 @@ PROTOTYPES = {
     "pivlfn_prep_images": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(_f), _p]),
     "pivlfn_avgpool2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "pivlfn_conv_simt": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
-    "pivlfn_conv_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
+    "pivlfn_conv_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pivlfn_conv_stem_tc": (_i, [_p, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "pivlfn_deconv4x4s2_dw": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pivlfn_warp_nhwc": (_i, [_p, _i, _p, _f, _p, _i, _i, _i, _i, _i, _p]),

@@ -117,8 +117,9 @@ def _split_tf32(wt: torch.Tensor):
 
 
 def tc_eligible(cin: int, cout: int, kh: int, kw: int, stride: int) -> bool:
-    """Stride-1 convolutions with at least 8 input channels run on the tensor cores (any odd kernel up to 7x7)."""
-    return stride == 1 and cout <= 128 and cin >= 8 and kh <= 7 and kw <= 7
+    """Convolutions with at least 8 input channels and at most 128 output channels run on the tensor cores (any odd
+    kernel up to 7x7, stride 1 or 2)."""
+    return stride in (1, 2) and cout <= 128 and cin >= 8 and kh <= 7 and kw <= 7
 
 
 class Engine:
@@ -274,7 +275,7 @@ class Plan:
         if cw.stem and eng.precision != SIMT:
             ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes, c16)
         elif cw.w_hi is not None and eng.precision != SIMT:
-            ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res, c16)
+            ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res, c16, cw.stride)
         else:
             ops.conv_simt(x, n, h, w, cw.w_simt, cw.bias, y, cw.kh, cw.kw, cw.stride, lrelu, res)
 

@@ -108,13 +108,14 @@ def conv_simt(x: View, N, H, W, w, bias, y: View, KH, KW, stride, lrelu, res: Op
                                     _stream()), "conv_simt")
 
 
-def conv_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, KH, KW, lrelu, passes, res: Optional[View] = None, w_c16=None):
+def conv_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, KH, KW, lrelu, passes, res: Optional[View] = None, w_c16=None,
+            stride: int = 1):
     lib = _lib.load()
     _lib.check(lib.pivlfn_conv_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),
                                   w_lo.data_ptr() if w_lo is not None else None,
                                   w_c16.data_ptr() if w_c16 is not None else None,
                                   bias.data_ptr() if bias is not None else None,
-                                  y.ptr, y.ld, y.C, KH, KW, int(lrelu),
+                                  y.ptr, y.ld, y.C, KH, KW, int(stride), int(lrelu),
                                   res.ptr if res is not None else None, res.ld if res is not None else 0,
                                   int(passes), _stream()), "conv_tc")
 

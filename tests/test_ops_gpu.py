@@ -174,6 +174,23 @@ def test_conv_tc_vs_torch(case, passes, tol):
     assert y[..., cout:].abs().max().item() == 0          # never writes outside its channel slice
 
 
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("case", [(32, 32, 16, 24), (32, 64, 64, 64), (64, 96, 17, 31), (96, 128, 8, 8), (32, 32, 256, 128)])
+def test_conv_tc_stride2_vs_torch(case, passes, tol):
+    """3x3 stride-2 convolutions of NetC (src/models.py:77-106): every tap's box is fetched with TMA element stride 2."""
+    cin, cout, H, W = case
+    w, b = _rand(cout, cin, 3, 3, seed=1, scale=1.0 / math.sqrt(cin * 9)), _rand(cout, seed=2)
+    x = _rand(2, cin, H, W, seed=3)
+    ref = O.lrelu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1).float())
+    cw = pack_conv(w.to(DEV), b.to(DEV), 2)
+    assert cw.w_hi is not None
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    y = torch.zeros(2, Ho, Wo, cout, device=DEV)
+    ops.conv_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, cw.w_hi, cw.w_lo, cw.bias, ops.view(y), 3, 3, True, passes, None,
+                cw.w_c16 if passes == 2 else None, stride=2)
+    assert (_nchw(y, cout) - ref).abs().max().item() <= tol
+
+
 @pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 2e-2)])
 @pytest.mark.parametrize("hw", [(16, 16), (40, 56), (8, 8)])
 def test_conv_stem_tc_vs_torch(hw, passes, tol):
