@@ -15,10 +15,12 @@ B = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 H = int(sys.argv[3]) if len(sys.argv) > 3 else 256
 cin = int(sys.argv[4]) if len(sys.argv) > 4 else 128
 cout = int(sys.argv[5]) if len(sys.argv) > 5 else 128
-k = int(sys.argv[6]) if len(sys.argv) > 6 else 3
+kspec = sys.argv[6] if len(sys.argv) > 6 and not sys.argv[6].startswith("--") else "3"
+kh, kw = (int(v) for v in kspec.split("x")) if "x" in kspec else (int(kspec), int(kspec))
+k = kh
 dev = torch.device("cuda", 0)
 g = torch.Generator(device="cpu").manual_seed(0)
-w = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).to(dev)
+w = (torch.randn(cout, cin, kh, kw, generator=g) / (cin * kh * kw) ** 0.5).to(dev)
 b = torch.randn(cout, generator=g).to(dev)
 cw = pack_conv(w, b, 1)
 x = torch.randn(B, H, H, (cin + 3) & ~3, generator=g).to(dev)
@@ -37,12 +39,12 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 for i in range(4):
     if i == 1:
         e0.record()
-    ops.conv_tc(ops.view(x, 0, cin), B, H, H, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), k, k, True, passes, None,
+    ops.conv_tc(ops.view(x, 0, cin), B, H, H, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), kh, kw, True, passes, None,
                 cw.w_c16 if passes == 2 else None)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3
-print(f"{prec} conv {cin}->{cout} {k}x{k} @ {B}x{H}x{H}: {ms:.3f} ms, {2.0 * B * H * H * cin * cout * k * k / ms / 1e9:.1f} TFLOP/s")
+print(f"{prec} conv {cin}->{cout} {kh}x{kw} @ {B}x{H}x{H}: {ms:.3f} ms, {2.0 * B * H * H * cin * cout * kh * kw / ms / 1e9:.1f} TFLOP/s")
 if trace:
     torch.cuda.synchronize()
     t = dbg.cpu().tolist()
