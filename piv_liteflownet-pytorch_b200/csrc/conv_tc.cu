@@ -426,6 +426,8 @@ struct ConvHaloArgs {
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
                              // B200, kept as an experiment switch
+    int cout_st;             // channels the epilogue may store: Cout, or Cout rounded up to 4 when the output rows are
+                             // exactly that wide (dense buffer with its own padding) so that float4 stores can be used
     int x_shift;             // x coordinate of tap column 0 relative to the output pixel (normally -(KW/2); +1 for the stem)
     int split_trunc;         // 3xTF32 split: 1 (default) = leave a in place (measured: the tensor core reads only the top
                              // 19 bits of an fp32 operand, i.e. truncates) and write lo = a - trunc_tf32(a);
@@ -808,15 +810,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 if (a.lrelu) t = lrelu_f(t);
                                 o[j] = t;
                             }
-                            if (a.vec_store == 2 && cb + 16 <= a.Cout && !rsd) {
+                            if (a.vec_store == 2 && cb + 16 <= a.cout_st && !rsd) {
                                 st_global_v8(dst + cb, o);
                                 st_global_v8(dst + cb + 8, o + 8);
-                            } else if (a.vec_store && cb + 16 <= a.Cout) {
+                            } else if (a.vec_store) {
 #pragma unroll
                                 for (int j = 0; j < 16; j += 4) {
-                                    float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-                                    if (rsd) { w4.x += rsd[cb + j]; w4.y += rsd[cb + j + 1]; w4.z += rsd[cb + j + 2]; w4.w += rsd[cb + j + 3]; }
-                                    *reinterpret_cast<float4*>(dst + cb + j) = w4;
+                                    if (cb + j + 4 <= a.cout_st) {
+                                        float4 w4 = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+                                        if (rsd) { w4.x += rsd[cb + j]; w4.y += rsd[cb + j + 1]; w4.z += rsd[cb + j + 2]; w4.w += rsd[cb + j + 3]; }
+                                        *reinterpret_cast<float4*>(dst + cb + j) = w4;
+                                    } else {
+#pragma unroll
+                                        for (int jj = j; jj < j + 4; ++jj)
+                                            if (cb + jj < a.Cout) dst[cb + jj] = o[jj] + (rsd ? rsd[cb + jj] : 0.f);
+                                    }
                                 }
                             } else {
 #pragma unroll
@@ -1035,8 +1043,11 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
 
     const int CoutP = (Cout + 15) & ~15;
     const int CinP = (Cin + KC - 1) / KC * KC;
-    // 2: 32-byte aligned rows -> 256-bit stores; 1: 16-byte aligned -> 128-bit stores; 0: scalar stores
-    const int vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7) && !(Cout & 7)) ? 2 : ((!((uintptr_t)y & 15) && !(y_ld & 3) && !(Cout & 3)) ? 1 : 0);
+    // cout_st: channels the epilogue may store (Cout rounded up to 4 when the rows are exactly that wide and no residual
+    // is added).  vec_store 2: 32-byte aligned rows -> 256-bit stores; 1: 16-byte aligned -> 128-bit stores; 0: scalar
+    const int cout_st = (!res && y_ld == ((Cout + 3) & ~3)) ? y_ld : Cout;
+    const int vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7) && !(cout_st & 7)) ? 2
+                        : ((!((uintptr_t)y & 15) && !(y_ld & 3) && cout_st >= 4) ? 1 : 0);
     cudaStream_t st = (cudaStream_t)stream;
     CUtensorMap tmA, tmBhi, tmBlo;
     if (encode_weights(enc, &tmBhi, w_hi, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
@@ -1055,7 +1066,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         ConvHaloArgs h;
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
-        h.lrelu = lrelu; h.vec_store = vec_store; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
+        h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1078,7 +1089,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     const int Ho = (H + 2 * (KH / 2) - KH) / stride + 1, Wo = (W + 2 * (KW / 2) - KW) / stride + 1;
     a.N = N; a.H = Ho; a.W = Wo; a.Cin = Cin; a.Cout = Cout; a.CoutP = CoutP; a.lrelu = lrelu;
     a.KW = KW; a.ntaps = KH * KW; a.ox = -(KW / 2); a.oy = -(KH / 2); a.sx = stride;
-    a.vec_store = vec_store;
+    a.vec_store = (vec_store && !(Cout & 3)) ? 1 : 0;
     choose_tile(a);
     const long long grid = (long long)a.tiles_x * a.tiles_y * cdiv(N, a.bn);
     if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
@@ -1116,7 +1127,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         ConvHaloArgs h;
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
-        h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
+        h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
