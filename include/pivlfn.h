@@ -78,6 +78,18 @@ int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                    const float* res, int res_ld, int passes, void* stream);
 
+/* Flow heads, the last layer of conv_M / conv_S (src/models.py:161,205: KxK, Cin -> 2), restated in two steps so that
+ * the tensor cores see N = 2*K*K useful columns instead of 2:
+ *   pivlfn_conv1x1_pairs_tc:  D[pixel, tap*2+co] = sum_c x[pixel,c] * w[co,c,tap]  (1x1 convolution, no bias / activation)
+ *                             stored as tap planes  planes[tap][pixel][2]
+ *   pivlfn_flow_head_sum:     out[p,co] = bias[co] + res[p,co] + sum_tap planes[tap][p + offset(tap)][co], zero outside.
+ * w_hi / w_lo / w_c16: packed like pivlfn_conv_tc for a 1x1 convolution with Cout = 2*npair rows (row = tap*2 + co). */
+int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
+                            const float* w_hi, const float* w_lo, const void* w_c16,
+                            float* planes, int npair, int passes, void* stream);
+int pivlfn_flow_head_sum(const float* planes, int K, const float* bias, const float* res, int res_ld,
+                         float* out, int out_ld, int N, int H, int W, void* stream);
+
 /* NetC.conv1 (src/models.py:70-73): 7x7, 3 -> 32, stride 1, on the tensor cores.  img_pad: [N,H,W+8,4], the
  * zero-bordered NHWC4 image written by pivlfn_prep_images (pixel x at column x+4).  One GEMM-K row of 32 floats
  * per filter row = the 8 pixels x-3..x+4, fetched through an overlapping-window tensor map.

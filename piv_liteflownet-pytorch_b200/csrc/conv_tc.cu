@@ -428,6 +428,8 @@ struct ConvHaloArgs {
                              // B200, kept as an experiment switch
     int cout_st;             // channels the epilogue may store: Cout, or Cout rounded up to 4 when the output rows are
                              // exactly that wide (dense buffer with its own padding) so that float4 stores can be used
+    long long planar;        // 0: NHWC rows; else the output is stored as channel-PAIR planes, plane p = channels (2p, 2p+1)
+                             // of all pixels, [pair][pixel][2] with this many floats per plane (flow-head tap planes)
     int x_shift;             // x coordinate of tap column 0 relative to the output pixel (normally -(KW/2); +1 for the stem)
     int split_trunc;         // 3xTF32 split: 1 (default) = leave a in place (measured: the tensor core reads only the top
                              // 19 bits of an fp32 operand, i.e. truncates) and write lo = a - trunc_tf32(a);
@@ -810,7 +812,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 if (a.lrelu) t = lrelu_f(t);
                                 o[j] = t;
                             }
-                            if (a.vec_store == 2 && cb + 16 <= a.cout_st && !rsd) {
+                            if (a.planar) {
+#pragma unroll
+                                for (int j = 0; j < 16; j += 2)
+                                    if (cb + j < a.Cout)
+                                        *reinterpret_cast<float2*>(a.y + (size_t)((cb + j) >> 1) * a.planar + pix * 2) =
+                                            make_float2(o[j], o[j + 1]);
+                            } else if (a.vec_store == 2 && cb + 16 <= a.cout_st && !rsd) {
                                 st_global_v8(dst + cb, o);
                                 st_global_v8(dst + cb + 8, o + 8);
                             } else if (a.vec_store) {
@@ -1067,6 +1075,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.bias = bias; h.res = res; h.res_ld = res_ld; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
+        h.planar = 0;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1127,7 +1136,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         ConvHaloArgs h;
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
-        h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1;
+        h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1; h.planar = 0;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1177,4 +1186,50 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
     else tmBlo = tmBhi;
     cudaStream_t st = (cudaStream_t)stream;
     return passes == 3 ? launch<3>(tmA, tmBhi, tmBlo, a, (int)grid, st) : launch<1>(tmA, tmBhi, tmBlo, a, (int)grid, st);
+}
+
+// Flow heads (last layer of conv_M / conv_S, src/models.py:161,205: KxK, 32 -> 2, K = 7 or 5) restated as
+//   D[pixel, tap*2 + co] = sum_c x[pixel, c] * w[co, c, tap]          (a 1x1 convolution to 2*K*K channels: this call)
+//   flow[p, co] = bias[co] + res[p, co] + sum_tap D[p + offset(tap), tap*2 + co]        (pivlfn_flow_head_sum)
+// The direct KxK form needs K*K * Cin/8 tensor-core instructions per 128 pixels with only 2 of N = 16 columns useful
+// (and tcgen05.mma has a ~39-cycle floor per instruction); this form needs Cin/8 instructions at N = 112.
+// planes: [K*K][N*H*W][2] fp32, written as channel-pair planes so that the gather of the second step is coalesced.
+extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
+                                       const float* w_hi, const float* w_lo, const void* w_c16,
+                                       float* planes, int npair, int passes, void* stream) {
+    if (!x || !w_hi || !planes || N <= 0 || H <= 0 || W < HT_W || Cin <= 0 || npair <= 0 || 2 * npair > 128) return PIVLFN_EINVAL;
+    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
+    if (passes == 2 && !w_c16) return PIVLFN_EINVAL;
+    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)planes & 7)) return PIVLFN_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+    const int Cout = 2 * npair, CoutP = (Cout + 15) & ~15, CinP = (Cin + KC - 1) / KC * KC;
+    CUtensorMap tmA, tmBhi, tmBlo;
+    if (encode_weights(enc, &tmBhi, w_hi, CinP, 1, CoutP)) return PIVLFN_EINVAL;
+    if (passes >= 2) { if (encode_weights(enc, &tmBlo, w_lo, CinP, 1, CoutP)) return PIVLFN_EINVAL; }
+    else tmBlo = tmBhi;
+    CUtensorMap tmB16 = tmBhi, tmBlo16 = tmBhi;
+    if (passes == 2) {
+        const size_t half = (size_t)CoutP * CinP * 2;
+        if (encode_weights_bf16(enc, &tmB16, w_c16, CinP, 1, CoutP)) return PIVLFN_EINVAL;
+        if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, 1, CoutP)) return PIVLFN_EINVAL;
+    }
+    ConvHaloArgs h;
+    h.bias = nullptr; h.res = nullptr; h.res_ld = 0; h.y = planes; h.y_ld = 0;
+    h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = 1; h.KW = 1;
+    h.lrelu = 0; h.vec_store = 0; h.cout_st = Cout; h.dbg = g_conv_tc_dbg; h.x_shift = 0;
+    h.planar = (long long)N * H * W * 2;
+    int halo_rows = 0;
+    const int smem = halo_configure(h, passes, &halo_rows);
+    if (smem <= 0) return PIVLFN_EUNSUPPORTED;
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)HT_W, (cuuint32_t)halo_rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }

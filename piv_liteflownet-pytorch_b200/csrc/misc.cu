@@ -436,6 +436,38 @@ __global__ void resize_bilinear_nchw_kernel(const float* __restrict__ in, float*
     }
 }
 
+// ---- second half of a restated flow head (see pivlfn_conv1x1_pairs_tc): gather-sum of the K*K tap planes --------------
+template <int K>
+__global__ void __launch_bounds__(256)
+flow_head_sum_kernel(const float2* __restrict__ planes, long long plane_pix, const float* __restrict__ bias,
+                     const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld, int N, int H, int W) {
+    constexpr int P = K / 2;
+    const long long HW = (long long)H * W, total = (long long)N * HW;
+    const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+         p += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(p % W), y = (int)((p / W) % H);
+        float su = 0.f, sv = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+            const int yy = y + ky - P;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int xx = x + kx - P;
+                if (xx >= 0 && xx < W) {
+                    const float2 d = __ldg(planes + (long long)(ky * K + kx) * plane_pix + p + (long long)(ky - P) * W + (kx - P));
+                    su += d.x; sv += d.y;
+                }
+            }
+        }
+        su += b0; sv += b1;
+        if (res) { su += __ldg(res + p * res_ld); sv += __ldg(res + p * res_ld + 1); }
+        out[p * out_ld] = su;
+        out[p * out_ld + 1] = sv;
+    }
+}
+
 inline int grid_for(long long total, int block) {
     long long g = (total + block - 1) / block;
     const long long cap = 148LL * 32;       // a few waves of the 148 SMs, grid-stride beyond
@@ -554,6 +586,24 @@ extern "C" int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, 
     const long long total = (long long)NC * Ho * Wo;
     resize_bilinear_nchw_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(in, out, NC, H, W, Ho, Wo,
                                                                                          mul_even, mul_odd);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+
+extern "C" int pivlfn_flow_head_sum(const float* planes, int K, const float* bias, const float* res, int res_ld,
+                                    float* out, int out_ld, int N, int H, int W, void* stream) {
+    if (!planes || !out || N <= 0 || H <= 0 || W <= 0 || out_ld < 2 || (res && res_ld < 2)) return PIVLFN_EINVAL;
+    if ((uintptr_t)planes & 7) return PIVLFN_EINVAL;
+    const long long total = (long long)N * H * W;
+    const float2* pl = reinterpret_cast<const float2*>(planes);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = grid_for(total, 256);
+    switch (K) {
+        case 3: flow_head_sum_kernel<3><<<g, 256, 0, st>>>(pl, total, bias, res, res_ld, out, out_ld, N, H, W); break;
+        case 5: flow_head_sum_kernel<5><<<g, 256, 0, st>>>(pl, total, bias, res, res_ld, out, out_ld, N, H, W); break;
+        case 7: flow_head_sum_kernel<7><<<g, 256, 0, st>>>(pl, total, bias, res, res_ld, out, out_ld, N, H, W); break;
+        default: return PIVLFN_EINVAL;
+    }
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }

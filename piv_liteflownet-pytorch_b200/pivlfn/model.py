@@ -172,6 +172,12 @@ class Engine:
             for j in range(nh + 1):
                 conv(f"NetE_M.{i}.conv_M.{2 * j}")
                 conv(f"NetE_S.{i}.conv_S.{2 * j}")
+            if use_tc and KSIZE[lv] >= 5:
+                # flow heads restated as a 1x1 convolution to 2*K*K channels (row = tap*2 + co) + a gather-sum
+                for key in (f"NetE_M.{i}.conv_M.{2 * nh}", f"NetE_S.{i}.conv_S.{2 * nh}"):
+                    w = g(key + ".weight")                                   # [2, cin, K, K]
+                    w2 = w.permute(2, 3, 0, 1).reshape(-1, w.shape[1], 1, 1)   # [(K*K*2), cin, 1, 1]
+                    self.w[key + "#pairs"] = pack_conv(w2, None, 1, tc=True)
             for nm in ("upConv_M", "upCorr_M"):
                 key = f"NetE_M.{i}.{nm}.weight"
                 if key in sd:
@@ -255,6 +261,8 @@ class Plan:
                 partial=E(B, ops.flow_mean_parts(), 2),
                 dist=E(B, h, w, _r4(DIST_CH[l])), dist0=E(B, h, w, _r4(DIST_CH[l])) if l < 5 else None,
             )
+            d["planes"] = (E(KSIZE[l] * KSIZE[l], B * h * w, 2)
+                           if (eng.precision != SIMT and KSIZE[l] >= 5 and w >= 8) else None)
             widths = sorted(set(cfg.head) | set(CONV_R))
             d["t"] = {c: [E(B, h, w, c), E(B, h, w, c)] for c in widths}   # ping-pong per width
             self.lv[l] = d
@@ -292,7 +300,16 @@ class Plan:
             y = view(t[c][k])
             self._conv(f"{prefix}.{j}", x, B, h, w, y)
             x = y
-        self._conv(f"{prefix}.{idxs[-1]}", x, B, h, w, out, lrelu=False, res=res)
+        key = f"{prefix}.{idxs[-1]}"
+        pk = self.eng.w.get(key + "#pairs")
+        if pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
+            K = KSIZE[l]
+            passes = PASSES.get(self.eng.precision, 1)
+            ops.conv1x1_pairs_tc(x, B, h, w, pk.w_hi, pk.w_lo, pk.w_c16 if passes == 2 else None, self.lv[l]["planes"],
+                                 K * K, passes)
+            ops.flow_head_sum(self.lv[l]["planes"], K, self.eng.w[key].bias, res, out, B, h, w)
+        else:
+            self._conv(key, x, B, h, w, out, lrelu=False, res=res)
 
     def launch_all(self):
         """Enqueue the whole forward on the current stream (inputs already in self.in1 / self.in2)."""

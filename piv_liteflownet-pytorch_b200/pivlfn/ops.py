@@ -120,6 +120,21 @@ def conv_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, KH, KW, lrelu, passes, 
                                   int(passes), _stream()), "conv_tc")
 
 
+def conv1x1_pairs_tc(x: View, N, H, W, w_hi, w_lo, w_c16, planes: torch.Tensor, npair: int, passes: int):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_conv1x1_pairs_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),
+                                           w_lo.data_ptr() if w_lo is not None else None,
+                                           w_c16.data_ptr() if w_c16 is not None else None,
+                                           planes.data_ptr(), int(npair), int(passes), _stream()), "conv1x1_pairs_tc")
+
+
+def flow_head_sum(planes: torch.Tensor, K: int, bias, res: Optional[View], out: View, N, H, W):
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_flow_head_sum(planes.data_ptr(), int(K), bias.data_ptr() if bias is not None else None,
+                                        res.ptr if res is not None else None, res.ld if res is not None else 0,
+                                        out.ptr, out.ld, N, H, W, _stream()), "flow_head_sum")
+
+
 def conv_stem_tc(img_pad: torch.Tensor, N, H, W, w_hi, w_lo, bias, y: View, lrelu, passes, w_c16=None):
     lib = _lib.load()
     _lib.check(lib.pivlfn_conv_stem_tc(img_pad.data_ptr(), N, H, W, w_hi.data_ptr(),

@@ -296,3 +296,21 @@ def test_copy_nhwc_slices():
     dst2 = torch.zeros(1, 3, 5, 12, device=DEV)
     ops.copy(ops.view(src, 2, 2), ops.view(dst2, 6, 2), 15)
     assert torch.equal(dst2[..., 6:8], src[..., 2:4])
+
+
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("K,cin,H,W", [(7, 32, 24, 40), (5, 32, 16, 16), (7, 32, 64, 8)])
+def test_flow_head_pairs_plus_gather_vs_torch(K, cin, H, W, passes, tol):
+    """Flow head restated as a 1x1 convolution to 2*K*K channels (tap planes) + gather-sum: equals the KxK convolution."""
+    w, b = _rand(2, cin, K, K, seed=1, scale=1.0 / math.sqrt(cin * K * K)), _rand(2, seed=2)
+    x = _rand(2, cin, H, W, seed=3)
+    res = _rand(2, 2, H, W, seed=4)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=K // 2).float() + res
+    w2 = w.permute(2, 3, 0, 1).reshape(-1, cin, 1, 1)
+    pk = pack_conv(w2.to(DEV), None, 1)
+    planes = torch.full((K * K, 2 * H * W, 2), float("nan"), device=DEV)
+    ops.conv1x1_pairs_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, pk.w_hi, pk.w_lo, pk.w_c16 if passes == 2 else None, planes,
+                         K * K, passes)
+    out = torch.zeros(2, H, W, 2, device=DEV)
+    ops.flow_head_sum(planes, K, b.to(DEV), ops.view(_nhwc(res), 0, 2), ops.view(out), 2, H, W)
+    assert (_nchw(out, 2) - ref).abs().max().item() <= tol
