@@ -255,8 +255,8 @@ def forward(sd: Dict[str, torch.Tensor], img1: torch.Tensor, img2: torch.Tensor,
     Does NOT mutate its inputs (the reference subtracts the mean in place, :321-323)."""
     _, start, lowest, mean = MODEL_CFG[model]
     sf = scalefactor(start)
-    m1 = torch.tensor(mean[:3], dtype=img1.dtype).view(1, 3, 1, 1)
-    m2 = torch.tensor(mean[3:], dtype=img1.dtype).view(1, 3, 1, 1)
+    m1 = torch.tensor(mean[:3], dtype=img1.dtype, device=img1.device).view(1, 3, 1, 1)
+    m2 = torch.tensor(mean[3:], dtype=img1.dtype, device=img1.device).view(1, 3, 1, 1)
     img1 = img1 - m1
     img2 = img2 - m2
     feat1 = features(sd, img1)

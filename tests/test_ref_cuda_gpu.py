@@ -1,0 +1,173 @@
+"""Parity against the REFERENCE'S OWN CUDA PATH on the B200.
+
+``oracle/_ref/*.cubin`` are the reference's correlation kernels (src/correlation.py:9-104), compiled from the kernel
+strings where they lie through the reference's own ``cupy_kernel()`` templating (recipe: oracle/build_ref.py) and
+launched with the reference's geometry (oracle/ref_cuda.py).  These tests
+
+  * pin the CPU oracle's correlation restatements against the real kernels,
+  * compare this repo's ``FunctionCorrelation`` with the real kernels on the same inputs,
+  * run the whole forward the way the reference does on a GPU -- torch/cuDNN fp32 convolutions, ATen grid_sample /
+    unfold / interpolate, and the reference's correlation kernels -- and compare this repo's forward with it
+    (north_star tolerance: flow max <= 1e-2 px, mean <= 1e-3 px), and
+  * time that reference CUDA path next to this repo's at 1024x1024 (a report, not an assertion on speed).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import lfn_oracle as O
+from oracle import ref_cuda as RC
+from pivlfn import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda"
+SHAPES = RC.shapes()
+
+
+def test_ref_manifest_lists_existing_binaries():
+    """CPU check: when oracle/_ref was built, every file of the manifest exists and is an ELF cubin."""
+    m = RC.manifest()
+    if m is None:
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py needs /root/reference)")
+    assert len(m["entries"]) >= 9
+    for e in m["entries"]:
+        for f in e["files"].values():
+            with open(os.path.join(RC.REF, f), "rb") as fh:
+                assert fh.read(4) == b"\x7fELF"
+
+
+needs_ref = pytest.mark.skipif(not SHAPES, reason="oracle/_ref not built")
+
+
+def _rand(shape, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g)
+
+
+def _report(line):
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        with open(os.path.join(d, "parity_report.txt"), "a") as fh:
+            fh.write(line + "\n")
+    print(line)
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("shape", [s for s in SHAPES if s[2] * s[3] <= 128 * 128], ids=str)
+def test_correlation_vs_reference_cuda_kernels(shape):
+    from src.correlation import FunctionCorrelation
+    B, C, H, W, s = shape
+    f1, f2 = _rand((B, C, H, W), 11 * C + H), _rand((B, C, H, W), 13 * C + W)
+    ref = RC.reference_correlation(f1.to(DEV), f2.to(DEV), s)
+    # (1) the oracle's vectorised restatement vs the real kernels (different fp32 association order)
+    orc = O.correlation(f1, f2, s)
+    assert ref.shape == orc.shape
+    assert (ref.cpu() - orc).abs().max().item() <= 1e-5
+    # (2) the literal emulation (same 32-lane partial-sum order) vs the real kernels: the only freedom left is FMA
+    # contraction inside a lane's accumulation, so a few ulp of the O(1) values
+    if B * H * W <= 64 * 96:
+        lit = O.correlation_literal(f1.numpy(), f2.numpy(), s)
+        assert np.abs(ref.cpu().numpy() - lit).max() <= 2e-6
+    # (3) this repo's drop-in operator vs the real kernels
+    out = FunctionCorrelation(tensorFirst=f1.to(DEV), tensorSecond=f2.to(DEV), intStride=s)
+    d = (out - ref).abs().max().item()
+    _report(f"FunctionCorrelation vs reference CUDA kernels {shape}: max|diff| {d:.3e}")
+    assert out.shape == ref.shape and d <= 1e-5
+
+
+def _reference_cuda_forward(sd, a, b, model):
+    """The reference's GPU path: stock torch ops in true fp32 (TF32 off) + its own correlation kernels."""
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        sdd = {k: v.to(DEV) for k, v in sd.items()}
+        with torch.no_grad():
+            return O.forward(sdd, a.to(DEV), b.to(DEV), model,
+                             corr_fn=lambda x, y, s: RC.reference_correlation(x.contiguous(), y.contiguous(), s))
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.gpu
+@needs_ref
+@pytest.mark.parametrize("precision", ["tf32c", "3xtf32", "simt"])
+@pytest.mark.parametrize("model,B,H,W,kind", [("piv", 1, 128, 128, "rankine"), ("piv", 2, 64, 96, "shear"),
+                                             ("hui", 1, 64, 128, "uniform")])
+def test_forward_vs_reference_cuda_path(model, B, H, W, kind, precision):
+    from src.models import hui_liteflownet, piv_liteflownet
+    sd = synth.synthetic_state_dict(model, 5)
+    a, b, _ = synth.particle_batch(B, H, W, 300 + H, kind)
+    ref = _reference_cuda_forward(sd, a, b, model)
+    net = (piv_liteflownet if model == "piv" else hui_liteflownet)(sd, 1).to(DEV).eval()
+    net.precision = precision
+    with torch.no_grad():
+        out = net(a.to(DEV), b.to(DEV))
+    diff = (out - ref).abs()
+    _report(f"forward vs reference CUDA path {model} {B}x{H}x{W} {precision}: max {diff.max().item():.3e} "
+            f"mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
+    assert out.shape == ref.shape
+    # Hui flows carry the x20 output scale (|flow| ~ 40 px): tolerance relative to that scale, 1e-2 px at PIV scale
+    scale = max(1.0, ref.abs().max().item() / 10.0)
+    assert diff.max().item() <= 1e-2 * scale and diff.mean().item() <= 1e-3 * scale
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_cuda_path_rate_report_1024():
+    """Times the reference's GPU path (eager torch/cuDNN + its correlation kernels, one 1024x1024 pair per step as
+    run.py does) in fp32 and with torch's default TF32 convolutions, next to this repo's forward; also checks they
+    agree.  Written to gpurun_out/ref_cuda_rate.json."""
+    from src.models import piv_liteflownet
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b, _ = synth.particle_batch(1, 1024, 1024, 77, "rankine")
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    ad, bd = a.to(DEV), b.to(DEV)
+    corr = lambda x, y, s: RC.reference_correlation(x.contiguous(), y.contiguous(), s)
+    res = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32_default", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    ref = O.forward(sdd, ad, bd, "piv", corr_fn=corr)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    r = O.forward(sdd, ad, bd, "piv", corr_fn=corr)
+                e1.record()
+                torch.cuda.synchronize()
+            res[tag] = {"ms_per_pair": e0.elapsed_time(e1) / 3, "pairs_per_s": 3e3 / e0.elapsed_time(e1)}
+            if not tf32:
+                ref32 = ref
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    net = piv_liteflownet(sd, 1).to(DEV).eval()
+    with torch.no_grad():
+        for _ in range(3):
+            out = net(ad.clone(), bd.clone())
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            out = net(ad.clone(), bd.clone())
+        e1.record()
+        torch.cuda.synchronize()
+    res["pivlfn_" + net.engine().precision] = {"ms_per_pair": e0.elapsed_time(e1) / 5, "pairs_per_s": 5e3 / e0.elapsed_time(e1)}
+    diff = (out - ref32).abs()
+    res["flow_max_abs_diff_vs_fp32_reference"] = diff.max().item()
+    res["flow_mean_abs_diff_vs_fp32_reference"] = diff.mean().item()
+    res["note"] = ("reference CUDA path = stock torch 2.11/cuDNN ops driven by the oracle restatement of src/models.py + the "
+                   "reference's correlation kernels (cubins), batch 1 of 1024x1024, eager, CUDA-event timed")
+    _report("reference CUDA path @1024x1024: " + json.dumps(res))
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        json.dump(res, open(os.path.join(d, "ref_cuda_rate.json"), "w"), indent=1)
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
