@@ -179,7 +179,7 @@ def kernel_rooflines(eng, pk):
         from pivlfn.model import PASSES
         passes = PASSES.get(eng.precision, 1)
         ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes, None,
-                                             cw.w_c16 if passes == 2 else None), 10)
+                                             cw.pack16(passes)), 10)
         name = f"conv_tc_halo_kernel<{passes}> (tcgen05 kind::tf32" + (" + kind::f16 bf16 corrections)" if passes == 2 else f", {passes} pass)")
     else:
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)

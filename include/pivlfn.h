@@ -69,14 +69,22 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
 /* Same operator for every convolution with odd KH, KW <= 7 and stride 1 or 2 on the tcgen05 tensor cores: implicit GEMM,
  * TMA-fed (zero padding = TMA out-of-bounds fill), TMEM accumulators, fused bias + LeakyReLU (+ residual).
  * w_hi / w_lo: [CoutP, KH*KW, CinP] (CoutP = Cout rounded up to 16, CinP = Cin rounded up to 32, zero padded):
- * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32), 3 (error-compensated 3xTF32 ~ fp32) or
- * 2 (TF32 main product + the two low-order products in bf16: same accuracy class, 2/3 of the tensor-core work).
- * w_c16 (passes == 2 only, else NULL): bf16 pack [bf16(w) | bf16(w - w_hi)], each [CoutP, KH*KW, CinP].
+ * TF32 split of the weights (w ~= w_hi + w_lo); passes = 1 (plain TF32), 3 (error-compensated 3xTF32 ~ fp32),
+ * 2 (TF32 main product + the two low-order products in bf16: same accuracy class, 2/3 of the tensor-core work) or
+ * 4 (all three products in fp16, operands split as x = f16(x) + 2^-11 * f16((x - f16(x)) * 2^11): same accuracy class,
+ * half the tensor-core work of passes == 3; activations must stay inside the fp16 range, see pivlfn_f16_range_flag).
+ * w_c16 (passes == 2 / 4 only, else NULL): 16-bit pack, two tensors of [CoutP, KH*KW, CinP] each:
+ * passes == 2: [bf16(w) | bf16(w - w_hi)];  passes == 4: [f16(w) | f16((w - f16(w)) * 2048)].
  * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
 int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                    float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                    const float* res, int res_ld, int passes, void* stream);
+
+/* passes == 4 convolutions convert their input activations to fp16 pairs; a value outside the fp16 range (|x| > 65504,
+ * or non-finite) raises a sticky device flag instead of being silently saturated.  Returns the flag (0 / 1, -1 on a
+ * CUDA error) and clears it when reset != 0.  Synchronises the device.  The host re-runs with passes == 2 when set. */
+int pivlfn_f16_range_flag(int reset);
 
 /* Flow heads, the last layer of conv_M / conv_S (src/models.py:161,205: KxK, Cin -> 2), restated in two steps so that
  * the tensor cores see N = 2*K*K useful columns instead of 2:

@@ -133,6 +133,24 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
 __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
+// kind::f16 with fp16 operands (mode PASSES == 4): A and B format F16
+__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// two fp32 -> packed f16x2 (round to nearest even), low half = first value
+__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+// packed f16x2 -> the residuals (a - f16(a)) * 2^11, (b - f16(b)) * 2^11 packed the same way
+__device__ __forceinline__ uint32_t pack_f16_lo(float a, float b, uint32_t h) {
+    float ha, hb;
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(ha), "=f"(hb) : "r"(h));
+    return pack_f16((a - ha) * 2048.f, (b - hb) * 2048.f);
+}
+// Sticky flag: an activation outside the fp16 range reached a PASSES == 4 convolution (host: pivlfn_f16_range_flag)
+__device__ int g_f16_range_flag = 0;
 // two fp32 -> packed bf16x2 (round to nearest even), low half = first value
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     uint32_t r;
@@ -463,7 +481,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // PASSES: 1 = plain TF32; 3 = 3xTF32 (all three products in tf32); 2 = TF32 main product + the two low-order
     // products in bf16 (kind::f16, K = 16: half the MMA instructions of the tf32 corrections, same fp32 accuracy class
     // because the corrections are ~2^-11 of the result and bf16 keeps 8 bits of them)
+    //         4 = all three products in fp16 (kind::f16, fp16 has the 11 significant bits of tf32 at twice the MMA rate):
+    //             a = f16(a) + 2^-11 * f16((a - f16(a)) * 2^11), same for w; D = a_hi*w_hi + 2^-11 * (a_lo'*w_hi + a_hi*w_lo');
+    //             the raw fp32 tile is only the source of the split.  Activations must lie in the fp16 range (|a| < 65504;
+    //             g_f16_range_flag is raised otherwise and the host falls back to mode 2).
     constexpr bool SPLIT = PASSES >= 2;
+    constexpr bool F16 = PASSES == 4;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int pitch = HT_W + a.KW - 1;
@@ -471,7 +494,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int halo_bytes = halo_rows * pitch * 128;
     const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int b_bytes = a.CoutP * KC * 4;
-    const int b_stage = (SPLIT ? 2 : 1) * b_bytes;                      // [hi | lo]  or  [hi | bf16(w) | bf16(w_lo)]
+    const int b_stage = F16 ? b_bytes : (SPLIT ? 2 : 1) * b_bytes;      // [hi | lo], [hi | bf16(w) | bf16(w_lo)] or [f16(w) | f16(w_lo')]
     uint8_t* smemB = smem + (size_t)a.nBuf * slot_bytes;
     __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
         acc_full[2], acc_empty[2];
@@ -498,9 +521,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmBhi);
+        if (!F16) tma_prefetch_desc(&tmBhi);
         if (PASSES == 3) tma_prefetch_desc(&tmBlo);
-        if (PASSES == 2) { tma_prefetch_desc(&tmB16); tma_prefetch_desc(&tmBlo16); }
+        if (PASSES == 2 || F16) { tma_prefetch_desc(&tmB16); tma_prefetch_desc(&tmBlo16); }
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
@@ -544,7 +567,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         { DBG_T0(); mbar_wait(&b_empty[bs], bphase ^ 1); DBG_ADD(p_b); }
                         uint8_t* sB = smemB + (size_t)bs * b_stage;
                         mbar_expect_tx(&b_full[bs], b_stage);
-                        tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
+                        if (F16) {
+                            tma_load_3d(sB, &tmB16, &b_full[bs], c * KC, t, 0);
+                            tma_load_3d(sB + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
+                        } else tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 2) {
                             tma_load_3d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, t, 0);
@@ -581,7 +607,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // bf16 operand descriptors (mode 2): 64-byte rows, SWIZZLE_64B (layout type 4), 8-row group stride = pitch * 64 B
             const uint32_t hiA16 = (uint32_t)((((uint64_t)((pitch * 64) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
             const uint32_t hiB16 = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
-            const uint32_t idesc16 = make_idesc_bf16(a.CoutP);
+            const uint32_t idesc16 = F16 ? make_idesc_f16(a.CoutP) : make_idesc_bf16(a.CoutP);
+            const uint32_t idesc16w = make_idesc_f16(2 * a.CoutP);
+            const uint32_t tile_cols = (uint32_t)(F16 ? 2 * a.CoutP : a.CoutP);     // mode 4: [main | corr] per stacked tile
             const uint32_t half16 = (uint32_t)(halo_rows * pitch * 64) >> 4;       // bf16(a_lo) tile behind bf16(a)
             int bs = 0;
             uint32_t bphase = 0;
@@ -613,8 +641,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         tc_fence_after();
                         const uint32_t bHi16 = (smem_u32(smemB + (size_t)bs * b_stage) >> 4) | lbo_bits;
                         uint32_t a_hi = aHi16 + woff16 + issuer * tile16, a_lo = aLo16 + woff16 + issuer * tile16;
-                        uint32_t t_main = tset + (uint32_t)(issuer * a.CoutP);
+                        uint32_t t_main = tset + (uint32_t)issuer * tile_cols;
                         for (int i = issuer; i < a.NT; i += n_issuers) {
+                            if (F16) {
+                                // [f16(a) | f16(a_lo')] in the pair slot; [f16(w) | f16(w_lo')] in the weight stage are ONE
+                                // K-major tile of 2*CoutP rows, so a_hi * [w_hi | w_lo'] is a single MMA of N = 2*CoutP that
+                                // fills [main | corr] (the A tile is read from shared memory once instead of twice --
+                                // shared-memory bandwidth, not the tensor pipe, bounds these layers), then a_lo' * w_hi -> corr
+                                const uint32_t pa16 = p16_base + woff16 / 2 + (uint32_t)i * (tile16 / 2);
+#pragma unroll
+                                for (int kk = 0; kk < KC / 16; ++kk) {
+                                    if (2 * kk < nk) {
+                                        const uint32_t first = acc | (uint32_t)(kk > 0);
+                                        umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16w, first);
+                                        umma_bf16_lohi(t_main + (uint32_t)a.CoutP, pa16 + half16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, 1);
+                                    }
+                                }
+                            } else {
 #pragma unroll
                             for (int k = 0; k < KC / 8; ++k) {
                                 if (k < nk) {
@@ -625,6 +668,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                         umma_tf32_lohi(t_main + corr_off, a_hi + 2 * k, hiA, bHi16 + blo16 + 2 * k, hiB, idesc, 1);
                                     }
                                 }
+                            }
                             }
                             if (PASSES == 2) {
                                 // bf16 tiles: 64-byte rows (32 channels), 64B swizzle; [bf16(a) | bf16(a_lo)] in the pair slot,
@@ -642,7 +686,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     }
                                 }
                             }
-                            a_hi += n_issuers * tile16; a_lo += n_issuers * tile16; t_main += (uint32_t)(n_issuers * a.CoutP);
+                            a_hi += n_issuers * tile16; a_lo += n_issuers * tile16; t_main += (uint32_t)n_issuers * tile_cols;
                         }
                         acc = 1;
                         umma_commit(&b_empty[bs]);
@@ -680,8 +724,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // all loads of a batch are issued before the first use (latency-bound otherwise: the MMAs wait
                     // for this between two chunks)
                     constexpr int SB = 6;
-                    if (PASSES == 2) {
-                        // bf16(a) and bf16(a - trunc_tf32(a)) into the pair slot, 64-byte rows with the 64B swizzle applied
+                    if (PASSES == 2 || F16) {
+                        // bf16(a) and bf16(a - trunc_tf32(a)) (mode 4: f16(a) and f16((a - f16(a)) * 2^11)) into the pair slot, 64-byte rows with the 64B swizzle applied
                         // by hand (absolute shared-memory address bits [7:8] -> [4:5], the rule TMA / UMMA use)
                         const uint32_t pair_abs = smem_u32(pl);
                         const uint32_t half_b = (uint32_t)(halo_rows * pitch * 64);
@@ -706,12 +750,23 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     const float4 a0 = (lc0 & 1u) ? v1[j] : v0[j];             // channels 8L .. 8L+3
                                     const float4 a1 = (lc0 & 1u) ? v0[j] : v1[j];             // channels 8L+4 .. 8L+7
                                     uint4 h, l;
+                                    if (F16) {
+                                        h.x = pack_f16(a0.x, a0.y); h.y = pack_f16(a0.z, a0.w);
+                                        h.z = pack_f16(a1.x, a1.y); h.w = pack_f16(a1.z, a1.w);
+                                        l.x = pack_f16_lo(a0.x, a0.y, h.x); l.y = pack_f16_lo(a0.z, a0.w, h.y);
+                                        l.z = pack_f16_lo(a1.x, a1.y, h.z); l.w = pack_f16_lo(a1.z, a1.w, h.w);
+                                        // inf / nan exponent in any half: the activation left the fp16 range
+                                        const uint32_t ex = (__vcmpeq2(h.x & 0x7C007C00u, 0x7C007C00u) | __vcmpeq2(h.y & 0x7C007C00u, 0x7C007C00u) |
+                                                             __vcmpeq2(h.z & 0x7C007C00u, 0x7C007C00u) | __vcmpeq2(h.w & 0x7C007C00u, 0x7C007C00u));
+                                        if (ex) g_f16_range_flag = 1;
+                                    } else {
                                     h.x = pack_bf16(a0.x, a0.y); h.y = pack_bf16(a0.z, a0.w);
                                     h.z = pack_bf16(a1.x, a1.y); h.w = pack_bf16(a1.z, a1.w);
 #define PIVLFN_LO(f) ((f) - __uint_as_float(__float_as_uint(f) & 0xFFFFE000u))
                                     l.x = pack_bf16(PIVLFN_LO(a0.x), PIVLFN_LO(a0.y)); l.y = pack_bf16(PIVLFN_LO(a0.z), PIVLFN_LO(a0.w));
                                     l.z = pack_bf16(PIVLFN_LO(a1.x), PIVLFN_LO(a1.y)); l.w = pack_bf16(PIVLFN_LO(a1.z), PIVLFN_LO(a1.w));
 #undef PIVLFN_LO
+                                    }
                                     const uint32_t off = pix * 64u + (lc0 >> 1) * 16u;
                                     uint32_t ad = pair_abs + off;
                                     ad ^= ((ad >> 7) & 3u) << 4;
@@ -792,13 +847,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c0 = cbeg; c0 < cend; c0 += cstep) {
                     uint32_t v[16], u[16];
                     const bool second = dual || (c0 + 16 < cend);
-                    tmem_ld16_nowait(trow + (uint32_t)(i * a.CoutP + c0), v);
+                    tmem_ld16_nowait(trow + (uint32_t)((F16 ? 2 * i : i) * a.CoutP + c0), v);
                     if (second)
-                        tmem_ld16_nowait(trow + (uint32_t)(dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16), u);
+                        tmem_ld16_nowait(trow + (uint32_t)(F16 ? (2 * i + 1) * a.CoutP + c0
+                                                               : (dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16)), u);
                     tmem_ld_wait();
                     if (dual) {
+                        const float cs = F16 ? (1.f / 2048.f) : 1.f;     // mode 4 keeps the low-order products scaled by 2^11
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+                        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), cs, __uint_as_float(v[j])));
                     }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -972,8 +1029,8 @@ const HaloEnv& halo_env() {
 int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
     const HaloEnv& env = halo_env();
     const int pitch = HT_W + h.KW - 1;
-    const int b_stage = (passes >= 2 ? 2 : 1) * h.CoutP * KC * 4;
-    const int corr = (passes >= 2 && env.corr_mode) ? 1 : 0;
+    const int b_stage = (passes == 4 ? 1 : (passes >= 2 ? 2 : 1)) * h.CoutP * KC * 4;
+    const int corr = (passes == 4 || (passes >= 2 && env.corr_mode)) ? 1 : 0;   // mode 4 scales its corrections: own accumulator
     const int acc_mult = corr ? 2 : 1;
     // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the epilogue
     // overlaps the next item's MMAs), by the image height and by shared memory
@@ -1009,9 +1066,12 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
 int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmB16,
                 const CUtensorMap& tmBlo16, const ConvHaloArgs& h, int passes, int smem, cudaStream_t st) {
     const int grid = h.total < num_sms() ? h.total : num_sms();
-    static bool cfg1 = false, cfg2 = false, cfg3 = false;
+    static bool cfg1 = false, cfg2 = false, cfg3 = false, cfg4 = false;
     cudaError_t e = cudaSuccess;
-    if (passes == 3) {
+    if (passes == 4) {
+        if (!cfg4) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg4 = true; }
+        conv_tc_halo_kernel<4><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+    } else if (passes == 3) {
         if (!cfg3) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
         conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
     } else if (passes == 2) {
@@ -1027,6 +1087,14 @@ int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensor
 
 }  // namespace
 
+/* Reads (and optionally clears) the sticky fp16-range flag of the passes == 4 convolutions.  Synchronises the device. */
+extern "C" int pivlfn_f16_range_flag(int reset) {
+    int v = 0;
+    if (cudaMemcpyFromSymbol(&v, g_f16_range_flag, sizeof(int)) != cudaSuccess) return -1;
+    if (reset && v) { const int z = 0; cudaMemcpyToSymbol(g_f16_range_flag, &z, sizeof(int)); }
+    return v;
+}
+
 static long long* g_conv_tc_dbg = nullptr;
 /* Debug hook (not part of the public header): device buffer of >= 16 int64 that CTA 0 of the persistent conv kernel
  * fills with per-role wait-cycle totals; NULL switches the instrumentation off. */
@@ -1037,9 +1105,9 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                               float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                               const float* res, int res_ld, int passes, void* stream) {
     if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
-    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes < 1 || passes > 4) return PIVLFN_EINVAL;
     if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
-    if (passes == 2 && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
+    if ((passes == 2 || passes == 4) && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
     if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
     if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
     if (Cout > 128) return PIVLFN_EUNSUPPORTED;
@@ -1062,8 +1130,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes >= 2) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
     CUtensorMap tmB16 = tmBhi, tmBlo16 = tmBhi;
-    if (passes == 2) {
-        // w_c16 = [bf16(w) | bf16(w - tf32(w))], each [CoutP][taps][CinP]
+    if (passes == 2 || passes == 4) {
+        // w_c16 = [bf16(w) | bf16(w - tf32(w))] (mode 4: [f16(w) | f16((w - f16(w)) * 2^11)]), each [CoutP][taps][CinP]
         const size_t half = (size_t)CoutP * KH * KW * CinP * 2;
         if (encode_weights_bf16(enc, &tmB16, w_c16, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
         if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
@@ -1090,7 +1158,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
             return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, st);
         }
     }
-    if (passes == 2) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
+    if (passes == 2 || passes == 4) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
 
     // ---- per-tap kernel: tiny levels, and stride-2 convolutions (the tap's box is fetched with TMA element stride 2) ----
     ConvTcArgs a;
@@ -1124,9 +1192,9 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
                                    const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
                                    float* y, int y_ld, int lrelu, int passes, void* stream) {
     if (!img_pad || !w_hi || !y || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
-    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes < 1 || passes > 4) return PIVLFN_EINVAL;
     if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
-    if (passes == 2 && !w_c16) return PIVLFN_EINVAL;
+    if ((passes == 2 || passes == 4) && !w_c16) return PIVLFN_EINVAL;
     if (((uintptr_t)img_pad & 15) || ((uintptr_t)y & 15) || (y_ld & 3) || y_ld < 32) return PIVLFN_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
@@ -1154,7 +1222,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
             if (passes >= 2) { if (encode_weights(enc, &tBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
             else tBlo = tBhi;
             CUtensorMap tB16 = tBhi, tBlo16 = tBhi;
-            if (passes == 2) {
+            if (passes == 2 || passes == 4) {
                 if (encode_weights_bf16(enc, &tB16, w_c16, 32, 7, 32)) return PIVLFN_EINVAL;
                 if (encode_weights_bf16(enc, &tBlo16, (const char*)w_c16 + (size_t)32 * 7 * 32 * 2, 32, 7, 32)) return PIVLFN_EINVAL;
             }
@@ -1180,7 +1248,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
     }
-    if (passes == 2) passes = 3;
+    if (passes == 2 || passes == 4) passes = 3;
     if (encode_weights(enc, &tmBhi, w_hi, 32, 7, 32)) return PIVLFN_EINVAL;
     if (passes == 3) { if (encode_weights(enc, &tmBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
@@ -1198,9 +1266,9 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
                                        const float* w_hi, const float* w_lo, const void* w_c16,
                                        float* planes, int npair, int passes, void* stream) {
     if (!x || !w_hi || !planes || N <= 0 || H <= 0 || W < HT_W || Cin <= 0 || npair <= 0 || 2 * npair > 128) return PIVLFN_EINVAL;
-    if (passes != 1 && passes != 2 && passes != 3) return PIVLFN_EINVAL;
+    if (passes < 1 || passes > 4) return PIVLFN_EINVAL;
     if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
-    if (passes == 2 && !w_c16) return PIVLFN_EINVAL;
+    if ((passes == 2 || passes == 4) && !w_c16) return PIVLFN_EINVAL;
     if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)planes & 7)) return PIVLFN_EINVAL;
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
@@ -1210,7 +1278,7 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
     if (passes >= 2) { if (encode_weights(enc, &tmBlo, w_lo, CinP, 1, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
     CUtensorMap tmB16 = tmBhi, tmBlo16 = tmBhi;
-    if (passes == 2) {
+    if (passes == 2 || passes == 4) {
         const size_t half = (size_t)CoutP * CinP * 2;
         if (encode_weights_bf16(enc, &tmB16, w_c16, CinP, 1, CoutP)) return PIVLFN_EINVAL;
         if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, 1, CoutP)) return PIVLFN_EINVAL;

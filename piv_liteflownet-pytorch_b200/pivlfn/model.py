@@ -10,8 +10,9 @@ Data layout in HBM.  Every activation is NHWC fp32.  The reference's ``torch.cat
 each concatenated tensor is ONE buffer whose channel slices are written in place by their producers
 (``View`` = pointer + channel count + pixel pitch):
 
-    Sbuf[l] = [ f1 (Cm) | backwarp(f2) (Cm) | flow_M (2) | pad (2) ]       input of conv_S  (src/models.py:216)
-    Rbuf[l] = [ feat (Cr) | err (1) | flow_S - mean (2) | pad (1) ]        input of conv_R  (src/models.py:280)
+    Sbuf[l] = [ f1 (Cm) | backwarp(f2) (Cm) | flow_M (2) | pad ]       input of conv_S  (src/models.py:216)
+    Rbuf[l] = [ feat (Cr) | err (1) | flow_S - mean (2) | pad ]        input of conv_R  (src/models.py:280)
+    (pixel pitch rounded up to 8 floats = 32 bytes)
 
 Rbuf's channel order differs from the reference's (err, rm, feat): the first conv_R weight is permuted
 at pack time instead, so that every slice stays 16-byte aligned.
@@ -38,12 +39,21 @@ SIMT = "simt"          # exact fp32 FFMA on the CUDA cores
 TC_TF32 = "tf32"       # tcgen05 kind::tf32, one pass
 TC_3XTF32 = "3xtf32"   # tcgen05 kind::tf32, error-compensated three passes (fp32-equivalent)
 TC_TF32C = "tf32c"     # tf32 main product + the two low-order products in bf16 (fp32-equivalent, 2/3 of the MMA work)
-PRECISIONS = (SIMT, TC_TF32, TC_3XTF32, TC_TF32C)
-PASSES = {TC_TF32: 1, TC_3XTF32: 3, TC_TF32C: 2}
+TC_F16C = "f16c"       # all three products in fp16 on split operands (fp32-equivalent, 1/2 of the MMA work; activations
+                       # must stay inside the fp16 range -- checked on the device, falls back to tf32c otherwise)
+PRECISIONS = (SIMT, TC_TF32, TC_3XTF32, TC_TF32C, TC_F16C)
+PASSES = {TC_TF32: 1, TC_3XTF32: 3, TC_TF32C: 2, TC_F16C: 4}
 
 
 def _r4(c: int) -> int:
     return (c + 3) & ~3
+
+
+def _r8(c: int) -> int:
+    """Pixel pitch of the concat buffers: a multiple of 8 floats, so that every row starts on a 32-byte sector and the
+    convolution epilogues can use 256-bit stores into the slices (measured: 2.5x faster than 16-byte stores at a
+    528-byte pitch)."""
+    return (c + 7) & ~7
 
 
 def tf32_round(w: torch.Tensor) -> torch.Tensor:
@@ -66,6 +76,10 @@ class ConvW:
     w_hi: Optional[torch.Tensor] = None     # [CoutP16, KH*KW, CinP32] TF32 split for the tcgen05 kernel
     w_lo: Optional[torch.Tensor] = None
     w_c16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] bf16: bf16(w), bf16(w - w_hi)  (precision tf32c)
+    w_f16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] fp16: f16(w), f16((w - f16(w)) * 2048)  (precision f16c)
+
+    def pack16(self, passes: int) -> Optional[torch.Tensor]:
+        return self.w_c16 if passes == 2 else (self.w_f16 if passes == 4 else None)
     stem: bool = False                      # 7x7 3->32 packed as [32, 7, 32] for pivlfn_conv_stem_tc
 
 
@@ -91,11 +105,21 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         wt = torch.nn.functional.pad(wt, (0, cinp - cin, 0, 0, 0, coutp - cout))
         cw.w_hi, cw.w_lo = _split_tf32(wt)
         cw.w_c16 = _pack_c16(wt, cw.w_hi)
+        cw.w_f16 = _pack_f16(wt)
     return cw
 
 
 def _pack_c16(wt: torch.Tensor, w_hi: torch.Tensor) -> torch.Tensor:
     return torch.stack([wt.to(torch.bfloat16), (wt - w_hi).to(torch.bfloat16)]).contiguous()
+
+
+def _pack_f16(wt: torch.Tensor) -> torch.Tensor:
+    """w = f16(w) + 2^-11 * f16((w - f16(w)) * 2^11) up to ~2^-24 |w|."""
+    hi = wt.to(torch.float16)
+    if not torch.isfinite(hi).all():
+        return None                      # a weight outside the fp16 range: the engine falls back to tf32c
+    lo = ((wt - hi.to(torch.float32)) * 2048.0).to(torch.float16)
+    return torch.stack([hi, lo]).contiguous()
 
 
 def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
@@ -106,6 +130,7 @@ def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
     wt[:, :, :7, :3] = w.permute(0, 2, 3, 1)           # [cout, ky, kx, c]
     cw.w_hi, cw.w_lo = _split_tf32(wt.reshape(32, 7, 32))
     cw.w_c16 = _pack_c16(wt.reshape(32, 7, 32), cw.w_hi)
+    cw.w_f16 = _pack_f16(wt.reshape(32, 7, 32))
     cw.stem = True
     return cw
 
@@ -136,12 +161,17 @@ class Engine:
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.use_graph = (os.environ.get("PIVLFN_GRAPH", "1") != "0") if use_graph is None else use_graph
+        self.range_check = os.environ.get("PIVLFN_RANGE_CHECK", "1") != "0"
         self.sf = cfg.scalefactor
         self.w: Dict[str, ConvW] = {}
         self.raw: Dict[str, torch.Tensor] = {}
         self._plans: Dict[Tuple[int, int, int], "Plan"] = {}
         self.launches = 0          # kernels launched (graph replays counted by their captured node count)
         self._pack(state_dict)
+        if self.precision == TC_F16C and any(cw.w_hi is not None and cw.w_f16 is None for cw in self.w.values()):
+            import warnings
+            warnings.warn("pivlfn: a weight lies outside the fp16 range; precision 'f16c' replaced by 'tf32c'")
+            self.precision = TC_TF32C
 
     # ---------------------------------------------------------------------------------------------
     def _pack(self, sd: Dict[str, torch.Tensor]):
@@ -216,7 +246,26 @@ class Engine:
         if H % 32 or W % 32:
             raise RuntimeError(f"pivlfn: H and W must be multiples of 32 (got {H}x{W}); use estimate() which resizes "
                                "like the reference (inference.py:39-49)")
-        return self.plan(B, H, W).run(img1, img2, return_levels)
+        plan = self.plan(B, H, W)
+        res = plan.run(img1, img2, return_levels, mutate_inputs=False)
+        if self.precision == TC_F16C and self.range_check:
+            # f16c converts activations to fp16 pairs: a value outside the fp16 range raises a sticky device flag
+            # (never a silent saturation).  One stream sync + 4-byte read per forward; on a hit this engine switches to
+            # tf32c for good and the forward is repeated from the caller's (still unmodified) images.
+            torch.cuda.current_stream().synchronize()
+            flag = int(self.lib.pivlfn_f16_range_flag(1))
+            if flag < 0:
+                raise _lib.PivlfnError("pivlfn_f16_range_flag: CUDA error")
+            if flag:
+                import warnings
+                warnings.warn("pivlfn: an activation left the fp16 range in precision 'f16c'; switching this model to "
+                              "'tf32c' and repeating the forward")
+                self.precision = TC_TF32C
+                self._plans.clear()
+                plan = self.plan(B, H, W)
+                res = plan.run(img1, img2, return_levels, mutate_inputs=False)
+        plan.mutate_inputs(img1, img2)
+        return res
 
 
 class Plan:
@@ -255,8 +304,8 @@ class Plan:
                 flowU=E(B, h, w, 2) if l != 6 else None,
                 corr=Z(B, (h + s - 1) // s, (w + s - 1) // s, 52),
                 corrU=Z(B, h, w, 52) if l < 4 else None,
-                Sbuf=Z(B, h, w, 2 * cm + 4),
-                Rbuf=Z(B, h, w, cr + 4),
+                Sbuf=Z(B, h, w, _r8(2 * cm + 4)),
+                Rbuf=Z(B, h, w, _r8(cr + 4)),
                 flowM=E(B, h, w, 2), flowS=E(B, h, w, 2), flowR=E(B, h, w, 2),
                 partial=E(B, ops.flow_mean_parts(), 2),
                 dist=E(B, h, w, _r4(DIST_CH[l])), dist0=E(B, h, w, _r4(DIST_CH[l])) if l < 5 else None,
@@ -279,7 +328,7 @@ class Plan:
         cw = eng.w[key]
         assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
         passes = PASSES.get(eng.precision, 1)
-        c16 = cw.w_c16 if passes == 2 else None
+        c16 = cw.pack16(passes)
         if cw.stem and eng.precision != SIMT:
             ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes, c16)
         elif cw.w_hi is not None and eng.precision != SIMT:
@@ -305,8 +354,7 @@ class Plan:
         if pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
             K = KSIZE[l]
             passes = PASSES.get(self.eng.precision, 1)
-            ops.conv1x1_pairs_tc(x, B, h, w, pk.w_hi, pk.w_lo, pk.w_c16 if passes == 2 else None, self.lv[l]["planes"],
-                                 K * K, passes)
+            ops.conv1x1_pairs_tc(x, B, h, w, pk.w_hi, pk.w_lo, pk.pack16(passes), self.lv[l]["planes"], K * K, passes)
             ops.flow_head_sum(self.lv[l]["planes"], K, self.eng.w[key].bias, res, out, B, h, w)
         else:
             self._conv(key, x, B, h, w, out, lrelu=False, res=res)
@@ -432,14 +480,17 @@ class Plan:
         self.graph.replay()
         eng.launches += self.graph_launches
 
+    def mutate_inputs(self, img1: torch.Tensor, img2: torch.Tensor):
+        """The reference subtracts the per-channel mean from the CALLER's tensors (src/models.py:321-323)."""
+        img1.copy_(self.in1)
+        img2.copy_(self.in2)
+
     def run(self, img1: torch.Tensor, img2: torch.Tensor, return_levels: bool = False, mutate_inputs: bool = True):
         self.in1.copy_(img1)
         self.in2.copy_(img2)
         self.run_static()
         if mutate_inputs:
-            # the reference subtracts the per-channel mean from the CALLER's tensors (src/models.py:321-323)
-            img1.copy_(self.in1)
-            img2.copy_(self.in2)
+            self.mutate_inputs(img1, img2)
         out = self.out.clone()
         if not return_levels:
             return out

@@ -27,7 +27,7 @@ import torch
 
 from . import ops
 from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
-from .model import PASSES, SIMT, Engine
+from .model import PASSES, SIMT, Engine, _r8
 from .ops import View, view
 
 
@@ -129,7 +129,7 @@ class TiledPlan:
             self._need(res, 0)
         N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
         passes = PASSES.get(eng.precision, 1)
-        c16 = cw.w_c16 if passes == 2 else None
+        c16 = cw.pack16(passes)
 
         def run():
             for n in range(N):
@@ -285,7 +285,7 @@ class TiledPlan:
             im1 = TT(img[l].t[0:1], l, img[l].tiled, f"im1_{l}"); im1.valid = img[l].valid
             im2 = TT(img[l].t[1:2], l, img[l].tiled, f"im2_{l}"); im2.valid = img[l].valid
             self.handles += [im1, im2]
-            Sbuf = self.new(f"Sbuf{l}", l, 2 * cm + 4, zero=True)
+            Sbuf = self.new(f"Sbuf{l}", l, _r8(2 * cm + 4), zero=True)
             S_f2w, S_fl = self.alias(Sbuf, f"S_f2w{l}"), self.alias(Sbuf, f"S_fl{l}")
             if l <= 2:
                 e = (l - 2) % cfg.n_ext
@@ -349,7 +349,7 @@ class TiledPlan:
             if flowS.tiled:
                 self.steps.append(Step("allreduce", src=partial))
                 self.steps.append(Step("op", fn=lambda partial=partial, frac=frac: partial.mul_(frac)))
-            Rbuf = self.new(f"Rbuf{l}", l, cr + 4, zero=True)
+            Rbuf = self.new(f"Rbuf{l}", l, _r8(cr + 4), zero=True)
             R_in = self.alias(Rbuf, f"R_in{l}")
             self._need(im2, self.wr)
             self._need(im1, 0)

@@ -18,7 +18,7 @@ from pivlfn import synth
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 CASES = ["piv_b2_64x96", "piv_b1_128x128", "hui_b1_64x128", "piv2_b1_64x64", "hui2_b1_64x64"]
-TOL = {"simt": (1e-2, 1e-3), "3xtf32": (1e-2, 1e-3), "tf32c": (1e-2, 1e-3)}          # absolute, px
+TOL = {"simt": (1e-2, 1e-3), "3xtf32": (1e-2, 1e-3), "tf32c": (1e-2, 1e-3), "f16c": (1e-2, 1e-3)}          # absolute, px
 TOL_TF32_REL = (3e-2, 5e-3)                                     # relative to |flow|max of the case
 
 
@@ -49,7 +49,7 @@ def _load(golden_dir, name):
     return d, model, sd, a, b
 
 
-@pytest.mark.parametrize("precision", ["simt", "3xtf32", "tf32c", "tf32"])
+@pytest.mark.parametrize("precision", ["simt", "3xtf32", "tf32c", "f16c", "tf32"])
 @pytest.mark.parametrize("name", CASES)
 def test_forward_matches_reference_golden(golden_dir, name, precision):
     d, model, sd, a, b = _load(golden_dir, name)
@@ -138,3 +138,38 @@ def test_full_size_1024_runs_and_matches_simt():
     diff = (o3 - os_).abs()
     _report(f"1024x1024 piv tf32c vs simt: max {diff.max().item():.3e} mean {diff.mean().item():.3e}")
     assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
+
+
+def test_f16c_range_flag_falls_back_to_tf32c():
+    """precision f16c converts activations to fp16 pairs; an activation outside the fp16 range must not be saturated
+    silently: the device flag is raised, the engine switches to tf32c and the forward is repeated (same result as a
+    tf32c model).  Weights scaled so that NetC features exceed 65504."""
+    import warnings
+    sd = synth.synthetic_state_dict("piv", 0)
+    sd = {k: v.clone() for k, v in sd.items()}
+    for k in ("NetC.conv1.0.weight", "NetC.conv1.0.bias", "NetC.conv2.0.weight"):
+        sd[k] *= 300.0                 # level-2 features ~9e4 x O(1): inside fp32, outside fp16; every weight stays inside
+    a, b, _ = synth.particle_batch(1, 64, 64, 5, "uniform")
+    ref_net = _net("piv", sd, "tf32c")
+    net = _net("piv", sd, "f16c")
+    with torch.no_grad():
+        ref = ref_net(a.to(DEV), b.to(DEV))
+        with warnings.catch_warnings(record=True) as wlist:
+            warnings.simplefilter("always")
+            out = net(a.to(DEV), b.to(DEV))
+    assert any("fp16 range" in str(w.message) for w in wlist)
+    assert net.engine().precision == "tf32c"
+    assert torch.equal(out, ref)
+    # a well-scaled model stays in f16c
+    net2 = _net("piv", synth.synthetic_state_dict("piv", 0), "f16c")
+    with torch.no_grad():
+        net2(a.to(DEV), b.to(DEV))
+    assert net2.engine().precision == "f16c"
+    # a weight outside the fp16 range is caught when the weights are packed
+    sd3 = {k: v.clone() for k, v in synth.synthetic_state_dict("piv", 0).items()}
+    sd3["NetE_R.0.conv_R.2.weight"][0, 0, 0, 0] = 1.0e5
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        net3 = _net("piv", sd3, "f16c")
+        assert net3.engine().precision == "tf32c"
+    assert any("fp16 range" in str(w.message) for w in wlist)

@@ -147,7 +147,7 @@ TC_CASES = [  # cin, cout, kh, kw, H, W, lrelu
 ]
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (1, 4e-3)])
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_vs_torch(case, passes, tol):
     """tcgen05 implicit-GEMM convolution.  3 passes (3xTF32) is the fp32-equivalent mode: tolerance 1e-4
@@ -167,14 +167,14 @@ def test_conv_tc_vs_torch(case, passes, tol):
     pad = 4 if cout % 4 == 0 else 3
     y = torch.zeros(2, H, W, cout + pad, device=DEV)       # written through a strided view, like Sbuf/Rbuf slices
     ops.conv_tc(ops.view(xin, 0, cin), 2, H, W, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), kh, kw, act, passes,
-                ops.view(_nhwc(res), 0, cout) if res is not None else None, cw.w_c16 if passes == 2 else None)
+                ops.view(_nhwc(res), 0, cout) if res is not None else None, cw.pack16(passes))
     err = (_nchw(y, cout) - ref).abs().max().item()
     print(f"conv_tc {case} passes={passes}: max err {err:.2e}")
     assert err <= tol
     assert y[..., cout:].abs().max().item() == 0          # never writes outside its channel slice
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (1, 4e-3)])
 @pytest.mark.parametrize("case", [(32, 32, 16, 24), (32, 64, 64, 64), (64, 96, 17, 31), (96, 128, 8, 8), (32, 32, 256, 128)])
 def test_conv_tc_stride2_vs_torch(case, passes, tol):
     """3x3 stride-2 convolutions of NetC (src/models.py:77-106): every tap's box is fetched with TMA element stride 2."""
@@ -187,11 +187,11 @@ def test_conv_tc_stride2_vs_torch(case, passes, tol):
     Ho, Wo = ref.shape[2], ref.shape[3]
     y = torch.zeros(2, Ho, Wo, cout, device=DEV)
     ops.conv_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, cw.w_hi, cw.w_lo, cw.bias, ops.view(y), 3, 3, True, passes, None,
-                cw.w_c16 if passes == 2 else None, stride=2)
+                cw.pack16(passes), stride=2)
     assert (_nchw(y, cout) - ref).abs().max().item() <= tol
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 2e-2)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (1, 2e-2)])
 @pytest.mark.parametrize("hw", [(16, 16), (40, 56), (8, 8)])
 def test_conv_stem_tc_vs_torch(hw, passes, tol):
     """NetC.conv1 (7x7, 3 -> 32) through the overlapping-window tensor map on the zero-bordered image."""
@@ -208,7 +208,7 @@ def test_conv_stem_tc_vs_torch(hw, passes, tol):
     assert torch.equal(img_pad[:, :, 4:W + 4], img) and img_pad[:, :, :4].abs().max() == 0 and img_pad[:, :, W + 4:].abs().max() == 0
     cw = pack_stem(w.to(DEV), b.to(DEV))
     y = torch.zeros(4, H, W, 32, device=DEV)
-    ops.conv_stem_tc(img_pad, 4, H, W, cw.w_hi, cw.w_lo, cw.bias, ops.view(y), True, passes, cw.w_c16 if passes == 2 else None)
+    ops.conv_stem_tc(img_pad, 4, H, W, cw.w_hi, cw.w_lo, cw.bias, ops.view(y), True, passes, cw.pack16(passes))
     assert (_nchw(y, 32) - ref).abs().max().item() <= tol
 
 
@@ -298,7 +298,7 @@ def test_copy_nhwc_slices():
     assert torch.equal(dst2[..., 6:8], src[..., 2:4])
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (1, 4e-3)])
 @pytest.mark.parametrize("K,cin,H,W", [(7, 32, 24, 40), (5, 32, 16, 16), (7, 32, 64, 8)])
 def test_flow_head_pairs_plus_gather_vs_torch(K, cin, H, W, passes, tol):
     """Flow head restated as a 1x1 convolution to 2*K*K channels (tap planes) + gather-sum: equals the KxK convolution."""
@@ -309,7 +309,7 @@ def test_flow_head_pairs_plus_gather_vs_torch(K, cin, H, W, passes, tol):
     w2 = w.permute(2, 3, 0, 1).reshape(-1, cin, 1, 1)
     pk = pack_conv(w2.to(DEV), None, 1)
     planes = torch.full((K * K, 2 * H * W, 2), float("nan"), device=DEV)
-    ops.conv1x1_pairs_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, pk.w_hi, pk.w_lo, pk.w_c16 if passes == 2 else None, planes,
+    ops.conv1x1_pairs_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, pk.w_hi, pk.w_lo, pk.pack16(passes), planes,
                          K * K, passes)
     out = torch.zeros(2, H, W, 2, device=DEV)
     ops.flow_head_sum(planes, K, b.to(DEV), ops.view(_nhwc(res), 0, 2), ops.view(out), 2, H, W)

@@ -95,7 +95,7 @@ def _reference_cuda_forward(sd, a, b, model):
 
 @pytest.mark.gpu
 @needs_ref
-@pytest.mark.parametrize("precision", ["tf32c", "3xtf32", "simt"])
+@pytest.mark.parametrize("precision", ["f16c", "tf32c", "3xtf32", "simt"])
 @pytest.mark.parametrize("model,B,H,W,kind", [("piv", 1, 128, 128, "rankine"), ("piv", 2, 64, 96, "shear"),
                                              ("hui", 1, 64, 128, "uniform")])
 def test_forward_vs_reference_cuda_path(model, B, H, W, kind, precision):

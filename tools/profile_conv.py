@@ -25,7 +25,7 @@ b = torch.randn(cout, generator=g).to(dev)
 cw = pack_conv(w, b, 1)
 x = torch.randn(B, H, H, (cin + 3) & ~3, generator=g).to(dev)
 y = torch.empty(B, H, H, (cout + 3) & ~3, device=dev)
-passes = {"3xtf32": 3, "tf32c": 2}.get(prec, 1)
+passes = {"3xtf32": 3, "tf32c": 2, "f16c": 4}.get(prec, 1)
 trace = "--trace" in sys.argv
 if trace:
     import ctypes
@@ -40,7 +40,7 @@ for i in range(4):
     if i == 1:
         e0.record()
     ops.conv_tc(ops.view(x, 0, cin), B, H, H, cw.w_hi, cw.w_lo, cw.bias, ops.view(y, 0, cout), kh, kw, True, passes, None,
-                cw.w_c16 if passes == 2 else None)
+                cw.pack16(passes))
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 3

@@ -14,7 +14,7 @@ H = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 dev = torch.device("cuda", 0)
 g = torch.Generator(device="cpu").manual_seed(0)
 cm = 64
-Sbuf = torch.randn(B, H, H, 2 * cm + 4, generator=g).to(dev)
+Sbuf = torch.randn(B, H, H, 2 * cm + 8, generator=g).to(dev)
 f2 = torch.randn(B, H, H, cm, generator=g).to(dev)
 flow = (2.0 * torch.randn(B, H, H, 2, generator=g)).to(dev)
 corr = torch.zeros(B, H // 2, H // 2, 52, device=dev)
