@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the PIV-LiteFlowNet-en forward pass (BASELINE.json metric: PIV pairs/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision 3xtf32|tf32c|tf32|simt]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision f16c|tf32c|3xtf32|tf32|simt]
 
 One "step" = one forward pass over a batch of 64 synthetic 256x256 particle-image pairs (BASELINE.json
 configs[1]); under torchrun every rank owns its own 64 pairs (independent pairs shard with no data-path
@@ -10,8 +10,10 @@ collective -> weak scaling), and the only collective is the max-over-ranks of th
   value      pairs/s, inputs already resident in HBM, timed with CUDA events on the launching stream
   e2e        pairs/s through the drop-in API (src.models net(img1, img2)) with PINNED HOST inputs:
              H2D of both image batches and D2H of the flow are inside the timed region
-  precision  tf32c (default): fp32-equivalent -- tf32 main product + bf16 low-order products on the tensor cores;
-             3xtf32: the same with all three products in tf32; tf32: one pass (reported separately); simt: fp32 FFMA
+  precision  f16c (default): fp32-equivalent -- operands split into fp16 pairs, the three significant products on the
+             tensor cores in kind::f16 (activations outside the fp16 range are detected and re-run in tf32c);
+             tf32c: tf32 main product + bf16 low-order products; 3xtf32: all three products in tf32;
+             tf32: one pass (NOT fp32-equivalent, reported separately); simt: fp32 FFMA on the CUDA cores
   roofline   the dominant kernel (tcgen05 3x3 implicit-GEMM convolution, the level-1 128->128 layer of conv_R)
              timed alone with CUDA events: algorithmic FLOPs / launch duration vs the measured bf16 peak
   cpu_baseline  the CPU oracle (oracle/lfn_oracle.py, a restatement of the reference's forward) on this box's
@@ -180,7 +182,9 @@ def kernel_rooflines(eng, pk):
         passes = PASSES.get(eng.precision, 1)
         ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes, None,
                                              cw.pack16(passes)), 10)
-        name = f"conv_tc_halo_kernel<{passes}> (tcgen05 kind::tf32" + (" + kind::f16 bf16 corrections)" if passes == 2 else f", {passes} pass)")
+        name = {4: "conv_tc_halo_kernel<4> (tcgen05 kind::f16, fp16 split operands, 3 products)",
+                2: "conv_tc_halo_kernel<2> (tcgen05 kind::tf32 + kind::f16 bf16 corrections)"}.get(
+                    passes, f"conv_tc_halo_kernel<{passes}> (tcgen05 kind::tf32, {passes} pass)")
     else:
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
         name = "conv_simt_kernel (fp32 FFMA)"
@@ -195,7 +199,8 @@ def kernel_rooflines(eng, pk):
             traffic = None
     out["roofline"] = {"kernel": name, "layer": key + " 3x3 128->128 @256x256 x64", "bound": "tensor",
                        "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-                       "peak_source": pk["src"] + ", dense bf16 burst; kind::tf32 peak is half of it",
+                       "peak_source": pk["src"] + ", dense bf16 burst (kind::f16 runs at this rate, kind::tf32 at half); the fp32-"
+                                      "equivalent modes spend 3 products per useful one (f16c), so their ceiling is 1/3 of it",
                        "ms_per_launch": ms, "traffic": traffic, "flops_per_launch": flops,
                        "algorithmic_bytes_per_launch": 4.0 * B * h * w * (128 + 128)}
     # memory-bound: level-1 cost volume (stride 2, C=64, fused backwarp + LeakyReLU)
@@ -229,7 +234,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="pivlfn", choices=["pivlfn", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("PIVLFN_PRECISION", "tf32c"))
+    ap.add_argument("--precision", default=os.environ.get("PIVLFN_PRECISION", "f16c"))
     ap.add_argument("--no-extra", action="store_true", help="skip the 1024x1024 and per-kernel side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "pivlfn" else args.warmup

@@ -86,7 +86,15 @@ int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
  * CUDA error) and clears it when reset != 0.  Synchronises the device.  The host re-runs with passes == 2 when set. */
 int pivlfn_f16_range_flag(int reset);
 
-/* Flow heads, the last layer of conv_M / conv_S (src/models.py:161,205: KxK, Cin -> 2), restated in two steps so that
+/* Flow heads, the last layer of conv_M / conv_S (src/models.py:161,205; LiteFlowNet2 :499,547): KxK convolution
+ * (K = 3, 5 or 7) from Cin = 32 channels to the 2 flow components, no activation, + bias + optional residual flow
+ * ("+ xflow", src/models.py:186,216), in exact fp32 on the CUDA cores (3136 FMA per pixel at K = 7: the halo tile and all
+ * weights stay in shared memory, ~9 FMA per shared-memory load).  x: NHWC view, 16-byte aligned, x_ld % 4 == 0.
+ * w: [K*K][32][2] (tap, input channel, flow component), 16-byte aligned.  res / out: NHWC views with >= 2 channels. */
+int pivlfn_flow_head(const float* x, int x_ld, int N, int H, int W, int Cin, const float* w, const float* bias,
+                     const float* res, int res_ld, float* out, int out_ld, int K, void* stream);
+
+/* The same layer on the tensor cores (kept as an alternative, PIVLFN_HEAD=pairs), restated in two steps so that
  * the tensor cores see N = 2*K*K useful columns instead of 2:
  *   pivlfn_conv1x1_pairs_tc:  D[pixel, tap*2+co] = sum_c x[pixel,c] * w[co,c,tap]  (1x1 convolution, no bias / activation)
  *                             stored as tap planes  planes[tap][pixel][2]

@@ -42,6 +42,7 @@ TC_TF32C = "tf32c"     # tf32 main product + the two low-order products in bf16 
 TC_F16C = "f16c"       # all three products in fp16 on split operands (fp32-equivalent, 1/2 of the MMA work; activations
                        # must stay inside the fp16 range -- checked on the device, falls back to tf32c otherwise)
 PRECISIONS = (SIMT, TC_TF32, TC_3XTF32, TC_TF32C, TC_F16C)
+DEFAULT_PRECISION = TC_F16C
 PASSES = {TC_TF32: 1, TC_3XTF32: 3, TC_TF32C: 2, TC_F16C: 4}
 
 
@@ -157,11 +158,14 @@ class Engine:
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device
-        self.precision = precision or os.environ.get("PIVLFN_PRECISION", TC_TF32C)
+        self.precision = precision or os.environ.get("PIVLFN_PRECISION", DEFAULT_PRECISION)
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.use_graph = (os.environ.get("PIVLFN_GRAPH", "1") != "0") if use_graph is None else use_graph
         self.range_check = os.environ.get("PIVLFN_RANGE_CHECK", "1") != "0"
+        # flow heads (KxK, 32 -> 2): "simt" = exact-fp32 CUDA-core kernel (default), "pairs" = 1x1 tensor-core convolution to
+        # tap planes + gather-sum, "conv" = the generic convolution path
+        self.head_mode = os.environ.get("PIVLFN_HEAD", "simt")
         self.sf = cfg.scalefactor
         self.w: Dict[str, ConvW] = {}
         self.raw: Dict[str, torch.Tensor] = {}
@@ -202,10 +206,13 @@ class Engine:
             for j in range(nh + 1):
                 conv(f"NetE_M.{i}.conv_M.{2 * j}")
                 conv(f"NetE_S.{i}.conv_S.{2 * j}")
-            if use_tc and KSIZE[lv] >= 5:
-                # flow heads restated as a 1x1 convolution to 2*K*K channels (row = tap*2 + co) + a gather-sum
-                for key in (f"NetE_M.{i}.conv_M.{2 * nh}", f"NetE_S.{i}.conv_S.{2 * nh}"):
-                    w = g(key + ".weight")                                   # [2, cin, K, K]
+            for key in (f"NetE_M.{i}.conv_M.{2 * nh}", f"NetE_S.{i}.conv_S.{2 * nh}"):
+                w = g(key + ".weight")                                       # [2, cin, K, K]
+                if self.head_mode == "simt" and w.shape[1] == 32:
+                    # exact-fp32 CUDA-core flow head (pivlfn_flow_head): weights as [K*K][32][2]
+                    self.raw[key + "#head"] = w.permute(2, 3, 1, 0).reshape(-1, 32, 2).contiguous()
+                elif self.head_mode == "pairs" and use_tc and KSIZE[lv] >= 5:
+                    # flow head restated as a 1x1 convolution to 2*K*K channels (row = tap*2 + co) + a gather-sum
                     w2 = w.permute(2, 3, 0, 1).reshape(-1, w.shape[1], 1, 1)   # [(K*K*2), cin, 1, 1]
                     self.w[key + "#pairs"] = pack_conv(w2, None, 1, tc=True)
             for nm in ("upConv_M", "upCorr_M"):
@@ -311,7 +318,7 @@ class Plan:
                 dist=E(B, h, w, _r4(DIST_CH[l])), dist0=E(B, h, w, _r4(DIST_CH[l])) if l < 5 else None,
             )
             d["planes"] = (E(KSIZE[l] * KSIZE[l], B * h * w, 2)
-                           if (eng.precision != SIMT and KSIZE[l] >= 5 and w >= 8) else None)
+                           if (eng.head_mode == "pairs" and eng.precision != SIMT and KSIZE[l] >= 5 and w >= 8) else None)
             widths = sorted(set(cfg.head) | set(CONV_R))
             d["t"] = {c: [E(B, h, w, c), E(B, h, w, c)] for c in widths}   # ping-pong per width
             self.lv[l] = d
@@ -351,7 +358,10 @@ class Plan:
             x = y
         key = f"{prefix}.{idxs[-1]}"
         pk = self.eng.w.get(key + "#pairs")
-        if pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
+        hw_ = self.eng.raw.get(key + "#head")
+        if hw_ is not None:
+            ops.flow_head(x, B, h, w, hw_, self.eng.w[key].bias, res, out, KSIZE[l])
+        elif pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
             K = KSIZE[l]
             passes = PASSES.get(self.eng.precision, 1)
             ops.conv1x1_pairs_tc(x, B, h, w, pk.w_hi, pk.w_lo, pk.pack16(passes), self.lv[l]["planes"], K * K, passes)

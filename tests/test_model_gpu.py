@@ -101,11 +101,11 @@ def test_estimate_non_multiple_of_32_vs_oracle():
     sd = synth.synthetic_state_dict("hui", 12)
     a, b, _ = synth.particle_batch(1, 50, 70, 901, "uniform")
     ref = O.estimate(sd, a, b, "hui")
-    net = _net("hui", sd, "tf32c")
+    net = _net("hui", sd, None)
     a0 = a.to(DEV)
     out = estimate(net, a0, b.to(DEV), tensor=True)
     assert out.shape == (1, 2, 50, 70)
-    _report(f"estimate hui 50x70 tf32c vs oracle: max {(out.cpu() - ref).abs().max().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
+    _report(f"estimate hui 50x70 (default precision) vs oracle: max {(out.cpu() - ref).abs().max().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
     # Hui flows carry the x20 output scale (|flow| ~ 40 px here): 1e-2 px absolute is 2.5e-4 relative
     assert (out.cpu() - ref).abs().max().item() <= 2e-2
     assert torch.equal(a0.cpu(), a)            # estimate does not mutate the caller's images (interpolate copies)
@@ -119,7 +119,7 @@ def test_batch_independence_at_bench_size():
     displacement direction with non-trivial magnitude."""
     sd = synth.synthetic_state_dict("piv", 0)
     a, b, _ = synth.particle_batch(3, 256, 256, 40, "uniform")
-    net = _net("piv", sd, "tf32c")
+    net = _net("piv", sd, None)
     with torch.no_grad():
         full = net(a.to(DEV), b.to(DEV))
         singles = torch.cat([net(a[i:i + 1].to(DEV), b[i:i + 1].to(DEV)) for i in range(3)])
@@ -133,10 +133,10 @@ def test_full_size_1024_runs_and_matches_simt():
     sd = synth.synthetic_state_dict("piv", 0)
     a, b, _ = synth.particle_batch(1, 1024, 1024, 77, "rankine")
     with torch.no_grad():
-        o3 = _net("piv", sd, "tf32c")(a.to(DEV), b.to(DEV))
+        o3 = _net("piv", sd, None)(a.to(DEV), b.to(DEV))
         os_ = _net("piv", sd, "simt")(a.to(DEV), b.to(DEV))
     diff = (o3 - os_).abs()
-    _report(f"1024x1024 piv tf32c vs simt: max {diff.max().item():.3e} mean {diff.mean().item():.3e}")
+    _report(f"1024x1024 piv default precision (f16c) vs simt: max {diff.max().item():.3e} mean {diff.mean().item():.3e}")
     assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
 
 

@@ -314,3 +314,23 @@ def test_flow_head_pairs_plus_gather_vs_torch(K, cin, H, W, passes, tol):
     out = torch.zeros(2, H, W, 2, device=DEV)
     ops.flow_head_sum(planes, K, b.to(DEV), ops.view(_nhwc(res), 0, 2), ops.view(out), 2, H, W)
     assert (_nchw(out, 2) - ref).abs().max().item() <= tol
+
+
+@pytest.mark.parametrize("K,H,W", [(7, 24, 40), (7, 8, 8), (5, 16, 16), (5, 37, 70), (3, 4, 4), (3, 9, 33), (7, 64, 96)])
+def test_flow_head_simt_vs_torch(K, H, W):
+    """Exact-fp32 CUDA-core flow head (KxK, 32 -> 2, + bias + residual flow) against torch in float64: fp32 round-off only."""
+    w, b = _rand(2, 32, K, K, seed=1, scale=1.0 / math.sqrt(32 * K * K)), _rand(2, seed=2)
+    x = _rand(2, 32, H, W, seed=3)
+    res = _rand(2, 2, H, W, seed=4)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=K // 2).float() + res
+    wh = w.permute(2, 3, 1, 0).reshape(K * K, 32, 2).contiguous().to(DEV)
+    xin = torch.zeros(2, H, W, 36, device=DEV)                 # read through a strided view
+    xin[..., :32] = _nhwc(x)
+    out = torch.full((2, H, W, 4), float("nan"), device=DEV)   # written through a strided view
+    ops.flow_head(ops.view(xin, 0, 32), 2, H, W, wh, b.to(DEV), ops.view(_nhwc(res), 0, 2), ops.view(out, 0, 2), K)
+    assert (_nchw(out, 2) - ref).abs().max().item() <= 2e-5
+    assert torch.isnan(out[..., 2:]).all()
+    out2 = torch.zeros(2, H, W, 2, device=DEV)
+    ops.flow_head(ops.view(xin, 0, 32), 2, H, W, wh, None, None, ops.view(out2), K)
+    ref2 = F.conv2d(x.double(), w.double(), None, padding=K // 2).float()
+    assert (_nchw(out2, 2) - ref2).abs().max().item() <= 2e-5

@@ -15,7 +15,7 @@ DEV = "cuda"
 
 
 @pytest.mark.parametrize("model,H,W,P,precision", [("piv", 256, 128, 2, "simt"), ("piv", 384, 96, 3, "3xtf32"),
-                                                    ("hui", 256, 64, 2, "tf32c"), ("piv", 512, 64, 4, "tf32c")])
+                                                    ("hui", 256, 64, 2, "tf32c"), ("piv", 512, 64, 4, "f16c")])
 def test_tiled_equals_single_gpu(model, H, W, P, precision):
     sd = {k: v.to(DEV) for k, v in synth.synthetic_state_dict(model, 0).items()}
     eng = Engine(CFGS[model], sd, torch.device(DEV), precision, use_graph=False)

@@ -68,6 +68,10 @@ def w_pairs(x, N, Hh, Ww, w_hi, w_lo, w_c16, planes, npair, passes):
     return 2.0 * N * Hh * Ww * x.C * 2 * npair, "F", f"flow head as 1x1 {x.C}->{2 * npair} @{Hh}x{Ww}"
 
 
+def w_head(x, N, Hh, Ww, w, bias, res, out, K):
+    return 2.0 * N * Hh * Ww * 32 * 2 * K * K, "F", f"flow head (fp32 CUDA cores) 32->2 {K}x{K} @{Hh}x{Ww}"
+
+
 def w_headsum(planes, K, bias, res, out, N, Hh, Ww):
     return 4.0 * N * Hh * Ww * (2 * K * K + 4), "B", f"flow_head_sum K={K} @{Hh}x{Ww}"
 
@@ -105,7 +109,7 @@ def w_small(*a, **k):
 
 
 for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_tc", w_stem), ("conv1x1_pairs_tc", w_pairs),
-               ("flow_head_sum", w_headsum), ("deconv4x4s2_dw", w_deconv), ("warp", w_warp), ("corr_nhwc", w_corr),
+               ("flow_head_sum", w_headsum), ("flow_head", w_head), ("deconv4x4s2_dw", w_deconv), ("warp", w_warp), ("corr_nhwc", w_corr),
                ("reg_tail", w_regtail), ("reg_input", w_reginput), ("copy", w_copy), ("flow_mean", w_small),
                ("prep_images", w_small), ("avgpool2", w_small)):
     wrap(nm, wk)
