@@ -452,6 +452,11 @@ struct ConvHaloArgs {
     int split_trunc;         // 3xTF32 split: 1 (default) = leave a in place (measured: the tensor core reads only the top
                              // 19 bits of an fp32 operand, i.e. truncates) and write lo = a - trunc_tf32(a);
                              // 0 = hi = rna_tf32(a) written back, lo = a - hi
+    int stagger;             // > 0: CTA i delays its first load by stagger * i / gridDim.x cycles (one work-item period spread
+                             // over the grid).  With a single TMEM accumulator set (Cout = 128) the epilogue cannot overlap the
+                             // MMAs, and 148 CTAs in lock step all store their 128 KB tiles at the same moment: the burst runs at
+                             // HBM write speed (measured 10.2k cycles per item) while the tensor cores idle.  De-phased CTAs
+                             // store at the average rate instead.
     long long* dbg;          // optional: CTA 0 writes per-role wait-cycle totals (tools/profile_conv.py --trace)
 };
 
@@ -552,6 +557,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
             auto next_of = [&](int w, int c, int& w2, int& c2) { c2 = c + 1; w2 = w; if (c2 == nchunk) { c2 = 0; w2 = w + G; } };
             bool pre = false;                             // is chunk gc already issued?
+            if (a.stagger > 0) {
+                const long long t0 = clock64(), d = (long long)a.stagger * blockIdx.x / G;
+                while (clock64() - t0 < d) __nanosleep(256);
+            }
             for (int w = blockIdx.x; w < a.total; w += G) {
                 for (int c = 0; c < nchunk; ++c, ++gc) {
                     if (!pre) load_A(gc, w, c);
@@ -824,7 +833,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int q = warp & 3;
         const int row = q * 32 + lane;
         int wl = 0;
-        long long e_wait = 0, e_busy = 0;
+        long long e_wait = 0, e_busy = 0, e_ld = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
             const int as = wl % a.nsets;
             const uint32_t use = (uint32_t)(wl / a.nsets);
@@ -836,7 +845,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
             for (int i = 0; i < a.NT; ++i) {
                 const int yy = (ty * a.NT + i) * HT_H + row / HT_W;
-                const bool live = x < a.W && yy < a.H;
+                const bool live = x < a.W && yy < a.H && a.vec_store != 3;      // vec_store 3: experiment, no stores
                 const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
                 float* dst = a.y + pix * a.y_ld;
                 const float* rsd = a.res ? a.res + pix * a.res_ld : nullptr;
@@ -847,11 +856,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 for (int c0 = cbeg; c0 < cend; c0 += cstep) {
                     uint32_t v[16], u[16];
                     const bool second = dual || (c0 + 16 < cend);
+                    const long long l_t0 = a.dbg ? clock64() : 0;
                     tmem_ld16_nowait(trow + (uint32_t)((F16 ? 2 * i : i) * a.CoutP + c0), v);
                     if (second)
                         tmem_ld16_nowait(trow + (uint32_t)(F16 ? (2 * i + 1) * a.CoutP + c0
                                                                : (dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16)), u);
                     tmem_ld_wait();
+                    if (a.dbg) e_ld += clock64() - l_t0;
                     if (dual) {
                         const float cs = F16 ? (1.f / 2048.f) : 1.f;     // mode 4 keeps the low-order products scaled by 2^11
 #pragma unroll
@@ -861,7 +872,47 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int half = 0; half < 2; ++half) {
                         if (half == 1 && (dual || !second)) break;
                         const int cb = c0 + half * 16;
-                        if (live) {
+                        if (a.vec_store == 4 && cb + 16 <= a.cout_st) {
+                            // Quad-transposed stores.  A thread owns one pixel's 16 channels (64 B); written directly, every
+                            // store instruction touches 32 different 128-byte lines with one sector each, and these stores
+                            // were measured to cost 7k cycles per 128 KB work item (the LSU/L1 path they share with the
+                            // split warps, not HBM).  After a 4x4 transpose of float4 chunks inside each lane quad (4
+                            // consecutive pixels of a tile row), lane j holds chunk j of all four pixels, so one store
+                            // instruction writes 64 contiguous bytes per quad: 8 lines per instruction instead of 32.
+                            float4 t4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float e[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float t = __uint_as_float(half ? u[4 * j + k] : v[4 * j + k]) + bias_s[cb + 4 * j + k];
+                                    e[k] = a.lrelu ? lrelu_f(t) : t;
+                                }
+                                t4[j] = make_float4(e[0], e[1], e[2], e[3]);
+                            }
+#pragma unroll
+                            for (int sft = 2; sft >= 1; sft >>= 1) {
+                                const bool up = (lane & sft) != 0;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    if (i & sft) continue;
+                                    // lanes with the bit clear keep t4[i] and trade t4[i ^ sft]; the others the opposite
+                                    float4 snd = up ? t4[i] : t4[i ^ sft];
+                                    float4 rcv;
+                                    rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, sft);
+                                    rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, sft);
+                                    rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, sft);
+                                    rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, sft);
+                                    if (up) t4[i] = rcv; else t4[i ^ sft] = rcv;
+                                }
+                            }
+                            const int lq = lane & 3;
+                            if (yy < a.H && x - lq < a.W) {          // W % 4 == 0: a quad is live or dead as a whole
+                                float* qb = a.y + (pix - lq) * a.y_ld + cb + lq * 4;
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(qb + (size_t)r * a.y_ld) = t4[r];
+                            }
+                        } else if (live) {
                             float o[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
@@ -905,7 +956,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[as]);
             if (a.dbg) e_busy += clock64() - e_t0;
         }
-        if (a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { a.dbg[7] = e_wait; a.dbg[8] = e_busy; }
+        if (a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { a.dbg[7] = e_wait; a.dbg[8] = e_busy; a.dbg[12] = e_ld; }
     }
     tc_fence_before();
     __syncthreads();
@@ -1006,9 +1057,9 @@ void choose_tile(ConvTcArgs& a) {
 }
 
 // Environment switches of the halo kernel (experiments; defaults are the measured best).
-struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc; };
+struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store; };
 const HaloEnv& halo_env() {
-    static HaloEnv e = {-1, 0, 0, 1, 0};
+    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1};
     if (e.use_halo < 0) {
         const char* v = getenv("PIVLFN_TC_HALO");
         e.use_halo = (v && v[0] == '0') ? 0 : 1;
@@ -1020,6 +1071,10 @@ const HaloEnv& halo_env() {
         e.corr_mode = (v && v[0] == '0') ? 0 : 1;
         v = getenv("PIVLFN_TC_SPLIT_TRUNC");
         e.split_trunc = (v && v[0] == '0') ? 0 : 1;
+        v = getenv("PIVLFN_TC_STAGGER");          // percent of one estimated work-item period; 0 = off
+        e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
+        v = getenv("PIVLFN_TC_QUADSTORE");
+        e.quad_store = (v && v[0] == '0') ? 0 : 1;
     }
     return e;
 }
@@ -1057,6 +1112,14 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         if (total > 0x7FFFFFFFLL) return 0;
         h.total = (int)total;
         h.bo_mode = env.bo_mode; h.split_trunc = env.split_trunc;
+        {
+            // estimated tensor-core cycles of one work item: M = 128 MMAs take N/2 cycles per 32 bytes of K
+            const int nchunk = (h.Cin + KC - 1) / KC;
+            const int per_chunk_tap = passes == 4 ? 2 * 3 : (passes == 3 ? 4 * 3 : (passes == 2 ? 4 + 4 : 4));
+            const long long item = (long long)h.KH * h.KW * nchunk * NT * per_chunk_tap * (h.CoutP / 2);
+            const int n_cta = h.total < num_sms() ? h.total : num_sms();
+            h.stagger = (h.nsets == 1 && h.total >= 4 * n_cta) ? (int)(item * env.stagger / 100) : 0;
+        }
         *halo_rows_out = halo_rows;
         return nBuf * slot + nB * b_stage;
     }
@@ -1065,7 +1128,8 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
 
 int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmB16,
                 const CUtensorMap& tmBlo16, const ConvHaloArgs& h, int passes, int smem, cudaStream_t st) {
-    const int grid = h.total < num_sms() ? h.total : num_sms();
+    int grid = h.total < num_sms() ? h.total : num_sms();
+    { static int cap = -1; if (cap < 0) { const char* v = getenv("PIVLFN_TC_GRID"); cap = v ? atoi(v) : 0; } if (cap > 0 && cap < grid) grid = cap; }
     static bool cfg1 = false, cfg2 = false, cfg3 = false, cfg4 = false;
     cudaError_t e = cudaSuccess;
     if (passes == 4) {
@@ -1144,6 +1208,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         h.planar = 0;
+        if (vec_store >= 1 && !res && !(W & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
+        if (getenv("PIVLFN_TC_NOSTORE")) h.vec_store = 3;      // timing experiment only: results are not written
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
