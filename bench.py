@@ -179,10 +179,11 @@ def kernel_rooflines(eng, pk):
     flops = 2.0 * B * h * w * 128 * 128 * 9
     if eng.precision != SIMT and cw.w_hi is not None:
         from pivlfn.model import PASSES
-        passes = PASSES.get(eng.precision, 1)
+        passes = cw.passes_for(PASSES.get(eng.precision, 1))
         ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes, None,
                                              cw.pack16(passes)), 10)
-        name = {4: "conv_tc_halo_kernel<4> (tcgen05 kind::f16, fp16 split operands, 3 products)",
+        name = {5: "conv_tc_halo_kernel<5> (tcgen05 kind::f16, fp16 split operands, 3 products, one accumulator)",
+                4: "conv_tc_halo_kernel<4> (tcgen05 kind::f16, fp16 split operands, 3 products)",
                 2: "conv_tc_halo_kernel<2> (tcgen05 kind::tf32 + kind::f16 bf16 corrections)"}.get(
                     passes, f"conv_tc_halo_kernel<{passes}> (tcgen05 kind::tf32, {passes} pass)")
     else:

@@ -74,7 +74,10 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
  * 4 (all three products in fp16, operands split as x = f16(x) + 2^-11 * f16((x - f16(x)) * 2^11): same accuracy class,
  * half the tensor-core work of passes == 3; activations must stay inside the fp16 range, see pivlfn_f16_range_flag).
  * w_c16 (passes == 2 / 4 only, else NULL): 16-bit pack, two tensors of [CoutP, KH*KW, CinP] each:
- * passes == 2: [bf16(w) | bf16(w - w_hi)];  passes == 4: [f16(w) | f16((w - f16(w)) * 2048)].
+ * passes == 2: [bf16(w) | bf16(w - w_hi)];  passes == 4: [f16(w) | f16((w - f16(w)) * 2048)];
+ * passes == 5: the passes == 4 arithmetic with ONE accumulator per tile (used for Cout > 64, where two accumulators per
+ * tile would leave no TMEM for double buffering), THREE tiles of the pre-scaled weights W = 256 w:
+ * [f16(W) | f16(W - f16(W)) | f16(f16(W) / 2048)]; the kernel multiplies the result by 1/256.
  * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
 int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,

@@ -76,6 +76,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+// shared -> global tile store through the TMA engine (bulk async-group completion); out-of-bounds parts are clipped
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -440,6 +449,7 @@ struct ConvHaloArgs {
     int lrelu, vec_store;
     int NT;                  // vertically stacked 8x16 tiles per work item
     int nBuf, nB;            // activation buffer slots, weight ring depth
+    int slot_mode;           // 1 (fp16 modes with 3 slots): one raw slot + two pair slots, see slot_x / slot_l
     int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
     int bo_mode;             // 0 (default): descriptor base_offset = 0 (see above); 1: base_offset = kx -- wrong on
@@ -452,6 +462,8 @@ struct ConvHaloArgs {
     int split_trunc;         // 3xTF32 split: 1 (default) = leave a in place (measured: the tensor core reads only the top
                              // 19 bits of an fp32 operand, i.e. truncates) and write lo = a - trunc_tf32(a);
                              // 0 = hi = rna_tf32(a) written back, lo = a - hi
+    int stage_off;           // vec_store == 5: byte offset (from the aligned dynamic shared memory base) of the epilogue staging
+                             // area, 2 KB per epilogue warp; the output leaves through TMA tile stores (tmY)
     int stagger;             // > 0: CTA i delays its first load by stagger * i / gridDim.x cycles (one work-item period spread
                              // over the grid).  With a single TMEM accumulator set (Cout = 128) the epilogue cannot overlap the
                              // MMAs, and 148 CTAs in lock step all store their 128 KB tiles at the same moment: the burst runs at
@@ -466,10 +478,14 @@ struct ConvHaloArgs {
 // buffer slot of chunk c's activations (hi after the split) and of its low-order part
 // nbuf == 4: two (x, lo) pairs, plain double buffering -- the split of chunk c+1 overlaps the MMAs of chunk c;
 // nbuf == 3: rotation raw(c+1) / x(c) / lo(c) when shared memory has no room for a fourth slot (N = 128)
+// nbuf == -3 (fp16 modes, where the MMAs never read the raw tile): one raw slot + two pair slots; the raw slot is free as
+// soon as chunk c's split is done, the pair slots alternate like in the 4-slot scheme
 __device__ __forceinline__ int slot_x(int c, int nbuf) {
+    if (nbuf == -3) return 0;
     return nbuf == 4 ? 2 * (c & 1) : (nbuf == 3 ? ((c % 3) == 0 ? 0 : ((c % 3) == 1 ? 2 : 1)) : c % nbuf);
 }
 __device__ __forceinline__ int slot_l(int c, int nbuf) {
+    if (nbuf == -3) return 1 + (c & 1);
     return nbuf == 4 ? 2 * (c & 1) + 1 : (nbuf == 3 ? ((c % 3) == 0 ? 1 : ((c % 3) == 1 ? 0 : 2)) : 1);
 }
 
@@ -482,7 +498,8 @@ template <int PASSES>
 __global__ void __launch_bounds__(HALO_THREADS, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
                     const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmB16,
-                    const __grid_constant__ CUtensorMap tmBlo16, const ConvHaloArgs a) {
+                    const __grid_constant__ CUtensorMap tmBlo16, const __grid_constant__ CUtensorMap tmY,
+                    const ConvHaloArgs a) {
     // PASSES: 1 = plain TF32; 3 = 3xTF32 (all three products in tf32); 2 = TF32 main product + the two low-order
     // products in bf16 (kind::f16, K = 16: half the MMA instructions of the tf32 corrections, same fp32 accuracy class
     // because the corrections are ~2^-11 of the result and bf16 keeps 8 bits of them)
@@ -491,7 +508,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     //             the raw fp32 tile is only the source of the split.  Activations must lie in the fp16 range (|a| < 65504;
     //             g_f16_range_flag is raised otherwise and the host falls back to mode 2).
     constexpr bool SPLIT = PASSES >= 2;
-    constexpr bool F16 = PASSES == 4;
+    //         5 = mode 4 with ONE accumulator per tile (Cout = 128: [main | corr] for two stacked tiles fills all 512 TMEM
+    //             columns, so the epilogue cannot overlap the next item's MMAs and its global stores -- a per-SM limit of
+    //             ~18 B/clk -- leave the tensor cores idle a quarter of the time).  Weights are pre-scaled, W = 256 w, and come
+    //             as three tiles [f16(W) | f16(W - f16(W)) | f16(f16(W) * 2^-11)]: a_hi*W_hi + a_hi*W_lo + a_lo'*W_hi2 all
+    //             carry the same scale and add up in the same TMEM columns; the epilogue multiplies by 2^-8.
+    constexpr bool F16 = PASSES == 4 || PASSES == 5;
+    constexpr bool F16D = PASSES == 4;          // dual accumulators [main | corr]
+    constexpr bool F16S = PASSES == 5;          // single accumulator, three weight tiles
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int pitch = HT_W + a.KW - 1;
@@ -499,8 +523,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int halo_bytes = halo_rows * pitch * 128;
     const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int b_bytes = a.CoutP * KC * 4;
-    const int b_stage = F16 ? b_bytes : (SPLIT ? 2 : 1) * b_bytes;      // [hi | lo], [hi | bf16(w) | bf16(w_lo)] or [f16(w) | f16(w_lo')]
+    const int b_stage = F16S ? 3 * (b_bytes / 2) : F16 ? b_bytes : (SPLIT ? 2 : 1) * b_bytes;      // [hi | lo], [hi | bf16(w) | bf16(w_lo)] or [f16(w) | f16(w_lo')]
     uint8_t* smemB = smem + (size_t)a.nBuf * slot_bytes;
+    const int nbuf_k = a.slot_mode ? -3 : a.nBuf;
     __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
         acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -527,8 +552,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
         if (!F16) tma_prefetch_desc(&tmBhi);
-        if (PASSES == 3) tma_prefetch_desc(&tmBlo);
+        if (PASSES == 3 || F16S) tma_prefetch_desc(&tmBlo);
         if (PASSES == 2 || F16) { tma_prefetch_desc(&tmB16); tma_prefetch_desc(&tmBlo16); }
+        if (a.vec_store == 5) tma_prefetch_desc(&tmY);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
@@ -549,9 +575,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             auto load_A = [&](int g, int w, int c) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
                 // slot_x(g) was last read by global chunk g-2's MMAs (as its hi or its lo slot)
-                if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
+                // (slot_mode 1: the single raw slot is free once chunk g-1 has been split)
+                if (a.slot_mode) {
+                    if (g >= 1) { DBG_T0(); mbar_wait(&a_ready[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1)); DBG_ADD(p_a); }
+                } else if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
                 mbar_expect_tx(&a_full[g & 1], halo_bytes);
-                tma_load_4d(smem + (size_t)slot_x(g, a.nBuf) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
+                tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
                             tx * HT_W + a.x_shift, ty * HT_H * a.NT - a.KH / 2, n);
             };
             // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
@@ -579,6 +608,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         if (F16) {
                             tma_load_3d(sB, &tmB16, &b_full[bs], c * KC, t, 0);
                             tma_load_3d(sB + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
+                            if (F16S) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
                         } else tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 2) {
@@ -618,7 +648,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t hiB16 = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
             const uint32_t idesc16 = F16 ? make_idesc_f16(a.CoutP) : make_idesc_bf16(a.CoutP);
             const uint32_t idesc16w = make_idesc_f16(2 * a.CoutP);
-            const uint32_t tile_cols = (uint32_t)(F16 ? 2 * a.CoutP : a.CoutP);     // mode 4: [main | corr] per stacked tile
+            const uint32_t tile_cols = (uint32_t)(F16D ? 2 * a.CoutP : a.CoutP);    // mode 4: [main | corr] per stacked tile
             const uint32_t half16 = (uint32_t)(halo_rows * pitch * 64) >> 4;       // bf16(a_lo) tile behind bf16(a)
             int bs = 0;
             uint32_t bphase = 0;
@@ -638,8 +668,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int nk = kleft >= KC ? KC / 8 : (kleft + 7) / 8;
                     { DBG_T0(); mbar_wait(SPLIT ? &a_ready[gc & 1] : &a_full[gc & 1], par); DBG_ADD(w_a); }
                     tc_fence_after();
-                    const uint32_t aHi16 = (smem_u32(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
-                    const uint32_t aLo16 = (smem_u32(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes) >> 4) | lbo_bits;
+                    const uint32_t aHi16 = (smem_u32(smem + (size_t)slot_x(gc, nbuf_k) * slot_bytes) >> 4) | lbo_bits;
+                    const uint32_t aLo16 = (smem_u32(smem + (size_t)slot_l(gc, nbuf_k) * slot_bytes) >> 4) | lbo_bits;
                     const uint32_t p16_base = aLo16;                 // mode 2: the "lo" slot holds the two bf16 tiles
                     uint32_t row16 = 0;                               // (ky * pitch) * 8
                     int kx = 0;
@@ -662,8 +692,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 for (int kk = 0; kk < KC / 16; ++kk) {
                                     if (2 * kk < nk) {
                                         const uint32_t first = acc | (uint32_t)(kk > 0);
+                                        if (F16S) {
+                                            umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, first);
+                                            umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + blo16 / 2 + 2 * kk, hiB16, idesc16, 1);
+                                            umma_bf16_lohi(t_main, pa16 + half16 + 2 * kk, hiA16, bHi16 + blo16 + 2 * kk, hiB16, idesc16, 1);
+                                        } else {
                                         umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16w, first);
                                         umma_bf16_lohi(t_main + (uint32_t)a.CoutP, pa16 + half16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, 1);
+                                        }
                                     }
                                 }
                             } else {
@@ -722,14 +758,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // the lo slot of chunk gc was last in use by chunk gc-1's MMAs (3 slots) or chunk gc-2's (4 slots)
                     {
                         DBG_T0();
-                        const int dep = gc - (a.nBuf == 4 ? 2 : 1);
+                        const int dep = gc - ((a.nBuf == 4 || a.slot_mode) ? 2 : 1);
                         if (dep >= 0) mbar_wait(&chunk_done[dep & 1], (uint32_t)((dep >> 1) & 1));
                         DBG_ADD(s_w1);
                     }
                     { DBG_T0(); mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1)); DBG_ADD(s_w2); }
                     const long long s_t0 = a.dbg ? clock64() : 0;
-                    float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, a.nBuf) * slot_bytes);
-                    float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, a.nBuf) * slot_bytes);
+                    float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, nbuf_k) * slot_bytes);
+                    float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, nbuf_k) * slot_bytes);
                     // all loads of a batch are issued before the first use (latency-bound otherwise: the MMAs wait
                     // for this between two chunks)
                     constexpr int SB = 6;
@@ -832,6 +868,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int cend = halves ? cbeg + chalf : (egrp == 0 ? a.CoutP : 0);
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const float osc = F16S ? (1.f / 256.f) : 1.f;        // mode 5: the weights carry a factor 2^8 (fmaf(x, 1, b) == x + b)
         int wl = 0;
         long long e_wait = 0, e_busy = 0, e_ld = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
@@ -857,14 +894,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     uint32_t v[16], u[16];
                     const bool second = dual || (c0 + 16 < cend);
                     const long long l_t0 = a.dbg ? clock64() : 0;
-                    tmem_ld16_nowait(trow + (uint32_t)((F16 ? 2 * i : i) * a.CoutP + c0), v);
+                    tmem_ld16_nowait(trow + (uint32_t)((F16D ? 2 * i : i) * a.CoutP + c0), v);
                     if (second)
-                        tmem_ld16_nowait(trow + (uint32_t)(F16 ? (2 * i + 1) * a.CoutP + c0
+                        tmem_ld16_nowait(trow + (uint32_t)(F16D ? (2 * i + 1) * a.CoutP + c0
                                                                : (dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16)), u);
                     tmem_ld_wait();
                     if (a.dbg) e_ld += clock64() - l_t0;
                     if (dual) {
-                        const float cs = F16 ? (1.f / 2048.f) : 1.f;     // mode 4 keeps the low-order products scaled by 2^11
+                        const float cs = F16D ? (1.f / 2048.f) : 1.f;    // mode 4 keeps the low-order products scaled by 2^11
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), cs, __uint_as_float(v[j])));
                     }
@@ -872,7 +909,38 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int half = 0; half < 2; ++half) {
                         if (half == 1 && (dual || !second)) break;
                         const int cb = c0 + half * 16;
-                        if (a.vec_store == 4 && cb + 16 <= a.cout_st) {
+                        if (a.vec_store == 5 && cb + 16 <= a.cout_st) {
+                            // TMA tile store.  Direct st.global from the epilogue threads was measured to be a per-SM
+                            // limit of ~18 B/clk (7k of the 10k epilogue cycles of a 128 KB work item, whatever the
+                            // access pattern), and with one TMEM accumulator set the tensor cores idle meanwhile.  Here
+                            // each warp parks its 32 pixels x 16 channels in a 2 KB staging tile (64B swizzle: conflict-free
+                            // float4 stores) and one lane hands it to the TMA engine; the accumulators are released as soon
+                            // as the last tile is parked, the global writes drain in the background.
+                            const int ew = (warp & 3) + 4 * egrp;
+                            uint8_t* stg = smem + a.stage_off + ew * 2048;
+                            float4 t4[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float e[4];
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bias_s[cb + 4 * j + k]);
+                                    e[k] = a.lrelu ? lrelu_f(t) : t;
+                                }
+                                t4[j] = make_float4(e[0], e[1], e[2], e[3]);
+                            }
+                            if (lane == 0) bulk_wait_read0();          // the previous store has finished reading the tile
+                            __syncwarp();
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                *reinterpret_cast<float4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = t4[j];
+                            fence_proxy_async();
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(&tmY, stg, cb, tx * HT_W, (ty * a.NT + i) * HT_H + 4 * q, n);
+                                bulk_commit();
+                            }
+                        } else if (a.vec_store == 4 && cb + 16 <= a.cout_st) {
                             // Quad-transposed stores.  A thread owns one pixel's 16 channels (64 B); written directly, every
                             // store instruction touches 32 different 128-byte lines with one sector each, and these stores
                             // were measured to cost 7k cycles per 128 KB work item (the LSU/L1 path they share with the
@@ -885,7 +953,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 float e[4];
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float t = __uint_as_float(half ? u[4 * j + k] : v[4 * j + k]) + bias_s[cb + 4 * j + k];
+                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bias_s[cb + 4 * j + k]);
                                     e[k] = a.lrelu ? lrelu_f(t) : t;
                                 }
                                 t4[j] = make_float4(e[0], e[1], e[2], e[3]);
@@ -916,7 +984,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float o[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                float t = __uint_as_float(half ? u[j] : v[j]) + bias_s[cb + j];
+                                float t = fmaf(__uint_as_float(half ? u[j] : v[j]), osc, bias_s[cb + j]);
                                 if (a.lrelu) t = lrelu_f(t);
                                 o[j] = t;
                             }
@@ -956,6 +1024,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[as]);
             if (a.dbg) e_busy += clock64() - e_t0;
         }
+        if (a.vec_store == 5 && lane == 0) bulk_wait0();      // all tile stores of this warp have completed
         if (a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { a.dbg[7] = e_wait; a.dbg[8] = e_busy; a.dbg[12] = e_ld; }
     }
     tc_fence_before();
@@ -1057,9 +1126,9 @@ void choose_tile(ConvTcArgs& a) {
 }
 
 // Environment switches of the halo kernel (experiments; defaults are the measured best).
-struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store; };
+struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store, tma_store; };
 const HaloEnv& halo_env() {
-    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1};
+    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1, 0};
     if (e.use_halo < 0) {
         const char* v = getenv("PIVLFN_TC_HALO");
         e.use_halo = (v && v[0] == '0') ? 0 : 1;
@@ -1075,17 +1144,22 @@ const HaloEnv& halo_env() {
         e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
         v = getenv("PIVLFN_TC_QUADSTORE");
         e.quad_store = (v && v[0] == '0') ? 0 : 1;
+        v = getenv("PIVLFN_TC_TMASTORE");         // measured: no faster than direct stores (the limit is downstream of the SM,
+        e.tma_store = (v && v[0] == '1') ? 1 : 0; // ~18 B/clk per SM either way) and it costs a weight-ring stage: off by default
     }
     return e;
 }
 
 // Choose NT / buffers / ring depth for the halo kernel; fills h and returns the dynamic shared memory size, or 0 when
 // no configuration fits (caller falls back to the per-tap kernel).
+constexpr int EPI_STAGE_BYTES = 8 * 2048;      // TMA-store staging: 2 KB per epilogue warp
+
 int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
     const HaloEnv& env = halo_env();
     const int pitch = HT_W + h.KW - 1;
-    const int b_stage = (passes == 4 ? 1 : (passes >= 2 ? 2 : 1)) * h.CoutP * KC * 4;
-    const int corr = (passes == 4 || (passes >= 2 && env.corr_mode)) ? 1 : 0;   // mode 4 scales its corrections: own accumulator
+    const int b_stage = passes == 5 ? h.CoutP * KC * 6 : (passes == 4 ? 1 : (passes >= 2 ? 2 : 1)) * h.CoutP * KC * 4;
+    // mode 4 scales its corrections: own accumulator; mode 5: everything in one accumulator
+    const int corr = passes == 5 ? 0 : ((passes == 4 || (passes >= 2 && env.corr_mode)) ? 1 : 0);
     const int acc_mult = corr ? 2 : 1;
     // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the epilogue
     // overlaps the next item's MMAs), by the image height and by shared memory
@@ -1099,14 +1173,16 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         int nBuf = passes >= 2 ? 3 : 2;
         // a fourth slot (double-buffered (x, lo) pairs: no split bubble between chunks) when it still leaves a 3-deep
         // weight ring
-        if (passes >= 2 && (HALO_SMEM_BUDGET - 4 * slot) / b_stage >= 3) nBuf = 4;
-        int nB = (HALO_SMEM_BUDGET - nBuf * slot) / b_stage;
+        const int stage = h.vec_store == 5 ? EPI_STAGE_BYTES : 0;
+        if (passes >= 2 && (HALO_SMEM_BUDGET - stage - 4 * slot) / b_stage >= (stage ? 2 : 3)) nBuf = 4;
+        int nB = (HALO_SMEM_BUDGET - stage - nBuf * slot) / b_stage;
         if (nB > MAX_STAGES) nB = MAX_STAGES;
         const int need = passes >= 2 ? 2 : 3;
         if (nB < need || halo_rows > 256) continue;
         h.corr = corr;
         h.nsets = (2 * acc_mult * NT * h.CoutP <= 512) ? 2 : 1;
         h.NT = NT; h.nBuf = nBuf; h.nB = nB;
+        h.slot_mode = (passes >= 4 && nBuf == 3) ? 1 : 0;
         h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
         const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
         if (total > 0x7FFFFFFFLL) return 0;
@@ -1115,35 +1191,41 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         {
             // estimated tensor-core cycles of one work item: M = 128 MMAs take N/2 cycles per 32 bytes of K
             const int nchunk = (h.Cin + KC - 1) / KC;
-            const int per_chunk_tap = passes == 4 ? 2 * 3 : (passes == 3 ? 4 * 3 : (passes == 2 ? 4 + 4 : 4));
+            const int per_chunk_tap = passes >= 4 ? 2 * 3 : (passes == 3 ? 4 * 3 : (passes == 2 ? 4 + 4 : 4));
             const long long item = (long long)h.KH * h.KW * nchunk * NT * per_chunk_tap * (h.CoutP / 2);
             const int n_cta = h.total < num_sms() ? h.total : num_sms();
             h.stagger = (h.nsets == 1 && h.total >= 4 * n_cta) ? (int)(item * env.stagger / 100) : 0;
         }
         *halo_rows_out = halo_rows;
-        return nBuf * slot + nB * b_stage;
+        h.stage_off = (nBuf * slot + nB * b_stage + 1023) & ~1023;
+        return stage ? h.stage_off + stage : nBuf * slot + nB * b_stage;
     }
     return 0;
 }
 
 int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const CUtensorMap& tmB16,
-                const CUtensorMap& tmBlo16, const ConvHaloArgs& h, int passes, int smem, cudaStream_t st) {
+                const CUtensorMap& tmBlo16, const ConvHaloArgs& h, int passes, int smem, cudaStream_t st,
+                const CUtensorMap* tmYp = nullptr) {
+    const CUtensorMap& tmY = tmYp ? *tmYp : tmA;
     int grid = h.total < num_sms() ? h.total : num_sms();
     { static int cap = -1; if (cap < 0) { const char* v = getenv("PIVLFN_TC_GRID"); cap = v ? atoi(v) : 0; } if (cap > 0 && cap < grid) grid = cap; }
-    static bool cfg1 = false, cfg2 = false, cfg3 = false, cfg4 = false;
+    static bool cfg1 = false, cfg2 = false, cfg3 = false, cfg4 = false, cfg5 = false;
     cudaError_t e = cudaSuccess;
-    if (passes == 4) {
+    if (passes == 5) {
+        if (!cfg5) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg5 = true; }
+        conv_tc_halo_kernel<5><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
+    } else if (passes == 4) {
         if (!cfg4) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg4 = true; }
-        conv_tc_halo_kernel<4><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+        conv_tc_halo_kernel<4><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else if (passes == 3) {
         if (!cfg3) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
-        conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+        conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else if (passes == 2) {
         if (!cfg2) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg2 = true; }
-        conv_tc_halo_kernel<2><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+        conv_tc_halo_kernel<2><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else {
         if (!cfg1) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
-        conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h);
+        conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     }
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
@@ -1169,9 +1251,9 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                               float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                               const float* res, int res_ld, int passes, void* stream) {
     if (!x || !w_hi || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
-    if (passes < 1 || passes > 4) return PIVLFN_EINVAL;
+    if (passes < 1 || passes > 5) return PIVLFN_EINVAL;
     if (passes >= 2 && !w_lo) return PIVLFN_EINVAL;
-    if ((passes == 2 || passes == 4) && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
+    if ((passes == 2 || passes >= 4) && (!w_c16 || ((uintptr_t)w_c16 & 15))) return PIVLFN_EINVAL;
     if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
     if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
     if (Cout > 128) return PIVLFN_EUNSUPPORTED;
@@ -1194,11 +1276,14 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
     if (passes >= 2) { if (encode_weights(enc, &tmBlo, w_lo, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL; }
     else tmBlo = tmBhi;
     CUtensorMap tmB16 = tmBhi, tmBlo16 = tmBhi;
-    if (passes == 2 || passes == 4) {
-        // w_c16 = [bf16(w) | bf16(w - tf32(w))] (mode 4: [f16(w) | f16((w - f16(w)) * 2^11)]), each [CoutP][taps][CinP]
+    CUtensorMap tmB3 = tmBlo;
+    if (passes == 2 || passes >= 4) {
+        // w_c16 = [bf16(w) | bf16(w - tf32(w))]; mode 4: [f16(w) | f16((w - f16(w)) * 2^11)]; mode 5 (W = 256 w):
+        // [f16(W) | f16(W - f16(W)) | f16(f16(W) * 2^-11)]; each tile [CoutP][taps][CinP]
         const size_t half = (size_t)CoutP * KH * KW * CinP * 2;
         if (encode_weights_bf16(enc, &tmB16, w_c16, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
         if (encode_weights_bf16(enc, &tmBlo16, (const char*)w_c16 + half, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
+        if (passes == 5 && encode_weights_bf16(enc, &tmB3, (const char*)w_c16 + 2 * half, CinP, KH * KW, CoutP)) return PIVLFN_EINVAL;
     }
 
     if (halo_env().use_halo && W >= HT_W && stride == 1) {
@@ -1208,10 +1293,30 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         h.planar = 0;
+        h.stage_off = 0;
         if (vec_store >= 1 && !res && !(W & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
+        // TMA tile stores: rows 16-byte aligned, at least one full 16-channel group, no residual to add
+        const bool tma_ok = vec_store >= 1 && !res && cout_st >= 16 && halo_env().tma_store;
+        if (tma_ok) h.vec_store = 5;
         if (getenv("PIVLFN_TC_NOSTORE")) h.vec_store = 3;      // timing experiment only: results are not written
         int halo_rows = 0;
-        const int smem = halo_configure(h, passes, &halo_rows);
+        int smem = halo_configure(h, passes, &halo_rows);
+        if (smem <= 0 && h.vec_store == 5) {                   // no room for the staging area: direct stores
+            h.vec_store = (!(W & 3) && !(cout_st & 15) && halo_env().quad_store) ? 4 : vec_store;
+            smem = halo_configure(h, passes, &halo_rows);
+        }
+        CUtensorMap tmY;
+        if (smem > 0 && h.vec_store == 5) {
+            // output [N][H][W][cout_st] with pixel pitch y_ld; box = 16 channels x 8 pixels x 4 rows (one epilogue warp)
+            cuuint64_t dims[4] = {(cuuint64_t)cout_st, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+            cuuint64_t strides[3] = {(cuuint64_t)y_ld * 4, (cuuint64_t)W * y_ld * 4, (cuuint64_t)H * W * y_ld * 4};
+            cuuint32_t box[4] = {16, (cuuint32_t)HT_W, 4, 1};
+            cuuint32_t estr[4] = {1, 1, 1, 1};
+            CUresult r = enc(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, y, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+        }
         if (smem > 0) {
             cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
             cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
@@ -1221,10 +1326,10 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, st);
+            return halo_launch(tmA, tmBhi, passes == 5 ? tmB3 : tmBlo, tmB16, tmBlo16, h, passes, smem, st, h.vec_store == 5 ? &tmY : nullptr);
         }
     }
-    if (passes == 2 || passes == 4) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
+    if (passes == 2 || passes >= 4) passes = 3;          // the per-tap kernel (tiny levels) has no bf16-correction variant
 
     // ---- per-tap kernel: tiny levels, and stride-2 convolutions (the tap's box is fetched with TMA element stride 2) ----
     ConvTcArgs a;
@@ -1271,6 +1376,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
         h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1; h.planar = 0;
+        h.stage_off = 0;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1354,6 +1460,7 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = 1; h.KW = 1;
     h.lrelu = 0; h.vec_store = 0; h.cout_st = Cout; h.dbg = g_conv_tc_dbg; h.x_shift = 0;
     h.planar = (long long)N * H * W * 2;
+    h.stage_off = 0;
     int halo_rows = 0;
     const int smem = halo_configure(h, passes, &halo_rows);
     if (smem <= 0) return PIVLFN_EUNSUPPORTED;

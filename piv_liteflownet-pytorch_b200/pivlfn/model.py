@@ -79,8 +79,16 @@ class ConvW:
     w_c16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] bf16: bf16(w), bf16(w - w_hi)  (precision tf32c)
     w_f16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] fp16: f16(w), f16((w - f16(w)) * 2048)  (precision f16c)
 
+    w_f16s: Optional[torch.Tensor] = None   # [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
+                                            # (single-accumulator variant of f16c, packed for Cout > 64 only)
+
+    def passes_for(self, passes: int) -> int:
+        """The kernel mode of this layer for an engine-level mode: f16c (4) runs its single-accumulator variant (5) on the
+        wide layers, where [main | corr] accumulators for two stacked tiles would fill all of TMEM."""
+        return 5 if (passes == 4 and self.w_f16s is not None) else passes
+
     def pack16(self, passes: int) -> Optional[torch.Tensor]:
-        return self.w_c16 if passes == 2 else (self.w_f16 if passes == 4 else None)
+        return {2: self.w_c16, 4: self.w_f16, 5: self.w_f16s}.get(passes)
     stem: bool = False                      # 7x7 3->32 packed as [32, 7, 32] for pivlfn_conv_stem_tc
 
 
@@ -107,6 +115,8 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         cw.w_hi, cw.w_lo = _split_tf32(wt)
         cw.w_c16 = _pack_c16(wt, cw.w_hi)
         cw.w_f16 = _pack_f16(wt)
+        if coutp > 64 and stride == 1 and cw.w_f16 is not None and os.environ.get("PIVLFN_F16_SINGLE", "1") != "0":
+            cw.w_f16s = _pack_f16_single(wt)
     return cw
 
 
@@ -121,6 +131,19 @@ def _pack_f16(wt: torch.Tensor) -> torch.Tensor:
         return None                      # a weight outside the fp16 range: the engine falls back to tf32c
     lo = ((wt - hi.to(torch.float32)) * 2048.0).to(torch.float16)
     return torch.stack([hi, lo]).contiguous()
+
+
+def _pack_f16_single(wt: torch.Tensor) -> Optional[torch.Tensor]:
+    """Three fp16 tiles of W = 256 w whose products with the activation pair (a_hi, a_lo' = (a - a_hi) * 2^11) all carry
+    the same scale: W_hi = f16(W), W_lo = f16(W - W_hi) (unscaled: |W_lo| <= 2^-12 |W| stays a normal fp16 number for
+    |w| >= 1e-3, and below that its absolute error is 2^-25 of W's unit), W_hi2 = f16(W_hi * 2^-11)."""
+    W = wt * 256.0
+    hi = W.to(torch.float16)
+    if not torch.isfinite(hi).all():
+        return None
+    lo = (W - hi.to(torch.float32)).to(torch.float16)
+    hi2 = (hi.to(torch.float32) / 2048.0).to(torch.float16)
+    return torch.stack([hi, lo, hi2]).contiguous()
 
 
 def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
@@ -334,7 +357,7 @@ class Plan:
         eng = self.eng
         cw = eng.w[key]
         assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
-        passes = PASSES.get(eng.precision, 1)
+        passes = cw.passes_for(PASSES.get(eng.precision, 1))
         c16 = cw.pack16(passes)
         if cw.stem and eng.precision != SIMT:
             ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes, c16)

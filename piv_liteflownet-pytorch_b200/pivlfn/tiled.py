@@ -128,7 +128,7 @@ class TiledPlan:
         if res is not None:
             self._need(res, 0)
         N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
-        passes = PASSES.get(eng.precision, 1)
+        passes = cw.passes_for(PASSES.get(eng.precision, 1))
         c16 = cw.pack16(passes)
 
         def run():

@@ -147,7 +147,7 @@ TC_CASES = [  # cin, cout, kh, kw, H, W, lrelu
 ]
 
 
-@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (1, 4e-3)])
+@pytest.mark.parametrize("passes,tol", [(3, 1e-4), (2, 1e-4), (4, 1e-4), (5, 1e-4), (1, 4e-3)])
 @pytest.mark.parametrize("case", TC_CASES)
 def test_conv_tc_vs_torch(case, passes, tol):
     """tcgen05 implicit-GEMM convolution.  3 passes (3xTF32) is the fp32-equivalent mode: tolerance 1e-4
@@ -163,6 +163,8 @@ def test_conv_tc_vs_torch(case, passes, tol):
         ref = ref + res
     cw = pack_conv(w.to(DEV), b.to(DEV), 1)
     assert cw.w_hi is not None
+    if passes == 5 and cw.w_f16s is None:
+        pytest.skip("the single-accumulator fp16 variant is packed for Cout > 64 only")
     xin = _nhwc(x)
     pad = 4 if cout % 4 == 0 else 3
     y = torch.zeros(2, H, W, cout + pad, device=DEV)       # written through a strided view, like Sbuf/Rbuf slices

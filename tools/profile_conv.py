@@ -25,7 +25,7 @@ b = torch.randn(cout, generator=g).to(dev)
 cw = pack_conv(w, b, 1)
 x = torch.randn(B, H, H, (cin + 3) & ~3, generator=g).to(dev)
 y = torch.empty(B, H, H, (cout + 3) & ~3, device=dev)
-passes = {"3xtf32": 3, "tf32c": 2, "f16c": 4}.get(prec, 1)
+passes = cw.passes_for({"3xtf32": 3, "tf32c": 2, "f16c": 4}.get(prec, 1))
 trace = "--trace" in sys.argv
 if trace:
     import ctypes
