@@ -32,7 +32,7 @@ os.environ.setdefault("MASTER_PORT", "29533")
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
 sd = {k: v.to(dev) for k, v in synth.synthetic_state_dict("piv", 0).items()}
-eng = Engine(CFGS["piv"], sd, dev, os.environ.get("PIVLFN_PRECISION", "tf32c"), use_graph=False)
+eng = Engine(CFGS["piv"], sd, dev, os.environ.get("PIVLFN_PRECISION"), use_graph=False)
 # a 512x512 synthetic particle pair tiled to the frame size (host-side generation is O(particles) python)
 i1, i2, _ = synth.particle_pair(512, 512, 7, "shear")
 reps = ((H + 511) // 512, (W + 511) // 512)
