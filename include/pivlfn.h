@@ -131,7 +131,8 @@ int pivlfn_warp_nhwc(const float* in, int in_ld, const float* flow, float scale,
 /* Matching cost volume (src/models.py:169-184): optional backwarp of f2 by scale*flow fused into the
  * tile load (the warped features never reach HBM), 49-displacement correlation at stride 1 or 2
  * (src/correlation.py:36-104), /C, then LeakyReLU(0.1).  flow may be NULL (level 6).
- * out: NHWC view [N,ceil(H/s),ceil(W/s),49]. */
+ * out: NHWC view [N,ceil(H/s),ceil(W/s),49]; when out_ld == 52 (a dedicated buffer padded to 4 floats) the three pad channels
+ * are written as zeros (whole float4 rows). */
 int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld,
                      const float* flow, float flow_scale, float* out, int out_ld,
                      int N, int H, int W, int C, int stride, int lrelu, void* stream);

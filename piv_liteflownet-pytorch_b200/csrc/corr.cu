@@ -74,43 +74,28 @@ corr_nchw_kernel(const float* __restrict__ f1, const float* __restrict__ f2, flo
 }
 
 // ------------------------------------------------------------------------------------------------
-// NHWC: CTA = 16 x 8 output pixels, 256 threads = 128 pixels x 2 halves of the displacement rows (half 0: dy rows
-// 0..3 = 28 displacements, half 1: rows 4..6 = 21), accumulators in registers.  Channels are staged 16 at a time into
-// shared memory: the f1 tile and the f2 tile (+-3 halo, sampled every s pixels).  The backwarp of f2
+// NHWC: CTA = 16 x 8 output pixels, 224 threads = 7 warps.  Warp = displacement row dy, lane = (4-pixel segment of an
+// output row, row): a thread owns 4 horizontally adjacent pixels x 7 displacements dx = 28 accumulators, so that per
+// channel quad it reads its 4 f1 pixels and the 4+6 f2 pixels they share ONCE (14 float4 loads for 112 FMA; one pixel per
+// thread needed 29 loads for the same work, and shared-memory reads, not HBM, bound this kernel).  Channels are staged 32
+// at a time into shared memory (one full 128-byte line per gathered pixel): the f1 tile and the f2 tile (+-3 halo, sampled every s pixels).  The backwarp of f2
 // (src/models.py:171) is folded into the tile load: the bilinear taps of every tile pixel are computed ONCE per CTA
 // (they do not depend on the channel chunk), so the per-chunk gathers are independent loads with no flow -> address
 // dependency and are issued twelve at a time per thread.  Two CTAs per SM overlap one CTA's load phase with the
-// other's compute phase.  Pixel pitch in shared memory is 20 floats so that float4 reads of 8
-// neighbouring pixels are bank-conflict free.
+// other's compute phase.
+// Bank conflicts: pixel pitch 36 floats = 9 float4 (odd), so 8 CONSECUTIVE pixels are conflict-free, but lanes here are 4
+// pixels apart.  Each lane therefore walks the 8 channel quads of a chunk in a rotated order, q = (qi + (seg >> 1)) & 7;
+// with row pitches of 22 (f2) and 18 (f1, padded) pixels the eight float4 addresses of every quarter-warp then fall into
+// eight different 16-byte bank groups.  The channel sum is order-independent per thread, so the rotation only permutes
+// the fp32 summation order.
 // ------------------------------------------------------------------------------------------------
-constexpr int NH_TX = 16, NH_TY = 8, NH_CK = 16, NH_PITCH = 20;
+constexpr int NH_TX = 16, NH_TY = 8, NH_CK = 32, NH_PITCH = 36, NH_NQ = NH_CK / 4;
 constexpr int NH_SW = NH_TX + 6, NH_SH = NH_TY + 6;
+constexpr int NH_S1W = NH_TX + 2;                        // padded f1 row pitch (pixels)
 constexpr int NH_NPIX2 = NH_SW * NH_SH;                 // 308 tile pixels of f2
-constexpr int NH_THREADS = 256;
-constexpr int NH_S1 = NH_TX * NH_TY * NH_PITCH, NH_S2 = NH_NPIX2 * NH_PITCH;
-
-template <int ROWS>
-__device__ __forceinline__ void corr_accumulate(float (&acc)[28], const float* __restrict__ s1,
-                                                const float* __restrict__ s2row0) {
-    // s1: this pixel's 16 channels; s2row0: f2 tile pixel (ty+dy0, tx) -> walks ROWS rows x 7 cols
-#pragma unroll
-    for (int q = 0; q < NH_CK / 4; ++q) {
-        const float4 a = *reinterpret_cast<const float4*>(s1 + q * 4);
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-#pragma unroll
-            for (int dx = 0; dx < 7; ++dx) {
-                const float4 v = *reinterpret_cast<const float4*>(s2row0 + (r * NH_SW + dx) * NH_PITCH + q * 4);
-                float t = acc[r * 7 + dx];
-                t = fmaf(a.x, v.x, t);
-                t = fmaf(a.y, v.y, t);
-                t = fmaf(a.z, v.z, t);
-                t = fmaf(a.w, v.w, t);
-                acc[r * 7 + dx] = t;
-            }
-        }
-    }
-}
+constexpr int NH_THREADS = 224;
+constexpr int NH_S1 = NH_S1W * NH_TY * NH_PITCH, NH_S2 = NH_NPIX2 * NH_PITCH;
+constexpr int NH_OLD = 52;                               // staged output row: 49 displacements + pad
 
 __device__ __forceinline__ float4 ld_quad(const float* src, int c, int C) {
     if (c + 3 < C) return __ldg(reinterpret_cast<const float4*>(src));
@@ -125,10 +110,12 @@ __global__ void __launch_bounds__(NH_THREADS, 2)
 corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
                  const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
                  int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
-    __shared__ __align__(16) float s1[NH_S1];
-    __shared__ __align__(16) float s2[NH_S2];
-    __shared__ float4 tapw[NH_NPIX2];                    // bilinear weights of the tile pixels
-    __shared__ int2 tapxy[NH_NPIX2];                     // top-left tap (x0, y0)
+    extern __shared__ __align__(16) float sbuf[];        // f1 tile | f2 tile (reused as the output staging tile [128][NH_OLD]) | taps
+    float* const s1 = sbuf;
+    float* const s2 = sbuf + NH_S1;
+    float4* const tapw = reinterpret_cast<float4*>(sbuf + NH_S1 + NH_S2);      // bilinear weights of the tile pixels
+    int2* const tapxy = reinterpret_cast<int2*>(tapw + NH_NPIX2);              // top-left tap (x0, y0)
+    static_assert(NH_TX * NH_TY * NH_OLD <= NH_S1 + NH_S2 && NH_S1 % 4 == 0, "output staging must fit in the tiles");
     const int n = blockIdx.z;
     const int x0 = blockIdx.x * NH_TX, y0 = blockIdx.y * NH_TY;
     const int tid = threadIdx.x;
@@ -155,37 +142,39 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
         tapxy[p] = xy;
     }
 
-    const int pix = tid & 127, half = tid >> 7;
-    const int tx = pix % NH_TX, ty = pix / NH_TX;
-    float acc[28];
+    const int lane = tid & 31, dy = tid >> 5;            // warp = displacement row
+    const int seg = lane & 3, ty = lane >> 2;            // 4-pixel segment of row ty
+    const int rot = seg >> 1;
+    float acc[4][7];
 #pragma unroll
-    for (int i = 0; i < 28; ++i) acc[i] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int d = 0; d < 7; ++d) acc[i][d] = 0.f;
 
     for (int ch = 0; ch < nch; ++ch) {
         const int c0 = ch * NH_CK;
         __syncthreads();                                  // previous chunk consumed (and tap table visible)
-        // ---- f1 tile: 128 pixels x 4 quads = 2 items per thread ----------------------------------------------
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-            const int item = tid + k * NH_THREADS;
-            const int q = item & 3, p = item >> 2;
-            const int px = x0 + p % NH_TX, py = y0 + p / NH_TX;
+        // ---- f1 tile: 128 pixels x 4 quads ------------------------------------------------------------------
+        for (int item = tid; item < NH_TX * NH_TY * NH_NQ; item += NH_THREADS) {
+            const int q = item % NH_NQ, p = item / NH_NQ;
+            const int lx = p % NH_TX, ly = p / NH_TX;
+            const int px = x0 + lx, py = y0 + ly;
             const int c = c0 + q * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (px < Wo && py < Ho && c < C) v = ld_quad(f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c, c, C);
-            *reinterpret_cast<float4*>(&s1[p * NH_PITCH + q * 4]) = v;
+            *reinterpret_cast<float4*>(&s1[(ly * NH_S1W + lx) * NH_PITCH + q * 4]) = v;
         }
         // ---- f2 tile (+halo): 1232 items, three at a time (12 independent gathers in flight per thread) --------
         constexpr int UNR = 3;
-        for (int base = tid; base < NH_NPIX2 * 4; base += UNR * NH_THREADS) {
+        for (int base = tid; base < NH_NPIX2 * NH_NQ; base += UNR * NH_THREADS) {
             float4 u[UNR][4];
             float4 wv[UNR];
             bool ok[UNR];
 #pragma unroll
             for (int e = 0; e < UNR; ++e) {
                 const int item = base + e * NH_THREADS;
-                ok[e] = item < NH_NPIX2 * 4;
-                const int q = item & 3, p = ok[e] ? (item >> 2) : 0;
+                ok[e] = item < NH_NPIX2 * NH_NQ;
+                const int q = item % NH_NQ, p = ok[e] ? (item / NH_NQ) : 0;
                 const int c = c0 + q * 4;
                 wv[e] = tapw[p];
                 const int2 xy = tapxy[p];
@@ -201,7 +190,7 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             for (int e = 0; e < UNR; ++e) {
                 if (ok[e]) {
                     const int item = base + e * NH_THREADS;
-                    const int q = item & 3, p = item >> 2;
+                    const int q = item % NH_NQ, p = item / NH_NQ;
                     const float wgt[4] = {wv[e].x, wv[e].y, wv[e].z, wv[e].w};
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -214,21 +203,59 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             }
         }
         __syncthreads();
-        const float* a = &s1[pix * NH_PITCH];
-        if (half == 0) corr_accumulate<4>(acc, a, &s2[((ty + 0) * NH_SW + tx) * NH_PITCH]);
-        else           corr_accumulate<3>(acc, a, &s2[((ty + 4) * NH_SW + tx) * NH_PITCH]);
-    }
-    const int ox = x0 + tx, oy = y0 + ty;
-    if (ox < Wo && oy < Ho) {
-        const float inv = 1.f / (float)C;
-        float* o = out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + half * 28;
-        const int cnt = half == 0 ? 28 : 21;
+        // ---- 4 pixels x 7 dx per thread, channel quads in rotated order ----------------------------------------
+        const float* a0 = &s1[(ty * NH_S1W + seg * 4) * NH_PITCH];
+        const float* b0 = &s2[((ty + dy) * NH_SW + seg * 4) * NH_PITCH];
+#pragma unroll 2
+        for (int qi = 0; qi < NH_NQ; ++qi) {
+            const int q = ((qi + rot) & (NH_NQ - 1)) * 4;
+            float4 a[4], v[10];
 #pragma unroll
-        for (int k = 0; k < 28; ++k) {
-            if (k < cnt) {
-                float v = acc[k] * inv;
-                o[k] = lrelu ? lrelu_f(v) : v;
+            for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * NH_PITCH + q);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) v[j] = *reinterpret_cast<const float4*>(b0 + j * NH_PITCH + q);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int d = 0; d < 7; ++d) {
+                    float t = acc[i][d];
+                    t = fmaf(a[i].x, v[i + d].x, t);
+                    t = fmaf(a[i].y, v[i + d].y, t);
+                    t = fmaf(a[i].z, v[i + d].z, t);
+                    t = fmaf(a[i].w, v[i + d].w, t);
+                    acc[i][d] = t;
+                }
+        }
+    }
+    // ---- stage the 128 x 49 results in shared memory, then store whole pixel rows ---------------------------------
+    __syncthreads();                                      // everyone is done reading the tiles
+    const float inv = 1.f / (float)C;
+    float* so = sbuf;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int d = 0; d < 7; ++d) {
+            const float v = acc[i][d] * inv;
+            so[(ty * NH_TX + seg * 4 + i) * NH_OLD + dy * 7 + d] = lrelu ? lrelu_f(v) : v;
+        }
+    __syncthreads();
+    // rows of exactly 52 floats are a dedicated buffer with its own padding: whole float4 rows (pad channels written as 0)
+    const bool vec = out_ld == NH_OLD && !((uintptr_t)out & 15);
+    if (vec) {
+        for (int item = tid; item < NH_TX * NH_TY * (NH_OLD / 4); item += NH_THREADS) {
+            const int p = item / (NH_OLD / 4), q = item % (NH_OLD / 4);
+            const int ox = x0 + p % NH_TX, oy = y0 + p / NH_TX;
+            if (ox < Wo && oy < Ho) {
+                float4 v = *reinterpret_cast<const float4*>(&so[p * NH_OLD + q * 4]);
+                if (q == NH_OLD / 4 - 1) { v.y = 0.f; v.z = 0.f; v.w = 0.f; }
+                *reinterpret_cast<float4*>(out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + q * 4) = v;
             }
+        }
+    } else {
+        for (int item = tid; item < NH_TX * NH_TY * 49; item += NH_THREADS) {
+            const int p = item / 49, k = item % 49;
+            const int ox = x0 + p % NH_TX, oy = y0 + p / NH_TX;
+            if (ox < Wo && oy < Ho) out[((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld + k] = so[p * NH_OLD + k];
         }
     }
 }
@@ -258,7 +285,14 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
     if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
     const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
     dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
-    corr_nhwc_kernel<<<grid, NH_THREADS, 0, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
+    constexpr int smem = (NH_S1 + NH_S2) * 4 + NH_NPIX2 * (16 + 8);
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(corr_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return (int)e;
+        configured = true;
+    }
+    corr_nhwc_kernel<<<grid, NH_THREADS, smem, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
                                                                           C, H, W, Ho, Wo, stride, lrelu);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
