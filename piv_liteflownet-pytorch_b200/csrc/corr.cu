@@ -106,7 +106,7 @@ __device__ __forceinline__ float4 ld_quad(const float* src, int c, int C) {
     return v;
 }
 
-__global__ void __launch_bounds__(NH_THREADS, 2)
+__global__ void __launch_bounds__(NH_THREADS, 3)
 corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
                  const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
                  int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
@@ -165,7 +165,7 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             *reinterpret_cast<float4*>(&s1[(ly * NH_S1W + lx) * NH_PITCH + q * 4]) = v;
         }
         // ---- f2 tile (+halo): 1232 items, three at a time (12 independent gathers in flight per thread) --------
-        constexpr int UNR = 3;
+        constexpr int UNR = 2;
         for (int base = tid; base < NH_NPIX2 * NH_NQ; base += UNR * NH_THREADS) {
             float4 u[UNR][4];
             float4 wv[UNR];
