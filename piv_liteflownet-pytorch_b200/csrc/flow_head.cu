@@ -7,21 +7,21 @@
 // traffic per pixel.  It is 3136 FMA per pixel at K = 7 -- small enough for the CUDA cores in exact fp32, if the inner
 // loop is FMA-bound rather than shared-memory-bound:
 //
-//   CTA  = 32 x 8 output pixels, 128 threads; the (32+K-1) x (8+K-1) x 32-channel input halo tile and all weights live
-//          in shared memory (89 KB at K = 7 -> two CTAs per SM, one loading while the other computes)
-//   warp = (channel half, row quad); lane = output column.  A thread owns 4 vertically adjacent outputs x 2 flow
-//          components for 16 of the 32 input channels: per (kx, channel quad) it loads the 4+K-1 input pixels of its
-//          column once (float4 = 4 channels; consecutive lanes = consecutive pixels, pitch 36 floats: conflict-free)
+//   CTA  = 32 x 8 output pixels, 128 threads; the (32+K-1) x (8+K-1) input halo tile of 16 channels at a time and all
+//          weights live in shared memory (55 KB at K = 7 -> four CTAs per SM cover each other's load phases)
+//   warp = (channel group, row quad); lane = output column.  A thread owns 4 vertically adjacent outputs x 2 flow
+//          components for 8 of the 16 channels of a phase: per (kx, channel quad) it loads the 4+K-1 input pixels of its
+//          column once (float4 = 4 channels; consecutive lanes = consecutive pixels, pitch 20 floats: conflict-free)
 //          and the K x 8 weights as warp-uniform broadcasts, then issues 4*K*8 FMAs -> ~9 FMA per shared-memory load.
 //   The two channel halves are added through shared memory in a fixed order (deterministic).
 #include "common.cuh"
 
 namespace {
 
-constexpr int FH_TX = 32, FH_TY = 8, FH_C = 32, FH_PITCH = 36, FH_THREADS = 128;
+constexpr int FH_TX = 32, FH_TY = 8, FH_C = 32, FH_CP = 16, FH_PITCH = 20, FH_THREADS = 128;
 
 template <int K>
-__global__ void __launch_bounds__(FH_THREADS, 2)
+__global__ void __launch_bounds__(FH_THREADS, 4)
 flow_head_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w, const float* __restrict__ bias,
                  const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld, int H, int W,
                  int tiles_x, int tiles_y) {
@@ -37,55 +37,62 @@ flow_head_kernel(const float* __restrict__ x, int x_ld, const float* __restrict_
 
     for (int i = tid; i < K * K * FH_C * 2 / 4; i += FH_THREADS)
         reinterpret_cast<float4*>(ws)[i] = __ldg(reinterpret_cast<const float4*>(w) + i);
-    // halo tile: 8 lanes per pixel (8 float4 = 32 channels), four independent loads in flight per thread
-    constexpr int NITEM = NPIX * 8;
-    for (int base = tid; base < NITEM; base += 4 * FH_THREADS) {
-        float4 v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int item = base + e * FH_THREADS;
-            v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (item < NITEM) {
-                const int p = item >> 3, q = item & 7;
-                const int gy = y0 + p / SW - R, gx = x0 + p % SW - R;
-                if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-                    v[e] = __ldg(reinterpret_cast<const float4*>(x + (img + (size_t)gy * W + gx) * x_ld) + q);
-            }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int item = base + e * FH_THREADS;
-            if (item < NITEM) *reinterpret_cast<float4*>(&xs[(item >> 3) * FH_PITCH + (item & 7) * 4]) = v[e];
-        }
-    }
-    __syncthreads();
-
     const int lane = tid & 31, wp = tid >> 5;
     const int yq = wp & 1, half = wp >> 1;
     float acc[4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.f;
 
+    // two phases of 16 input channels: the tile of one phase is 42.6 KB, so four CTAs fit on an SM and cover each other's
+    // load phases; inside a phase warp pair `half` takes channel quads 2*half, 2*half + 1
 #pragma unroll 1
-    for (int kx = 0; kx < K; ++kx) {
+    for (int ph = 0; ph < FH_C / FH_CP; ++ph) {
+        if (ph) __syncthreads();                       // everyone is done reading the previous phase's tile
+        // halo tile: 4 lanes per pixel (4 float4 = 16 channels), four independent loads in flight per thread
+        constexpr int NITEM = NPIX * 4;
+        for (int base = tid; base < NITEM; base += 4 * FH_THREADS) {
+            float4 v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int item = base + e * FH_THREADS;
+                v[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (item < NITEM) {
+                    const int p = item >> 2, q = item & 3;
+                    const int gy = y0 + p / SW - R, gx = x0 + p % SW - R;
+                    if (gy >= 0 && gy < H && gx >= 0 && gx < W)
+                        v[e] = __ldg(reinterpret_cast<const float4*>(x + (img + (size_t)gy * W + gx) * x_ld) + ph * 4 + q);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int item = base + e * FH_THREADS;
+                if (item < NITEM) *reinterpret_cast<float4*>(&xs[(item >> 2) * FH_PITCH + (item & 3) * 4]) = v[e];
+            }
+        }
+        __syncthreads();
+
 #pragma unroll 1
-        for (int qi = 0; qi < 4; ++qi) {
-            const int cq = half * 4 + qi;
-            float4 xv[NV];
+        for (int kx = 0; kx < K; ++kx) {
+#pragma unroll 1
+            for (int qi = 0; qi < 2; ++qi) {
+                const int ql = half * 2 + qi;          // channel quad inside the phase
+                const int cq = ph * 4 + ql;            // channel quad of the layer
+                float4 xv[NV];
 #pragma unroll
-            for (int r = 0; r < NV; ++r)
-                xv[r] = *reinterpret_cast<const float4*>(&xs[((yq * 4 + r) * SW + lane + kx) * FH_PITCH + cq * 4]);
+                for (int r = 0; r < NV; ++r)
+                    xv[r] = *reinterpret_cast<const float4*>(&xs[((yq * 4 + r) * SW + lane + kx) * FH_PITCH + ql * 4]);
 #pragma unroll
-            for (int ky = 0; ky < K; ++ky) {
-                const float4 w0 = *reinterpret_cast<const float4*>(&ws[(ky * K + kx) * 64 + cq * 8]);       // c0: (u,v), c1: (u,v)
-                const float4 w1 = *reinterpret_cast<const float4*>(&ws[(ky * K + kx) * 64 + cq * 8 + 4]);   // c2, c3
+                for (int ky = 0; ky < K; ++ky) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(&ws[(ky * K + kx) * 64 + cq * 8]);       // c0: (u,v), c1: (u,v)
+                    const float4 w1 = *reinterpret_cast<const float4*>(&ws[(ky * K + kx) * 64 + cq * 8 + 4]);   // c2, c3
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 v = xv[i + ky];
-                    acc[i][0] = fmaf(v.x, w0.x, acc[i][0]); acc[i][1] = fmaf(v.x, w0.y, acc[i][1]);
-                    acc[i][0] = fmaf(v.y, w0.z, acc[i][0]); acc[i][1] = fmaf(v.y, w0.w, acc[i][1]);
-                    acc[i][0] = fmaf(v.z, w1.x, acc[i][0]); acc[i][1] = fmaf(v.z, w1.y, acc[i][1]);
-                    acc[i][0] = fmaf(v.w, w1.z, acc[i][0]); acc[i][1] = fmaf(v.w, w1.w, acc[i][1]);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 v = xv[i + ky];
+                        acc[i][0] = fmaf(v.x, w0.x, acc[i][0]); acc[i][1] = fmaf(v.x, w0.y, acc[i][1]);
+                        acc[i][0] = fmaf(v.y, w0.z, acc[i][0]); acc[i][1] = fmaf(v.y, w0.w, acc[i][1]);
+                        acc[i][0] = fmaf(v.z, w1.x, acc[i][0]); acc[i][1] = fmaf(v.z, w1.y, acc[i][1]);
+                        acc[i][0] = fmaf(v.w, w1.z, acc[i][0]); acc[i][1] = fmaf(v.w, w1.w, acc[i][1]);
+                    }
                 }
             }
         }
