@@ -93,9 +93,11 @@ int pivlfn_f16_range_flag(int reset);
  * (K = 3, 5 or 7) from Cin = 32 channels to the 2 flow components, no activation, + bias + optional residual flow
  * ("+ xflow", src/models.py:186,216), in exact fp32 on the CUDA cores (3136 FMA per pixel at K = 7: the halo tile and all
  * weights stay in shared memory, ~9 FMA per shared-memory load).  x: NHWC view, 16-byte aligned, x_ld % 4 == 0.
- * w: [K*K][32][2] (tap, input channel, flow component), 16-byte aligned.  res / out: NHWC views with >= 2 channels. */
+ * w: [K*K][32][2] (tap, input channel, flow component), 16-byte aligned.  res / out: NHWC views with >= 2 channels.
+ * out2 (optional): a second NHWC view that receives the same result (the flow slice of the Subpixel concat buffer,
+ * src/models.py:216, so that the torch.cat copy disappears). */
 int pivlfn_flow_head(const float* x, int x_ld, int N, int H, int W, int Cin, const float* w, const float* bias,
-                     const float* res, int res_ld, float* out, int out_ld, int K, void* stream);
+                     const float* res, int res_ld, float* out, int out_ld, float* out2, int out2_ld, int K, void* stream);
 
 /* The same layer on the tensor cores (kept as an alternative, PIVLFN_HEAD=pairs), restated in two steps so that
  * the tensor cores see N = 2*K*K useful columns instead of 2:

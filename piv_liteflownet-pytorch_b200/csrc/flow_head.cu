@@ -23,8 +23,8 @@ constexpr int FH_TX = 32, FH_TY = 8, FH_C = 32, FH_CP = 16, FH_PITCH = 20, FH_TH
 template <int K>
 __global__ void __launch_bounds__(FH_THREADS, 4)
 flow_head_kernel(const float* __restrict__ x, int x_ld, const float* __restrict__ w, const float* __restrict__ bias,
-                 const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld, int H, int W,
-                 int tiles_x, int tiles_y) {
+                 const float* __restrict__ res, int res_ld, float* __restrict__ out, int out_ld,
+                 float* __restrict__ out2, int out2_ld, int H, int W, int tiles_x, int tiles_y) {
     constexpr int R = K / 2, SW = FH_TX + K - 1, SH = FH_TY + K - 1, NPIX = SW * SH, NV = 4 + K - 1;
     extern __shared__ __align__(16) float smem[];
     float* xs = smem;                              // [NPIX][FH_PITCH]
@@ -118,6 +118,7 @@ flow_head_kernel(const float* __restrict__ x, int x_ld, const float* __restrict_
                 if (res) { u += __ldg(res + pix * res_ld); v += __ldg(res + pix * res_ld + 1); }
                 out[pix * out_ld] = u;
                 out[pix * out_ld + 1] = v;
+                if (out2) { out2[pix * out2_ld] = u; out2[pix * out2_ld + 1] = v; }
             }
         }
     }
@@ -125,7 +126,7 @@ flow_head_kernel(const float* __restrict__ x, int x_ld, const float* __restrict_
 
 template <int K>
 int launch_flow_head(const float* x, int x_ld, const float* w, const float* bias, const float* res, int res_ld,
-                     float* out, int out_ld, int N, int H, int W, cudaStream_t st) {
+                     float* out, int out_ld, float* out2, int out2_ld, int N, int H, int W, cudaStream_t st) {
     constexpr int SW = FH_TX + K - 1, SH = FH_TY + K - 1;
     constexpr int smem = (SW * SH * FH_PITCH + K * K * FH_C * 2) * 4;
     static bool configured = false;
@@ -137,7 +138,7 @@ int launch_flow_head(const float* x, int x_ld, const float* w, const float* bias
     const int tiles_x = cdiv(W, FH_TX), tiles_y = cdiv(H, FH_TY);
     const long long grid = (long long)tiles_x * tiles_y * N;
     if (grid > 0x7FFFFFFFLL) return PIVLFN_EINVAL;
-    flow_head_kernel<K><<<(int)grid, FH_THREADS, smem, st>>>(x, x_ld, w, bias, res, res_ld, out, out_ld, H, W, tiles_x, tiles_y);
+    flow_head_kernel<K><<<(int)grid, FH_THREADS, smem, st>>>(x, x_ld, w, bias, res, res_ld, out, out_ld, out2, out2_ld, H, W, tiles_x, tiles_y);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
@@ -145,15 +146,16 @@ int launch_flow_head(const float* x, int x_ld, const float* w, const float* bias
 }  // namespace
 
 extern "C" int pivlfn_flow_head(const float* x, int x_ld, int N, int H, int W, int Cin, const float* w, const float* bias,
-                                const float* res, int res_ld, float* out, int out_ld, int K, void* stream) {
+                                const float* res, int res_ld, float* out, int out_ld, float* out2, int out2_ld, int K,
+                                void* stream) {
     if (!x || !w || !out || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
     if (Cin != FH_C) return PIVLFN_EUNSUPPORTED;
-    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)w & 15) || out_ld < 2 || (res && res_ld < 2)) return PIVLFN_EINVAL;
+    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)w & 15) || out_ld < 2 || (res && res_ld < 2) || (out2 && out2_ld < 2)) return PIVLFN_EINVAL;
     cudaStream_t st = (cudaStream_t)stream;
     switch (K) {
-        case 3: return launch_flow_head<3>(x, x_ld, w, bias, res, res_ld, out, out_ld, N, H, W, st);
-        case 5: return launch_flow_head<5>(x, x_ld, w, bias, res, res_ld, out, out_ld, N, H, W, st);
-        case 7: return launch_flow_head<7>(x, x_ld, w, bias, res, res_ld, out, out_ld, N, H, W, st);
+        case 3: return launch_flow_head<3>(x, x_ld, w, bias, res, res_ld, out, out_ld, out2, out2_ld, N, H, W, st);
+        case 5: return launch_flow_head<5>(x, x_ld, w, bias, res, res_ld, out, out_ld, out2, out2_ld, N, H, W, st);
+        case 7: return launch_flow_head<7>(x, x_ld, w, bias, res, res_ld, out, out_ld, out2, out2_ld, N, H, W, st);
         default: return PIVLFN_EINVAL;
     }
 }

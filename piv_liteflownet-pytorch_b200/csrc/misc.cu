@@ -327,24 +327,52 @@ __global__ void reg_input_kernel(const float4* __restrict__ img1, const float4* 
 // reads its own row as float4 (pitch dist_ld = 52 / 28 / 12 floats: the 8 lanes of a quarter-warp hit disjoint banks).
 __device__ __forceinline__ uint32_t smem_addr_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// exp(-x^2 - max_j(-x_j^2)) = 2^((min_j x_j^2 - x^2) * log2 e): FADD + FMUL + one MUFU.EX2 (ex2.approx: relative error 2^-22,
+// far inside the flow tolerance; the argument is <= 0, the result in (0, 1])
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <int K>
 __device__ __forceinline__ void reg_tail_pixel(const float* __restrict__ d, const float2* __restrict__ flow, long long n,
                                                int x, int y, int H, int W, const float* swx, const float* swy, float bxv,
                                                float byv, float& u, float& v) {
     constexpr int KK = K * K, P = K / 2;
-    float mx = -INFINITY;
+    constexpr float LOG2E = 1.4426950408889634f;
+    float s[KK];
+    float mn = INFINITY;
 #pragma unroll
-    for (int k = 0; k < KK; ++k) mx = fmaxf(mx, -(d[k] * d[k]));
+    for (int k = 0; k < KK; ++k) { s[k] = d[k] * d[k]; mn = fminf(mn, s[k]); }
     float sum = 0.f, au = 0.f, av = 0.f;
+    if (x >= P && x < W - P && y >= P && y < H - P) {
+        // interior pixel (almost all of them): no bounds tests, K row pointers with constant column offsets
+        const float2* c0 = flow + (n * H + (y - P)) * W + (x - P);
 #pragma unroll
-    for (int k = 0; k < KK; ++k) {
-        const float e = expf(-(d[k] * d[k]) - mx);
-        sum += e;
-        const int yy = y + k / K - P, xx = x + k % K - P;
-        float2 f = make_float2(0.f, 0.f);
-        if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
-        au = fmaf(swx[k], e * f.x, au);
-        av = fmaf(swy[k], e * f.y, av);
+        for (int ky = 0; ky < K; ++ky) {
+            const float2* row = c0 + (long long)ky * W;
+#pragma unroll
+            for (int kx = 0; kx < K; ++kx) {
+                const int k = ky * K + kx;
+                const float e = ex2_approx((mn - s[k]) * LOG2E);       // (mn - s) first: no overflow of mn * log2 e
+                sum += e;
+                const float2 f = __ldg(row + kx);
+                au = fmaf(swx[k], e * f.x, au);
+                av = fmaf(swy[k], e * f.y, av);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KK; ++k) {
+            const float e = ex2_approx((mn - s[k]) * LOG2E);       // (mn - s) first: no overflow of mn * log2 e
+            sum += e;
+            const int yy = y + k / K - P, xx = x + k % K - P;
+            float2 f = make_float2(0.f, 0.f);
+            if (yy >= 0 && yy < H && xx >= 0 && xx < W) f = __ldg(flow + (n * H + yy) * W + xx);
+            au = fmaf(swx[k], e * f.x, au);
+            av = fmaf(swy[k], e * f.y, av);
+        }
     }
     const float r = 1.f / sum;
     u = (au + bxv) * r;

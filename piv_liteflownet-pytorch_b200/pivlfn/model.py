@@ -366,7 +366,7 @@ class Plan:
         else:
             ops.conv_simt(x, n, h, w, cw.w_simt, cw.bias, y, cw.kh, cw.kw, cw.stride, lrelu, res)
 
-    def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: View, out: View):
+    def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: View, out: View, out2: Optional[View] = None):
         """conv_M / conv_S: 3x3 conv + LeakyReLU ..., then the KxK 32->2 flow head plus residual flow."""
         B = self.B
         h, w = self.hw[l]
@@ -383,14 +383,17 @@ class Plan:
         pk = self.eng.w.get(key + "#pairs")
         hw_ = self.eng.raw.get(key + "#head")
         if hw_ is not None:
-            ops.flow_head(x, B, h, w, hw_, self.eng.w[key].bias, res, out, KSIZE[l])
-        elif pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
+            ops.flow_head(x, B, h, w, hw_, self.eng.w[key].bias, res, out, KSIZE[l], out2)
+            return
+        if pk is not None and w >= 8 and self.lv[l].get("planes") is not None:
             K = KSIZE[l]
             passes = PASSES.get(self.eng.precision, 1)
             ops.conv1x1_pairs_tc(x, B, h, w, pk.w_hi, pk.w_lo, pk.pack16(passes), self.lv[l]["planes"], K * K, passes)
             ops.flow_head_sum(self.lv[l]["planes"], K, self.eng.w[key].bias, res, out, B, h, w)
         else:
             self._conv(key, x, B, h, w, out, lrelu=False, res=res)
+        if out2 is not None:
+            ops.copy(out, out2, B * h * w)
 
     def launch_all(self):
         """Enqueue the whole forward on the current stream (inputs already in self.in1 / self.in2)."""
@@ -447,11 +450,11 @@ class Plan:
                 cin = view(d["corrU"], 0, 49)
             else:
                 cin = view(d["corr"], 0, 49)
+            # flow_M is written twice by the flow head: dense (flowM) and into its slice of the Subpixel concat buffer
             self._chain(f"NetE_M.{i}.conv_M", head_idx, cin, l, view(flowU) if flowU is not None else None,
-                        view(d["flowM"]))
+                        view(d["flowM"]), S_fl)
             # ---- Subpixel (src/models.py:209-217) ------------------------------------------------------------
             ops.warp(f2, d["flowM"], scale, S_f2w, B, h, w)
-            ops.copy(view(d["flowM"]), S_fl, B * h * w)
             self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"], 0, 2 * cm + 2), l, view(d["flowM"]),
                         view(d["flowS"]))
             # ---- Regularization (src/models.py:274-303) ------------------------------------------------------

@@ -135,11 +135,12 @@ def flow_head_sum(planes: torch.Tensor, K: int, bias, res: Optional[View], out: 
                                         out.ptr, out.ld, N, H, W, _stream()), "flow_head_sum")
 
 
-def flow_head(x: View, N, H, W, w, bias, res: Optional[View], out: View, K: int):
+def flow_head(x: View, N, H, W, w, bias, res: Optional[View], out: View, K: int, out2: Optional[View] = None):
     lib = _lib.load()
     _lib.check(lib.pivlfn_flow_head(x.ptr, x.ld, N, H, W, x.C, w.data_ptr(), bias.data_ptr() if bias is not None else None,
                                     res.ptr if res is not None else None, res.ld if res is not None else 0,
-                                    out.ptr, out.ld, int(K), _stream()), "flow_head")
+                                    out.ptr, out.ld, out2.ptr if out2 is not None else None,
+                                    out2.ld if out2 is not None else 0, int(K), _stream()), "flow_head")
 
 
 def conv_stem_tc(img_pad: torch.Tensor, N, H, W, w_hi, w_lo, bias, y: View, lrelu, passes, w_c16=None):

@@ -68,7 +68,7 @@ def w_pairs(x, N, Hh, Ww, w_hi, w_lo, w_c16, planes, npair, passes):
     return 2.0 * N * Hh * Ww * x.C * 2 * npair, "F", f"flow head as 1x1 {x.C}->{2 * npair} @{Hh}x{Ww}"
 
 
-def w_head(x, N, Hh, Ww, w, bias, res, out, K):
+def w_head(x, N, Hh, Ww, w, bias, res, out, K, out2=None):
     return 2.0 * N * Hh * Ww * 32 * 2 * K * K, "F", f"flow head (fp32 CUDA cores) 32->2 {K}x{K} @{Hh}x{Ww}"
 
 
