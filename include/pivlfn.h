@@ -84,6 +84,14 @@ int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    float* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                    const float* res, int res_ld, int passes, void* stream);
 
+/* The 3x3 stride-2 convolutions of NetC (src/models.py:77-106) in the fp16 modes (passes 4 or 5) of pivlfn_conv_tc, restated as
+ * a 2x2-tap stride-1 convolution over the four pixel-parity phases of the input; TMA element strides fetch a phase directly,
+ * so no space-to-depth copy exists.  H, W: INPUT size (even), output [N,H/2,W/2,Cout]; Cin % 32 == 0; W/2 >= 8.
+ * w16: the passes-4 / passes-5 16-bit pack of the restated weights [CoutP][4][4*Cin], tap = (by+1)*2 + (bx+1),
+ * channel = (py*2 + px)*Cin + c, where input row 2y + ky - 1 = 2(y + by) + py (zero weights for (by, py) = (-1, 0)). */
+int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, int Cin, const void* w16, const float* bias,
+                      float* y, int y_ld, int Cout, int lrelu, int passes, void* stream);
+
 /* passes == 4 convolutions convert their input activations to fp16 pairs; a value outside the fp16 range (|x| > 65504,
  * or non-finite) raises a sticky device flag instead of being silently saturated.  Returns the flag (0 / 1, -1 on a
  * CUDA error) and clears it when reset != 0.  Synchronises the device.  The host re-runs with passes == 2 when set. */

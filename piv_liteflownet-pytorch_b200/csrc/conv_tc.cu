@@ -449,6 +449,9 @@ struct ConvHaloArgs {
     int lrelu, vec_store;
     int NT;                  // vertically stacked 8x16 tiles per work item
     int nBuf, nB;            // activation buffer slots, weight ring depth
+    int s2, cpp;             // s2 = 1: 3x3 stride-2 convolution restated as 2x2 block taps over the four pixel-parity phases of
+                             // the input (space-to-depth done by TMA element strides): chunk c = parity (c / cpp) x 32-channel
+                             // group (c % cpp); H, W are the OUTPUT size and Cin = 4 * input channels
     int slot_mode;           // 1 (fp16 modes with 3 slots): one raw slot + two pair slots, see slot_x / slot_l
     int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
@@ -580,6 +583,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (g >= 1) { DBG_T0(); mbar_wait(&a_ready[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1)); DBG_ADD(p_a); }
                 } else if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
                 mbar_expect_tx(&a_full[g & 1], halo_bytes);
+                if (a.s2) {
+                    // parity phase (py, px) of the input, sampled every second pixel; the tile starts one block left / above
+                    const int par = c / a.cpp, cc = c - par * a.cpp;
+                    tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], cc * KC,
+                                2 * (tx * HT_W - 1) + (par & 1), 2 * (ty * HT_H * a.NT - 1) + (par >> 1), n);
+                } else
                 tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
                             tx * HT_W + a.x_shift, ty * HT_H * a.NT - a.KH / 2, n);
             };
@@ -1293,7 +1302,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         h.planar = 0;
-        h.stage_off = 0;
+        h.stage_off = 0; h.s2 = 0; h.cpp = 1;
         if (vec_store >= 1 && !res && !(W & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
         // TMA tile stores: rows 16-byte aligned, at least one full 16-channel group, no residual to add
         const bool tma_ok = vec_store >= 1 && !res && cout_st >= 16 && halo_env().tma_store;
@@ -1376,7 +1385,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
         h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1; h.planar = 0;
-        h.stage_off = 0;
+        h.stage_off = 0; h.s2 = 0; h.cpp = 1;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1460,7 +1469,7 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = 1; h.KW = 1;
     h.lrelu = 0; h.vec_store = 0; h.cout_st = Cout; h.dbg = g_conv_tc_dbg; h.x_shift = 0;
     h.planar = (long long)N * H * W * 2;
-    h.stage_off = 0;
+    h.stage_off = 0; h.s2 = 0; h.cpp = 1;
     int halo_rows = 0;
     const int smem = halo_configure(h, passes, &halo_rows);
     if (smem <= 0) return PIVLFN_EUNSUPPORTED;
@@ -1473,4 +1482,52 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
     return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
+}
+
+// 3x3 stride-2 convolutions of NetC (src/models.py:77-106) on the halo kernel in the fp16 modes.  out(y, x) reads input rows
+// 2y-1, 2y, 2y+1: written as 2(y + by) + py these are (by, py) = (-1, 1), (0, 0), (0, 1), so the layer is a 2x2-tap stride-1
+// convolution over the four parity phases of the input (space-to-depth), and a parity phase is exactly what a TMA box with
+// element stride 2 fetches: no rearranged copy of the input exists anywhere.  The (by, py) = (-1, 0) combinations carry zero
+// weights.  w16: the 16-bit pack of pivlfn_conv_tc for passes 4 / 5 of the restated weights [CoutP][4 taps][4 * Cin]
+// (tap = (by + 1) * 2 + (bx + 1), channel = (py * 2 + px) * Cin + c).  H, W: INPUT size (even); Cin % 32 == 0.
+extern "C" int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, int Cin, const void* w16, const float* bias,
+                                 float* y, int y_ld, int Cout, int lrelu, int passes, void* stream) {
+    if (!x || !w16 || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
+    if (passes != 4 && passes != 5) return PIVLFN_EINVAL;
+    if ((H & 1) || (W & 1) || (Cin % KC) || Cout > 128) return PIVLFN_EUNSUPPORTED;
+    if (((uintptr_t)x & 15) || (x_ld & 3) || x_ld < Cin || ((uintptr_t)y & 3) || y_ld < Cout || ((uintptr_t)w16 & 15)) return PIVLFN_EINVAL;
+    const int Ho = H / 2, Wo = W / 2;
+    if (Wo < HT_W) return PIVLFN_EUNSUPPORTED;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+    const int CoutP = (Cout + 15) & ~15, CinR = 4 * Cin;
+    const int cout_st = (y_ld == ((Cout + 3) & ~3)) ? y_ld : Cout;
+    const int vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7) && !(cout_st & 7)) ? 2
+                        : ((!((uintptr_t)y & 15) && !(y_ld & 3) && cout_st >= 4) ? 1 : 0);
+    ConvHaloArgs h;
+    h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
+    h.N = N; h.H = Ho; h.W = Wo; h.Cin = CinR; h.Cout = Cout; h.CoutP = CoutP; h.KH = 2; h.KW = 2;
+    h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = 0; h.planar = 0;
+    h.stage_off = 0; h.s2 = 1; h.cpp = Cin / KC;
+    if (vec_store >= 1 && !(Wo & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
+    int halo_rows = 0;
+    const int smem = halo_configure(h, passes, &halo_rows);
+    if (smem <= 0) return PIVLFN_EUNSUPPORTED;
+    CUtensorMap tmA, tmB16, tmBlo16, tmB3;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
+        cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)(2 * (HT_W + 1)), (cuuint32_t)(2 * halo_rows), 1};
+        cuuint32_t estr[4] = {1, 2, 2, 1};
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    }
+    const size_t tile = (size_t)CoutP * 4 * CinR * 2;
+    if (encode_weights_bf16(enc, &tmB16, w16, CinR, 4, CoutP)) return PIVLFN_EINVAL;
+    if (encode_weights_bf16(enc, &tmBlo16, (const char*)w16 + tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
+    tmB3 = tmBlo16;
+    if (passes == 5 && encode_weights_bf16(enc, &tmB3, (const char*)w16 + 2 * tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
+    return halo_launch(tmA, tmB16, tmB3, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }

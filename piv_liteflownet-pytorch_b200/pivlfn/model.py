@@ -79,6 +79,8 @@ class ConvW:
     w_c16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] bf16: bf16(w), bf16(w - w_hi)  (precision tf32c)
     w_f16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] fp16: f16(w), f16((w - f16(w)) * 2048)  (precision f16c)
 
+    w_s2: Optional[torch.Tensor] = None     # 3x3 stride-2 layers restated over the four input parities: fp16 pack (2 or 3 tiles)
+    s2_passes: int = 0                      # of [CoutP16, 4, 4*Cin] for pivlfn_conv_s2_tc, and its kernel mode (4 or 5)
     w_f16s: Optional[torch.Tensor] = None   # [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
                                             # (single-accumulator variant of f16c, packed for Cout > 64 only)
 
@@ -117,7 +119,29 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         cw.w_f16 = _pack_f16(wt)
         if coutp > 64 and stride == 1 and cw.w_f16 is not None and os.environ.get("PIVLFN_F16_SINGLE", "1") != "0":
             cw.w_f16s = _pack_f16_single(wt)
+        if stride == 2 and kh == 3 and kw == 3 and cin % 32 == 0 and os.environ.get("PIVLFN_S2_HALO", "1") != "0":
+            w2 = _restate_s2(w)                                      # [cout, 4, 4*cin]
+            w2 = torch.nn.functional.pad(w2, (0, 0, 0, 0, 0, coutp - cout))
+            if coutp > 64:
+                cw.w_s2, cw.s2_passes = _pack_f16_single(w2), 5
+            else:
+                cw.w_s2, cw.s2_passes = _pack_f16(w2), 4
     return cw
+
+
+def _restate_s2(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, 3, 3] stride-2 weights -> [Cout, 4 taps, 4*Cin] of the equivalent 2x2-tap convolution over the four
+    pixel-parity phases of the input: input row 2y + ky - 1 = 2(y + by) + py with (by, py) = (-1, 1), (0, 0), (0, 1) for
+    ky = 0, 1, 2; tap = (by + 1) * 2 + (bx + 1), channel = (py * 2 + px) * Cin + c."""
+    cout, cin = w.shape[0], w.shape[1]
+    m = {0: (0, 1), 1: (1, 0), 2: (1, 1)}                            # k -> (block-tap index, parity)
+    w2 = w.new_zeros(cout, 4, 4, cin)
+    for ky in range(3):
+        ty, py = m[ky]
+        for kx in range(3):
+            tx, px = m[kx]
+            w2[:, ty * 2 + tx, py * 2 + px, :] = w[:, :, ky, kx]
+    return w2.reshape(cout, 4, 4 * cin)
 
 
 def _pack_c16(wt: torch.Tensor, w_hi: torch.Tensor) -> torch.Tensor:
@@ -359,7 +383,9 @@ class Plan:
         assert x.C == cw.cin and y.C == cw.cout, (key, x.C, cw.cin, y.C, cw.cout)
         passes = cw.passes_for(PASSES.get(eng.precision, 1))
         c16 = cw.pack16(passes)
-        if cw.stem and eng.precision != SIMT:
+        if eng.precision == TC_F16C and cw.w_s2 is not None and w // 2 >= 8 and res is None:
+            ops.conv_s2_tc(x, n, h, w, cw.w_s2, cw.bias, y, lrelu, cw.s2_passes)
+        elif cw.stem and eng.precision != SIMT:
             ops.conv_stem_tc(self.img_pad, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, lrelu, passes, c16)
         elif cw.w_hi is not None and eng.precision != SIMT:
             ops.conv_tc(x, n, h, w, cw.w_hi, cw.w_lo, cw.bias, y, cw.kh, cw.kw, lrelu, passes, res, c16, cw.stride)

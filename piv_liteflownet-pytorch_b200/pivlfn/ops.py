@@ -120,6 +120,13 @@ def conv_tc(x: View, N, H, W, w_hi, w_lo, bias, y: View, KH, KW, lrelu, passes, 
                                   int(passes), _stream()), "conv_tc")
 
 
+def conv_s2_tc(x: View, N, H, W, w16, bias, y: View, lrelu, passes):
+    """3x3 stride-2 convolution in the fp16 modes; H, W are the INPUT size."""
+    lib = _lib.load()
+    _lib.check(lib.pivlfn_conv_s2_tc(x.ptr, x.ld, N, H, W, x.C, w16.data_ptr(), bias.data_ptr() if bias is not None else None,
+                                     y.ptr, y.ld, y.C, int(lrelu), int(passes), _stream()), "conv_s2_tc")
+
+
 def conv1x1_pairs_tc(x: View, N, H, W, w_hi, w_lo, w_c16, planes: torch.Tensor, npair: int, passes: int):
     lib = _lib.load()
     _lib.check(lib.pivlfn_conv1x1_pairs_tc(x.ptr, x.ld, N, H, W, x.C, w_hi.data_ptr(),

@@ -336,3 +336,21 @@ def test_flow_head_simt_vs_torch(K, H, W):
     ops.flow_head(ops.view(xin, 0, 32), 2, H, W, wh, None, None, ops.view(out2), K)
     ref2 = F.conv2d(x.double(), w.double(), None, padding=K // 2).float()
     assert (_nchw(out2, 2) - ref2).abs().max().item() <= 2e-5
+
+
+@pytest.mark.parametrize("case", [(32, 32, 16, 24), (32, 64, 64, 64), (64, 96, 34, 62), (96, 128, 16, 16), (32, 32, 256, 128)])
+def test_conv_s2_halo_vs_torch(case):
+    """3x3 stride-2 convolutions of NetC restated over the four input parities (TMA element strides do the space-to-depth),
+    fp16 split-operand modes 4 (Cout <= 64) and 5 (Cout > 64): fp32-equivalent tolerance."""
+    cin, cout, H, W = case
+    w, b = _rand(cout, cin, 3, 3, seed=1, scale=1.0 / math.sqrt(cin * 9)), _rand(cout, seed=2)
+    x = _rand(2, cin, H, W, seed=3)
+    ref = O.lrelu(F.conv2d(x.double(), w.double(), b.double(), stride=2, padding=1).float())
+    cw = pack_conv(w.to(DEV), b.to(DEV), 2)
+    assert cw.w_s2 is not None and cw.s2_passes == (5 if cout > 64 else 4)
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    y = torch.zeros(2, Ho, Wo, cout, device=DEV)
+    ops.conv_s2_tc(ops.view(_nhwc(x), 0, cin), 2, H, W, cw.w_s2, cw.bias, ops.view(y), True, cw.s2_passes)
+    err = (_nchw(y, cout) - ref).abs().max().item()
+    print(f"conv_s2 {case}: max err {err:.2e}")
+    assert err <= 1e-4

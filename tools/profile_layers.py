@@ -60,6 +60,10 @@ def w_conv_simt(x, N, Hh, Ww, w, bias, y, KH, KW, stride, lrelu, res=None):
     return 2.0 * N * (Hh // stride) * (Ww // stride) * x.C * y.C * KH * KW, "F", f"{x.C}->{y.C} {KH}x{KW} s{stride} @{Hh}x{Ww}"
 
 
+def w_s2(x, N, Hh, Ww, w16, bias, y, lrelu, passes):
+    return 2.0 * N * (Hh // 2) * (Ww // 2) * x.C * y.C * 9, "F", f"{x.C}->{y.C} 3x3 s2 (parity phases) @{Hh}x{Ww}"
+
+
 def w_stem(img_pad, N, Hh, Ww, w_hi, w_lo, bias, y, lrelu, passes, w_c16=None):
     return 2.0 * N * Hh * Ww * 3 * 32 * 49, "F", f"stem 3->32 7x7 @{Hh}x{Ww}"
 
@@ -108,7 +112,7 @@ def w_small(*a, **k):
     return 0.0, "B", ""
 
 
-for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_tc", w_stem), ("conv1x1_pairs_tc", w_pairs),
+for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_tc", w_stem), ("conv_s2_tc", w_s2), ("conv1x1_pairs_tc", w_pairs),
                ("flow_head_sum", w_headsum), ("flow_head", w_head), ("deconv4x4s2_dw", w_deconv), ("warp", w_warp), ("corr_nhwc", w_corr),
                ("reg_tail", w_regtail), ("reg_input", w_reginput), ("copy", w_copy), ("flow_mean", w_small),
                ("prep_images", w_small), ("avgpool2", w_small)):
