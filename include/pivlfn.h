@@ -173,6 +173,22 @@ int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow_in,
 int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, int H, int W, int Ho, int Wo,
                                 float mul_even, float mul_odd, void* stream);
 
+/* ---- stereo-PIV post-processing (stereo_run.py:104-163) ------------------------------------------------------------------
+ * stereo/dewarp.py:255-270 nl_trans: new_x = P(A[0:6]) / P(A[6:12]), new_y = P(A[12:18]) / P(A[18:24]) with
+ * P(a) = a0 x + a1 y + a2 + a3 x^2 + a4 y^2 + a5 x y, evaluated in float32 in the reference's operation order.
+ * x, y, new_x, new_y: n device floats; A24: 24 HOST floats. */
+int pivlfn_nl_trans(const float* x, const float* y, const float* A24, float* new_x, float* new_y, long long n, void* stream);
+
+/* stereo_run._stereo_cal (:153-163) on both camera flows + stereo/vel3d.py:4-24 willert, fused.  flow_left / flow_right:
+ * [B,2,H,W] device (what estimate(..., tensor=True) returns); A_left / A_right: 24 HOST floats each, or both NULL to skip the
+ * mapping (willert only); use_calib: multiply the mapped flows by calib and then by fps (two float32 products);
+ * tan_*: np.tan of the signed camera angles (theta = off-axis half angle, beta = off-axis half angle in the y-z plane) as
+ * float64 scalars; like the reference under its pinned numpy 1.17 they (and their float64 differences) are rounded to float32
+ * where they meet the float32 flows.  out: [B,H,W,3] device float32 (U, V, W), the 3-band .flo layout. */
+int pivlfn_stereo_2d3c(const float* flow_left, const float* flow_right, const float* A_left, const float* A_right,
+                       int use_calib, float calib, float fps, double tan_theta0, double tan_theta1,
+                       double tan_beta0, double tan_beta1, float* out, int B, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpivlfn.so")
 
-_p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
+_p, _i, _f, _ll, _d = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_double
 
 # name -> (restype, argtypes); mirrors include/pivlfn.h one to one (checked by tests/test_abi.py)
 PROTOTYPES = {
@@ -33,6 +33,8 @@ PROTOTYPES = {
     "pivlfn_reg_input": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _p]),
     "pivlfn_reg_tail": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _p, _f, _i, _i, _i, _i, _p]),
     "pivlfn_copy_nhwc": (_i, [_p, _i, _p, _i, _ll, _i, _p]),
+    "pivlfn_nl_trans": (_i, [_p, _p, C.POINTER(_f), _p, _p, _ll, _p]),
+    "pivlfn_stereo_2d3c": (_i, [_p, _p, C.POINTER(_f), C.POINTER(_f), _i, _f, _f, _d, _d, _d, _d, _p, _i, _i, _i, _p]),
     "pivlfn_resize_bilinear_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),
 }
 

@@ -216,5 +216,39 @@ def resize_bilinear(x: torch.Tensor, Ho: int, Wo: int, mul_even: float = 1.0, mu
     return out
 
 
+def nl_trans(x: torch.Tensor, y: torch.Tensor, A):
+    """stereo/dewarp.py:255-270 on CUDA float32 tensors of equal shape; A: 24 coefficients (host)."""
+    lib = _lib.load()
+    _need_cuda(x, y)
+    assert x.shape == y.shape and len(A) == 24
+    x, y = x.contiguous(), y.contiguous()
+    nx, ny = torch.empty_like(x), torch.empty_like(y)
+    arr = (C.c_float * 24)(*[float(a) for a in A])
+    _lib.check(lib.pivlfn_nl_trans(x.data_ptr(), y.data_ptr(), arr, nx.data_ptr(), ny.data_ptr(), x.numel(), _stream()),
+               "nl_trans")
+    return nx, ny
+
+
+def stereo_2d3c(flow_left: torch.Tensor, flow_right: torch.Tensor, A_left, A_right, calib, fps, theta, beta) -> torch.Tensor:
+    """stereo_run._stereo_cal (:153-163) on both camera flows + willert (stereo/vel3d.py:4-24), fused.
+    flow_*: [B,2,H,W] CUDA float32 (estimate(..., tensor=True)); A_*: 24 mapping coefficients each, or None for willert
+    only; calib: None or the real-length calibration factor; theta, beta: signed camera angles in radians (left, right).
+    Returns [B,H,W,3] float32 (U, V, W)."""
+    lib = _lib.load()
+    _need_cuda(flow_left, flow_right)
+    assert flow_left.shape == flow_right.shape and flow_left.dim() == 4 and flow_left.shape[1] == 2
+    fl, fr = flow_left.contiguous(), flow_right.contiguous()
+    B, _, H, W = fl.shape
+    out = torch.empty((B, H, W, 3), device=fl.device, dtype=torch.float32)
+    al = (C.c_float * 24)(*[float(a) for a in A_left]) if A_left is not None else None
+    ar = (C.c_float * 24)(*[float(a) for a in A_right]) if A_right is not None else None
+    tt = [math.tan(float(t)) for t in theta]
+    tb = [math.tan(float(b)) for b in beta]
+    _lib.check(lib.pivlfn_stereo_2d3c(fl.data_ptr(), fr.data_ptr(), al, ar, int(calib is not None),
+                                      float(calib) if calib is not None else 1.0, float(fps), tt[0], tt[1], tb[0], tb[1],
+                                      out.data_ptr(), B, H, W, _stream()), "stereo_2d3c")
+    return out
+
+
 def launch_count() -> int:
     return int(_lib.load().pivlfn_launch_count())

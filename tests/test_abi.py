@@ -55,6 +55,8 @@ def test_ctypes_prototypes_match_header():
                 assert t is ctypes.c_float, (name, a)
             elif a.startswith("long long"):
                 assert t is ctypes.c_longlong, (name, a)
+            elif a.startswith("double"):
+                assert t is ctypes.c_double, (name, a)
             else:
                 assert t is ctypes.c_int, (name, a)
 
