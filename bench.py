@@ -341,6 +341,10 @@ def main():
 
     if rank == 0 and not args.no_extra:
         try:
+            # per-kernel rooflines are "kernel timed alone" figures (MEASURED_PEAKS burst): let the power-capped GPU settle
+            # after the timed forward loops before timing single kernels
+            torch.cuda.synchronize()
+            time.sleep(1.5)
             line.update(kernel_rooflines(eng, pk))
         except Exception as ex:  # a side measurement must not lose the headline
             line["roofline"] = {"error": repr(ex)}

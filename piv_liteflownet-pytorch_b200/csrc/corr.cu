@@ -209,22 +209,27 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
 #pragma unroll 2
         for (int qi = 0; qi < NH_NQ; ++qi) {
             const int q = ((qi + rot) & (NH_NQ - 1)) * 4;
-            float4 a[4], v[10];
+            float4 a[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(a0 + i * NH_PITCH + q);
+            // stream the 10 f2 pixels: pixel j serves (i, d = j - i) for every output pixel i it is in range of, so only two
+            // of them are live at a time (register pressure decides how many CTAs share an SM during the gather phases)
 #pragma unroll
-            for (int j = 0; j < 10; ++j) v[j] = *reinterpret_cast<const float4*>(b0 + j * NH_PITCH + q);
+            for (int j = 0; j < 10; ++j) {
+                const float4 v = *reinterpret_cast<const float4*>(b0 + j * NH_PITCH + q);
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int d = 0; d < 7; ++d) {
-                    float t = acc[i][d];
-                    t = fmaf(a[i].x, v[i + d].x, t);
-                    t = fmaf(a[i].y, v[i + d].y, t);
-                    t = fmaf(a[i].z, v[i + d].z, t);
-                    t = fmaf(a[i].w, v[i + d].w, t);
-                    acc[i][d] = t;
+                for (int i = 0; i < 4; ++i) {
+                    const int d = j - i;
+                    if (d >= 0 && d < 7) {
+                        float t = acc[i][d];
+                        t = fmaf(a[i].x, v.x, t);
+                        t = fmaf(a[i].y, v.y, t);
+                        t = fmaf(a[i].z, v.z, t);
+                        t = fmaf(a[i].w, v.w, t);
+                        acc[i][d] = t;
+                    }
                 }
+            }
         }
     }
     // ---- stage the 128 x 49 results in shared memory, then store whole pixel rows ---------------------------------
