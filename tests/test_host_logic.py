@@ -165,3 +165,42 @@ def test_particle_generator_statistics_and_determinism():
     assert dx in (2, 3) and dy in (-1, -2)
     t = synth.to_rgb_tensor(i1)
     assert t.shape == (3, 128, 128) and float(t.max()) <= 1.0 and torch.equal(t[0], t[2])
+
+
+def test_fp16_operand_packs_reconstruct_the_weights():
+    """f16c packs (host logic): [f16(w) | f16((w - f16(w)) * 2^11)] and the single-accumulator pack of W = 256 w,
+    [f16(W) | f16(W - f16(W)) | f16(f16(W) / 2^11)], reconstruct the weights to ~2^-22 relative; a weight outside the fp16
+    range is reported (None) instead of being saturated."""
+    from pivlfn.model import _pack_f16, _pack_f16_single
+    g = torch.Generator().manual_seed(9)
+    w = torch.randn(32, 9, 64, generator=g) * torch.logspace(-4, 1, 64)[None, None, :]       # 5 decades of magnitudes
+    p = _pack_f16(w)
+    assert p.dtype == torch.float16 and p.shape == (2, 32, 9, 64)
+    rec = p[0].double() + p[1].double() / 2048.0
+    # absolute floor: the scaled residual bottoms out at the fp16 subnormal spacing, 2^-24 / 2^11
+    assert ((rec - w.double()).abs() <= w.abs().double() * 2.0 ** -21 + 2e-11).all()
+    s = _pack_f16_single(w)
+    assert s.shape == (3, 32, 9, 64)
+    rec = (s[0].double() + s[1].double()) / 256.0
+    assert ((rec - w.double()).abs() <= w.abs().double() * 2.0 ** -21 + 2.5e-10).all()       # floor 2^-24 / 2^8
+    assert torch.equal(s[2], (s[0].float() / 2048.0).half())
+    big = w.clone()
+    big[0, 0, 0] = 1.0e5
+    assert _pack_f16(big) is None and _pack_f16_single(big) is None
+
+
+def test_stride2_restatement_equals_the_strided_convolution():
+    """3x3 stride-2 convolution == 2x2-tap stride-1 convolution over the four input parities with the restated weights
+    (host logic of pivlfn_conv_s2_tc; block taps at offsets -1 and 0, zero padding)."""
+    from pivlfn.model import _restate_s2
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(8, 5, 3, 3, generator=g)
+    x = torch.randn(2, 5, 12, 10, generator=g)
+    ref = F.conv2d(x, w, None, stride=2, padding=1)
+    w2 = _restate_s2(w)                                                   # [8, 4 taps, 4*5]
+    # space-to-depth: channel (py*2 + px)*Cin + c holds x[c, 2y + py, 2x + px]
+    s2d = torch.cat([x[:, :, py::2, px::2] for py in (0, 1) for px in (0, 1)], 1)
+    wk = w2.reshape(8, 2, 2, 20).permute(0, 3, 1, 2)                      # [cout, 4*cin, by, bx]
+    out = F.conv2d(F.pad(s2d, (1, 0, 1, 0)), wk, None)                    # taps at block offsets -1, 0
+    assert out.shape == ref.shape and (out - ref).abs().max() <= 1e-5
+    assert (w2 == 0).float().mean() > 0.4                                 # 7 of 16 (tap, parity) products are zero
