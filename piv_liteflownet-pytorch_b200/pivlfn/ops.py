@@ -99,6 +99,18 @@ def copy(src: View, dst: View, npix: int):
     _lib.check(lib.pivlfn_copy_nhwc(src.ptr, src.ld, dst.ptr, dst.ld, npix, src.C, _stream()), "copy_nhwc")
 
 
+def copy_dense(src: torch.Tensor, dst: torch.Tensor):
+    """dst <- src for two dense fp32 CUDA tensors of equal size, by a KERNEL (float4 lanes), not cudaMemcpy: the copy
+    engines stay free for host <-> device traffic of neighbouring batches (pivlfn.pipeline)."""
+    lib = _lib.load()
+    n = src.numel()
+    assert dst.numel() == n and src.is_contiguous() and dst.is_contiguous() and src.dtype == dst.dtype == torch.float32
+    if n % 4 or (src.data_ptr() & 15) or (dst.data_ptr() & 15):
+        _lib.check(lib.pivlfn_copy_nhwc(src.data_ptr(), 1, dst.data_ptr(), 1, n, 1, _stream()), "copy_dense")
+    else:
+        _lib.check(lib.pivlfn_copy_nhwc(src.data_ptr(), 4, dst.data_ptr(), 4, n // 4, 4, _stream()), "copy_dense")
+
+
 def conv_simt(x: View, N, H, W, w, bias, y: View, KH, KW, stride, lrelu, res: Optional[View] = None):
     lib = _lib.load()
     _lib.check(lib.pivlfn_conv_simt(x.ptr, x.ld, N, H, W, x.C, w.data_ptr(),
