@@ -478,6 +478,13 @@ struct ConvHaloArgs {
 #define DBG_T0() long long _t0 = a.dbg ? clock64() : 0
 #define DBG_ADD(var) do { if (a.dbg) var += clock64() - _t0; } while (0)
 
+// Stride-2 restatement (ConvHaloArgs::s2): block tap t = (ty, tx) of parity phase par = (py, px) carries a non-zero weight
+// only if ty >= 1 - py and tx >= 1 - px (input row 2y-1 is the odd row of block y-1; the even row of block y-1 is never
+// read).  Every role skips the other (tap, parity) pairs in the same way: 9 of 16 products remain, the original 9 taps.
+__device__ __forceinline__ bool s2_tap_used(int t, int par) {
+    return ((t >> 1) >= 1 - (par >> 1)) && ((t & 1) >= 1 - (par & 1));
+}
+
 // buffer slot of chunk c's activations (hi after the split) and of its low-order part
 // nbuf == 4: two (x, lo) pairs, plain double buffering -- the split of chunk c+1 overlaps the MMAs of chunk c;
 // nbuf == 3: rotation raw(c+1) / x(c) / lo(c) when shared memory has no room for a fourth slot (N = 128)
@@ -610,7 +617,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     // retired; issue it after nB weight tiles (by then chunk gc-1 has certainly retired)
                     bool next_issued = !has_next || a.nBuf < 2;
                     if (!next_issued && gc == 0) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                    int issued = 0;
                     for (int t = 0; t < ntaps; ++t) {
+                        if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
+                        ++issued;
                         { DBG_T0(); mbar_wait(&b_empty[bs], bphase ^ 1); DBG_ADD(p_b); }
                         uint8_t* sB = smemB + (size_t)bs * b_stage;
                         mbar_expect_tx(&b_full[bs], b_stage);
@@ -625,7 +635,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_3d(sB + b_bytes + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
                         }
                         if (++bs == a.nB) { bs = 0; bphase ^= 1; }
-                        if (!next_issued && t + 1 >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                        if (!next_issued && issued >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
                     }
                     if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
@@ -685,6 +695,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     for (int t = 0; t < ntaps; ++t) {
                         const uint32_t woff16 = row16 + (uint32_t)(kx * 8);
                         if (++kx == a.KW) { kx = 0; row16 += pitch8; }
+                        if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
                         { DBG_T0(); mbar_wait(&b_full[bs], bphase); DBG_ADD(w_b); }
                         tc_fence_after();
                         const uint32_t bHi16 = (smem_u32(smemB + (size_t)bs * b_stage) >> 4) | lbo_bits;
