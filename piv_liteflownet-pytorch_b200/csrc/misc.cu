@@ -204,7 +204,7 @@ __global__ void copy_nhwc_kernel(const float* __restrict__ in, int in_ld, float*
 // ...: every load instruction fetches 64 contiguous bytes per pixel and tap, and the per-quad instruction count is ~45
 // (the previous one-quad-per-thread version spent 229 instructions per quad on index arithmetic and taps and was
 // issue-bound at 64 % issue utilisation with DRAM at 40 %).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restrict__ flow, float scale,
                  float* __restrict__ out, int out_ld, int N, int H, int W, int C) {
     const int Q = (C + 3) >> 2;
@@ -233,18 +233,18 @@ warp_nhwc_kernel(const float* __restrict__ in, int in_ld, const float2* __restri
         }
         float* o = out + p * out_ld;
         if ((C & 3) == 0) {
-            for (int q0 = lq; q0 < Q; q0 += 16) {
-                // up to four quads in flight: 16 independent 16-byte loads per thread
-                float4 u[4][4];
+            for (int q0 = lq; q0 < Q; q0 += 8) {
+                // two quads in flight: 8 independent 16-byte loads per thread (more would cost the third resident block)
+                float4 u[2][4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                     const int q = q0 + 4 * j;
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         u[j][k] = (q < Q && on[k]) ? __ldg(reinterpret_cast<const float4*>(src[k]) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 2; ++j) {
                     const int q = q0 + 4 * j;
                     if (q < Q) {
                         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);

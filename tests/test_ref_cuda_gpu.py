@@ -171,3 +171,32 @@ def test_reference_cuda_path_rate_report_1024():
     if os.path.isdir(d):
         json.dump(res, open(os.path.join(d, "ref_cuda_rate.json"), "w"), indent=1)
     assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_correlation_operator_rate_report():
+    """The drop-in FunctionCorrelation operator next to the reference's own three kernels (+ its three zero-fills) on the
+    level-1 shape of a 1024x1024 frame and on a stride-1 level: a report (gpurun_out/parity_report.txt), plus agreement."""
+    from src.correlation import FunctionCorrelation
+    res = {}
+    for shape in [(1, 64, 1024, 1024, 2), (1, 96, 128, 128, 1)]:
+        B, C, H, W, s = shape
+        f1, f2 = _rand((B, C, H, W), 3).to(DEV), _rand((B, C, H, W), 4).to(DEV)
+        ref = RC.reference_correlation(f1, f2, s)
+        out = FunctionCorrelation(tensorFirst=f1, tensorSecond=f2, intStride=s)
+        assert (out - ref).abs().max().item() <= 1e-5
+        t = {}
+        for name, fn in (("reference", lambda: RC.reference_correlation(f1, f2, s)),
+                         ("pivlfn", lambda: FunctionCorrelation(tensorFirst=f1, tensorSecond=f2, intStride=s))):
+            fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t[name] = e0.elapsed_time(e1) / 5
+        res[str(shape)] = t
+    _report("FunctionCorrelation operator, ms per call (reference CUDA kernels vs pivlfn_corr_nchw): " + json.dumps(res))

@@ -1,5 +1,5 @@
-"""Level-1 memory-bound operators alone (cost volume with fused backwarp, backwarp, regularisation tail) for ncu and
-for quick timing.   python tools/profile_ops.py [B] [H]"""
+"""Level-1 glue operators alone (cost volume with fused backwarp, backwarp, regularisation tail, depthwise up-convolution,
+flow head) for ncu and for quick timing.   python tools/profile_ops.py [B] [H]"""
 import os
 import sys
 
@@ -41,3 +41,15 @@ timeit(lambda: ops.corr_nhwc(ops.view(Sbuf, 0, cm), ops.view(f2), flow, 5.0, ops
 timeit(lambda: ops.warp(ops.view(f2), flow, 5.0, ops.view(Sbuf, cm, cm), B, H, H), "warp_nhwc C=64", 4.0 * B * H * H * (2 * cm + 2))
 timeit(lambda: ops.reg_tail(ops.view(dist, 0, 49), flow, wx, bx, wy, by, flow_out, None, 5.0, 7), "reg_tail K=7",
        4.0 * B * H * H * (49 + 4))
+
+import math
+corr_half = torch.randn(B, H // 2, H // 2, 52, generator=g).to(dev)
+corr_up = torch.zeros(B, H, H, 52, device=dev)
+wdw = torch.randn(49, 16, generator=g).to(dev)
+timeit(lambda: ops.deconv4x4s2_dw(ops.view(corr_half, 0, 49), B, H // 2, H // 2, wdw, ops.view(corr_up, 0, 49)),
+       "deconv4x4s2_dw C=49 (H/2 -> H)", 4.0 * B * (H // 2) ** 2 * 52 * 5)
+x32 = torch.randn(B, H, H, 32, generator=g).to(dev)
+wh = (torch.randn(49, 32, 2, generator=g) / math.sqrt(32 * 49)).to(dev)
+bh = torch.zeros(2, device=dev)
+timeit(lambda: ops.flow_head(ops.view(x32), B, H, H, wh, bh, ops.view(flow), ops.view(flow_out), 7),
+       "flow_head K=7 (fp32 FMA: GFLOP/s in the GB/s column)", 2.0 * B * H * H * 32 * 2 * 49)
