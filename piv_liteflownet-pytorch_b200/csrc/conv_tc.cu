@@ -452,10 +452,6 @@ struct ConvHaloArgs {
     int s2, cpp;             // s2 = 1: 3x3 stride-2 convolution restated as 2x2 block taps over the four pixel-parity phases of
                              // the input (space-to-depth done by TMA element strides): chunk c = parity (c / cpp) x 32-channel
                              // group (c % cpp); H, W are the OUTPUT size and Cin = 4 * input channels
-    int kbank;               // mode 4, small Cout: 2 = the two 16-channel K steps of a chunk accumulate in separate TMEM banks (summed
-                             // by the epilogue).  All MMAs of a tile are one dependency chain through its accumulator; at N <= 32
-                             // an MMA is shorter than the pipeline latency between dependent MMAs (measured ~80 cycles per MMA
-                             // against a 39-cycle issue floor), so two tiles = two chains leave the tensor pipe half idle.
     int slot_mode;           // 1 (fp16 modes with 3 slots): one raw slot + two pair slots, see slot_x / slot_l
     int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
@@ -552,8 +548,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int i = threadIdx.x - 128;
         bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
     }
-    const int set_cols = ((SPLIT && a.corr) ? 2 : 1) * a.NT * a.CoutP * a.kbank;
-    const uint32_t bank_cols = (uint32_t)(2 * a.NT * a.CoutP);            // mode 4: bank b of a set starts b * bank_cols further
+    const int set_cols = ((SPLIT && a.corr) ? 2 : 1) * a.NT * a.CoutP;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
     const int G = gridDim.x;
 
@@ -716,15 +711,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                                 for (int kk = 0; kk < KC / 16; ++kk) {
                                     if (2 * kk < nk) {
-                                        const uint32_t first = acc | (uint32_t)(kk >= a.kbank);
+                                        const uint32_t first = acc | (uint32_t)(kk > 0);
                                         if (F16S) {
                                             umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, first);
                                             umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + blo16 / 2 + 2 * kk, hiB16, idesc16, 1);
                                             umma_bf16_lohi(t_main, pa16 + half16 + 2 * kk, hiA16, bHi16 + blo16 + 2 * kk, hiB16, idesc16, 1);
                                         } else {
-                                        const uint32_t tb = t_main + (uint32_t)(kk & (a.kbank - 1)) * bank_cols;
-                                        umma_bf16_lohi(tb, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16w, first);
-                                        umma_bf16_lohi(tb + (uint32_t)a.CoutP, pa16 + half16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, 1);
+                                        umma_bf16_lohi(t_main, pa16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16w, first);
+                                        umma_bf16_lohi(t_main + (uint32_t)a.CoutP, pa16 + half16 + 2 * kk, hiA16, bHi16 + 2 * kk, hiB16, idesc16, 1);
                                         }
                                     }
                                 }
@@ -930,16 +924,6 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const float cs = F16D ? (1.f / 2048.f) : 1.f;    // mode 4 keeps the low-order products scaled by 2^11
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(u[j]), cs, __uint_as_float(v[j])));
-                        if (F16D && a.kbank == 2) {
-                            // second K bank of the same columns: main1 into u, corr1 into w
-                            uint32_t w[16];
-                            tmem_ld16_nowait(trow + bank_cols + (uint32_t)(2 * i * a.CoutP + c0), u);
-                            tmem_ld16_nowait(trow + bank_cols + (uint32_t)((2 * i + 1) * a.CoutP + c0), w);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                v[j] = __float_as_uint(fmaf(__uint_as_float(w[j]), cs, __uint_as_float(v[j]) + __uint_as_float(u[j])));
-                        }
                     }
 #pragma unroll
                     for (int half = 0; half < 2; ++half) {
@@ -1162,9 +1146,9 @@ void choose_tile(ConvTcArgs& a) {
 }
 
 // Environment switches of the halo kernel (experiments; defaults are the measured best).
-struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store, tma_store, kbank; };
+struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store, tma_store; };
 const HaloEnv& halo_env() {
-    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1, 0, 1};
+    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1, 0};
     if (e.use_halo < 0) {
         const char* v = getenv("PIVLFN_TC_HALO");
         e.use_halo = (v && v[0] == '0') ? 0 : 1;
@@ -1180,8 +1164,6 @@ const HaloEnv& halo_env() {
         e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
         v = getenv("PIVLFN_TC_QUADSTORE");
         e.quad_store = (v && v[0] == '0') ? 0 : 1;
-        v = getenv("PIVLFN_TC_KBANK");
-        e.kbank = (v && v[0] == '0') ? 0 : 1;
         v = getenv("PIVLFN_TC_TMASTORE");         // measured: no faster than direct stores (the limit is downstream of the SM,
         e.tma_store = (v && v[0] == '1') ? 1 : 0; // ~18 B/clk per SM either way) and it costs a weight-ring stage: off by default
     }
@@ -1198,9 +1180,7 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
     const int b_stage = passes == 5 ? h.CoutP * KC * 6 : (passes == 4 ? 1 : (passes >= 2 ? 2 : 1)) * h.CoutP * KC * 4;
     // mode 4 scales its corrections: own accumulator; mode 5: everything in one accumulator
     const int corr = passes == 5 ? 0 : ((passes == 4 || (passes >= 2 && env.corr_mode)) ? 1 : 0);
-    // two K banks (see ConvHaloArgs::kbank): mode 4, N <= 32, at least two K steps in every chunk that starts an item
-    const int kbank = (passes == 4 && h.CoutP <= 32 && h.Cin >= KC && env.kbank) ? 2 : 1;
-    const int acc_mult = (corr ? 2 : 1) * kbank;
+    const int acc_mult = corr ? 2 : 1;
     // NT stacked tiles per work item: bounded by TMEM (512 columns, two accumulator sets wanted so that the epilogue
     // overlaps the next item's MMAs), by the image height and by shared memory
     int NT = env.nt_limit > 0 ? env.nt_limit : 2;
@@ -1221,7 +1201,7 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         if (nB < need || halo_rows > 256) continue;
         h.corr = corr;
         h.nsets = (2 * acc_mult * NT * h.CoutP <= 512) ? 2 : 1;
-        h.NT = NT; h.nBuf = nBuf; h.nB = nB; h.kbank = kbank;
+        h.NT = NT; h.nBuf = nBuf; h.nB = nB;
         h.slot_mode = (passes >= 4 && nBuf == 3) ? 1 : 0;
         h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
         const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
@@ -1334,8 +1314,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         h.planar = 0;
         h.stage_off = 0; h.s2 = 0; h.cpp = 1;
-        // quad-transposed stores for every full 16-channel group (the tail of Cout = 49 / 25 goes through the float4 path)
-        if (vec_store >= 1 && !res && !(W & 3) && cout_st >= 16 && halo_env().quad_store) h.vec_store = 4;
+        if (vec_store >= 1 && !res && !(W & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
         // TMA tile stores: rows 16-byte aligned, at least one full 16-channel group, no residual to add
         const bool tma_ok = vec_store >= 1 && !res && cout_st >= 16 && halo_env().tma_store;
         if (tma_ok) h.vec_store = 5;
