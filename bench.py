@@ -154,8 +154,14 @@ def run_reference(args, rank, world):
 
 def time_kernel(fn, iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(3):
+    # warm-up: at least 3 launches and ~20 ms of this kernel (clocks and caches in the state the timed launches see)
+    t0 = time.perf_counter()
+    n = 0
+    while n < 3 or (time.perf_counter() - t0 < 0.02 and n < 200):
         fn()
+        n += 1
+        if n % 8 == 0:
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     e0.record()
     for _ in range(iters):
@@ -341,10 +347,6 @@ def main():
 
     if rank == 0 and not args.no_extra:
         try:
-            # per-kernel rooflines are "kernel timed alone" figures (MEASURED_PEAKS burst): let the power-capped GPU settle
-            # after the timed forward loops before timing single kernels
-            torch.cuda.synchronize()
-            time.sleep(1.5)
             line.update(kernel_rooflines(eng, pk))
         except Exception as ex:  # a side measurement must not lose the headline
             line["roofline"] = {"error": repr(ex)}
