@@ -34,8 +34,8 @@ def model_shapes(B, H, W, lowest=1):
 
 
 # (B, C, H, W, stride): operator-level cases (odd sizes at stride 2 -> Ho = ceil(H/2), batch > 1, few channels), then every
-# correlation shape of whole forwards: PIV 1x128x128, PIV 2x64x96, Hui 1x64x128 (parity) and PIV 1x1024x1024 (timing
-# of the reference's CUDA path)
+# correlation shape of whole forwards: PIV 1x128x128, PIV 2x64x96, Hui 1x64x128 (parity), PIV 1x1024x1024 and Hui 16x448x1024
+# (BASELINE configs[2] after estimate()'s resize: timing of the reference's CUDA path)
 SHAPES = sorted(set([
     (2, 64, 32, 32, 2),
     (1, 64, 33, 35, 2),
@@ -44,7 +44,7 @@ SHAPES = sorted(set([
     (1, 32, 9, 5, 1),
     (3, 64, 64, 96, 2),
 ] + model_shapes(1, 128, 128) + model_shapes(2, 64, 96) + model_shapes(1, 64, 128, lowest=2)
-  + model_shapes(1, 1024, 1024)))
+  + model_shapes(1, 1024, 1024) + model_shapes(16, 448, 1024, lowest=2)))
 
 
 def shape_tag(B, C, H, W, s):

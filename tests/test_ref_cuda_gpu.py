@@ -200,3 +200,73 @@ def test_correlation_operator_rate_report():
             t[name] = e0.elapsed_time(e1) / 5
         res[str(shape)] = t
     _report("FunctionCorrelation operator, ms per call (reference CUDA kernels vs pivlfn_corr_nchw): " + json.dumps(res))
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_reference_cuda_path_rate_report_hui_cfg3():
+    """BASELINE configs[2]: original LiteFlowNet ('hui') on batch 16 of 1024x436 pairs through estimate() (resized to
+    1024x448, output at half resolution resized back).  Reference GPU path (eager torch/cuDNN + its correlation kernels,
+    fp32 and torch's TF32 default) next to this repo; also checks that they agree.  A report, not an assertion on speed."""
+    from inference import estimate
+    from src.models import hui_liteflownet
+    sd = synth.synthetic_state_dict("hui", 0)
+    a, b, _ = synth.particle_batch(2, 436, 1024, 11, "shear")
+    a, b = a.repeat(8, 1, 1, 1).contiguous(), b.repeat(8, 1, 1, 1).contiguous()          # batch 16
+    sdd = {k: v.to(DEV) for k, v in sd.items()}
+    ad, bd = a.to(DEV), b.to(DEV)
+    corr = lambda x, y, s: RC.reference_correlation(x.contiguous(), y.contiguous(), s)
+
+    def ref_estimate():
+        # inference.py:39-61 around the reference forward
+        import torch.nn.functional as F
+        x1 = F.interpolate(ad, size=(448, 1024), mode="bilinear", align_corners=False)
+        x2 = F.interpolate(bd, size=(448, 1024), mode="bilinear", align_corners=False)
+        raw = O.forward(sdd, x1, x2, "hui", corr_fn=corr)
+        flow = F.interpolate(raw, size=(436, 1024), mode="bilinear", align_corners=False)
+        flow[:, 1] *= 436.0 / 448.0
+        return flow
+
+    res = {}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        for tag, tf32 in (("fp32", False), ("tf32_default", True)):
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            with torch.no_grad():
+                ref = ref_estimate()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    r = ref_estimate()
+                e1.record()
+                torch.cuda.synchronize()
+            res[tag] = {"ms_per_batch": e0.elapsed_time(e1) / 2, "pairs_per_s": 16 * 2e3 / e0.elapsed_time(e1)}
+            if not tf32:
+                ref32 = ref
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    net = hui_liteflownet(sd, 1).to(DEV).eval()
+    with torch.no_grad():
+        for _ in range(2):
+            out = estimate(net, ad, bd, tensor=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            out = estimate(net, ad, bd, tensor=True)
+        e1.record()
+        torch.cuda.synchronize()
+    res["pivlfn_" + net.engine().precision] = {"ms_per_batch": e0.elapsed_time(e1) / 5, "pairs_per_s": 16 * 5e3 / e0.elapsed_time(e1)}
+    diff = (out - ref32).abs()
+    res["flow_max_abs_diff_vs_fp32_reference"] = diff.max().item()
+    res["flow_mean_abs_diff_vs_fp32_reference"] = diff.mean().item()
+    res["flow_abs_max"] = ref32.abs().max().item()
+    _report("reference CUDA path, Hui LiteFlowNet batch 16 of 1024x436 through estimate(): " + json.dumps(res))
+    d = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(d):
+        json.dump(res, open(os.path.join(d, "ref_cuda_rate_hui_cfg3.json"), "w"), indent=1)
+    # Hui flows carry the x20 output scale: tolerance relative to the flow magnitude (1e-2 px at 10 px)
+    scale = max(1.0, res["flow_abs_max"] / 10.0)
+    assert diff.max().item() <= 1e-2 * scale and diff.mean().item() <= 1e-3 * scale
