@@ -452,6 +452,10 @@ struct ConvHaloArgs {
     int s2, cpp;             // s2 = 1: 3x3 stride-2 convolution restated as 2x2 block taps over the four pixel-parity phases of
                              // the input (space-to-depth done by TMA element strides): chunk c = parity (c / cpp) x 32-channel
                              // group (c % cpp); H, W are the OUTPUT size and Cin = 4 * input channels
+    int tps;                 // filter taps per weight-ring stage (1, or 3 for small Cout: one barrier round trip and one
+                             // tcgen05.commit per THREE taps -- at N <= 64 the per-tap waits / fences of the issuing thread, not
+                             // the tensor pipe, set the pace: measured 320 cycles per (tap, 16 channels) against a pipe floor of
+                             // 176, tools/ubench/umma_f16_rate.cu)
     int slot_mode;           // 1 (fp16 modes with 3 slots): one raw slot + two pair slots, see slot_x / slot_l
     int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
@@ -620,10 +624,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     int issued = 0;
                     for (int t = 0; t < ntaps; ++t) {
                         if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
-                        ++issued;
-                        { DBG_T0(); mbar_wait(&b_empty[bs], bphase ^ 1); DBG_ADD(p_b); }
-                        uint8_t* sB = smemB + (size_t)bs * b_stage;
-                        mbar_expect_tx(&b_full[bs], b_stage);
+                        const int sub = a.tps > 1 ? t % a.tps : 0;            // position inside the stage (tps divides ntaps)
+                        if (sub == 0) {
+                            ++issued;
+                            { DBG_T0(); mbar_wait(&b_empty[bs], bphase ^ 1); DBG_ADD(p_b); }
+                            mbar_expect_tx(&b_full[bs], a.tps * b_stage);
+                        }
+                        uint8_t* sB = smemB + ((size_t)bs * a.tps + sub) * b_stage;
                         if (F16) {
                             tma_load_3d(sB, &tmB16, &b_full[bs], c * KC, t, 0);
                             tma_load_3d(sB + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
@@ -634,8 +641,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             tma_load_3d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, t, 0);
                             tma_load_3d(sB + b_bytes + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
                         }
-                        if (++bs == a.nB) { bs = 0; bphase ^= 1; }
-                        if (!next_issued && issued >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                        if (sub == a.tps - 1) {
+                            if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                            if (!next_issued && issued >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
+                        }
                     }
                     if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
@@ -696,9 +705,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         const uint32_t woff16 = row16 + (uint32_t)(kx * 8);
                         if (++kx == a.KW) { kx = 0; row16 += pitch8; }
                         if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
-                        { DBG_T0(); mbar_wait(&b_full[bs], bphase); DBG_ADD(w_b); }
-                        tc_fence_after();
-                        const uint32_t bHi16 = (smem_u32(smemB + (size_t)bs * b_stage) >> 4) | lbo_bits;
+                        const int sub = a.tps > 1 ? t % a.tps : 0;
+                        if (sub == 0) {
+                            { DBG_T0(); mbar_wait(&b_full[bs], bphase); DBG_ADD(w_b); }
+                            tc_fence_after();
+                        }
+                        const uint32_t bHi16 = (smem_u32(smemB + ((size_t)bs * a.tps + sub) * b_stage) >> 4) | lbo_bits;
                         uint32_t a_hi = aHi16 + woff16 + issuer * tile16, a_lo = aLo16 + woff16 + issuer * tile16;
                         uint32_t t_main = tset + (uint32_t)issuer * tile_cols;
                         for (int i = issuer; i < a.NT; i += n_issuers) {
@@ -754,8 +766,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             a_hi += n_issuers * tile16; a_lo += n_issuers * tile16; t_main += (uint32_t)n_issuers * tile_cols;
                         }
                         acc = 1;
-                        umma_commit(&b_empty[bs]);
-                        if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                        if (sub == a.tps - 1) {
+                            umma_commit(&b_empty[bs]);
+                            if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                        }
                     }
                     umma_commit(&chunk_done[gc & 1]);
                 }
@@ -1146,9 +1160,9 @@ void choose_tile(ConvTcArgs& a) {
 }
 
 // Environment switches of the halo kernel (experiments; defaults are the measured best).
-struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store, tma_store; };
+struct HaloEnv { int use_halo, bo_mode, nt_limit, corr_mode, split_trunc, stagger, quad_store, tma_store, tps3; };
 const HaloEnv& halo_env() {
-    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1, 0};
+    static HaloEnv e = {-1, 0, 0, 1, 0, 0, 1, 0, 1};
     if (e.use_halo < 0) {
         const char* v = getenv("PIVLFN_TC_HALO");
         e.use_halo = (v && v[0] == '0') ? 0 : 1;
@@ -1164,6 +1178,8 @@ const HaloEnv& halo_env() {
         e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
         v = getenv("PIVLFN_TC_QUADSTORE");
         e.quad_store = (v && v[0] == '0') ? 0 : 1;
+        v = getenv("PIVLFN_TC_TPS3");
+        e.tps3 = (v && v[0] == '0') ? 0 : 1;
         v = getenv("PIVLFN_TC_TMASTORE");         // measured: no faster than direct stores (the limit is downstream of the SM,
         e.tma_store = (v && v[0] == '1') ? 1 : 0; // ~18 B/clk per SM either way) and it costs a weight-ring stage: off by default
     }
@@ -1195,13 +1211,17 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
         // weight ring
         const int stage = h.vec_store == 5 ? EPI_STAGE_BYTES : 0;
         if (passes >= 2 && (HALO_SMEM_BUDGET - stage - 4 * slot) / b_stage >= (stage ? 2 : 3)) nBuf = 4;
-        int nB = (HALO_SMEM_BUDGET - stage - nBuf * slot) / b_stage;
+        // three taps per weight stage for small Cout (see ConvHaloArgs::tps) when two such stages still fit
+        int tps = 1;
+        if (env.tps3 && passes >= 4 && !h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 &&
+            (HALO_SMEM_BUDGET - stage - nBuf * slot) / (3 * b_stage) >= 2) tps = 3;
+        int nB = (HALO_SMEM_BUDGET - stage - nBuf * slot) / (tps * b_stage);
         if (nB > MAX_STAGES) nB = MAX_STAGES;
         const int need = passes >= 2 ? 2 : 3;
         if (nB < need || halo_rows > 256) continue;
         h.corr = corr;
         h.nsets = (2 * acc_mult * NT * h.CoutP <= 512) ? 2 : 1;
-        h.NT = NT; h.nBuf = nBuf; h.nB = nB;
+        h.NT = NT; h.nBuf = nBuf; h.nB = nB; h.tps = tps;
         h.slot_mode = (passes >= 4 && nBuf == 3) ? 1 : 0;
         h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
         const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
@@ -1217,8 +1237,8 @@ int halo_configure(ConvHaloArgs& h, int passes, int* halo_rows_out) {
             h.stagger = (h.nsets == 1 && h.total >= 4 * n_cta) ? (int)(item * env.stagger / 100) : 0;
         }
         *halo_rows_out = halo_rows;
-        h.stage_off = (nBuf * slot + nB * b_stage + 1023) & ~1023;
-        return stage ? h.stage_off + stage : nBuf * slot + nB * b_stage;
+        h.stage_off = (nBuf * slot + nB * tps * b_stage + 1023) & ~1023;
+        return stage ? h.stage_off + stage : nBuf * slot + nB * tps * b_stage;
     }
     return 0;
 }
