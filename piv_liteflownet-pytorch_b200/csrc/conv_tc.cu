@@ -683,6 +683,66 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             int gc = 0, wl = 0;
             long long w_acc = 0, w_a = 0, w_b = 0;
             const long long t_begin = a.dbg ? clock64() : 0;
+            if (F16 && !a.s2 && a.NT <= 2) {
+                // ---- lean issue loop of the fp16 modes ------------------------------------------------------------------
+                // The issuing thread is a single in-order thread: the ~150 dependent scalar instructions the general loop
+                // below spends per tap (tap bookkeeping, stage addresses, mode tests) cost ~600 cycles, more than the MMAs
+                // of a tap take on the tensor pipe when Cout <= 64 (352 / 448 cycles for Cout = 32 / 64 over both tiles,
+                // tools/ubench/umma_f16_rate.cu).  Here a tap is: one add for the A window, one for the weight tile, the MMAs.
+                const uint32_t tileA = (uint32_t)issuer * (tile16 / 2);
+                const uint32_t stage16 = (uint32_t)(b_stage >> 4);
+                const uint32_t ring16 = stage16 * (uint32_t)a.tps;
+                const uint32_t bbase16 = (smem_u32(smemB) >> 4) | lbo_bits;
+                const uint32_t row_step = (uint32_t)((pitch - a.KW) * 4);      // A window: next filter row, in 16-byte units
+                const uint32_t cP = (uint32_t)a.CoutP;
+                uint32_t bcur = bbase16;
+                for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+                    const int as = wl % a.nsets;
+                    const uint32_t use = (uint32_t)(wl / a.nsets);
+                    { DBG_T0(); mbar_wait(&acc_empty[as], (use & 1) ^ 1); DBG_ADD(w_acc); }
+                    tc_fence_after();
+                    const uint32_t t_main = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)issuer * tile_cols;
+                    uint32_t acc = 0;
+                    for (int c = 0; c < nchunk; ++c, ++gc) {
+                        const bool two = a.Cin - c * KC > 16;                      // second 16-channel K step present
+                        { DBG_T0(); mbar_wait(&a_ready[gc & 1], (uint32_t)((gc >> 1) & 1)); DBG_ADD(w_a); }
+                        tc_fence_after();
+                        uint32_t A = ((smem_u32(smem + (size_t)slot_l(gc, nbuf_k) * slot_bytes) >> 4) | lbo_bits) + tileA;
+                        int kx = 0;
+                        for (int t = 0; t < ntaps;) {
+                            { DBG_T0(); mbar_wait(&b_full[bs], bphase); DBG_ADD(w_b); }
+                            tc_fence_after();
+                            uint32_t b = bcur;
+                            for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
+                                if (F16S) {
+                                    umma_bf16_lohi(t_main, A, hiA16, b, hiB16, idesc16, acc);
+                                    umma_bf16_lohi(t_main, A, hiA16, b + blo16 / 2, hiB16, idesc16, 1);
+                                    umma_bf16_lohi(t_main, A + half16, hiA16, b + blo16, hiB16, idesc16, 1);
+                                    if (two) {
+                                        umma_bf16_lohi(t_main, A + 2, hiA16, b + 2, hiB16, idesc16, 1);
+                                        umma_bf16_lohi(t_main, A + 2, hiA16, b + blo16 / 2 + 2, hiB16, idesc16, 1);
+                                        umma_bf16_lohi(t_main, A + half16 + 2, hiA16, b + blo16 + 2, hiB16, idesc16, 1);
+                                    }
+                                } else {
+                                    umma_bf16_lohi(t_main, A, hiA16, b, hiB16, idesc16w, acc);
+                                    umma_bf16_lohi(t_main + cP, A + half16, hiA16, b, hiB16, idesc16, 1);
+                                    if (two) {
+                                        umma_bf16_lohi(t_main, A + 2, hiA16, b + 2, hiB16, idesc16w, 1);
+                                        umma_bf16_lohi(t_main + cP, A + half16 + 2, hiA16, b + 2, hiB16, idesc16, 1);
+                                    }
+                                }
+                                acc = 1;
+                                A += 4;                                             // next tap of the filter row
+                                if (++kx == a.KW) { kx = 0; A += row_step; }
+                            }
+                            umma_commit(&b_empty[bs]);
+                            if (++bs == a.nB) { bs = 0; bphase ^= 1; bcur = bbase16; } else bcur += ring16;
+                        }
+                        umma_commit(&chunk_done[gc & 1]);
+                    }
+                    umma_commit(&acc_full[as]);
+                }
+            } else
             for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
                 const int as = wl % a.nsets;
                 const uint32_t use = (uint32_t)(wl / a.nsets);
