@@ -542,6 +542,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int nbuf_k = a.slot_mode ? -3 : a.nBuf;
     __shared__ __align__(8) uint64_t a_full[2], a_ready[2], chunk_done[2], b_full[MAX_STAGES], b_empty[MAX_STAGES],
         acc_full[2], acc_empty[2];
+    __shared__ long long dbg_a_issue[2];   // trace only: clock of the A load of chunk parity 0 / 1
     __shared__ uint32_t tmem_base_s;
     __shared__ float bias_s[128];          // fits in the 1 KB the static part is padded to anyway
 
@@ -567,7 +568,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tma_prefetch_desc(&tmA);
         if (!F16) tma_prefetch_desc(&tmBhi);
         if (PASSES == 3 || F16S) tma_prefetch_desc(&tmBlo);
-        if (PASSES == 2 || F16) { tma_prefetch_desc(&tmB16); tma_prefetch_desc(&tmBlo16); }
+        if (PASSES == 2 || F16) tma_prefetch_desc(&tmB16);
         if (a.vec_store == 5) tma_prefetch_desc(&tmY);
     }
     if (warp == 1) {
@@ -586,25 +587,34 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t bphase = 0;
             int gc = 0;                                   // global chunk counter
             long long p_b = 0, p_a = 0;
-            auto load_A = [&](int g, int w, int c) {
-                const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
-                // slot_x(g) was last read by global chunk g-2's MMAs (as its hi or its lo slot)
-                // (slot_mode 1: the single raw slot is free once chunk g-1 has been split)
-                if (a.slot_mode) {
-                    if (g >= 1) { DBG_T0(); mbar_wait(&a_ready[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1)); DBG_ADD(p_a); }
-                } else if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
-                mbar_expect_tx(&a_full[g & 1], halo_bytes);
+            const long long p_begin = a.dbg ? clock64() : 0;
+            // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
+            auto next_of = [&](int w, int c, int& w2, int& c2) { c2 = c + 1; w2 = w; if (c2 == nchunk) { c2 = 0; w2 = w + G; } };
+            auto coords_A = [&](int w, int c, int& c0, int& c1, int& c2, int& c3) {
+                const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y;
+                c3 = w / (a.tiles_x * a.tiles_y);
                 if (a.s2) {
                     // parity phase (py, px) of the input, sampled every second pixel; the tile starts one block left / above
                     const int par = c / a.cpp, cc = c - par * a.cpp;
-                    tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], cc * KC,
-                                2 * (tx * HT_W - 1) + (par & 1), 2 * (ty * HT_H * a.NT - 1) + (par >> 1), n);
-                } else
-                tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], c * KC,
-                            tx * HT_W + a.x_shift, ty * HT_H * a.NT - a.KH / 2, n);
+                    c0 = cc * KC; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
+                } else { c0 = c * KC; c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2; }
             };
-            // the chunk sequence (item, chunk) flattened: chunk g+1 follows chunk g across item boundaries
-            auto next_of = [&](int w, int c, int& w2, int& c2) { c2 = c + 1; w2 = w; if (c2 == nchunk) { c2 = 0; w2 = w + G; } };
+            auto load_A = [&](int g, int w, int c) {
+                // slot_x(g) was last read by global chunk g-2's MMAs (as its hi or its lo slot)
+                // (slot_mode 1: the single raw slot is free once chunk g-1 has been split)
+                // fp16 modes: the MMAs never read the raw tile, so its slot is free as soon as its previous tenant has been
+                // split (chunk g-2 with two raw slots) -- a whole chunk earlier than the MMAs retire
+                if (a.slot_mode) {
+                    if (g >= 1) { DBG_T0(); mbar_wait(&a_ready[(g - 1) & 1], (uint32_t)(((g - 1) >> 1) & 1)); DBG_ADD(p_a); }
+                } else if (F16 && a.nBuf == 4) {
+                    if (g >= 2) { DBG_T0(); mbar_wait(&a_ready[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
+                } else if (g >= 2) { DBG_T0(); mbar_wait(&chunk_done[(g - 2) & 1], (uint32_t)(((g - 2) >> 1) & 1)); DBG_ADD(p_a); }
+                mbar_expect_tx(&a_full[g & 1], halo_bytes);
+                if (a.dbg) *(volatile long long*)&dbg_a_issue[g & 1] = clock64();
+                int c0, c1, c2, c3;
+                coords_A(w, c, c0, c1, c2, c3);
+                tma_load_4d(smem + (size_t)slot_x(g, nbuf_k) * slot_bytes, &tmA, &a_full[g & 1], c0, c1, c2, c3);
+            };
             bool pre = false;                             // is chunk gc already issued?
             if (a.stagger > 0) {
                 const long long t0 = clock64(), d = (long long)a.stagger * blockIdx.x / G;
@@ -632,15 +642,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         uint8_t* sB = smemB + ((size_t)bs * a.tps + sub) * b_stage;
                         if (F16) {
-                            tma_load_3d(sB, &tmB16, &b_full[bs], c * KC, t, 0);
-                            tma_load_3d(sB + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
-                            if (F16S) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
+                            // one box = the tps taps x [hi | lo (| hi2)] tiles of the stage (encode_weights16_stage)
+                            if (sub == 0) tma_load_4d(sB, &tmB16, &b_full[bs], c * KC, 0, 0, t);
                         } else tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
-                        if (PASSES == 2) {
-                            tma_load_3d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, t, 0);
-                            tma_load_3d(sB + b_bytes + b_bytes / 2, &tmBlo16, &b_full[bs], c * KC, t, 0);
-                        }
+                        if (PASSES == 2) tma_load_4d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, 0, 0, t);   // [bf16(w) | bf16(w_lo)]
                         if (sub == a.tps - 1) {
                             if (++bs == a.nB) { bs = 0; bphase ^= 1; }
                             if (!next_issued && issued >= a.nB) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
@@ -649,7 +655,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
             }
-            if (a.dbg && blockIdx.x == 0) { a.dbg[5] = p_b; a.dbg[6] = p_a; }
+            if (a.dbg && blockIdx.x == 0) { a.dbg[5] = p_b; a.dbg[6] = p_a; a.dbg[13] = clock64() - p_begin; }
         }
     } else if (warp == 1 || warp == 2) {
         // ================================ MMA issuers =================================
@@ -677,7 +683,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const uint32_t idesc16 = F16 ? make_idesc_f16(a.CoutP) : make_idesc_bf16(a.CoutP);
             const uint32_t idesc16w = make_idesc_f16(2 * a.CoutP);
             const uint32_t tile_cols = (uint32_t)(F16D ? 2 * a.CoutP : a.CoutP);    // mode 4: [main | corr] per stacked tile
-            const uint32_t half16 = (uint32_t)(halo_rows * pitch * 64) >> 4;       // bf16(a_lo) tile behind bf16(a)
+            const uint32_t half16 = (((uint32_t)(halo_rows * pitch * 64) + 511u) & ~511u) >> 4;       // bf16(a_lo) tile behind bf16(a)
             int bs = 0;
             uint32_t bphase = 0;
             int gc = 0, wl = 0;
@@ -846,7 +852,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const int et = threadIdx.x - 8 * 32;
             const int nvec = halo_bytes / 16;
             int gc = 0;
-            long long s_w1 = 0, s_w2 = 0, s_busy = 0;
+            long long s_w1 = 0, s_w2 = 0, s_busy = 0, s_lat = 0;
             for (int w = blockIdx.x; w < a.total; w += G) {
                 for (int c = 0; c < nchunk; ++c, ++gc) {
                     // the lo slot of chunk gc was last in use by chunk gc-1's MMAs (3 slots) or chunk gc-2's (4 slots)
@@ -857,6 +863,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         DBG_ADD(s_w1);
                     }
                     { DBG_T0(); mbar_wait(&a_full[gc & 1], (uint32_t)((gc >> 1) & 1)); DBG_ADD(s_w2); }
+                    if (a.dbg) s_lat += clock64() - *(volatile long long*)&dbg_a_issue[gc & 1];
                     const long long s_t0 = a.dbg ? clock64() : 0;
                     float4* pa = reinterpret_cast<float4*>(smem + (size_t)slot_x(gc, nbuf_k) * slot_bytes);
                     float4* pl = reinterpret_cast<float4*>(smem + (size_t)slot_l(gc, nbuf_k) * slot_bytes);
@@ -866,38 +873,40 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (PASSES == 2 || F16) {
                         // bf16(a) and bf16(a - trunc_tf32(a)) (mode 4: f16(a) and f16((a - f16(a)) * 2^11)) into the pair slot, 64-byte rows with the 64B swizzle applied
                         // by hand (absolute shared-memory address bits [7:8] -> [4:5], the rule TMA / UMMA use)
-                        const uint32_t pair_abs = smem_u32(pl);
-                        const uint32_t half_b = (uint32_t)(halo_rows * pitch * 64);
-                        uint8_t* pair = reinterpret_cast<uint8_t*>(pl);
-                        // one thread = two adjacent 16-byte chunks of a row = 8 consecutive channels -> one 16-byte bf16 store
+                        // Slots are 1024-byte aligned and both halves of the pair slot start on a 512-byte boundary, so the
+                        // two swizzles compose to something simple.  Pair q = 16-byte chunks 2q, 2q+1 of the fp32 tile
+                        // (128B swizzle: logical chunk = p ^ (p >> 3 & 7)); with x = (q >> 2) & 1 chunk 2q + x is the even
+                        // logical chunk 2L (channels 8L .. 8L+3, L = (q & 3) ^ (q >> 3 & 3)) and its neighbour the odd one.
+                        // The pair row of pixel q >> 2 wants logical 16-byte chunk L at physical chunk L ^ (q >> 3 & 3)
+                        // = q & 3 (64B swizzle): the stores are linear in q.  Bonus: the x term makes the 8 lanes of a
+                        // quarter warp hit 8 different bank groups on the loads.
+                        const uint32_t half_b = ((uint32_t)(halo_rows * pitch * 64) + 511u) & ~511u;
+                        uint4* ph = reinterpret_cast<uint4*>(pl);
+                        uint4* plo = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(pl) + half_b);
+                        // one thread = two adjacent 16-byte chunks of a row = 8 consecutive channels -> one 16-byte store per half
                         const int npair = nvec >> 1;
                         constexpr int SP2 = 4;
+                        float amax = 0.f;
                         for (int base = et; base < npair; base += SP2 * SPLIT_THREADS) {
                             float4 v0[SP2], v1[SP2];
 #pragma unroll
                             for (int j = 0; j < SP2; ++j) {
                                 const int q = base + j * SPLIT_THREADS;
-                                if (q < npair) { v0[j] = pa[2 * q]; v1[j] = pa[2 * q + 1]; }
+                                if (q < npair) { const int p = 2 * q + ((q >> 2) & 1); v0[j] = pa[p]; v1[j] = pa[p ^ 1]; }
                             }
 #pragma unroll
                             for (int j = 0; j < SP2; ++j) {
                                 const int q = base + j * SPLIT_THREADS;
                                 if (q < npair) {
-                                    const uint32_t abs16 = (smem_u32(pa) >> 4) + (uint32_t)(2 * q);
-                                    const uint32_t lc0 = (abs16 & 7u) ^ ((abs16 >> 3) & 7u);   // logical chunk of v0 (v1: lc0 ^ 1)
-                                    const uint32_t pix = (uint32_t)q >> 2;
-                                    const float4 a0 = (lc0 & 1u) ? v1[j] : v0[j];             // channels 8L .. 8L+3
-                                    const float4 a1 = (lc0 & 1u) ? v0[j] : v1[j];             // channels 8L+4 .. 8L+7
+                                    const float4 a0 = v0[j], a1 = v1[j];
                                     uint4 h, l;
                                     if (F16) {
                                         h.x = pack_f16(a0.x, a0.y); h.y = pack_f16(a0.z, a0.w);
                                         h.z = pack_f16(a1.x, a1.y); h.w = pack_f16(a1.z, a1.w);
                                         l.x = pack_f16_lo(a0.x, a0.y, h.x); l.y = pack_f16_lo(a0.z, a0.w, h.y);
                                         l.z = pack_f16_lo(a1.x, a1.y, h.z); l.w = pack_f16_lo(a1.z, a1.w, h.w);
-                                        // inf / nan exponent in any half: the activation left the fp16 range
-                                        const uint32_t ex = (__vcmpeq2(h.x & 0x7C007C00u, 0x7C007C00u) | __vcmpeq2(h.y & 0x7C007C00u, 0x7C007C00u) |
-                                                             __vcmpeq2(h.z & 0x7C007C00u, 0x7C007C00u) | __vcmpeq2(h.w & 0x7C007C00u, 0x7C007C00u));
-                                        if (ex) g_f16_range_flag = 1;
+                                        amax = fmaxf(fmaxf(fmaxf(amax, fabsf(a0.x)), fmaxf(fabsf(a0.y), fabsf(a0.z))),
+                                                     fmaxf(fmaxf(fabsf(a0.w), fabsf(a1.x)), fmaxf(fabsf(a1.y), fmaxf(fabsf(a1.z), fabsf(a1.w)))));
                                     } else {
                                     h.x = pack_bf16(a0.x, a0.y); h.y = pack_bf16(a0.z, a0.w);
                                     h.z = pack_bf16(a1.x, a1.y); h.w = pack_bf16(a1.z, a1.w);
@@ -906,16 +915,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     l.z = pack_bf16(PIVLFN_LO(a1.x), PIVLFN_LO(a1.y)); l.w = pack_bf16(PIVLFN_LO(a1.z), PIVLFN_LO(a1.w));
 #undef PIVLFN_LO
                                     }
-                                    const uint32_t off = pix * 64u + (lc0 >> 1) * 16u;
-                                    uint32_t ad = pair_abs + off;
-                                    ad ^= ((ad >> 7) & 3u) << 4;
-                                    *reinterpret_cast<uint4*>(pair + (ad - pair_abs)) = h;
-                                    uint32_t ad2 = pair_abs + half_b + off;
-                                    ad2 ^= ((ad2 >> 7) & 3u) << 4;
-                                    *reinterpret_cast<uint4*>(pair + (ad2 - pair_abs)) = l;
+                                    ph[q] = h;
+                                    plo[q] = l;
                                 }
                             }
                         }
+                        // an activation that rounds to inf in fp16 (|x| >= 65520) left the range of this mode
+                        if (F16 && amax >= 65520.f) g_f16_range_flag = 1;
                     } else
                     for (int base = et; base < nvec; base += SB * SPLIT_THREADS) {
                         float4 v[SB];
@@ -950,7 +956,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (a.dbg) s_busy += clock64() - s_t0;
                 }
             }
-            if (a.dbg && blockIdx.x == 0 && threadIdx.x == 8 * 32) { a.dbg[9] = s_w1; a.dbg[10] = s_w2; a.dbg[11] = s_busy; }
+            if (a.dbg && blockIdx.x == 0 && threadIdx.x == 8 * 32) { a.dbg[9] = s_w1; a.dbg[10] = s_w2; a.dbg[11] = s_busy; a.dbg[14] = s_lat; }
         }
     } else if (warp >= 4) {
         // ================================ epilogue warps ================================
@@ -1210,6 +1216,21 @@ int encode_weights_bf16(EncodeTiledFn enc, CUtensorMap* tm, const void* w, int C
     return r == CUDA_SUCCESS ? PIVLFN_OK : PIVLFN_EINVAL;
 }
 
+// All 16-bit weight tiles of one ring stage in ONE TMA instruction (the producer thread is blocked ~250 cycles per tensor
+// load whatever its size, and a thin layer's chunk has 18 of them otherwise): the pack [parts][CoutP][ntaps][CinP] seen as
+// (channel, cout, part, tap) -> box (32 channels = 64 bytes, CoutP, parts, tps taps) lands in shared memory as
+// [tap][part][cout][64 B], i.e. per tap the [hi | lo (| hi2)] tiles the MMAs expect.
+int encode_weights16_stage(EncodeTiledFn enc, CUtensorMap* tm, const void* w, int CinP, int ntaps, int CoutP, int parts, int tps) {
+    cuuint64_t dims[4] = {(cuuint64_t)CinP, (cuuint64_t)CoutP, (cuuint64_t)parts, (cuuint64_t)ntaps};
+    cuuint64_t strides[3] = {(cuuint64_t)ntaps * CinP * 2, (cuuint64_t)CoutP * ntaps * CinP * 2, (cuuint64_t)CinP * 2};
+    cuuint32_t box[4] = {(cuuint32_t)KC, (cuuint32_t)CoutP, (cuuint32_t)parts, (cuuint32_t)tps};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(w), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? PIVLFN_OK : PIVLFN_EINVAL;
+}
+
 void choose_tile(ConvTcArgs& a) {
     a.bw = pow2_ceil(a.W < 16 ? a.W : 16);
     const int rem = TILE_M / a.bw;
@@ -1426,6 +1447,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+            if ((passes == 2 || passes >= 4) &&
+                encode_weights16_stage(enc, &tmB16, w_c16, CinP, KH * KW, CoutP, passes == 5 ? 3 : 2, h.tps)) return PIVLFN_EINVAL;
             return halo_launch(tmA, tmBhi, passes == 5 ? tmB3 : tmBlo, tmB16, tmBlo16, h, passes, smem, st, h.vec_store == 5 ? &tmY : nullptr);
         }
     }
@@ -1495,8 +1518,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
             else tBlo = tBhi;
             CUtensorMap tB16 = tBhi, tBlo16 = tBhi;
             if (passes == 2 || passes == 4) {
-                if (encode_weights_bf16(enc, &tB16, w_c16, 32, 7, 32)) return PIVLFN_EINVAL;
-                if (encode_weights_bf16(enc, &tBlo16, (const char*)w_c16 + (size_t)32 * 7 * 32 * 2, 32, 7, 32)) return PIVLFN_EINVAL;
+                if (encode_weights16_stage(enc, &tB16, w_c16, 32, 7, 32, 2, h.tps)) return PIVLFN_EINVAL;
             }
             return halo_launch(tA, tBhi, tBlo, tB16, tBlo16, h, passes, smem, (cudaStream_t)stream);
         }
@@ -1572,6 +1594,7 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    if ((passes == 2 || passes == 4) && encode_weights16_stage(enc, &tmB16, w_c16, CinP, 1, CoutP, 2, h.tps)) return PIVLFN_EINVAL;
     return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }
 
@@ -1620,5 +1643,6 @@ extern "C" int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, 
     if (encode_weights_bf16(enc, &tmBlo16, (const char*)w16 + tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
     tmB3 = tmBlo16;
     if (passes == 5 && encode_weights_bf16(enc, &tmB3, (const char*)w16 + 2 * tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
+    if (encode_weights16_stage(enc, &tmB16, w16, CinR, 4, CoutP, passes == 5 ? 3 : 2, h.tps)) return PIVLFN_EINVAL;
     return halo_launch(tmA, tmB16, tmB3, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }

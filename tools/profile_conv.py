@@ -49,5 +49,5 @@ if trace:
     torch.cuda.synchronize()
     t = dbg.cpu().tolist()
     names = ["mma_total", "mma_wait_acc_empty", "mma_wait_A", "mma_wait_B", "items", "prod_wait_b_empty", "prod_wait_slot",
-             "epi_wait_acc_full", "epi_busy", "split_wait_prev_chunk", "split_wait_raw", "split_busy", "epi_tmem_ld"]
+             "epi_wait_acc_full", "epi_busy", "split_wait_prev_chunk", "split_wait_raw", "split_busy", "epi_tmem_ld", "prod_total", "a_load_issue_to_seen"]
     print("  trace (CTA 0, cycles): " + ", ".join(f"{n}={v}" for n, v in zip(names, t)))
