@@ -15,7 +15,7 @@ from pivlfn.arch import CFGS  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 H = int(sys.argv[2]) if len(sys.argv) > 2 else 256
-prec = sys.argv[3] if len(sys.argv) > 3 else "tf32c"
+prec = sys.argv[3] if len(sys.argv) > 3 else "f16c"
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 3
 dev = torch.device("cuda", 0)
 sd = {k: v.to(dev) for k, v in synth.synthetic_state_dict("piv", 0).items()}
