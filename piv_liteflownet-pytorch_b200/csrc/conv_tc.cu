@@ -158,6 +158,16 @@ __device__ __forceinline__ uint32_t pack_f16_lo(float a, float b, uint32_t h) {
     asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(ha), "=f"(hb) : "r"(h));
     return pack_f16((a - ha) * 2048.f, (b - hb) * 2048.f);
 }
+// Explicit shared-space 128-bit accesses: the operand-split pointers are carved out of the aligned dynamic array by integer
+// arithmetic, after which the compiler no longer knows they are shared and emits generic LD.E / ST.E with 64-bit addressing
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // Sticky flag: an activation outside the fp16 range reached a PASSES == 4 convolution (host: pivlfn_f16_range_flag)
 __device__ int g_f16_range_flag = 0;
 // two fp32 -> packed bf16x2 (round to nearest even), low half = first value
@@ -544,7 +554,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         acc_full[2], acc_empty[2];
     __shared__ long long dbg_a_issue[2];   // trace only: clock of the A load of chunk parity 0 / 1
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[128];          // fits in the 1 KB the static part is padded to anyway
+    __shared__ __align__(16) float bias_s[128];   // fits in the 1 KB the static part is padded to anyway
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunk = (a.Cin + KC - 1) / KC;
@@ -881,8 +891,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         // = q & 3 (64B swizzle): the stores are linear in q.  Bonus: the x term makes the 8 lanes of a
                         // quarter warp hit 8 different bank groups on the loads.
                         const uint32_t half_b = ((uint32_t)(halo_rows * pitch * 64) + 511u) & ~511u;
-                        uint4* ph = reinterpret_cast<uint4*>(pl);
-                        uint4* plo = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(pl) + half_b);
+                        const uint32_t pa_s = smem_u32(pa), ph_s = smem_u32(pl), plo_s = ph_s + half_b;
                         // one thread = two adjacent 16-byte chunks of a row = 8 consecutive channels -> one 16-byte store per half
                         const int npair = nvec >> 1;
                         constexpr int SP2 = 4;
@@ -892,7 +901,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < SP2; ++j) {
                                 const int q = base + j * SPLIT_THREADS;
-                                if (q < npair) { const int p = 2 * q + ((q >> 2) & 1); v0[j] = pa[p]; v1[j] = pa[p ^ 1]; }
+                                if (q < npair) { const uint32_t p = (uint32_t)(2 * q + ((q >> 2) & 1)); v0[j] = lds128(pa_s + p * 16u); v1[j] = lds128(pa_s + (p ^ 1u) * 16u); }
                             }
 #pragma unroll
                             for (int j = 0; j < SP2; ++j) {
@@ -915,8 +924,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     l.z = pack_bf16(PIVLFN_LO(a1.x), PIVLFN_LO(a1.y)); l.w = pack_bf16(PIVLFN_LO(a1.z), PIVLFN_LO(a1.w));
 #undef PIVLFN_LO
                                     }
-                                    ph[q] = h;
-                                    plo[q] = l;
+                                    sts128(ph_s + (uint32_t)q * 16u, h);
+                                    sts128(plo_s + (uint32_t)q * 16u, l);
                                 }
                             }
                         }
@@ -1022,9 +1031,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float e[4];
+                                const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb + 4 * j]);      // one LDS.128, not four LDS
+                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bias_s[cb + 4 * j + k]);
+                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bb[k]);
                                     e[k] = a.lrelu ? lrelu_f(t) : t;
                                 }
                                 t4[j] = make_float4(e[0], e[1], e[2], e[3]);
@@ -1051,9 +1062,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
                                 float e[4];
+                                const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb + 4 * j]);      // one LDS.128, not four LDS
+                                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bias_s[cb + 4 * j + k]);
+                                    float t = fmaf(__uint_as_float(half ? u[4 * j + k] : v[4 * j + k]), osc, bb[k]);
                                     e[k] = a.lrelu ? lrelu_f(t) : t;
                                 }
                                 t4[j] = make_float4(e[0], e[1], e[2], e[3]);
@@ -1084,7 +1097,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             float o[16];
 #pragma unroll
                             for (int j = 0; j < 16; ++j) {
-                                float t = fmaf(__uint_as_float(half ? u[j] : v[j]), osc, bias_s[cb + j]);
+                                float t = fmaf(__uint_as_float(half ? u[j] : v[j]), osc, bias_s[cb + j]);   // (slow path: scalar LDS)
                                 if (a.lrelu) t = lrelu_f(t);
                                 o[j] = t;
                             }
