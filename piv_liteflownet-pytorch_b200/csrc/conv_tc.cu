@@ -590,9 +590,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
 
-    if (warp == 0) {
-        // ================================ TMA producer ================================
-        if (elect_one()) {
+    if (warp == 0 || warp == 3) {
+        // ================================ TMA producer(s) =============================
+        // fp16 modes with two raw slots: the activation tiles and the weight stages are issued by two different threads
+        // (warp 0 / warp 3).  A single producer sits inside its tensor-load instructions nearly all the time (the engine's
+        // queue is short), so the tile of chunk g+1 would only be issued after the weight stages of chunk g -- too late for
+        // the load -> split chain of a thin layer.  The two streams only meet at the barriers they already use.
+        const bool two_prod = F16 && a.nBuf == 4 && !a.slot_mode;
+        const bool do_A = warp == 0, do_W = two_prod ? warp == 3 : warp == 0;
+        if ((do_A || do_W) && elect_one()) {
             int bs = 0;
             uint32_t bphase = 0;
             int gc = 0;                                   // global chunk counter
@@ -630,8 +636,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const long long t0 = clock64(), d = (long long)a.stagger * blockIdx.x / G;
                 while (clock64() - t0 < d) __nanosleep(256);
             }
+            if (do_A && !do_W) {
+                for (int w = blockIdx.x; w < a.total; w += G)
+                    for (int c = 0; c < nchunk; ++c, ++gc) load_A(gc, w, c);
+            } else
             for (int w = blockIdx.x; w < a.total; w += G) {
                 for (int c = 0; c < nchunk; ++c, ++gc) {
+                    if (!do_A) pre = true;                // (the other producer thread loads the tiles)
                     if (!pre) load_A(gc, w, c);
                     pre = false;
                     int w2, c2;
@@ -639,7 +650,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const bool has_next = w2 < a.total;
                     // with >= 3 slots (or 2 slots in 1-pass mode) the next chunk's slot is free as soon as chunk gc-1
                     // retired; issue it after nB weight tiles (by then chunk gc-1 has certainly retired)
-                    bool next_issued = !has_next || a.nBuf < 2;
+                    bool next_issued = !has_next || a.nBuf < 2 || !do_A;
                     if (!next_issued && gc == 0) { load_A(gc + 1, w2, c2); next_issued = true; pre = true; }
                     int issued = 0;
                     for (int t = 0; t < ntaps; ++t) {
@@ -665,7 +676,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (!next_issued && a.nBuf >= 2) { load_A(gc + 1, w2, c2); pre = true; }
                 }
             }
-            if (a.dbg && blockIdx.x == 0) { a.dbg[5] = p_b; a.dbg[6] = p_a; a.dbg[13] = clock64() - p_begin; }
+            if (a.dbg && blockIdx.x == 0) { if (do_W) a.dbg[5] = p_b; if (do_A) { a.dbg[6] = p_a; a.dbg[13] = clock64() - p_begin; } }
         }
     } else if (warp == 1 || warp == 2) {
         // ================================ MMA issuers =================================

@@ -57,6 +57,36 @@ bench(const __grid_constant__ CUtensorMap tm, int depth, int nchunk, int tiles_x
     if (blockIdx.x == 0) { out[0] = clock64() - t0; out[1] = g; }
 }
 
+// Weight boxes of one ring stage (f16c, Cout = 32, 3 taps x [hi | lo] x 32 rows of 64 bytes = 12,288 bytes, L2-resident):
+// mode 0 = one 4-D tensor box per stage (what the conv kernel issues), mode 1 = the same bytes as ONE contiguous bulk copy
+__global__ void __launch_bounds__(32, 1)
+bench_w(const __grid_constant__ CUtensorMap tm, const uint8_t* img, int mode, int depth, int iters, int bytes, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar[MAXD];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < MAXD; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[i])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const long long t0 = clock64();
+    for (int g = 0; g < iters; ++g) {
+        const int s = g % depth, use = g / depth;
+        if (use > 0) mbar_wait(&bar[s], (uint32_t)((use - 1) & 1));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(bytes) : "memory");
+        const int c = (g / 3) & 1, t = (g % 3) * 3;
+        if (mode == 0)
+            asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                         ::"r"(smem_u32(smem + (size_t)s * 16384)), "l"(&tm), "r"(smem_u32(&bar[s])), "r"(c * 32), "r"(0), "r"(0), "r"(t) : "memory");
+        else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32(smem + (size_t)s * 16384)), "l"(img + (size_t)((c * 3 + g % 3) * bytes)), "r"(bytes), "r"(smem_u32(&bar[s])) : "memory");
+    }
+    for (int k = (iters > depth ? iters - depth : 0); k < iters; ++k) mbar_wait(&bar[k % depth], (uint32_t)((k / depth) & 1));
+    if (blockIdx.x == 0) { out[0] = clock64() - t0; out[1] = iters; }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -73,6 +103,7 @@ int main() {
     long long* out;
     cudaMalloc(&out, 16);
     cudaFuncSetAttribute(bench, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXD * SLOT + 1024);
+    cudaFuncSetAttribute(bench_w, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXD * SLOT + 1024);
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     for (int variant = 0; variant < 6; ++variant) {
@@ -107,6 +138,33 @@ int main() {
             printf("variant %d depth %d: %6.0f cycles/tile (%d B)  %5.1f B/clk/SM  %6.0f GB/s fetched  (%.3f ms)\n", variant, depth,
                    (double)h[0] / (double)h[1], bytes, (double)bytes * h[1] / h[0], (double)bytes * tiles * nchunk / ms / 1e6, ms);
         }
+    }
+    {
+        // weights: [parts = 2][CoutP = 32][ntaps = 9][CinP = 64] fp16
+        const int CinP = 64, CoutP = 32, ntaps = 9, parts = 2, tps = 3;
+        uint8_t* w;
+        cudaMalloc(&w, 1 << 20);
+        cudaMemset(w, 0, 1 << 20);
+        CUtensorMap tm;
+        cuuint64_t dims[4] = {(cuuint64_t)CinP, (cuuint64_t)CoutP, (cuuint64_t)parts, (cuuint64_t)ntaps};
+        cuuint64_t strides[3] = {(cuuint64_t)ntaps * CinP * 2, (cuuint64_t)CoutP * ntaps * CinP * 2, (cuuint64_t)CinP * 2};
+        cuuint32_t box[4] = {32, (cuuint32_t)CoutP, (cuuint32_t)parts, (cuuint32_t)tps};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("weight map: encode failed %d\n", (int)r); return 1; }
+        const int bytes = 32 * 2 * CoutP * parts * tps;
+        for (int mode = 0; mode < 2; ++mode)
+            for (int depth = 1; depth <= 4; ++depth) {
+                bench_w<<<sms, 32, MAXD * SLOT + 1024>>>(tm, w, mode, depth, 6000, bytes, out);
+                bench_w<<<sms, 32, MAXD * SLOT + 1024>>>(tm, w, mode, depth, 6000, bytes, out);
+                if (cudaDeviceSynchronize() != cudaSuccess) { printf("weights mode %d: %s\n", mode, cudaGetErrorString(cudaGetLastError())); return 1; }
+                long long h[2];
+                cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
+                printf("weight stage (%d B, L2-resident) %s depth %d: %6.0f cycles/stage  %5.1f B/clk/SM\n", bytes,
+                       mode == 0 ? "4-D tensor box, 192 rows of 64 B" : "one contiguous bulk copy      ", depth,
+                       (double)h[0] / h[1], (double)bytes * h[1] / h[0]);
+            }
     }
     return 0;
 }
