@@ -78,6 +78,10 @@ int pivlfn_conv_simt(const float* x, int x_ld, int N, int H, int W, int Cin,
  * passes == 5: the passes == 4 arithmetic with ONE accumulator per tile (used for Cout > 64, where two accumulators per
  * tile would leave no TMEM for double buffering), THREE tiles of the pre-scaled weights W = 256 w:
  * [f16(W) | f16(W - f16(W)) | f16(f16(W) / 2048)]; the kernel multiplies the result by 1/256.
+ * Storage order of w_c16: passes == 2: the tiles one after the other, [part][CoutP][KH*KW][CinP].  passes == 4 / 5: the
+ * shared-memory image of the kernel's weight ring, so that one ring stage is one contiguous bulk copy:
+ * [CinP/32 chunks][KH*KW taps][part][CoutP rows][64 bytes = 32 channels], the four 16-byte units of row r stored at
+ * unit ^ ((r >> 1) & 3) (the 64B swizzle of the MMA operand layout); pivlfn.model.stage_image builds it.
  * Requirements: x 16-byte aligned, x_ld % 4 == 0, Cout <= 128. */
 int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
                    const float* w_hi, const float* w_lo, const void* w_c16, const float* bias,
@@ -87,7 +91,7 @@ int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int Cin,
 /* The 3x3 stride-2 convolutions of NetC (src/models.py:77-106) in the fp16 modes (passes 4 or 5) of pivlfn_conv_tc, restated as
  * a 2x2-tap stride-1 convolution over the four pixel-parity phases of the input; TMA element strides fetch a phase directly,
  * so no space-to-depth copy exists.  H, W: INPUT size (even), output [N,H/2,W/2,Cout]; Cin % 32 == 0; W/2 >= 8.
- * w16: the passes-4 / passes-5 16-bit pack of the restated weights [CoutP][4][4*Cin], tap = (by+1)*2 + (bx+1),
+ * w16: the passes-4 / passes-5 16-bit pack (ring-stage image, see pivlfn_conv_tc) of the restated weights [CoutP][4][4*Cin], tap = (by+1)*2 + (bx+1),
  * channel = (py*2 + px)*Cin + c, where input row 2y + ky - 1 = 2(y + by) + py (zero weights for (by, py) = (-1, 0)). */
 int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, int Cin, const void* w16, const float* bias,
                       float* y, int y_ld, int Cout, int lrelu, int passes, void* stream);

@@ -71,6 +71,11 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
         ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// plain bulk copy global -> shared (contiguous bytes, 16-byte aligned, size a multiple of 16), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -466,6 +471,8 @@ struct ConvHaloArgs {
                              // tcgen05.commit per THREE taps -- at N <= 64 the per-tap waits / fences of the issuing thread, not
                              // the tensor pipe, set the pace: measured 320 cycles per (tap, 16 channels) against a pipe floor of
                              // 176, tools/ubench/umma_f16_rate.cu)
+    const uint8_t* w_img;    // fp16 modes: the weights as the shared-memory image of the ring stages (pivlfn.model.stage_image:
+                             // [chunk][tap][part][cout row][64 B, 64B-swizzled]) -- one stage = one contiguous bulk copy
     int slot_mode;           // 1 (fp16 modes with 3 slots): one raw slot + two pair slots, see slot_x / slot_l
     int corr;                // 3xTF32: accumulate the low-order terms in their own TMEM accumulator
     int nsets;               // TMEM accumulator sets (2 = epilogue of item i overlaps the MMAs of item i+1)
@@ -663,8 +670,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         }
                         uint8_t* sB = smemB + ((size_t)bs * a.tps + sub) * b_stage;
                         if (F16) {
-                            // one box = the tps taps x [hi | lo (| hi2)] tiles of the stage (encode_weights16_stage)
-                            if (sub == 0) tma_load_4d(sB, &tmB16, &b_full[bs], c * KC, 0, 0, t);
+                            // the tps taps x [hi | lo (| hi2)] tiles of the stage are contiguous in the weight image
+                            if (sub == 0) bulk_load(sB, a.w_img + ((size_t)c * ntaps + t) * b_stage, (uint32_t)(a.tps * b_stage), &b_full[bs]);
                         } else tma_load_3d(sB, &tmBhi, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 3) tma_load_3d(sB + b_bytes, &tmBlo, &b_full[bs], c * KC, t, 0);
                         if (PASSES == 2) tma_load_4d(sB + b_bytes, &tmB16, &b_full[bs], c * KC, 0, 0, t);   // [bf16(w) | bf16(w_lo)]
@@ -1471,8 +1478,8 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-            if ((passes == 2 || passes >= 4) &&
-                encode_weights16_stage(enc, &tmB16, w_c16, CinP, KH * KW, CoutP, passes == 5 ? 3 : 2, h.tps)) return PIVLFN_EINVAL;
+            h.w_img = passes >= 4 ? (const uint8_t*)w_c16 : nullptr;
+            if (passes == 2 && encode_weights16_stage(enc, &tmB16, w_c16, CinP, KH * KW, CoutP, 2, h.tps)) return PIVLFN_EINVAL;
             return halo_launch(tmA, tmBhi, passes == 5 ? tmB3 : tmBlo, tmB16, tmBlo16, h, passes, smem, st, h.vec_store == 5 ? &tmY : nullptr);
         }
     }
@@ -1541,9 +1548,8 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
             if (passes >= 2) { if (encode_weights(enc, &tBlo, w_lo, 32, 7, 32)) return PIVLFN_EINVAL; }
             else tBlo = tBhi;
             CUtensorMap tB16 = tBhi, tBlo16 = tBhi;
-            if (passes == 2 || passes == 4) {
-                if (encode_weights16_stage(enc, &tB16, w_c16, 32, 7, 32, 2, h.tps)) return PIVLFN_EINVAL;
-            }
+            h.w_img = passes == 4 ? (const uint8_t*)w_c16 : nullptr;
+            if (passes == 2 && encode_weights16_stage(enc, &tB16, w_c16, 32, 7, 32, 2, h.tps)) return PIVLFN_EINVAL;
             return halo_launch(tA, tBhi, tBlo, tB16, tBlo16, h, passes, smem, (cudaStream_t)stream);
         }
     }
@@ -1618,7 +1624,8 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
-    if ((passes == 2 || passes == 4) && encode_weights16_stage(enc, &tmB16, w_c16, CinP, 1, CoutP, 2, h.tps)) return PIVLFN_EINVAL;
+    h.w_img = passes == 4 ? (const uint8_t*)w_c16 : nullptr;
+    if (passes == 2 && encode_weights16_stage(enc, &tmB16, w_c16, CinP, 1, CoutP, 2, h.tps)) return PIVLFN_EINVAL;
     return halo_launch(tmA, tmBhi, tmBlo, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }
 
@@ -1667,6 +1674,6 @@ extern "C" int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, 
     if (encode_weights_bf16(enc, &tmBlo16, (const char*)w16 + tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
     tmB3 = tmBlo16;
     if (passes == 5 && encode_weights_bf16(enc, &tmB3, (const char*)w16 + 2 * tile, CinR, 4, CoutP)) return PIVLFN_EINVAL;
-    if (encode_weights16_stage(enc, &tmB16, w16, CinR, 4, CoutP, passes == 5 ? 3 : 2, h.tps)) return PIVLFN_EINVAL;
+    h.w_img = (const uint8_t*)w16;
     return halo_launch(tmA, tmB16, tmB3, tmB16, tmBlo16, h, passes, smem, (cudaStream_t)stream);
 }

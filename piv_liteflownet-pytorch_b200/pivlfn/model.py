@@ -77,11 +77,11 @@ class ConvW:
     w_hi: Optional[torch.Tensor] = None     # [CoutP16, KH*KW, CinP32] TF32 split for the tcgen05 kernel
     w_lo: Optional[torch.Tensor] = None
     w_c16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] bf16: bf16(w), bf16(w - w_hi)  (precision tf32c)
-    w_f16: Optional[torch.Tensor] = None    # [2, CoutP16, KH*KW, CinP32] fp16: f16(w), f16((w - f16(w)) * 2048)  (precision f16c)
+    w_f16: Optional[torch.Tensor] = None    # stage_image of [2, CoutP16, KH*KW, CinP32] fp16: f16(w), f16((w - f16(w)) * 2048)  (precision f16c)
 
     w_s2: Optional[torch.Tensor] = None     # 3x3 stride-2 layers restated over the four input parities: fp16 pack (2 or 3 tiles)
     s2_passes: int = 0                      # of [CoutP16, 4, 4*Cin] for pivlfn_conv_s2_tc, and its kernel mode (4 or 5)
-    w_f16s: Optional[torch.Tensor] = None   # [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
+    w_f16s: Optional[torch.Tensor] = None   # stage_image of [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
                                             # (single-accumulator variant of f16c, packed for Cout > 64 only)
 
     def passes_for(self, passes: int) -> int:
@@ -116,16 +116,16 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         wt = torch.nn.functional.pad(wt, (0, cinp - cin, 0, 0, 0, coutp - cout))
         cw.w_hi, cw.w_lo = _split_tf32(wt)
         cw.w_c16 = _pack_c16(wt, cw.w_hi)
-        cw.w_f16 = _pack_f16(wt)
+        cw.w_f16 = stage_image(_pack_f16(wt))
         if coutp > 64 and stride == 1 and cw.w_f16 is not None and os.environ.get("PIVLFN_F16_SINGLE", "1") != "0":
-            cw.w_f16s = _pack_f16_single(wt)
+            cw.w_f16s = stage_image(_pack_f16_single(wt))
         if stride == 2 and kh == 3 and kw == 3 and cin % 32 == 0 and os.environ.get("PIVLFN_S2_HALO", "1") != "0":
             w2 = _restate_s2(w)                                      # [cout, 4, 4*cin]
             w2 = torch.nn.functional.pad(w2, (0, 0, 0, 0, 0, coutp - cout))
             if coutp > 64:
-                cw.w_s2, cw.s2_passes = _pack_f16_single(w2), 5
+                cw.w_s2, cw.s2_passes = stage_image(_pack_f16_single(w2)), 5
             else:
-                cw.w_s2, cw.s2_passes = _pack_f16(w2), 4
+                cw.w_s2, cw.s2_passes = stage_image(_pack_f16(w2)), 4
     return cw
 
 
@@ -146,6 +146,23 @@ def _restate_s2(w: torch.Tensor) -> torch.Tensor:
 
 def _pack_c16(wt: torch.Tensor, w_hi: torch.Tensor) -> torch.Tensor:
     return torch.stack([wt.to(torch.bfloat16), (wt - w_hi).to(torch.bfloat16)]).contiguous()
+
+
+def stage_image(pack: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """[parts, CoutP, ntaps, CinP] fp16 operand tiles -> the exact shared-memory image of the kernel's weight ring, so that one
+    ring stage is ONE contiguous bulk copy (a tensor-map box of 64-byte rows streams at 29 B/clk per SM, a contiguous copy at
+    47: tools/ubench/tma_tile_rate.cu): [chunk of 32 channels][tap][part][cout row][64 bytes], with the 64B swizzle of the
+    MMA operand layout applied to the four 16-byte units of every row (unit u of row r sits at u ^ ((r >> 1) & 3); every
+    tile starts on a 512-byte boundary in shared memory)."""
+    if pack is None:
+        return None
+    parts, coutp, ntaps, cinp = pack.shape
+    assert cinp % 32 == 0 and coutp % 8 == 0
+    x = pack.reshape(parts, coutp, ntaps, cinp // 32, 4, 8).permute(3, 2, 0, 1, 4, 5)       # (chunk, tap, part, row, unit, elem)
+    r = torch.arange(coutp, device=pack.device)
+    u = torch.arange(4, device=pack.device)
+    src = (u[None, :] ^ ((r[:, None] >> 1) & 3)).view(1, 1, 1, coutp, 4, 1).expand(x.shape)
+    return torch.gather(x, 4, src).contiguous()
 
 
 def _pack_f16(wt: torch.Tensor) -> torch.Tensor:
@@ -178,7 +195,7 @@ def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
     wt[:, :, :7, :3] = w.permute(0, 2, 3, 1)           # [cout, ky, kx, c]
     cw.w_hi, cw.w_lo = _split_tf32(wt.reshape(32, 7, 32))
     cw.w_c16 = _pack_c16(wt.reshape(32, 7, 32), cw.w_hi)
-    cw.w_f16 = _pack_f16(wt.reshape(32, 7, 32))
+    cw.w_f16 = stage_image(_pack_f16(wt.reshape(32, 7, 32)))
     cw.stem = True
     return cw
 

@@ -204,3 +204,24 @@ def test_stride2_restatement_equals_the_strided_convolution():
     out = F.conv2d(F.pad(s2d, (1, 0, 1, 0)), wk, None)                    # taps at block offsets -1, 0
     assert out.shape == ref.shape and (out - ref).abs().max() <= 1e-5
     assert (w2 == 0).float().mean() > 0.4                                 # 7 of 16 (tap, parity) products are zero
+
+
+def test_weight_stage_image_is_the_swizzled_shared_memory_layout():
+    """pivlfn.model.stage_image: [parts, CoutP, taps, CinP] -> [chunk][tap][part][row][64 B] with the 64B swizzle; checked
+    against an independent byte-offset statement of the layout include/pivlfn.h documents, and for invertibility."""
+    from pivlfn.model import stage_image
+    parts, coutp, ntaps, cinp = 3, 48, 9, 96
+    g = torch.Generator().manual_seed(5)
+    pack = torch.randn(parts, coutp, ntaps, cinp, generator=g).to(torch.float16)
+    img = stage_image(pack)
+    assert img.shape == (cinp // 32, ntaps, parts, coutp, 4, 8) and img.is_contiguous()
+    flat = img.reshape(-1)
+    rng = np.random.default_rng(0)
+    for _ in range(500):
+        p, r, t, k = (int(rng.integers(n)) for n in (parts, coutp, ntaps, cinp))
+        c, kk = divmod(k, 32)
+        byte = ((((c * ntaps + t) * parts + p) * coutp + r) * 64) + (((kk // 8) ^ ((r >> 1) & 3)) * 16) + (kk % 8) * 2
+        assert flat[byte // 2] == pack[p, r, t, k]
+    # a stage of tps taps is a contiguous range of tps * parts * CoutP * 64 bytes
+    assert img[1, 3:6].reshape(-1).data_ptr() - img[1, 3].data_ptr() == 0
+    assert stage_image(None) is None
