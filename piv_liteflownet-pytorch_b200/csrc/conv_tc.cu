@@ -1007,6 +1007,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             const long long e_t0 = a.dbg ? clock64() : 0;
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
+            uint32_t v[16], u[16];
+            bool pre = false;                 // the (main, corr) columns of this group are already on their way (see below)
             for (int i = 0; i < a.NT; ++i) {
                 const int yy = (ty * a.NT + i) * HT_H + row / HT_W;
                 const bool live = x < a.W && yy < a.H && a.vec_store != 3;      // vec_store 3: experiment, no stores
@@ -1018,13 +1020,15 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const bool dual = (SPLIT && a.corr);
                 const int cstep = dual ? 16 : 32;
                 for (int c0 = cbeg; c0 < cend; c0 += cstep) {
-                    uint32_t v[16], u[16];
                     const bool second = dual || (c0 + 16 < cend);
                     const long long l_t0 = a.dbg ? clock64() : 0;
-                    tmem_ld16_nowait(trow + (uint32_t)((F16D ? 2 * i : i) * a.CoutP + c0), v);
-                    if (second)
-                        tmem_ld16_nowait(trow + (uint32_t)(F16D ? (2 * i + 1) * a.CoutP + c0
-                                                               : (dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16)), u);
+                    if (!pre) {
+                        tmem_ld16_nowait(trow + (uint32_t)((F16D ? 2 * i : i) * a.CoutP + c0), v);
+                        if (second)
+                            tmem_ld16_nowait(trow + (uint32_t)(F16D ? (2 * i + 1) * a.CoutP + c0
+                                                                   : (dual ? (a.NT + i) * a.CoutP + c0 : i * a.CoutP + c0 + 16)), u);
+                    }
+                    pre = false;
                     tmem_ld_wait();
                     if (a.dbg) e_ld += clock64() - l_t0;
                     if (dual) {
@@ -1088,6 +1092,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                     e[k] = a.lrelu ? lrelu_f(t) : t;
                                 }
                                 t4[j] = make_float4(e[0], e[1], e[2], e[3]);
+                            }
+                            if (dual) {
+                                // v / u are consumed: start the TMEM loads of the next 16-column group (next stacked tile
+                                // after the last group) now, so that their latency hides behind the transpose and the stores
+                                int ni = i, nc = c0 + 16;
+                                if (nc >= cend) { nc = cbeg; ++ni; }
+                                if (ni < a.NT) {
+                                    tmem_ld16_nowait(trow + (uint32_t)((F16D ? 2 * ni : ni) * a.CoutP + nc), v);
+                                    tmem_ld16_nowait(trow + (uint32_t)(F16D ? (2 * ni + 1) * a.CoutP + nc : (a.NT + ni) * a.CoutP + nc), u);
+                                    pre = true;
+                                }
                             }
 #pragma unroll
                             for (int sft = 2; sft >= 1; sft >>= 1) {
