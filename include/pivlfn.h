@@ -100,6 +100,9 @@ int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, int Cin, co
  * or non-finite) raises a sticky device flag instead of being silently saturated.  Returns the flag (0 / 1, -1 on a
  * CUDA error) and clears it when reset != 0.  Synchronises the device.  The host re-runs with passes == 2 when set. */
 int pivlfn_f16_range_flag(int reset);
+/* Clears the same flag of the CURRENT device in stream order (cudaMemsetAsync, no synchronisation): issued before a forward so
+ * that a stale hit left by another user of the library cannot be attributed to it. */
+int pivlfn_f16_range_flag_clear(void* stream);
 
 /* Flow heads, the last layer of conv_M / conv_S (src/models.py:161,205; LiteFlowNet2 :499,547): KxK convolution
  * (K = 3, 5 or 7) from Cin = 32 channels to the 2 flow components, no activation, + bias + optional residual flow

@@ -39,31 +39,50 @@ def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
     stamp = os.path.join(OBJ, "stamp")
     dig = _digest()
-    if not force and os.path.isfile(OUT) and os.path.isfile(stamp) and open(stamp).read() == dig:
+
+    def fresh():
+        return os.path.isfile(OUT) and os.path.isfile(stamp) and open(stamp).read() == dig
+
+    if not force and fresh():
         return OUT
     if not os.path.isfile(NVCC):
         if os.path.isfile(OUT):
             return OUT          # GPU box without a changed source tree: use the shipped library
         raise RuntimeError("nvcc not found and no prebuilt libpivlfn.so")
+    # N torchrun ranks import the package at the same moment: one of them builds, the others wait on the lock and find
+    # the stamp fresh.  Objects and the library are written under private names and renamed into place, so nobody can
+    # dlopen or link a half-written file.
+    import fcntl
+    with open(os.path.join(OBJ, "lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():
+                return OUT
+            tag = ".%d.tmp" % os.getpid()
 
-    def cc(src):
-        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
-        r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj], capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
-        return obj, r.stderr
+            def cc(src):
+                obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+                r = subprocess.run([NVCC, *FLAGS, "-c", src, "-o", obj + tag], capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))
+                os.replace(obj + tag, obj)
+                return obj, r.stderr
 
-    with ThreadPoolExecutor(max_workers=8) as ex:
-        res = list(ex.map(cc, sources()))
-    if verbose:
-        for _, log in res:
-            sys.stderr.write(log)
-    r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT,
-                        *[o for o, _ in res], "-cudart", "static"], capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n" + r.stderr)
-    with open(stamp, "w") as fh:
-        fh.write(dig)
+            with ThreadPoolExecutor(max_workers=8) as ex:
+                res = list(ex.map(cc, sources()))
+            if verbose:
+                for _, log in res:
+                    sys.stderr.write(log)
+            r = subprocess.run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT + tag,
+                                *[o for o, _ in res], "-cudart", "static"], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("link failed:\n" + r.stderr)
+            os.replace(OUT + tag, OUT)
+            with open(stamp + tag, "w") as fh:
+                fh.write(dig)
+            os.replace(stamp + tag, stamp)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return OUT
 
 

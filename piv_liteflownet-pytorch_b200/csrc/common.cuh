@@ -15,6 +15,31 @@ static inline int pivlfn_last_error() {
     return e == cudaSuccess ? PIVLFN_OK : (int)e;
 }
 
+// Per-device one-time opt-in to > 48 KB of dynamic shared memory.  The attribute belongs to the (function, device) pair, so
+// the "done" state is a bit per device ordinal: a process that drives several GPUs configures each of them.
+template <typename K>
+static inline cudaError_t pivlfn_optin_smem(K kern, int bytes, unsigned long long& done_mask) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && ((done_mask >> dev) & 1ull)) return cudaSuccess;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess && dev >= 0 && dev < 64) done_mask |= 1ull << dev;
+    return e;
+}
+
+// SM count of the current device (cached per device ordinal)
+static inline int pivlfn_num_sms() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) cache[dev] = n;
+    return n;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline long long cdivll(long long a, long long b) { return (a + b - 1) / b; }
 

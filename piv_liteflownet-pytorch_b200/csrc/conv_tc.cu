@@ -1199,15 +1199,7 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-    }
-    return n;
-}
+int num_sms() { return pivlfn_num_sms(); }
 
 int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
@@ -1227,11 +1219,10 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& 
     a.stages = stages;
     const int smem = stages * stage_bytes + 1024;
     auto kern = conv_tc_kernel<PASSES>;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET);
+    static unsigned long long configured = 0;
+    {
+        cudaError_t e = pivlfn_optin_smem(kern, SMEM_BUDGET, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     kern<<<grid, NTHREADS, smem, st>>>(tmA, tmBhi, tmBlo, a);
     PIVLFN_LAUNCHED();
@@ -1376,22 +1367,22 @@ int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensor
     const CUtensorMap& tmY = tmYp ? *tmYp : tmA;
     int grid = h.total < num_sms() ? h.total : num_sms();
     { static int cap = -1; if (cap < 0) { const char* v = getenv("PIVLFN_TC_GRID"); cap = v ? atoi(v) : 0; } if (cap > 0 && cap < grid) grid = cap; }
-    static bool cfg1 = false, cfg2 = false, cfg3 = false, cfg4 = false, cfg5 = false;
+    static unsigned long long cfg1 = 0, cfg2 = 0, cfg3 = 0, cfg4 = 0, cfg5 = 0;
     cudaError_t e = cudaSuccess;
     if (passes == 5) {
-        if (!cfg5) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg5 = true; }
+        e = pivlfn_optin_smem(conv_tc_halo_kernel<5>, HALO_SMEM_BUDGET, cfg5); if (e != cudaSuccess) return (int)e;
         conv_tc_halo_kernel<5><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else if (passes == 4) {
-        if (!cfg4) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg4 = true; }
+        e = pivlfn_optin_smem(conv_tc_halo_kernel<4>, HALO_SMEM_BUDGET, cfg4); if (e != cudaSuccess) return (int)e;
         conv_tc_halo_kernel<4><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else if (passes == 3) {
-        if (!cfg3) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg3 = true; }
+        e = pivlfn_optin_smem(conv_tc_halo_kernel<3>, HALO_SMEM_BUDGET, cfg3); if (e != cudaSuccess) return (int)e;
         conv_tc_halo_kernel<3><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else if (passes == 2) {
-        if (!cfg2) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg2 = true; }
+        e = pivlfn_optin_smem(conv_tc_halo_kernel<2>, HALO_SMEM_BUDGET, cfg2); if (e != cudaSuccess) return (int)e;
         conv_tc_halo_kernel<2><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     } else {
-        if (!cfg1) { e = cudaFuncSetAttribute(conv_tc_halo_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, HALO_SMEM_BUDGET); if (e != cudaSuccess) return (int)e; cfg1 = true; }
+        e = pivlfn_optin_smem(conv_tc_halo_kernel<1>, HALO_SMEM_BUDGET, cfg1); if (e != cudaSuccess) return (int)e;
         conv_tc_halo_kernel<1><<<grid, HALO_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, tmB16, tmBlo16, tmY, h);
     }
     PIVLFN_LAUNCHED();
@@ -1406,6 +1397,12 @@ extern "C" int pivlfn_f16_range_flag(int reset) {
     if (cudaMemcpyFromSymbol(&v, g_f16_range_flag, sizeof(int)) != cudaSuccess) return -1;
     if (reset && v) { const int z = 0; cudaMemcpyToSymbol(g_f16_range_flag, &z, sizeof(int)); }
     return v;
+}
+
+extern "C" int pivlfn_f16_range_flag_clear(void* stream) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_f16_range_flag) != cudaSuccess) return -1;
+    return cudaMemsetAsync(p, 0, sizeof(int), (cudaStream_t)stream) == cudaSuccess ? PIVLFN_OK : -1;
 }
 
 static long long* g_conv_tc_dbg = nullptr;

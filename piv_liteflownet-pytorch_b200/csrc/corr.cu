@@ -361,11 +361,10 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
     const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
     dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
     constexpr int smem = (NH_S1 + NH_S2) * 4 + NH_NPIX2 * (16 + 8);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(corr_nhwc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static unsigned long long configured = 0;
+    {
+        cudaError_t e = pivlfn_optin_smem(corr_nhwc_kernel, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     corr_nhwc_kernel<<<grid, NH_THREADS, smem, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
                                                                           C, H, W, Ho, Wo, stride, lrelu);

@@ -129,11 +129,10 @@ int launch_flow_head(const float* x, int x_ld, const float* w, const float* bias
                      float* out, int out_ld, float* out2, int out2_ld, int N, int H, int W, cudaStream_t st) {
     constexpr int SW = FH_TX + K - 1, SH = FH_TY + K - 1;
     constexpr int smem = (SW * SH * FH_PITCH + K * K * FH_C * 2) * 4;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(flow_head_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    static unsigned long long configured = 0;
+    {
+        cudaError_t e = pivlfn_optin_smem(flow_head_kernel<K>, smem, configured);
         if (e != cudaSuccess) return (int)e;
-        configured = true;
     }
     const int tiles_x = cdiv(W, FH_TX), tiles_y = cdiv(H, FH_TY);
     const long long grid = (long long)tiles_x * tiles_y * N;

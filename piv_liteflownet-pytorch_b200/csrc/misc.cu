@@ -496,14 +496,14 @@ int launch_reg_tail(const float* dist, int dist_ld, const float2* fi, const floa
     const bool bulk = !((uintptr_t)dist & 15) && !(dist_ld & 3) && dist_ld >= ((K * K + 3) & ~3) && dist_ld <= 64;
     if (bulk) {
         const int smem = 2 * 128 * dist_ld * 4;
-        static bool configured = false;
-        if (!configured) {
-            cudaError_t e = cudaFuncSetAttribute(reg_tail_bulk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 128 * 64 * 4);
+        static unsigned long long configured = 0;
+        {
+            cudaError_t e = pivlfn_optin_smem(reg_tail_bulk_kernel<K>, 2 * 128 * 64 * 4, configured);
             if (e != cudaSuccess) return (int)e;
-            configured = true;
         }
         const long long ntiles = (total + 127) / 128;
-        const int grid = (int)(ntiles < 148LL * 4 ? ntiles : 148LL * 4);
+        const long long cap = 4LL * pivlfn_num_sms();
+        const int grid = (int)(ntiles < cap ? ntiles : cap);
         reg_tail_bulk_kernel<K><<<grid, 128, smem, st>>>(dist, dist_ld, fi, wx, bx, wy, by, fo, out_nchw, final_scale, N, H, W);
     } else {
         long long g = (total + 127) / 128;

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "pivlfn_conv_simt": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),
     "pivlfn_conv_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _i, _p]),
     "pivlfn_f16_range_flag": (_i, [_i]),
+    "pivlfn_f16_range_flag_clear": (_i, [_p]),
     "pivlfn_conv_s2_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "pivlfn_conv1x1_pairs_tc": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
     "pivlfn_flow_head": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p, _i, _p, _i, _i, _p]),

@@ -84,6 +84,13 @@ class ConvW:
     w_f16s: Optional[torch.Tensor] = None   # stage_image of [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
                                             # (single-accumulator variant of f16c, packed for Cout > 64 only)
 
+    def to_(self, dev) -> "ConvW":
+        for f in ("w_simt", "bias", "w_hi", "w_lo", "w_c16", "w_f16", "w_s2", "w_f16s"):
+            t = getattr(self, f)
+            if t is not None:
+                setattr(self, f, t.to(dev))
+        return self
+
     def passes_for(self, passes: int) -> int:
         """The kernel mode of this layer for an engine-level mode: f16c (4) runs its single-accumulator variant (5) on the
         wide layers, where [main | corr] accumulators for two stacked tiles would fill all of TMEM."""
@@ -251,7 +258,10 @@ class Engine:
                 raise KeyError(f"missing parameter {k}")
             if tuple(sd[k].shape) != tuple(shp):
                 raise RuntimeError(f"size mismatch for {k}: expected {tuple(shp)}, got {tuple(sd[k].shape)}")
-        g = lambda k: sd[k].detach().to(device=dev, dtype=torch.float32)
+        # Packing runs on the HOST (a few dozen small torch CPU ops per layer) and every packed tensor is uploaded once:
+        # on the device the same repacking was ~1000 tiny ATen kernels per model, which drowned this library's own
+        # kernels in the driver's launch list of smoke().
+        g = lambda k: sd[k].detach().to(device="cpu", dtype=torch.float32)
         use_tc = self.precision != SIMT
 
         def conv(key, stride=1, cin_pad=0, in_perm=None):
@@ -287,7 +297,7 @@ class Engine:
             if lv < 5:
                 conv(p + ".moduleFeat.0")
             cr = 128 if lv < 5 else LEVEL_FEAT_CH[lv]
-            perm = torch.cat([torch.arange(3, 3 + cr), torch.arange(0, 3)]).to(dev)
+            perm = torch.cat([torch.arange(3, 3 + cr), torch.arange(0, 3)])
             conv(p + ".conv_R.0", in_perm=perm, cin_pad=1)
             for j in range(1, len(CONV_R)):
                 conv(f"{p}.conv_R.{2 * j}")
@@ -297,14 +307,24 @@ class Engine:
             for nm in ("moduleScaleX", "moduleScaleY"):
                 self.raw[f"{p}.{nm}.weight"] = g(f"{p}.{nm}.weight").reshape(-1).contiguous()
                 self.raw[f"{p}.{nm}.bias"] = g(f"{p}.{nm}.bias").reshape(-1).contiguous()
+        # ---- upload ------------------------------------------------------------------------------------------------
+        for cw in self.w.values():
+            cw.to_(dev)
+        self.raw = {k: v.to(dev) for k, v in self.raw.items()}
 
     # ---------------------------------------------------------------------------------------------
+    MAX_PLANS = 4       # workspaces + graphs kept alive per engine (least recently used ones are dropped)
+
     def plan(self, B: int, H: int, W: int) -> "Plan":
         key = (B, H, W)
-        p = self._plans.get(key)
+        p = self._plans.pop(key, None)
         if p is None:
-            p = Plan(self, B, H, W)
-            self._plans[key] = p
+            while len(self._plans) >= self.MAX_PLANS:
+                # a directory of mixed-size frames or many odd last batches must not grow device memory without bound
+                self._plans.pop(next(iter(self._plans)))
+            with torch.cuda.device(self.device):
+                p = Plan(self, B, H, W)
+        self._plans[key] = p            # (re)inserted last: dict order is the LRU order
         return p
 
     def forward(self, img1: torch.Tensor, img2: torch.Tensor, return_levels: bool = False):
@@ -312,14 +332,33 @@ class Engine:
             raise NotImplementedError("pivlfn: CUDA tensors required (there is no CPU path)")
         assert img1.dtype == torch.float32 and img2.dtype == torch.float32
         assert img1.dim() == 4 and img1.shape[1] == 3 and img1.shape == img2.shape
-        assert img1.is_contiguous() and img2.is_contiguous()
+        if img1.device != self.device or img2.device != self.device:
+            raise RuntimeError(f"pivlfn: inputs on {img1.device}, model on {self.device}")
         B, _, H, W = img1.shape
         if H % 32 or W % 32:
             raise RuntimeError(f"pivlfn: H and W must be multiples of 32 (got {H}x{W}); use estimate() which resizes "
                                "like the reference (inference.py:39-49)")
+        # strided inputs are accepted like the reference does; the in-place mean subtraction still lands in the caller's
+        # tensors (mutate_inputs writes through a strided copy_)
+        c1, c2 = img1.contiguous(), img2.contiguous()
+        with torch.cuda.device(self.device):     # launches, the current stream and the range flag all belong to self.device
+            res = self._forward_on_device(c1, c2, B, H, W, return_levels)
+        if c1 is not img1:
+            img1.copy_(c1)
+        if c2 is not img2:
+            img2.copy_(c2)
+        return res
+
+    def _forward_on_device(self, img1, img2, B, H, W, return_levels):
         plan = self.plan(B, H, W)
+        check = self.precision == TC_F16C and self.range_check
+        if check:
+            # the flag is sticky and process-wide per device: a stale hit (a direct ops call, another engine, the tiled
+            # path) must not downgrade THIS engine, so it is cleared before the forward it is meant to judge
+            if int(self.lib.pivlfn_f16_range_flag_clear(torch.cuda.current_stream().cuda_stream)) != 0:
+                raise _lib.PivlfnError("pivlfn_f16_range_flag_clear: CUDA error")
         res = plan.run(img1, img2, return_levels, mutate_inputs=False)
-        if self.precision == TC_F16C and self.range_check:
+        if check:
             # f16c converts activations to fp16 pairs: a value outside the fp16 range raises a sticky device flag
             # (never a silent saturation).  One stream sync + 4-byte read per forward; on a hit this engine switches to
             # tf32c for good and the forward is repeated from the caller's (still unmodified) images.

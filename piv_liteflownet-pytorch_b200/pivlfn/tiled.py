@@ -68,6 +68,7 @@ class TiledPlan:
         self.top, self.bottom = rank == 0, rank == world - 1
         self.steps: List[Step] = []
         self.handles: List[TT] = []
+        self.warp_flows: List[Tuple[TT, int]] = []
         dev = eng.device
         self._E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         self._Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
@@ -154,9 +155,17 @@ class TiledPlan:
                 ops.copy(view(a, xo, C), view(b, yo, C), a.shape[1] * a.shape[2])
         self._op(run, y, x.valid)
 
+    def _steers_warp(self, flow: TT, out_valid: int):
+        """Remember a flow tensor that steers a backwarp (cost volume: flowU, Subpixel: flowM, brightness error: flowS)
+        together with the halo depth down to which the warped result is consumed: the displacement bound is checked on
+        exactly those rows after every run (``check_bounds``)."""
+        if flow.tiled:
+            self.warp_flows.append((flow, max(0, min(out_valid, self.E))))
+
     def warp(self, f2: TT, C: int, flow: TT, scale: float, y: TT, yo: int):
         self._need(f2, self.wr)
         self._need(flow, 0)
+        self._steers_warp(flow, min(flow.valid, f2.valid - self.wr))
 
         def run():
             a, fl, b = self._img(f2, 0), self._img(flow, 0), self._img(y, 0)
@@ -315,6 +324,8 @@ class TiledPlan:
             self.steps.append(Step("op", fn=run_corr))
             vin = min(Sbuf.valid, f2.valid - 3 * s - (self.wr if flowU is not None else 0),
                       flowU.valid - 3 * s if flowU is not None else 1 << 30)
+            if flowU is not None:
+                self._steers_warp(flowU, flowU.valid)
             if s == 2:
                 corrU = self.new(f"corrU{l}", l, 52, zero=True)
 
@@ -358,6 +369,7 @@ class TiledPlan:
             def run_ri(im1=im1, im2=im2, flowS=flowS, partial=partial, Rbuf=Rbuf, cr=cr, scale=scale):
                 ops.reg_input(self._img(im1, 0), self._img(im2, 0), self._img(flowS, 0), scale, partial,
                               view(self._img(Rbuf, 0), cr, 3))
+            self._steers_warp(flowS, min(im1.valid, flowS.valid, im2.valid - self.wr))
             self._op(run_ri, R_in, min(im1.valid, flowS.valid, im2.valid - self.wr))
             if l < 5:
                 self.conv(f"NetE_R.{i}.moduleFeat.0", f1, 0, LEVEL_FEAT_CH[l], Rbuf, 0)
@@ -424,13 +436,38 @@ class TiledPlan:
         l = self.eng.cfg.lowest_level
         return self.out_local[:, :, self.E:self.E + self.own[l]]
 
-    def check_warp_reach(self):
-        """The provisioned backwarp reach must cover the largest vertical displacement that was actually sampled."""
-        for l, f in self.flows.items():
-            if f.tiled:
-                m = float(f.t[..., 1].abs().max()) * self.eng.sf[l]
-                if m + 1.0 > self.wr:
-                    raise RuntimeError(f"tiled mode: vertical displacement {m:.2f} px at level {l} exceeds warp_reach={self.wr}")
+    def local_bounds(self) -> torch.Tensor:
+        """[largest vertical displacement (px at its level, + 1 px bilinear footprint) that steered a backwarp on rows this
+        rank's results depend on, fp16-range flag of this device].  Device tensor of 2 floats; reduced with MAX over the
+        ranks by the group's ``run``."""
+        m = torch.zeros((), device=self.eng.device, dtype=torch.float32)
+        for f, v in self.warp_flows:
+            E, own = self.E, self.own[f.level]
+            rows = f.t[:, E - v:E + own + v, :, 1]
+            m = torch.maximum(m, rows.abs().max() * self.eng.sf[f.level] + 1.0)
+        flag = 0.0
+        if self.eng.precision == "f16c":
+            torch.cuda.current_stream().synchronize()
+            flag = float(int(self.eng.lib.pivlfn_f16_range_flag(1)) != 0)
+        return torch.stack([m, torch.full((), flag, device=self.eng.device)])
+
+    def check_bounds(self, reduced: torch.Tensor):
+        """Raise -- on EVERY rank, ``reduced`` being the MAX over ranks of ``local_bounds`` -- when a seam could be wrong."""
+        m, flag = float(reduced[0]), float(reduced[1])
+        if not (m <= self.wr):          # also catches NaN
+            raise TiledBoundsError(f"tiled mode: a vertical displacement of {m - 1.0:.2f} px (+1 px bilinear footprint) "
+                                   f"exceeds warp_reach={self.wr}; rebuild the plan with a larger halo / warp_reach")
+        if flag:
+            raise TiledBoundsError("tiled mode: an activation left the fp16 range in precision 'f16c'; rebuild the plan "
+                                   "from an engine with precision 'tf32c'")
+
+    def clear_range_flag(self):
+        if self.eng.precision == "f16c":
+            self.eng.lib.pivlfn_f16_range_flag_clear(torch.cuda.current_stream().cuda_stream)
+
+
+class TiledBoundsError(RuntimeError):
+    """The data-dependent assumptions of a tiled run (backwarp reach, fp16 range) did not hold: the result is discarded."""
 
 
 def _zero_outside(tt: TT, plan: TiledPlan):
@@ -450,6 +487,14 @@ class LoopbackGroup:
         assert all(len(p.steps) == n for p in plans), "ranks must record identical step sequences"
 
     def run(self):
+        P = len(self.plans)
+        self.plans[0].clear_range_flag()
+        self._steps()
+        red = torch.stack([p.local_bounds() for p in self.plans]).max(0).values
+        for p in self.plans:
+            p.check_bounds(red)
+
+    def _steps(self):
         P = len(self.plans)
         for k in range(len(self.plans[0].steps)):
             kind = self.plans[0].steps[k].kind
@@ -489,6 +534,16 @@ class DistGroup:
         self.plan, self.dist = plan, dist
 
     def run(self):
+        """One forward; raises TiledBoundsError on all ranks together when any rank saw a displacement beyond the
+        provisioned backwarp reach or an fp16 range overflow (2-float MAX all-reduce)."""
+        p = self.plan
+        p.clear_range_flag()
+        self._steps()
+        red = p.local_bounds()
+        self.dist.all_reduce(red, op=self.dist.ReduceOp.MAX)
+        p.check_bounds(red)
+
+    def _steps(self):
         dist, p = self.dist, self.plan
         E = p.E
         for st in p.steps:

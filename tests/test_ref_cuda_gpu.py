@@ -111,9 +111,32 @@ def test_forward_vs_reference_cuda_path(model, B, H, W, kind, precision):
     _report(f"forward vs reference CUDA path {model} {B}x{H}x{W} {precision}: max {diff.max().item():.3e} "
             f"mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
     assert out.shape == ref.shape
-    # Hui flows carry the x20 output scale (|flow| ~ 40 px): tolerance relative to that scale, 1e-2 px at PIV scale
-    scale = max(1.0, ref.abs().max().item() / 10.0)
-    assert diff.max().item() <= 1e-2 * scale and diff.mean().item() <= 1e-3 * scale
+    # north_star tolerance, ABSOLUTE (also for Hui, whose flows carry the x20 output scale)
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@needs_ref
+def test_cfg2_bench_batch_vs_reference_cuda_path():
+    """BASELINE configs[1] at its own shape: the 64-pair 256x256 batch bench.py times goes through piv_liteflownet in ONE
+    forward (default precision); 8 of its pairs (every 8th: one of each pool image / roll) are checked against the
+    reference's GPU path (stock torch fp32 convolutions, TF32 off, + the reference's correlation cubins).  Absolute
+    north_star tolerance: flow max <= 1e-2 px, mean <= 1e-3 px."""
+    import bench
+    from src.models import piv_liteflownet
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b = bench.synthetic_batch(bench.BATCH, 10_000)
+    assert a.shape == (64, 3, 256, 256)
+    net = piv_liteflownet(sd, 1).to(DEV).eval()
+    with torch.no_grad():
+        out = net(a.to(DEV), b.to(DEV))
+    idx = list(range(0, 64, 9))                             # 0, 9, ..., 63: all 8 pool images, several rolls
+    ref = _reference_cuda_forward(sd, a[idx], b[idx], "piv")
+    diff = (out[idx] - ref).abs()
+    _report(f"cfg2 (batch 64 of 256x256, {net.engine().precision}) vs reference CUDA path on pairs {idx}: max {diff.max().item():.3e} "
+            f"mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
+    assert ref.abs().max().item() > 1.0
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
 
 
 @pytest.mark.gpu
@@ -267,6 +290,5 @@ def test_reference_cuda_path_rate_report_hui_cfg3():
     d = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(d):
         json.dump(res, open(os.path.join(d, "ref_cuda_rate_hui_cfg3.json"), "w"), indent=1)
-    # Hui flows carry the x20 output scale: tolerance relative to the flow magnitude (1e-2 px at 10 px)
-    scale = max(1.0, res["flow_abs_max"] / 10.0)
-    assert diff.max().item() <= 1e-2 * scale and diff.mean().item() <= 1e-3 * scale
+    # north_star tolerance, absolute
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3

@@ -27,10 +27,8 @@ def test_tiled_equals_single_gpu(model, H, W, P, precision):
     assert 1 <= plans[0].Lt <= 6
     for p in plans:
         p.load_inputs(a, b)
-    LoopbackGroup(plans).run()
+    LoopbackGroup(plans).run()          # includes the displacement-bound / fp16-range check on every rank
     torch.cuda.synchronize()
-    for p in plans:
-        p.check_warp_reach()
     out = torch.cat([p.owned_output() for p in plans], dim=2)
     assert out.shape == ref.shape
     diff = (out - ref).abs()
@@ -39,3 +37,23 @@ def test_tiled_equals_single_gpu(model, H, W, P, precision):
     print(f"tiled {model} {H}x{W} P={P} {precision}: Lt={plans[0].Lt} exchanges={n_ex} ops={n_op} max|diff|={diff.max().item():.3e}")
     # identical kernels on identical data; only the flow-mean summation order differs -> fp32 round-off
     assert diff.max().item() <= 2e-4
+
+
+def test_tiled_raises_when_displacement_exceeds_warp_reach():
+    """The backwarp reach is data dependent (flowU for the cost volume, flowM for the Subpixel warp, flowS for the brightness
+    error): a run whose vertical displacements exceed the provisioned reach must raise on every rank instead of
+    returning seams computed from stale halo rows."""
+    from pivlfn.tiled import TiledBoundsError
+    sd = {k: v.to(DEV) for k, v in synth.synthetic_state_dict("piv", 0).items()}
+    eng = Engine(CFGS["piv"], sd, torch.device(DEV), "f16c", use_graph=False)
+    i1, i2, _ = synth.particle_pair(256, 64, 31, "shear")
+    a = synth.to_rgb_tensor(i1)[None].to(DEV)
+    b = synth.to_rgb_tensor(i2)[None].to(DEV)
+    ref = eng.forward(a.clone(), b.clone())
+    assert ref[:, 1].abs().max().item() > 1.5          # the synthetic weights produce multi-pixel vertical flows
+    plans = [TiledPlan(eng, 256, 64, r, 2, halo=8, warp_reach=1) for r in range(2)]
+    assert len(plans[0].warp_flows) >= 3
+    for p in plans:
+        p.load_inputs(a, b)
+    with pytest.raises(TiledBoundsError):
+        LoopbackGroup(plans).run()

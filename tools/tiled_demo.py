@@ -54,7 +54,6 @@ e1.record()
 torch.cuda.synchronize()
 ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
 dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-plan.check_warp_reach()
 out = plan.owned_output()
 res = {"workload": f"PIV-LiteFlowNet-en one {H}x{W} pair tiled by rows", "n_gpus": world, "ms_per_frame": float(ms.item()),
        "frames_per_s": 1e3 / float(ms.item()), "tiled_levels": plan.Lt, "halo_rows": plan.E,
