@@ -180,6 +180,63 @@ int pivlfn_reg_tail(const float* dist, int dist_ld, const float* flow_in,
 int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, int H, int W, int Ho, int Wo,
                                 float mul_even, float mul_odd, void* stream);
 
+/* ---- the P16 pipeline (default for precision f16c) -----------------------------------------------------------------------
+ * P16 is the activation format of the fp16-split arithmetic: an fp32 value x is stored as the pair the tensor cores
+ * consume, hi = f16(x) and lo = f16((x - hi) * 2^11) (x = hi + lo / 2048, 22 significant bits, |x| < 65504), 4 bytes per
+ * element.  Channels are grouped by 16; one group of one pixel is 64 contiguous bytes [16 x hi | 16 x lo], so that a view
+ * (pointer, pixel pitch in 4-byte words, channel count rounded up to 16) addresses a P16 tensor like an fp32 NHWC one,
+ * channel slices start at multiples of 16 and a 32-channel chunk of a pixel is one 128-byte MMA-ready row.  Pad channels
+ * of the last group are zero.  P16 pointers are 64-byte aligned, pitches multiples of 16 words.
+ * range_flag (optional device int): set to 1 by any producer whose result is not finite in fp16 (|x| >= 65520 or NaN);
+ * the host then repeats the forward in the fp32-activation pipeline (precision tf32c).  Never cleared by the library. */
+
+/* fp32 NHWC view (C channels, pitch x_ld) <-> P16 view (pitch y_ld words). */
+int pivlfn_p16_encode(const float* x, int x_ld, int C, void* y, int y_ld, long long npix, int* range_flag, void* stream);
+int pivlfn_p16_decode(const void* x, int x_ld, int C, float* y, int y_ld, long long npix, void* stream);
+
+/* Convolution + bias + LeakyReLU on a P16 input (src/models.py:77-106,124,154-163,197-207,229-272): implicit GEMM on
+ * tcgen05 with the three fp16 products of pivlfn_conv_tc's passes 4 / 5, but with NO operand split inside the kernel: TMA
+ * delivers MMA-ready halo tiles.  Odd KH, KW <= 7 at stride 1; 3x3 at stride 2 (H, W = INPUT size, even; Cin % 32 == 0;
+ * w_img = pack of the parity-restated weights, see pivlfn_conv_s2_tc).  Cin: logical input channels (the buffer holds
+ * ceil16(Cin) words per pixel).  w_img: ring-stage image of the fp16 weights (see pivlfn_conv_tc: passes-4 pack for mode 4,
+ * Cout <= 64; passes-5 pack for mode 5, Cout <= 128).
+ * out_fmt 0: P16 view (pitch y_ld words, >= ceil16(Cout); pad channels written as zeros);
+ *         1: fp32 NHWC view (pitch y_ld floats);
+ *         2: fp32 channel-PAIR planes, plane p = channels (2p, 2p+1) as [pixel][2], plane_stride floats apart. */
+int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                    const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
+                    int out_fmt, long long plane_stride, int* range_flag, void* stream);
+
+/* NetC.conv1 (see pivlfn_conv_stem_tc) with the fp16-split arithmetic and a P16 output; w_img: stage image of the
+ * passes-4 pack of the [32, 7, 32] stem weights.  W % 4 == 0, W >= 8. */
+int pivlfn_conv_stem_p16(const float* img_pad, int N, int H, int W, const void* w_img, const float* bias,
+                         void* y, int y_ld, int lrelu, int* range_flag, void* stream);
+
+/* pivlfn_corr_nhwc with each of f1 / f2 / out either fp32 NHWC (flag 0) or P16 (flag 1; out: 64 channels, 49 + zero pad). */
+int pivlfn_corr_p16(const void* f1, int f1_ld, int f1_p16, const void* f2, int f2_ld, int f2_p16,
+                    const float* flow, float flow_scale, void* out, int out_ld, int out_p16,
+                    int N, int H, int W, int C, int stride, int lrelu, int* range_flag, void* stream);
+
+/* pivlfn_warp_nhwc writing a P16 view (C % 16 == 0); the input is fp32 NHWC (in_p16 = 0) or P16 (in_p16 = 1). */
+int pivlfn_warp_p16(const void* in, int in_ld, int in_p16, const float* flow, float scale, void* out, int out_ld,
+                    int N, int H, int W, int C, int* range_flag, void* stream);
+
+/* pivlfn_deconv4x4s2_dw (upCorr_M) from an fp32 NHWC view (16-byte aligned, in_ld % 4 == 0) to a P16 view; C <= 64. */
+int pivlfn_deconv4x4s2_dw_p16(const float* in, int in_ld, const float* w, void* out, int out_ld,
+                              int N, int H, int W, int C, int* range_flag, void* stream);
+
+/* pivlfn_reg_input writing (err, rm_u, rm_v) as the first three channels of one P16 group at out (the other 13 are
+ * left untouched: the concat buffer is zero-initialised once). */
+int pivlfn_reg_input_p16(const float* img1, const float* img2, const float* flow, float scale,
+                         const float* partial, void* out, int out_ld, int N, int H, int W, int* range_flag, void* stream);
+
+/* Second half of the tensor-core flow head (src/models.py:161,205): the KxK 32 -> 2 head runs as a 1xK convolution to 2K
+ * channels (row ky*2 + co; pivlfn_conv_p16 with out_fmt 2 -> K planes [pixel][2]); this adds the K planes at their vertical
+ * offsets (zero outside the frame) + bias + residual flow (res, dense [N,H,W,2], may be NULL) -> out (dense [N,H,W,2]) and
+ * optionally the flow's P16 group (2 channels + untouched pad) at out_p16 (the torch.cat of src/models.py:216). */
+int pivlfn_head_rows_sum(const float* planes, int K, const float* bias, const float* res, float* out,
+                         void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream);
+
 /* ---- stereo-PIV post-processing (stereo_run.py:104-163) ------------------------------------------------------------------
  * stereo/dewarp.py:255-270 nl_trans: new_x = P(A[0:6]) / P(A[6:12]), new_y = P(A[12:18]) / P(A[18:24]) with
  * P(a) = a0 x + a1 y + a2 + a3 x^2 + a4 y^2 + a5 x y, evaluated in float32 in the reference's operation order.

@@ -1,0 +1,477 @@
+// Convolution (+ bias + LeakyReLU) on P16 activations: implicit GEMM on the 5th-generation tensor cores with NO operand
+// preparation inside the kernel.
+//
+// The fp32-equivalent arithmetic is the three-product fp16 split of conv_tc.cu (modes 4 / 5),
+//     D = a_hi*w_hi + 2^-11 * (a_lo'*w_hi + a_hi*w_lo'),
+// but the activations arrive from HBM already as (hi, lo') pairs (p16.cuh): per 32-channel chunk ONE 4-D TMA box
+//     [16*NT + KH - 1 rows][8 + KW - 1 pixels][128 bytes = hi0 | lo0 | hi1 | lo1]       (128B swizzle, zero fill outside)
+// lands in shared memory as the MMA-ready K-major halo tile; every filter tap's A operand is a shifted window into it and
+// the four K = 16 steps of a tap are 32-byte advances of the descriptor start address.  Compared with conv_tc.cu's modes
+// 4 / 5 the 8 operand-split warps, the raw-tile slot and ~15-23 % of the shared-memory traffic are gone, and the freed
+// warps double the epilogue: 16 warps (4 per TMEM lane quarter) turn accumulators into P16 (or fp32) rows.
+//
+//   warp 0        TMA producer of the activation tiles          warp 3   producer of the weight ring (one bulk copy / stage)
+//   warps 1, 2    MMA issuers (stacked tile 0 / 1)              warps 4..19   epilogue
+//
+// MODE 4 (Cout <= 64): a_hi * [w_hi | w_lo'] is ONE MMA of N = 2*Cout filling [main | corr], then a_lo' * w_hi -> corr
+//                      (the A window is read from shared memory twice per tap instead of three times).
+// MODE 5 (Cout > 64):  weights pre-scaled by 2^8 as [W_hi | W_lo | W_hi * 2^-11]: all three products carry the same scale
+//                      and add up in ONE accumulator, which leaves room for two TMEM sets (epilogue overlaps the MMAs).
+// Replaces torch.nn.Conv2d (+LeakyReLU(0.1)) of src/models.py:77-106 (NetC), :124 (NetC_ext), :154-163 (conv_M),
+// :197-207 (conv_S), :229-272 (moduleFeat, conv_R, conv_dist_R).
+#include <cuda.h>
+#include <stdlib.h>
+#include "common.cuh"
+#include "p16.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+using namespace tcptx;
+
+constexpr int HT_W = 8, HT_H = 16;       // accumulator tile: 16 rows of 8 pixels = 128 GEMM rows
+constexpr int MAX_A = 3, MAX_B = 8;
+constexpr int P16_THREADS = 640;
+constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
+constexpr int SMEM_BUDGET = 226 * 1024;  // 227 KB opt-in minus the static part (padded to 1 KB by the 1024-byte alignment)
+
+enum { OUT_P16 = 0, OUT_F32 = 1, OUT_PLANES = 2 };
+
+struct ConvP16Args {
+    const float* bias;
+    uint32_t* y;             // output words (P16 words or fp32 bits)
+    int y_ld;                // output pixel pitch in words
+    int N, H, W;             // OUTPUT size
+    int Cw;                  // input channel words per pixel that exist (16 * groups)
+    int Cout, CoutP;
+    int KH, KW;
+    int tiles_x, tiles_y, total;
+    int lrelu, out_fmt;
+    int quad;                // rows 16-byte aligned and W % 4 == 0: quad-transposed 64-byte runs
+    int cout_st;             // OUT_F32: channels that may be stored (Cout, or Cout rounded up to 4 when the rows are that wide)
+    long long planar;        // OUT_PLANES: floats per channel-pair plane
+    int NT, nA, nB, tps, nsets;
+    int s2, cpp;             // stride-2 restatement over the four input parities (see conv_tc.cu): cpp chunks per parity
+    int x_shift;
+    const uint8_t* w_img;    // ring-stage image of the fp16 weights (pivlfn.model.stage_image)
+    int* range_flag;         // raised when an OUT_P16 result is not finite in fp16 (|x| >= 65520 or NaN); may be NULL
+};
+
+__device__ __forceinline__ bool s2_tap_used(int t, int par) {
+    return ((t >> 1) >= 1 - (par >> 1)) && ((t & 1) >= 1 - (par & 1));
+}
+
+__device__ __forceinline__ void st_global_v4(uint32_t* p, const uint4& v) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(P16_THREADS, 1)
+conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
+    constexpr bool DUAL = MODE == 4;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int pitch = HT_W + a.KW - 1;
+    const int halo_rows = HT_H * a.NT + a.KH - 1;
+    const int halo_bytes = halo_rows * pitch * 128;
+    const int slot_bytes = (halo_bytes + 1023) & ~1023;
+    const int part_bytes = a.CoutP * 64;                        // one fp16 weight tile: CoutP rows of 32 channels
+    const int b_stage = (DUAL ? 2 : 3) * part_bytes;            // per tap
+    uint8_t* smemB = smem + (size_t)a.nA * slot_bytes;
+    __shared__ __align__(8) uint64_t a_full[MAX_A], a_free[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_s[128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nchunk = a.s2 ? 4 * a.cpp : (a.Cw + 31) / 32;
+    const int ntaps = a.KH * a.KW;
+    const int G = gridDim.x;
+    const int n_iss = a.NT >= 2 ? 2 : 1;
+    const int tile_cols = DUAL ? 2 * a.CoutP : a.CoutP;
+    const int set_cols = a.NT * tile_cols;
+    const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
+
+    if (threadIdx.x >= 128 && threadIdx.x < 256) {
+        const int i = threadIdx.x - 128;
+        bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.nA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], n_iss); }
+        for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], EPI_WARPS); }
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(ncols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_s;
+
+    if (warp == 0) {
+        // ================================ activation tiles ==============================
+        if (elect_one()) {
+            int g = 0;                                        // global chunk counter: slot g % nA, use g / nA
+            int slot = 0;
+            uint32_t use = 0;
+            for (int w = blockIdx.x; w < a.total; w += G) {
+                const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
+                for (int c = 0; c < nchunk; ++c, ++g) {
+                    mbar_wait(&a_free[slot], (use & 1) ^ 1);  // the MMAs of the slot's previous tenant have retired
+                    mbar_expect_tx(&a_full[slot], halo_bytes);
+                    int c0, c1, c2;
+                    if (a.s2) {
+                        const int par = c / a.cpp, cc = c - par * a.cpp;
+                        c0 = cc * 32; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
+                    } else { c0 = c * 32; c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2; }
+                    tma_load_4d(smem + (size_t)slot * slot_bytes, &tmA, &a_full[slot], c0, c1, c2, n);
+                    if (++slot == a.nA) { slot = 0; ++use; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ================================ weight ring ====================================
+        if (elect_one()) {
+            int bs = 0;
+            uint32_t bphase = 0;
+            for (int w = blockIdx.x; w < a.total; w += G) {
+                for (int c = 0; c < nchunk; ++c) {
+                    for (int t = 0; t < ntaps; t += a.tps) {
+                        if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
+                        mbar_wait(&b_empty[bs], bphase ^ 1);
+                        mbar_expect_tx(&b_full[bs], a.tps * b_stage);
+                        bulk_load(smemB + (size_t)bs * a.tps * b_stage, a.w_img + ((size_t)c * ntaps + t) * b_stage,
+                                  (uint32_t)(a.tps * b_stage), &b_full[bs]);
+                        if (++bs == a.nB) { bs = 0; bphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ================================ MMA issuers ====================================
+        // One thread per stacked tile.  Per tap: one add for the A window, one for the weight tile, the MMAs (every scalar
+        // instruction between two tcgen05.mma of a single in-order thread is on the critical path for Cout <= 64).
+        const int issuer = warp - 1;
+        if (issuer < n_iss && elect_one()) {
+            const uint32_t lbo_bits = 1u << 16;
+            // A: 128-byte rows, SWIZZLE_128B, 8-row group stride = one halo row (pitch * 128 B); B: 64-byte rows, SWIZZLE_64B
+            const uint32_t hiA = (uint32_t)((((uint64_t)((pitch * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32);
+            const uint32_t hiB = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
+            const uint32_t idesc = make_idesc_f16(a.CoutP);
+            const uint32_t idesc_w = make_idesc_f16(2 * a.CoutP);
+            const uint32_t cP = (uint32_t)a.CoutP;
+            const uint32_t part16 = (uint32_t)(part_bytes >> 4);
+            const uint32_t stage16 = (uint32_t)(b_stage >> 4);
+            const uint32_t ring16 = stage16 * (uint32_t)a.tps;
+            const uint32_t bbase16 = (smem_u32(smemB) >> 4) | lbo_bits;
+            const uint32_t tileA = (uint32_t)issuer * (uint32_t)(HT_H * pitch * 8);
+            const uint32_t row_step = (uint32_t)((pitch - a.KW) * 8);
+            int bs = 0;
+            uint32_t bphase = 0, bcur = bbase16;
+            int slot = 0, wl = 0;
+            uint32_t ause = 0;
+            for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+                const int as = wl % a.nsets;
+                const uint32_t use = (uint32_t)(wl / a.nsets);
+                mbar_wait(&acc_empty[as], (use & 1) ^ 1);     // the epilogue drained this accumulator set
+                tc_fence_after();
+                const uint32_t t_main = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)(issuer * tile_cols);
+                uint32_t acc = 0;
+                for (int c = 0; c < nchunk; ++c) {
+                    const bool two = a.s2 ? true : (a.Cw - c * 32 > 16);        // second 16-channel K step present
+                    mbar_wait(&a_full[slot], ause & 1);
+                    tc_fence_after();
+                    uint32_t A = ((smem_u32(smem + (size_t)slot * slot_bytes) >> 4) | lbo_bits) + tileA;
+                    int kx = 0;
+                    for (int t = 0; t < ntaps;) {
+                        if (a.s2 && !s2_tap_used(t, c / a.cpp)) {
+                            ++t; A += 8;
+                            if (++kx == a.KW) { kx = 0; A += row_step; }
+                            continue;
+                        }
+                        mbar_wait(&b_full[bs], bphase);
+                        tc_fence_after();
+                        uint32_t b = bcur;
+                        for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
+                            if (DUAL) {
+                                umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc_w, acc);
+                                umma_bf16_lohi(t_main + cP, A + 2, hiA, b, hiB, idesc, 1);
+                                if (two) {
+                                    umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc_w, 1);
+                                    umma_bf16_lohi(t_main + cP, A + 6, hiA, b + 2, hiB, idesc, 1);
+                                }
+                            } else {
+                                umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
+                                umma_bf16_lohi(t_main, A, hiA, b + part16, hiB, idesc, 1);
+                                umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
+                                if (two) {
+                                    umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
+                                    umma_bf16_lohi(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
+                                    umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
+                                }
+                            }
+                            acc = 1;
+                            A += 8;                                             // next tap of the filter row (one pixel = 128 B)
+                            if (++kx == a.KW) { kx = 0; A += row_step; }
+                        }
+                        umma_commit(&b_empty[bs]);
+                        if (++bs == a.nB) { bs = 0; bphase ^= 1; bcur = bbase16; } else bcur += ring16;
+                    }
+                    umma_commit(&a_free[slot]);
+                    if (++slot == a.nA) { slot = 0; ++ause; }
+                }
+                umma_commit(&acc_full[as]);
+            }
+        }
+    } else {
+        // ================================ epilogue =======================================
+        // 16 warps: TMEM lane quarter q = warp % 4 (the hardware's rule), group eg = (warp - 4) / 4 takes the (tile, 16-column
+        // group) units eg, eg + 4, ...  A thread owns one pixel: 16 accumulator columns -> 16 output words (fp32 bits, or 8
+        // words of f16x2 hi + 8 of lo' = one P16 group), quad-transposed so that every store instruction writes 64 contiguous
+        // bytes per pixel.
+        const int eg = (warp - EPI_WARP0) >> 2, q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ncg = a.CoutP >> 4;
+        const int nunits = a.NT * ncg;
+        const float osc = DUAL ? 1.f : (1.f / 256.f);
+        uint32_t bad = 0;
+        int wl = 0;
+        for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+            const int as = wl % a.nsets;
+            const uint32_t use = (uint32_t)(wl / a.nsets);
+            const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
+            const int x = tx * HT_W + (row & (HT_W - 1));
+            mbar_wait(&acc_full[as], use & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
+            uint32_t v[16], u[16];
+            auto issue = [&](int unit) {
+                const int i = unit / ncg, cg = unit - i * ncg;
+                tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + cg * 16), v);
+                if (DUAL) tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + a.CoutP + cg * 16), u);
+            };
+            if (eg < nunits) issue(eg);
+            for (int unit = eg; unit < nunits; unit += 4) {
+                const int i = unit / ncg, cb = (unit - i * ncg) * 16;
+                tmem_ld_wait();
+                float r[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&bias_s[cb + 4 * j]);
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        float t;
+                        if (DUAL) t = fmaf(__uint_as_float(u[4 * j + k]), p16::LO_INV, __uint_as_float(v[4 * j + k])) + bb[k];
+                        else t = fmaf(__uint_as_float(v[4 * j + k]), osc, bb[k]);
+                        r[4 * j + k] = a.lrelu ? lrelu_f(t) : t;
+                    }
+                }
+                // v / u are consumed: the TMEM loads of this warp's next unit hide behind the conversion and the stores
+                if (unit + 4 < nunits) issue(unit + 4);
+                const int yy = (ty * a.NT + i) * HT_H + (row >> 3);
+                const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
+                if (a.out_fmt == OUT_PLANES) {
+                    if (x < a.W && yy < a.H) {
+#pragma unroll
+                        for (int j = 0; j < 16; j += 2)
+                            if (cb + j < a.Cout)
+                                *reinterpret_cast<float2*>(reinterpret_cast<float*>(a.y) + (size_t)((cb + j) >> 1) * a.planar + pix * 2) =
+                                    make_float2(r[j], r[j + 1]);
+                    }
+                    continue;
+                }
+                uint4 t4[4];
+                if (a.out_fmt == OUT_P16) {
+                    uint32_t h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { h[j] = p16::pack_hi(r[2 * j], r[2 * j + 1]); bad |= p16::nonfinite_bits(h[j]); }
+                    t4[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                    t4[1] = make_uint4(h[4], h[5], h[6], h[7]);
+                    t4[2] = make_uint4(p16::pack_lo(r[0], r[1], h[0]), p16::pack_lo(r[2], r[3], h[1]),
+                                       p16::pack_lo(r[4], r[5], h[2]), p16::pack_lo(r[6], r[7], h[3]));
+                    t4[3] = make_uint4(p16::pack_lo(r[8], r[9], h[4]), p16::pack_lo(r[10], r[11], h[5]),
+                                       p16::pack_lo(r[12], r[13], h[6]), p16::pack_lo(r[14], r[15], h[7]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        t4[j] = make_uint4(__float_as_uint(r[4 * j]), __float_as_uint(r[4 * j + 1]), __float_as_uint(r[4 * j + 2]),
+                                           __float_as_uint(r[4 * j + 3]));
+                }
+                const bool full = a.out_fmt == OUT_P16 || cb + 16 <= a.cout_st;
+                if (a.quad && full) {
+                    // 4x4 transpose of 16-byte chunks inside each lane quad (4 consecutive pixels of a tile row): afterwards lane
+                    // j of the quad holds chunk j of all four pixels
+#pragma unroll
+                    for (int sft = 2; sft >= 1; sft >>= 1) {
+                        const bool up = (lane & sft) != 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            if (k & sft) continue;
+                            const uint4 snd = up ? t4[k] : t4[k ^ sft];
+                            uint4 rcv;
+                            rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, sft);
+                            rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, sft);
+                            rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, sft);
+                            rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, sft);
+                            if (up) t4[k] = rcv; else t4[k ^ sft] = rcv;
+                        }
+                    }
+                    const int lq = lane & 3;
+                    if (yy < a.H && x - lq < a.W) {          // W % 4 == 0: a quad is live or dead as a whole
+                        uint32_t* qb = a.y + (pix - lq) * a.y_ld + cb + lq * 4;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) st_global_v4(qb + (size_t)k * a.y_ld, t4[k]);
+                    }
+                } else if (x < a.W && yy < a.H) {
+                    uint32_t* dst = a.y + pix * a.y_ld + cb;
+                    if (full && !(a.y_ld & 3)) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) st_global_v4(dst + 4 * k, t4[k]);
+                    } else {
+                        const uint32_t o[16] = {t4[0].x, t4[0].y, t4[0].z, t4[0].w, t4[1].x, t4[1].y, t4[1].z, t4[1].w,
+                                                t4[2].x, t4[2].y, t4[2].z, t4[2].w, t4[3].x, t4[3].y, t4[3].z, t4[3].w};
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (cb + j < a.cout_st) dst[j] = o[j];
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[as]);
+        }
+        if (a.range_flag && p16::any_nonfinite(bad)) *a.range_flag = 1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(ncols) : "memory");
+    }
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// NT / slots / ring depth; returns the dynamic shared memory size or 0
+int configure(ConvP16Args& h, int mode) {
+    const int pitch = HT_W + h.KW - 1;
+    const int b_stage = (mode == 4 ? 2 : 3) * h.CoutP * 64;
+    const int tile_cols = mode == 4 ? 2 * h.CoutP : h.CoutP;
+    int NT = 2;
+    static int nt_env = -1;
+    if (nt_env < 0) { const char* v = getenv("PIVLFN_P16_NT"); nt_env = v ? atoi(v) : 0; }
+    if (nt_env == 1) NT = 1;
+    while (NT > 1 && (NT * tile_cols > 512 || HT_H * (NT - 1) >= h.H)) --NT;
+    for (; NT >= 1; --NT) {
+        const int halo_rows = HT_H * NT + h.KH - 1;
+        if (halo_rows > 256 || pitch > 256) continue;
+        const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
+        int tps = 1;
+        if (!h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 && (SMEM_BUDGET - 2 * slot) / (3 * b_stage) >= 2) tps = 3;
+        // a third activation slot when it still leaves a deep weight ring
+        int nA = ((SMEM_BUDGET - 3 * slot) / (tps * b_stage) >= 4) ? 3 : 2;
+        int nB = (SMEM_BUDGET - nA * slot) / (tps * b_stage);
+        if (nB > MAX_B) nB = MAX_B;
+        if (nB < 2) continue;
+        h.NT = NT; h.nA = nA; h.nB = nB; h.tps = tps;
+        h.nsets = (2 * NT * tile_cols <= 512) ? 2 : 1;
+        h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
+        const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
+        if (total > 0x7FFFFFFFLL) return 0;
+        h.total = (int)total;
+        return nA * slot + nB * tps * b_stage;
+    }
+    return 0;
+}
+
+}  // namespace
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                               const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
+                               int out_fmt, long long plane_stride, int* range_flag, void* stream) {
+    if (!x || !w_img || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
+    if (mode != 4 && mode != 5) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
+    if (out_fmt < OUT_P16 || out_fmt > OUT_PLANES) return PIVLFN_EINVAL;
+    const int CoutP = (Cout + 15) & ~15;
+    if (CoutP > 128 || (mode == 4 && CoutP > 64)) return PIVLFN_EUNSUPPORTED;
+    const int Cw = (Cin + 15) & ~15;                        // the P16 buffer holds whole 16-channel groups
+    if (((uintptr_t)x & 63) || (x_ld & 15) || x_ld < Cw || ((uintptr_t)w_img & 15)) return PIVLFN_EINVAL;
+    ConvP16Args h;
+    h.s2 = 0; h.cpp = 1;
+    if (stride == 2) {
+        if (KH != 3 || KW != 3 || (H & 1) || (W & 1) || (Cin % 32)) return PIVLFN_EUNSUPPORTED;
+        h.s2 = 1; h.cpp = Cin / 32;
+        h.KH = 2; h.KW = 2; h.H = H / 2; h.W = W / 2; h.x_shift = 0;
+    } else {
+        if (KH < 1 || KW < 1 || !(KH & 1) || !(KW & 1) || KH > 7 || KW > 7) return PIVLFN_EINVAL;
+        h.KH = KH; h.KW = KW; h.H = H; h.W = W; h.x_shift = -(KW / 2);
+    }
+    h.bias = bias; h.y = reinterpret_cast<uint32_t*>(y); h.y_ld = y_ld;
+    h.N = N; h.Cw = Cw; h.Cout = Cout; h.CoutP = CoutP; h.lrelu = lrelu; h.out_fmt = out_fmt;
+    h.w_img = reinterpret_cast<const uint8_t*>(w_img); h.range_flag = range_flag; h.planar = 0; h.cout_st = Cout; h.quad = 0;
+    if (out_fmt == OUT_P16) {
+        if (((uintptr_t)y & 63) || (y_ld & 15) || y_ld < CoutP) return PIVLFN_EINVAL;
+        h.quad = !(h.W & 3);
+    } else if (out_fmt == OUT_F32) {
+        if (((uintptr_t)y & 3) || y_ld < Cout) return PIVLFN_EINVAL;
+        h.cout_st = (y_ld == ((Cout + 3) & ~3)) ? y_ld : Cout;
+        h.quad = !(h.W & 3) && !((uintptr_t)y & 15) && !(y_ld & 3);
+    } else {
+        if (((uintptr_t)y & 7) || plane_stride < 2LL * N * h.H * h.W) return PIVLFN_EINVAL;
+        h.planar = plane_stride;
+    }
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+    const int smem = configure(h, mode);
+    if (smem <= 0) return PIVLFN_EUNSUPPORTED;
+    const int halo_rows = HT_H * h.NT + h.KH - 1;
+    CUtensorMap tmA;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)Cw, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t strides[3] = {(cuuint64_t)x_ld * 4, (cuuint64_t)W * x_ld * 4, (cuuint64_t)H * W * x_ld * 4};
+        cuuint32_t box[4] = {32, (cuuint32_t)((HT_W + h.KW - 1) * stride), (cuuint32_t)(halo_rows * stride), 1};
+        cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+        if (box[1] > 256 || box[2] > 256) return PIVLFN_EUNSUPPORTED;
+        CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return PIVLFN_EINVAL;
+    }
+    const int nsm = pivlfn_num_sms();
+    const int grid = h.total < nsm ? h.total : nsm;
+    cudaStream_t st = (cudaStream_t)stream;
+    static unsigned long long cfg4 = 0, cfg5 = 0;
+    cudaError_t e;
+    if (mode == 4) {
+        e = pivlfn_optin_smem(conv_p16_kernel<4>, SMEM_BUDGET, cfg4);
+        if (e != cudaSuccess) return (int)e;
+        conv_p16_kernel<4><<<grid, P16_THREADS, smem, st>>>(tmA, h);
+    } else {
+        e = pivlfn_optin_smem(conv_p16_kernel<5>, SMEM_BUDGET, cfg5);
+        if (e != cudaSuccess) return (int)e;
+        conv_p16_kernel<5><<<grid, P16_THREADS, smem, st>>>(tmA, h);
+    }
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}

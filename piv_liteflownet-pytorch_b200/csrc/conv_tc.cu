@@ -16,211 +16,19 @@
 #include <cuda.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "p16.cuh"
+#include "tc_ptx.cuh"
 
 namespace {
+using namespace tcptx;
 
-constexpr int TILE_M = 128;          // output pixels per CTA (UMMA M)
 constexpr int KC = 32;               // channels per stage: 32 fp32 = one 128-byte swizzle row
 constexpr int A_BYTES = TILE_M * KC * 4;   // 16 KB
 constexpr int NTHREADS = 192;
 constexpr int EPI_WARP0 = 2;
 
-// ---- PTX wrappers ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-// One lane of a fully active warp (elect.sync): the compiler then knows the guarded region runs on a single thread
-// and emits tcgen05 / TMA instructions directly instead of a per-active-lane serialisation loop.
-__device__ __forceinline__ bool elect_one() {
-    uint32_t pred;
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P;\n\t"
-        "elect.sync _|P, 0xffffffff;\n\t"
-        "selp.u32 %0, 1, 0, P;\n\t"
-        "}" : "=r"(pred));
-    return pred != 0;
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n\t"
-            ".reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t"
-            "}" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-// plain bulk copy global -> shared (contiguous bytes, 16-byte aligned, size a multiple of 16), completion on an mbarrier
-__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
-}
-// shared -> global tile store through the TMA engine (bulk async-group completion); out-of-bounds parts are clipped
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-        ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major operand tile, 128-byte rows, SWIZZLE_128B: 8-row groups are 1024 B apart (SBO), LBO unused.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset
-    d |= (uint64_t)1 << 46;                 // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
-    return d;
-}
-// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t make_idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-// Same instruction with the two shared-memory descriptors given as (low word, constant high word): the issuing thread
-// only has to produce two 32-bit values per MMA.
-__device__ __forceinline__ void umma_tf32_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-// kind::f16 with bf16 operands (K = 16 per instruction), fp32 accumulate: the 3xTF32 correction terms at twice the
-// tf32 rate (mode PASSES == 2)
-__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                               uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-// kind::f16 with fp16 operands (mode PASSES == 4): A and B format F16
-__device__ __forceinline__ uint32_t make_idesc_f16(int n) {
-    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
-}
-// two fp32 -> packed f16x2 (round to nearest even), low half = first value
-__device__ __forceinline__ uint32_t pack_f16(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-// packed f16x2 -> the residuals (a - f16(a)) * 2^11, (b - f16(b)) * 2^11 packed the same way
-__device__ __forceinline__ uint32_t pack_f16_lo(float a, float b, uint32_t h) {
-    float ha, hb;
-    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}" : "=f"(ha), "=f"(hb) : "r"(h));
-    return pack_f16((a - ha) * 2048.f, (b - hb) * 2048.f);
-}
-// Explicit shared-space 128-bit accesses: the operand-split pointers are carved out of the aligned dynamic array by integer
-// arithmetic, after which the compiler no longer knows they are shared and emits generic LD.E / ST.E with 64-bit addressing
-__device__ __forceinline__ float4 lds128(uint32_t addr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
 // Sticky flag: an activation outside the fp16 range reached a PASSES == 4 convolution (host: pivlfn_f16_range_flag)
 __device__ int g_f16_range_flag = 0;
-// two fp32 -> packed bf16x2 (round to nearest even), low half = first value
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    uint32_t r;
-    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-    return r;
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
-}
-// 256-bit global store (sm_100: STG.E.256): one full 32-byte sector per lane
-__device__ __forceinline__ void st_global_v8(float* p, const float* o) {
-    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]),
-                 "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 struct ConvTcArgs {
     const float* bias;
@@ -239,9 +47,6 @@ struct ConvTcArgs {
 
 constexpr int MAX_STAGES = 8;
 
-__device__ __forceinline__ uint32_t tmem_cols_for(int n) {
-    return n <= 32 ? 32u : (n <= 64 ? 64u : (n <= 128 ? 128u : (n <= 256 ? 256u : 512u)));
-}
 
 // PASSES = 1 (TF32) or 3 (3xTF32).
 template <int PASSES>
@@ -494,6 +299,8 @@ struct ConvHaloArgs {
                              // HBM write speed (measured 10.2k cycles per item) while the tensor cores idle.  De-phased CTAs
                              // store at the average rate instead.
     long long* dbg;          // optional: CTA 0 writes per-role wait-cycle totals (tools/profile_conv.py --trace)
+    int out_p16;             // quad-store path only: the output rows are P16 groups (p16.cuh) instead of fp32
+    int* range_flag;         // out_p16: raised when a result is not finite in fp16
 };
 
 #define DBG_T0() long long _t0 = a.dbg ? clock64() : 0
@@ -997,6 +804,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int row = q * 32 + lane;
         const float osc = F16S ? (1.f / 256.f) : 1.f;        // mode 5: the weights carry a factor 2^8 (fmaf(x, 1, b) == x + b)
         int wl = 0;
+        uint32_t p16_bad = 0;
         long long e_wait = 0, e_busy = 0, e_ld = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
             const int as = wl % a.nsets;
@@ -1093,6 +901,21 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                 }
                                 t4[j] = make_float4(e[0], e[1], e[2], e[3]);
                             }
+                            if (a.out_p16) {
+                                const float r[16] = {t4[0].x, t4[0].y, t4[0].z, t4[0].w, t4[1].x, t4[1].y, t4[1].z, t4[1].w,
+                                                     t4[2].x, t4[2].y, t4[2].z, t4[2].w, t4[3].x, t4[3].y, t4[3].z, t4[3].w};
+                                uint32_t hh[8], ll[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    hh[j] = p16::pack_hi(r[2 * j], r[2 * j + 1]);
+                                    ll[j] = p16::pack_lo(r[2 * j], r[2 * j + 1], hh[j]);
+                                    p16_bad |= p16::nonfinite_bits(hh[j]);
+                                }
+                                t4[0] = make_float4(__uint_as_float(hh[0]), __uint_as_float(hh[1]), __uint_as_float(hh[2]), __uint_as_float(hh[3]));
+                                t4[1] = make_float4(__uint_as_float(hh[4]), __uint_as_float(hh[5]), __uint_as_float(hh[6]), __uint_as_float(hh[7]));
+                                t4[2] = make_float4(__uint_as_float(ll[0]), __uint_as_float(ll[1]), __uint_as_float(ll[2]), __uint_as_float(ll[3]));
+                                t4[3] = make_float4(__uint_as_float(ll[4]), __uint_as_float(ll[5]), __uint_as_float(ll[6]), __uint_as_float(ll[7]));
+                            }
                             if (dual) {
                                 // v / u are consumed: start the TMEM loads of the next 16-column group (next stacked tile
                                 // after the last group) now, so that their latency hides behind the transpose and the stores
@@ -1170,6 +993,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (lane == 0) mbar_arrive(&acc_empty[as]);
             if (a.dbg) e_busy += clock64() - e_t0;
         }
+        if (a.out_p16 && a.range_flag && p16::any_nonfinite(p16_bad)) *a.range_flag = 1;
         if (a.vec_store == 5 && lane == 0) bulk_wait0();      // all tile stores of this warp have completed
         if (a.dbg && blockIdx.x == 0 && warp == 4 && lane == 0) { a.dbg[7] = e_wait; a.dbg[8] = e_busy; a.dbg[12] = e_ld; }
     }
@@ -1457,7 +1281,7 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = KH; h.KW = KW;
         h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = -(KW / 2);
         h.planar = 0;
-        h.stage_off = 0; h.s2 = 0; h.cpp = 1;
+        h.stage_off = 0; h.s2 = 0; h.cpp = 1; h.out_p16 = 0; h.range_flag = nullptr;
         if (vec_store >= 1 && !res && !(W & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
         // TMA tile stores: rows 16-byte aligned, at least one full 16-channel group, no residual to add
         const bool tma_ok = vec_store >= 1 && !res && cout_st >= 16 && halo_env().tma_store;
@@ -1542,7 +1366,7 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
         h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
         h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
         h.lrelu = lrelu; h.vec_store = (!((uintptr_t)y & 31) && !(y_ld & 7)) ? 2 : 1; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1; h.planar = 0;
-        h.stage_off = 0; h.s2 = 0; h.cpp = 1;
+        h.stage_off = 0; h.s2 = 0; h.cpp = 1; h.out_p16 = 0; h.range_flag = nullptr;
         int halo_rows = 0;
         const int smem = halo_configure(h, passes, &halo_rows);
         if (smem > 0) {
@@ -1592,6 +1416,37 @@ extern "C" int pivlfn_conv_stem_tc(const float* img_pad, int N, int H, int W,
     return passes == 3 ? launch<3>(tmA, tmBhi, tmBlo, a, (int)grid, st) : launch<1>(tmA, tmBhi, tmBlo, a, (int)grid, st);
 }
 
+// The same stem for the P16 pipeline: fp16-split arithmetic (passes == 4: the image tile is split in shared memory -- the
+// image is the one activation that does not exist in P16 form), output written as P16 groups (p16.cuh) for the P16
+// consumers NetC.conv2, NetC_ext and moduleFeat.  w_img: stage_image of the [2][32][7][32] fp16 pack.
+extern "C" int pivlfn_conv_stem_p16(const float* img_pad, int N, int H, int W, const void* w_img, const float* bias,
+                                    void* y, int y_ld, int lrelu, int* range_flag, void* stream) {
+    if (!img_pad || !w_img || !y || N <= 0 || H <= 0 || W < HT_W || (W & 3)) return PIVLFN_EINVAL;
+    if (((uintptr_t)img_pad & 15) || ((uintptr_t)w_img & 15) || ((uintptr_t)y & 63) || (y_ld & 15) || y_ld < 32) return PIVLFN_EINVAL;
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return PIVLFN_EDRIVER;
+    ConvHaloArgs h;
+    h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = reinterpret_cast<float*>(y); h.y_ld = y_ld;
+    h.N = N; h.H = H; h.W = W; h.Cin = 32; h.Cout = 32; h.CoutP = 32; h.KH = 7; h.KW = 1;
+    h.lrelu = lrelu; h.vec_store = 4; h.cout_st = 32; h.dbg = g_conv_tc_dbg; h.x_shift = 1; h.planar = 0;
+    h.stage_off = 0; h.s2 = 0; h.cpp = 1; h.out_p16 = 1; h.range_flag = range_flag;
+    int halo_rows = 0;
+    const int smem = halo_configure(h, 4, &halo_rows);
+    if (smem <= 0) return PIVLFN_EUNSUPPORTED;
+    CUtensorMap tA;
+    const cuuint64_t Wp = (cuuint64_t)W + 8;
+    cuuint64_t dims[4] = {32, (cuuint64_t)W + 1, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {16, Wp * 16, (cuuint64_t)H * Wp * 16};
+    cuuint32_t box[4] = {32, (cuuint32_t)HT_W, (cuuint32_t)halo_rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&tA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(img_pad), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return PIVLFN_EUNSUPPORTED;
+    h.w_img = (const uint8_t*)w_img;
+    return halo_launch(tA, tA, tA, tA, tA, h, 4, smem, (cudaStream_t)stream);      // fp16 modes read weights through w_img only
+}
+
 // Flow heads (last layer of conv_M / conv_S, src/models.py:161,205: KxK, 32 -> 2, K = 7 or 5) restated as
 //   D[pixel, tap*2 + co] = sum_c x[pixel, c] * w[co, c, tap]          (a 1x1 convolution to 2*K*K channels: this call)
 //   flow[p, co] = bias[co] + res[p, co] + sum_tap D[p + offset(tap), tap*2 + co]        (pivlfn_flow_head_sum)
@@ -1624,7 +1479,7 @@ extern "C" int pivlfn_conv1x1_pairs_tc(const float* x, int x_ld, int N, int H, i
     h.N = N; h.H = H; h.W = W; h.Cin = Cin; h.Cout = Cout; h.CoutP = CoutP; h.KH = 1; h.KW = 1;
     h.lrelu = 0; h.vec_store = 0; h.cout_st = Cout; h.dbg = g_conv_tc_dbg; h.x_shift = 0;
     h.planar = (long long)N * H * W * 2;
-    h.stage_off = 0; h.s2 = 0; h.cpp = 1;
+    h.stage_off = 0; h.s2 = 0; h.cpp = 1; h.out_p16 = 0; h.range_flag = nullptr;
     int halo_rows = 0;
     const int smem = halo_configure(h, passes, &halo_rows);
     if (smem <= 0) return PIVLFN_EUNSUPPORTED;
@@ -1665,7 +1520,7 @@ extern "C" int pivlfn_conv_s2_tc(const float* x, int x_ld, int N, int H, int W, 
     h.bias = bias; h.res = nullptr; h.res_ld = 0; h.y = y; h.y_ld = y_ld;
     h.N = N; h.H = Ho; h.W = Wo; h.Cin = CinR; h.Cout = Cout; h.CoutP = CoutP; h.KH = 2; h.KW = 2;
     h.lrelu = lrelu; h.vec_store = vec_store; h.cout_st = cout_st; h.dbg = g_conv_tc_dbg; h.x_shift = 0; h.planar = 0;
-    h.stage_off = 0; h.s2 = 1; h.cpp = Cin / KC;
+    h.stage_off = 0; h.s2 = 1; h.cpp = Cin / KC; h.out_p16 = 0; h.range_flag = nullptr;
     if (vec_store >= 1 && !(Wo & 3) && !(cout_st & 15) && halo_env().quad_store) h.vec_store = 4;
     int halo_rows = 0;
     const int smem = halo_configure(h, passes, &halo_rows);

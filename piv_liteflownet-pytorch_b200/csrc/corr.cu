@@ -12,6 +12,7 @@
 // Two entry points: NCHW (the public FunctionCorrelation operator) and NHWC (model-internal, with the
 // backwarp of f2 and the LeakyReLU of src/models.py:171-184 fused in).
 #include "common.cuh"
+#include "p16.cuh"
 
 namespace {
 
@@ -176,10 +177,25 @@ __device__ __forceinline__ float4 ld_quad(const float* src, int c, int C) {
     return v;
 }
 
+// channels c .. c+3 of a P16 pixel row (p16.cuh): 8 bytes of hi + 8 bytes of lo' -> 4 floats (pad channels of the last group are
+// stored as zeros, so no channel-count test is needed)
+__device__ __forceinline__ float4 ld_quad_p16(const float* pixel_row, int c) {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(pixel_row) + (c >> 4) * 64 + (c & 15) * 2;
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
+    const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 32));
+    float4 v;
+    p16::decode2(h.x, l.x, v.x, v.y);
+    p16::decode2(h.y, l.y, v.z, v.w);
+    return v;
+}
+
+// F1P / F2P: the feature maps are P16 (f*_ld = pixel pitch in words either way); OUTP: the result is written as P16 groups
+// (64 channels: 49 displacements + zero pad) for a tensor-core consumer instead of fp32 rows
+template <bool F1P, bool F2P, bool OUTP>
 __global__ void __launch_bounds__(NH_THREADS, 3)
 corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restrict__ f2, int f2_ld,
                  const float* __restrict__ flow, float fscale, float* __restrict__ out, int out_ld,
-                 int C, int H, int W, int Ho, int Wo, int s, int lrelu) {
+                 int C, int H, int W, int Ho, int Wo, int s, int lrelu, int* __restrict__ range_flag) {
     extern __shared__ __align__(16) float sbuf[];        // f1 tile | f2 tile (reused as the output staging tile [128][NH_OLD]) | taps
     float* const s1 = sbuf;
     float* const s2 = sbuf + NH_S1;
@@ -231,7 +247,10 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             const int px = x0 + lx, py = y0 + ly;
             const int c = c0 + q * 4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (px < Wo && py < Ho && c < C) v = ld_quad(f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld + c, c, C);
+            if (px < Wo && py < Ho && c < C) {
+                const float* row = f1 + (img + (size_t)(py * s) * W + px * s) * f1_ld;
+                v = F1P ? ld_quad_p16(row, c) : ld_quad(row + c, c, C);
+            }
             *reinterpret_cast<float4*>(&s1[(ly * NH_S1W + lx) * NH_PITCH + q * 4]) = v;
         }
         // ---- f2 tile (+halo): 1232 items, three at a time (12 independent gathers in flight per thread) --------
@@ -252,8 +271,10 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     u[e][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (ok[e] && c < C && wgt[k] != 0.f)
-                        u[e][k] = ld_quad(f2 + (img + (size_t)(xy.y + (k >> 1)) * W + (xy.x + (k & 1))) * f2_ld + c, c, C);
+                    if (ok[e] && c < C && wgt[k] != 0.f) {
+                        const float* row = f2 + (img + (size_t)(xy.y + (k >> 1)) * W + (xy.x + (k & 1))) * f2_ld;
+                        u[e][k] = F2P ? ld_quad_p16(row, c) : ld_quad(row + c, c, C);
+                    }
                 }
             }
 #pragma unroll
@@ -314,6 +335,27 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
             so[(ty * NH_TX + seg * 4 + i) * NH_OLD + dy * 7 + d] = lrelu ? lrelu_f(v) : v;
         }
     __syncthreads();
+    if (OUTP) {
+        // 8 units of 8 channels per pixel (channels >= 49 are zero), each encoded as a 16-byte hi and a 16-byte lo' vector
+        uint32_t bad = 0;
+        for (int item = tid; item < NH_TX * NH_TY * 8; item += NH_THREADS) {
+            const int p = item >> 3, un = item & 7;
+            const int ox = x0 + p % NH_TX, oy = y0 + p / NH_TX;
+            if (ox < Wo && oy < Ho) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j] = (un * 8 + j < 49) ? so[p * NH_OLD + un * 8 + j] : 0.f;
+                uint4 h, l;
+                p16::encode8(v, h, l);
+                bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
+                uint8_t* o = reinterpret_cast<uint8_t*>(out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld) + p16::unit_off_bytes(un);
+                *reinterpret_cast<uint4*>(o) = h;
+                *reinterpret_cast<uint4*>(o + 32) = l;
+            }
+        }
+        if (range_flag && p16::any_nonfinite(bad)) *range_flag = 1;
+        return;
+    }
     // rows of exactly 52 floats are a dedicated buffer with its own padding: whole float4 rows (pad channels written as 0)
     const bool vec = out_ld == NH_OLD && !((uintptr_t)out & 15);
     if (vec) {
@@ -349,6 +391,25 @@ extern "C" int pivlfn_corr_nchw(const float* first, const float* second, float* 
     return pivlfn_last_error();
 }
 
+namespace {
+template <bool F1P, bool F2P, bool OUTP>
+int launch_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld, const float* flow, float flow_scale, float* out,
+                     int out_ld, int N, int H, int W, int C, int stride, int lrelu, int* range_flag, cudaStream_t st) {
+    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
+    dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
+    constexpr int smem = (NH_S1 + NH_S2) * 4 + NH_NPIX2 * (16 + 8);
+    static unsigned long long configured = 0;
+    {
+        cudaError_t e = pivlfn_optin_smem(corr_nhwc_kernel<F1P, F2P, OUTP>, smem, configured);
+        if (e != cudaSuccess) return (int)e;
+    }
+    corr_nhwc_kernel<F1P, F2P, OUTP><<<grid, NH_THREADS, smem, st>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
+                                                                      C, H, W, Ho, Wo, stride, lrelu, range_flag);
+    PIVLFN_LAUNCHED();
+    return pivlfn_last_error();
+}
+}  // namespace
+
 extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld,
                                 const float* flow, float flow_scale, float* out, int out_ld,
                                 int N, int H, int W, int C, int stride, int lrelu, void* stream) {
@@ -358,16 +419,36 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
     // float4 tile loads need 16-byte aligned pixel rows
     if (((uintptr_t)f1 & 15) || ((uintptr_t)f2 & 15) || (f1_ld & 3) || (f2_ld & 3)) return PIVLFN_EINVAL;
     if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
-    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
-    dim3 grid(cdiv(Wo, NH_TX), cdiv(Ho, NH_TY), N);
-    constexpr int smem = (NH_S1 + NH_S2) * 4 + NH_NPIX2 * (16 + 8);
-    static unsigned long long configured = 0;
-    {
-        cudaError_t e = pivlfn_optin_smem(corr_nhwc_kernel, smem, configured);
-        if (e != cudaSuccess) return (int)e;
-    }
-    corr_nhwc_kernel<<<grid, NH_THREADS, smem, (cudaStream_t)stream>>>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld,
-                                                                          C, H, W, Ho, Wo, stride, lrelu);
-    PIVLFN_LAUNCHED();
-    return pivlfn_last_error();
+    return launch_corr_nhwc<false, false, false>(f1, f1_ld, f2, f2_ld, flow, flow_scale, out, out_ld, N, H, W, C, stride, lrelu,
+                                                 nullptr, (cudaStream_t)stream);
+}
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_corr_p16(const void* f1, int f1_ld, int f1_p16, const void* f2, int f2_ld, int f2_p16,
+                               const float* flow, float flow_scale, void* out, int out_ld, int out_p16,
+                               int N, int H, int W, int C, int stride, int lrelu, int* range_flag, void* stream) {
+    if (!f1 || !f2 || !out || N <= 0 || C <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
+    if (f1_ld < C || f2_ld < C || N > 65535) return PIVLFN_EINVAL;
+    if (f1_p16 ? (((uintptr_t)f1 & 63) || (f1_ld & 15) || f1_ld < ((C + 15) & ~15)) : (((uintptr_t)f1 & 15) || (f1_ld & 3))) return PIVLFN_EINVAL;
+    if (f2_p16 ? (((uintptr_t)f2 & 63) || (f2_ld & 15) || f2_ld < ((C + 15) & ~15)) : (((uintptr_t)f2 & 15) || (f2_ld & 3))) return PIVLFN_EINVAL;
+    if (out_p16 ? (((uintptr_t)out & 63) || (out_ld & 15) || out_ld < 64) : (out_ld < 49)) return PIVLFN_EINVAL;
+    if (flow && ((uintptr_t)flow & 7)) return PIVLFN_EINVAL;
+    const float* a = reinterpret_cast<const float*>(f1);
+    const float* b = reinterpret_cast<const float*>(f2);
+    float* o = reinterpret_cast<float*>(out);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PIVLFN_CORR_CASE(A, B, O) \
+    if ((f1_p16 != 0) == A && (f2_p16 != 0) == B && (out_p16 != 0) == O) \
+        return launch_corr_nhwc<A, B, O>(a, f1_ld, b, f2_ld, flow, flow_scale, o, out_ld, N, H, W, C, stride, lrelu, range_flag, st);
+    PIVLFN_CORR_CASE(true, false, false)
+    PIVLFN_CORR_CASE(true, false, true)
+    PIVLFN_CORR_CASE(true, true, false)
+    PIVLFN_CORR_CASE(true, true, true)
+    PIVLFN_CORR_CASE(false, false, true)
+    PIVLFN_CORR_CASE(false, true, false)
+    PIVLFN_CORR_CASE(false, true, true)
+    PIVLFN_CORR_CASE(false, false, false)
+#undef PIVLFN_CORR_CASE
+    return PIVLFN_EINVAL;
 }

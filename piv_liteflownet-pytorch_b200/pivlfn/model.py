@@ -233,7 +233,20 @@ class Engine:
         if self.precision not in PRECISIONS:
             raise ValueError(f"precision must be one of {PRECISIONS}")
         self.use_graph = (os.environ.get("PIVLFN_GRAPH", "1") != "0") if use_graph is None else use_graph
-        self.range_check = os.environ.get("PIVLFN_RANGE_CHECK", "1") != "0"
+        # fp16 range check of precision f16c: "sync" = read the device flag after every forward and repeat it in tf32c on a
+        # hit (one stream sync per forward); "deferred" = read it asynchronously and switch at the NEXT call (an out-of-range
+        # forward returns non-finite values, never silently saturated ones); "auto" (default) = sync for large forwards,
+        # where the sync is free, deferred for small ones (run.py-style single pairs), where it would be a throughput cliff
+        rc = os.environ.get("PIVLFN_RANGE_CHECK", "auto")
+        self.range_check = {"1": "auto", "0": "off"}.get(rc, rc)
+        if self.range_check not in ("auto", "sync", "deferred", "off"):
+            raise ValueError("PIVLFN_RANGE_CHECK must be auto, sync, deferred or 0")
+        # precision f16c runs the P16 pipeline (activations kept in HBM as the fp16 pairs the MMAs read: plan16.py);
+        # PIVLFN_P16=0 selects the older fp32-activation plan whose kernels split the operands in shared memory
+        self.p16 = self.precision == TC_F16C and os.environ.get("PIVLFN_P16", "1") != "0"
+        self.flag = torch.zeros(1, device=device, dtype=torch.int32)          # P16 producers raise it (never cleared by them)
+        self._flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self._pending: Optional[torch.cuda.Event] = None
         # flow heads (KxK, 32 -> 2): "simt" = exact-fp32 CUDA-core kernel (default), "pairs" = 1x1 tensor-core convolution to
         # tap planes + gather-sum, "conv" = the generic convolution path
         self.head_mode = os.environ.get("PIVLFN_HEAD", "simt")
@@ -247,6 +260,7 @@ class Engine:
             import warnings
             warnings.warn("pivlfn: a weight lies outside the fp16 range; precision 'f16c' replaced by 'tf32c'")
             self.precision = TC_TF32C
+            self.p16 = False
 
     # ---------------------------------------------------------------------------------------------
     def _pack(self, sd: Dict[str, torch.Tensor]):
@@ -273,6 +287,11 @@ class Engine:
                 self.w[f"NetC.{seq}.{idx}"] = pack_stem(g(f"NetC.{seq}.{idx}.weight"), g(f"NetC.{seq}.{idx}.bias"))
             else:
                 conv(f"NetC.{seq}.{idx}", st, cin_pad=1 if cin == 3 else 0)
+        if self.p16:
+            # 128 -> 192 (stride 2): two 96-channel halves for the tensor-core kernel (at most 128 accumulator columns)
+            w6, b6 = g("NetC.conv6.0.weight"), g("NetC.conv6.0.bias")
+            self.w["NetC.conv6.0#a"] = pack_conv(w6[:96], b6[:96], 2, tc=True)
+            self.w["NetC.conv6.0#b"] = pack_conv(w6[96:], b6[96:], 2, tc=True)
         for e in range(cfg.n_ext):
             conv(f"NetC_ext.{e}.conv_ext.0")
         nh = len(cfg.head)
@@ -282,6 +301,11 @@ class Engine:
                 conv(f"NetE_S.{i}.conv_S.{2 * j}")
             for key in (f"NetE_M.{i}.conv_M.{2 * nh}", f"NetE_S.{i}.conv_S.{2 * nh}"):
                 w = g(key + ".weight")                                       # [2, cin, K, K]
+                if self.p16:
+                    # tensor-core flow head: 1xK convolution to the 2K row channels (ky*2 + co), summed over ky by
+                    # pivlfn_head_rows_sum (plan16.py)
+                    K = w.shape[2]
+                    self.w[key + "#rows"] = pack_conv(w.permute(2, 0, 1, 3).reshape(2 * K, w.shape[1], 1, K), None, 1, tc=True)
                 if self.head_mode == "simt" and w.shape[1] == 32:
                     # exact-fp32 CUDA-core flow head (pivlfn_flow_head): weights as [K*K][32][2]
                     self.raw[key + "#head"] = w.permute(2, 3, 1, 0).reshape(-1, 32, 2).contiguous()
@@ -323,7 +347,11 @@ class Engine:
                 # a directory of mixed-size frames or many odd last batches must not grow device memory without bound
                 self._plans.pop(next(iter(self._plans)))
             with torch.cuda.device(self.device):
-                p = Plan(self, B, H, W)
+                if self.p16:
+                    from .plan16 import Plan16
+                    p = Plan16(self, B, H, W)
+                else:
+                    p = Plan(self, B, H, W)
         self._plans[key] = p            # (re)inserted last: dict order is the LRU order
         return p
 
@@ -349,9 +377,34 @@ class Engine:
             img2.copy_(c2)
         return res
 
+    def _fall_back(self, what: str):
+        import warnings
+        warnings.warn(f"pivlfn: an activation left the fp16 range in precision 'f16c' ({what}); this model now runs in 'tf32c'")
+        self.precision = TC_TF32C
+        self.p16 = False
+        self._plans.clear()
+        self._pending = None
+        self.flag.zero_()
+
+    def check_range(self, wait: bool = True) -> bool:
+        """Resolve a deferred fp16-range check (P16 pipeline).  Returns True when the forward(s) since the last check left
+        the range: their output contains non-finite values and this engine has switched to 'tf32c'."""
+        if self._pending is None:
+            return False
+        if not wait and not self._pending.query():
+            return False
+        self._pending.synchronize()
+        self._pending = None
+        if int(self._flag_host[0]) != 0:
+            self._fall_back("detected after the forward returned: its output is not finite")
+            return True
+        return False
+
     def _forward_on_device(self, img1, img2, B, H, W, return_levels):
+        if self.p16:
+            return self._forward_p16(img1, img2, B, H, W, return_levels)
         plan = self.plan(B, H, W)
-        check = self.precision == TC_F16C and self.range_check
+        check = self.precision == TC_F16C and self.range_check != "off"
         if check:
             # the flag is sticky and process-wide per device: a stale hit (a direct ops call, another engine, the tiled
             # path) must not downgrade THIS engine, so it is cleared before the forward it is meant to judge
@@ -359,21 +412,40 @@ class Engine:
                 raise _lib.PivlfnError("pivlfn_f16_range_flag_clear: CUDA error")
         res = plan.run(img1, img2, return_levels, mutate_inputs=False)
         if check:
-            # f16c converts activations to fp16 pairs: a value outside the fp16 range raises a sticky device flag
-            # (never a silent saturation).  One stream sync + 4-byte read per forward; on a hit this engine switches to
-            # tf32c for good and the forward is repeated from the caller's (still unmodified) images.
+            # the fp32-activation f16c kernels convert activations to fp16 pairs in shared memory: a value outside the fp16
+            # range raises a sticky device flag (never a silent saturation).  One stream sync + 4-byte read per forward;
+            # on a hit this engine switches to tf32c for good and the forward is repeated from the caller's (still
+            # unmodified) images.
             torch.cuda.current_stream().synchronize()
             flag = int(self.lib.pivlfn_f16_range_flag(1))
             if flag < 0:
                 raise _lib.PivlfnError("pivlfn_f16_range_flag: CUDA error")
             if flag:
-                import warnings
-                warnings.warn("pivlfn: an activation left the fp16 range in precision 'f16c'; switching this model to "
-                              "'tf32c' and repeating the forward")
-                self.precision = TC_TF32C
-                self._plans.clear()
+                self._fall_back("forward repeated")
                 plan = self.plan(B, H, W)
                 res = plan.run(img1, img2, return_levels, mutate_inputs=False)
+        plan.mutate_inputs(img1, img2)
+        return res
+
+    def _forward_p16(self, img1, img2, B, H, W, return_levels):
+        """P16 pipeline: every producer of a P16 tensor raises ``self.flag`` (owned by this engine) when a value is not
+        finite in fp16."""
+        mode = self.range_check
+        if mode == "auto":
+            mode = "sync" if B * H * W >= (1 << 20) else "deferred"
+        if self.check_range(wait=False):                      # a deferred check of an earlier forward came back positive
+            return self._forward_on_device(img1, img2, B, H, W, return_levels)
+        plan = self.plan(B, H, W)
+        res = plan.run(img1, img2, return_levels, mutate_inputs=False)
+        if mode == "sync":
+            if int(self.flag.item()) != 0:                    # .item(): one stream sync + 4-byte read
+                self._fall_back("forward repeated")
+                return self._forward_on_device(img1, img2, B, H, W, return_levels)
+        elif mode == "deferred":
+            if self._pending is None or self._pending.query():
+                self._flag_host.copy_(self.flag, non_blocking=True)
+                self._pending = torch.cuda.Event()
+                self._pending.record()
         plan.mutate_inputs(img1, img2)
         return res
 

@@ -216,6 +216,71 @@ def reg_tail(dist: View, flow_in, wx, bx, wy, by, flow_out, out_nchw, final_scal
                                    K, N, H, W, _stream()), "reg_tail")
 
 
+# ---- P16 pipeline (include/pivlfn.h, "the P16 pipeline") -----------------------------------------------------------------
+OUT_P16, OUT_F32, OUT_PLANES = 0, 1, 2
+
+
+def _flag(flag: Optional[torch.Tensor]):
+    return flag.data_ptr() if flag is not None else None
+
+
+def p16_encode(x: View, y: View, npix: int, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_p16_encode(x.ptr, x.ld, x.C, y.ptr, y.ld, npix, _flag(flag), _stream()), "p16_encode")
+
+
+def p16_decode(x: View, C: int, y: View, npix: int):
+    _lib.check(_lib.load().pivlfn_p16_decode(x.ptr, x.ld, C, y.ptr, y.ld, npix, _stream()), "p16_decode")
+
+
+def conv_p16(x: View, N, H, W, cin, w_img, mode, bias, y: View, cout, KH, KW, stride=1, lrelu=True, out_fmt=OUT_P16,
+             plane_stride=0, flag: Optional[torch.Tensor] = None):
+    """H, W: input size.  x: P16 view holding ceil16(cin) words per pixel."""
+    _lib.check(_lib.load().pivlfn_conv_p16(x.ptr, x.ld, N, H, W, int(cin), w_img.data_ptr(), int(mode),
+                                           bias.data_ptr() if bias is not None else None, y.ptr, y.ld, int(cout),
+                                           int(KH), int(KW), int(stride), int(lrelu), int(out_fmt), int(plane_stride),
+                                           _flag(flag), _stream()), "conv_p16")
+
+
+def conv_stem_p16(img_pad: torch.Tensor, N, H, W, w_img, bias, y: View, lrelu=True, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_conv_stem_p16(img_pad.data_ptr(), N, H, W, w_img.data_ptr(),
+                                                bias.data_ptr() if bias is not None else None, y.ptr, y.ld, int(lrelu),
+                                                _flag(flag), _stream()), "conv_stem_p16")
+
+
+def corr_p16(f1: View, f1_p16: bool, f2: View, f2_p16: bool, flow: Optional[torch.Tensor], scale: float, out: View,
+             out_p16: bool, N, H, W, C, stride, lrelu=True, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_corr_p16(f1.ptr, f1.ld, int(f1_p16), f2.ptr, f2.ld, int(f2_p16),
+                                           flow.data_ptr() if flow is not None else None, float(scale), out.ptr, out.ld,
+                                           int(out_p16), N, H, W, int(C), int(stride), int(lrelu), _flag(flag), _stream()),
+               "corr_p16")
+
+
+def warp_p16(x: View, in_p16: bool, flow: torch.Tensor, scale: float, y: View, N, H, W, C, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_warp_p16(x.ptr, x.ld, int(in_p16), flow.data_ptr(), float(scale), y.ptr, y.ld, N, H, W,
+                                           int(C), _flag(flag), _stream()), "warp_p16")
+
+
+def deconv4x4s2_dw_p16(x: View, N, H, W, C, w, y: View, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_deconv4x4s2_dw_p16(x.ptr, x.ld, w.data_ptr(), y.ptr, y.ld, N, H, W, int(C), _flag(flag),
+                                                     _stream()), "deconv4x4s2_dw_p16")
+
+
+def reg_input_p16(img1, img2, flow, scale, partial, out: View, flag: Optional[torch.Tensor] = None):
+    N, H, W, _ = flow.shape
+    _lib.check(_lib.load().pivlfn_reg_input_p16(img1.data_ptr(), img2.data_ptr(), flow.data_ptr(), float(scale),
+                                                partial.data_ptr(), out.ptr, out.ld, N, H, W, _flag(flag), _stream()),
+               "reg_input_p16")
+
+
+def head_rows_sum(planes: torch.Tensor, K: int, bias, res: Optional[torch.Tensor], out: torch.Tensor,
+                  out_p16: Optional[View], N, H, W, flag: Optional[torch.Tensor] = None):
+    _lib.check(_lib.load().pivlfn_head_rows_sum(planes.data_ptr(), int(K), bias.data_ptr() if bias is not None else None,
+                                                res.data_ptr() if res is not None else None, out.data_ptr(),
+                                                out_p16.ptr if out_p16 is not None else None,
+                                                out_p16.ld if out_p16 is not None else 0, N, H, W, _flag(flag), _stream()),
+               "head_rows_sum")
+
+
 def resize_bilinear(x: torch.Tensor, Ho: int, Wo: int, mul_even: float = 1.0, mul_odd: float = 1.0) -> torch.Tensor:
     """[B,C,H,W] -> [B,C,Ho,Wo], bilinear, align_corners=False (inference.py:46-49,57-61)."""
     lib = _lib.load()

@@ -1,0 +1,224 @@
+"""Launch plan of the P16 pipeline (the default for precision ``f16c``): the forward of ``pivlfn.model.Plan`` with every
+activation that feeds a convolution kept in HBM as the fp16 (hi, lo') pairs the tensor cores consume (csrc/p16.cuh).
+
+Same reference semantics (src/models.py:319-370 / :660-716), same buffers-as-concats idea as ``Plan``:
+
+    Sbuf[l] = [ f1 (Cm) | backwarp(f2) (Cm) | flow_M (2) + 14 zero ]      P16, input of conv_S   (src/models.py:216)
+    Rbuf[l] = [ feat (Cr) | err, rm_u, rm_v + 13 zero ]                   P16, input of conv_R   (src/models.py:280)
+
+Channel slices start at multiples of 16 (one P16 group = 64 bytes per pixel).  What stays fp32 NHWC: the images, the
+flows, the second image's NetC_ext features at levels 1-2 (read only by the cost volume and the backwarp), the
+half-resolution cost volume in front of upCorr_M, the flow-head row planes and the distance maps of the regularisation tail.
+
+Differences from ``Plan`` besides the format:
+  * all convolutions (stride-2 NetC layers, the 192-channel conv6 as two 96-channel halves, tiny levels) run in ONE kernel
+    family, ``pivlfn_conv_p16``: no operand split in shared memory, 16 epilogue warps;
+  * the KxK 32 -> 2 flow heads run on the tensor cores as a 1xK convolution to 2K row planes + a K-row gather-sum
+    (``pivlfn_head_rows_sum``), which also writes flow_M's P16 group into Sbuf.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import ops
+from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
+from .model import Plan
+from .ops import OUT_F32, OUT_P16, OUT_PLANES, View, view
+
+
+def _r16(c: int) -> int:
+    return (c + 15) & ~15
+
+
+def _r4(c: int) -> int:
+    return (c + 3) & ~3
+
+
+class Plan16(Plan):
+    """Workspace and launch sequence for one (B, H, W) in the P16 format."""
+
+    def __init__(self, eng, B: int, H: int, W: int):     # noqa: D401  (does not call Plan.__init__: different buffers)
+        self.eng, self.B, self.H, self.W = eng, B, H, W
+        cfg = eng.cfg
+        dev = eng.device
+        E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
+        self.hw = {l: (H >> (l - 1), W >> (l - 1)) for l in range(1, 7)}
+        N2 = 2 * B
+        self.in1, self.in2 = E(B, 3, H, W), E(B, 3, H, W)
+        self.img = {1: E(N2, H, W, 4)}
+        self.img_pad = Z(N2, H, W + 8, 4)                # zero border written once
+        for l in range(2, 7):
+            self.img[l] = E(N2, *self.hw[l], 4)
+        # NetC intermediates and features: P16, channel counts are multiples of 16 (32, 64, 96, 128, 192)
+        self.netc_out: List[torch.Tensor] = []
+        lvl = 1
+        for seq, idx, cin, cout, k, st in NETC:
+            if st == 2:
+                lvl += 1
+            self.netc_out.append(E(N2, *self.hw[lvl], _r16(cout)))
+        self.feat = {l: self.netc_out[NETC_LEVEL_END[l]] for l in range(1, 7)}
+        self.lv: Dict[int, dict] = {}
+        for l in cfg.levels:
+            h, w = self.hw[l]
+            cm, cr = MATCH_FEAT_CH[l], (128 if l < 5 else LEVEL_FEAT_CH[l])
+            s = 2 if l < 4 else 1
+            K = KSIZE[l]
+            d = dict(
+                f2=E(B, h, w, cm) if l <= 2 else None,                                   # fp32 NHWC
+                flowU=E(B, h, w, 2) if l != 6 else None,
+                corr=Z(B, (h + s - 1) // s, (w + s - 1) // s, 52) if l < 4 else None,    # fp32, in front of upCorr_M
+                corrU=Z(B, h, w, 64),                                                    # P16: input of conv_M
+                Sbuf=Z(B, h, w, 2 * cm + 16),
+                Rbuf=Z(B, h, w, cr + 16),
+                flowM=E(B, h, w, 2), flowS=E(B, h, w, 2), flowR=E(B, h, w, 2),
+                partial=E(B, ops.flow_mean_parts(), 2),
+                dist=E(B, h, w, _r4(DIST_CH[l])),                                        # fp32: input of the tail
+                dist0=Z(B, h, w, _r16(DIST_CH[l])) if l < 5 else None,                   # P16
+                planes=E(K, B * h * w, 2),                                               # fp32 row planes of the flow heads
+            )
+            widths = sorted(set(cfg.head) | set(CONV_R))
+            d["t"] = {c: [E(B, h, w, _r16(c)), E(B, h, w, _r16(c))] for c in widths}     # P16 ping-pong per width
+            self.lv[l] = d
+        lo = cfg.lowest_level
+        self.out = E(B, 2, *self.hw[lo])
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.graph_launches = 0
+        self._warm = 0
+
+    # ---------------------------------------------------------------------------------------------
+    def _conv(self, key: str, x: View, n: int, h: int, w: int, y: View, lrelu: bool = True, out_fmt: int = OUT_P16,
+              cin: Optional[int] = None):
+        """h, w: INPUT size.  The weight pack decides the kernel mode: one accumulator (5) for Cout > 64, else [main | corr] (4)."""
+        eng = self.eng
+        cw = eng.w[key]
+        cin = cw.cin if cin is None else cin
+        assert x.C >= _r16(cin) or x.C == cin, (key, x.C, cin)
+        if cw.stride == 2:
+            assert cw.w_s2 is not None, key
+            w_img, mode = cw.w_s2, cw.s2_passes
+        elif cw.w_f16s is not None:
+            w_img, mode = cw.w_f16s, 5
+        else:
+            w_img, mode = cw.w_f16, 4
+        ops.conv_p16(x, n, h, w, cin, w_img, mode, cw.bias, y, cw.cout, cw.kh, cw.kw, cw.stride, lrelu, out_fmt, 0, eng.flag)
+
+    def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: Optional[torch.Tensor], out: torch.Tensor,
+               out_p16: Optional[View] = None):
+        """conv_M / conv_S: 3x3 conv + LeakyReLU ..., then the KxK 32->2 flow head plus residual flow."""
+        eng, B = self.eng, self.B
+        h, w = self.hw[l]
+        d = self.lv[l]
+        t = d["t"]
+        used: Dict[int, int] = {}
+        for j in idxs[:-1]:
+            c = eng.w[f"{prefix}.{j}"].cout
+            k = used.get(c, 0)
+            used[c] = k ^ 1
+            y = view(t[c][k])
+            self._conv(f"{prefix}.{j}", x, B, h, w, y)
+            x = y
+        key = f"{prefix}.{idxs[-1]}"
+        K = KSIZE[l]
+        rw = eng.w[key + "#rows"]                       # 1xK convolution to the 2K row channels (ky*2 + co)
+        ops.conv_p16(x, B, h, w, rw.cin, rw.w_f16, 4, None, view(d["planes"].view(1, K, B * h * w, 2)), 2 * K, 1, K, 1, False,
+                     OUT_PLANES, 2 * B * h * w, eng.flag)
+        ops.head_rows_sum(d["planes"], K, eng.w[key].bias, res, out, out_p16, B, h, w, eng.flag)
+
+    def launch_all(self):
+        """Enqueue the whole forward on the current stream (inputs already in self.in1 / self.in2)."""
+        eng, cfg, B = self.eng, self.eng.cfg, self.B
+        N2 = 2 * B
+        fl = eng.flag
+        ops.prep_images(self.in1, self.in2, self.img[1], cfg.mean, self.img_pad)
+        for l in range(2, 7):
+            ops.avgpool2(self.img[l - 1], self.img[l])
+        # ---- NetC on both images at once (shared weights): batch 2B ----------------------------------------
+        x = None
+        lvl = 1
+        for i, (seq, idx, cin, cout, k, st) in enumerate(NETC):
+            hi, wi = self.hw[lvl]
+            if st == 2:
+                lvl += 1
+            y = view(self.netc_out[i])
+            key = f"NetC.{seq}.{idx}"
+            if i == 0:
+                ops.conv_stem_p16(self.img_pad, N2, hi, wi, eng.w[key].w_f16, eng.w[key].bias, y, True, fl)
+            elif cout > 128:
+                # 128 -> 192: two 96-channel halves (the accumulator tile holds at most 128 columns)
+                for half, off in (("#a", 0), ("#b", 96)):
+                    self._conv(key + half, x, N2, hi, wi, view(self.netc_out[i], off, 96))
+            else:
+                self._conv(key, x, N2, hi, wi, y)
+            x = y
+        nh = len(cfg.head)
+        head_idx = [2 * j for j in range(nh + 1)]
+        rconv_idx = [2 * j for j in range(len(CONV_R))]
+        xflow = None
+        for i in reversed(range(len(cfg.levels))):
+            l = cfg.levels[i]
+            d = self.lv[l]
+            h, w = self.hw[l]
+            cm = MATCH_FEAT_CH[l]
+            cr = 128 if l < 5 else LEVEL_FEAT_CH[l]
+            s = 2 if l < 4 else 1
+            scale = eng.sf[l]
+            feat = self.feat[l]                      # [2B,h,w,Cf] P16
+            feat1, feat2 = feat[:B], feat[B:]
+            S_f1, S_f2w, S_fl = view(d["Sbuf"], 0, cm), view(d["Sbuf"], cm, cm), view(d["Sbuf"], 2 * cm, 16)
+            if l <= 2:
+                # NetC_ext (src/models.py:353-355): list index idx = l-1 uses NetC_ext[idx-1] (wraps to [-1])
+                e = (l - 2) % cfg.n_ext
+                self._conv(f"NetC_ext.{e}.conv_ext.0", view(feat1), B, h, w, S_f1)
+                self._conv(f"NetC_ext.{e}.conv_ext.0", view(feat2), B, h, w, view(d["f2"]), out_fmt=OUT_F32)
+                f2, f2_p16 = view(d["f2"]), False
+            else:
+                ops.copy(view(feat1), S_f1, B * h * w)
+                f2, f2_p16 = view(feat2), True
+            # ---- Matching (src/models.py:165-187) ------------------------------------------------------------
+            if xflow is not None:
+                ops.deconv4x4s2_dw(view(xflow), B, h // 2, w // 2, eng.raw[f"NetE_M.{i}.upConv_M.weight"], view(d["flowU"]))
+                flowU = d["flowU"]
+            else:
+                flowU = None
+            if l < 4:
+                ops.corr_p16(S_f1, True, f2, f2_p16, flowU, scale, view(d["corr"], 0, 49), False, B, h, w, cm, s, True, fl)
+                ops.deconv4x4s2_dw_p16(view(d["corr"], 0, 49), B, (h + 1) // 2, (w + 1) // 2, 49,
+                                       eng.raw[f"NetE_M.{i}.upCorr_M.weight"], view(d["corrU"]), fl)
+            else:
+                ops.corr_p16(S_f1, True, f2, f2_p16, flowU, scale, view(d["corrU"]), True, B, h, w, cm, s, True, fl)
+            self._chain(f"NetE_M.{i}.conv_M", head_idx, view(d["corrU"]), l, flowU, d["flowM"], S_fl)
+            # ---- Subpixel (src/models.py:209-217) ------------------------------------------------------------
+            ops.warp_p16(f2, f2_p16, d["flowM"], scale, S_f2w, B, h, w, cm, fl)
+            self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"]), l, d["flowM"], d["flowS"])
+            # ---- Regularization (src/models.py:274-303) ------------------------------------------------------
+            ops.flow_mean(d["flowS"], d["partial"])
+            ops.reg_input_p16(self.img[l][:B], self.img[l][B:], d["flowS"], scale, d["partial"], view(d["Rbuf"], cr, 16), fl)
+            if l < 5:
+                self._conv(f"NetE_R.{i}.moduleFeat.0", view(feat1), B, h, w, view(d["Rbuf"], 0, cr))
+            else:
+                ops.copy(view(feat1), view(d["Rbuf"], 0, cr), B * h * w)
+            x = view(d["Rbuf"])
+            t = d["t"]
+            used: Dict[int, int] = {}
+            for j in rconv_idx:
+                c = eng.w[f"NetE_R.{i}.conv_R.{j}"].cout
+                k = used.get(c, 0)
+                used[c] = k ^ 1
+                y = view(t[c][k])
+                self._conv(f"NetE_R.{i}.conv_R.{j}", x, B, h, w, y)
+                x = y
+            dc = DIST_CH[l]
+            if l < 5:
+                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist0"]), lrelu=False)
+                self._conv(f"NetE_R.{i}.conv_dist_R.1", view(d["dist0"]), B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
+            else:
+                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
+            p = f"NetE_R.{i}"
+            last = (l == cfg.lowest_level)
+            ops.reg_tail(view(d["dist"], 0, dc), d["flowS"], eng.raw[p + ".moduleScaleX.weight"],
+                         eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
+                         eng.raw[p + ".moduleScaleY.bias"], d["flowR"], self.out if last else None, eng.sf[1], KSIZE[l])
+            xflow = d["flowR"]

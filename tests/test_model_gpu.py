@@ -151,15 +151,36 @@ def test_f16c_range_flag_falls_back_to_tf32c():
         sd[k] *= 300.0                 # level-2 features ~9e4 x O(1): inside fp32, outside fp16; every weight stays inside
     a, b, _ = synth.particle_batch(1, 64, 64, 5, "uniform")
     ref_net = _net("piv", sd, "tf32c")
-    net = _net("piv", sd, "f16c")
     with torch.no_grad():
         ref = ref_net(a.to(DEV), b.to(DEV))
+    for p16 in ("1", "0"):                       # the P16 pipeline (engine-owned flag) and the fp32-activation f16c plan
+        os.environ["PIVLFN_P16"] = p16
+        try:
+            net = _net("piv", sd, "f16c")
+            net.engine().range_check = "sync"    # small forwards default to the deferred check (below)
+            assert net.engine().p16 == (p16 == "1")
+        finally:
+            del os.environ["PIVLFN_P16"]
+        with torch.no_grad():
+            with warnings.catch_warnings(record=True) as wlist:
+                warnings.simplefilter("always")
+                out = net(a.to(DEV), b.to(DEV))
+        assert any("fp16 range" in str(w.message) for w in wlist)
+        assert net.engine().precision == "tf32c"
+        assert torch.equal(out, ref)
+    # deferred check (the default for small forwards): the out-of-range forward returns non-finite values -- never silently
+    # saturated ones -- and the engine has switched by the next call
+    net = _net("piv", sd, "f16c")
+    assert net.engine().range_check == "auto"
+    with torch.no_grad():
+        first = net(a.to(DEV), b.to(DEV))
+        assert not torch.isfinite(first).all()
         with warnings.catch_warnings(record=True) as wlist:
             warnings.simplefilter("always")
-            out = net(a.to(DEV), b.to(DEV))
+            assert net.engine().check_range(wait=True)
+            second = net(a.to(DEV), b.to(DEV))
     assert any("fp16 range" in str(w.message) for w in wlist)
-    assert net.engine().precision == "tf32c"
-    assert torch.equal(out, ref)
+    assert net.engine().precision == "tf32c" and torch.equal(second, ref)
     # a well-scaled model stays in f16c
     net2 = _net("piv", synth.synthetic_state_dict("piv", 0), "f16c")
     with torch.no_grad():

@@ -1,0 +1,257 @@
+"""Operator-level parity of the P16 pipeline on the B200 (csrc/p16.cuh, conv_p16.cu, p16_ops.cu, the P16 variants of
+corr.cu and of the stem): every kernel against the torch fp32/fp64 op it replaces, on the same seeded inputs, through
+the C ABI.  P16 stores x as (f16(x), f16((x - f16(x)) * 2^11)): 22 significant bits, so references are evaluated on the
+P16-rounded inputs and compared at fp32-accumulation tolerances."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import lfn_oracle as O
+from pivlfn import ops
+from pivlfn.model import pack_conv, pack_stem
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _rand(*shape, seed=0, scale=1.0):
+    return scale * torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def _r16(c):
+    return (c + 15) & ~15
+
+
+def p16_ref_encode(x):
+    """[..., C] fp32 -> [..., 16 * G] words (viewed as float32): host restatement of csrc/p16.cuh."""
+    C = x.shape[-1]
+    G = (C + 15) // 16
+    xp = F.pad(x, (0, 16 * G - C))
+    hi = xp.half()
+    lo = ((xp - hi.float()) * 2048.0).half()
+    g = torch.stack([hi.reshape(*x.shape[:-1], G, 16), lo.reshape(*x.shape[:-1], G, 16)], dim=-2)
+    return g.reshape(*x.shape[:-1], G * 32).contiguous().view(torch.float32)
+
+
+def p16_ref_decode(wds, C):
+    h = wds.contiguous().view(torch.float16)
+    G = h.shape[-1] // 32
+    g = h.reshape(*h.shape[:-1], G, 2, 16).float()
+    x = g[..., 0, :] + g[..., 1, :] / 2048.0
+    return x.reshape(*h.shape[:-1], G * 16)[..., :C]
+
+
+def p16_round(x_nchw):
+    """what a P16 tensor holds for these fp32 values (NCHW in / out)"""
+    x = x_nchw.permute(0, 2, 3, 1).contiguous()
+    return p16_ref_decode(p16_ref_encode(x), x.shape[-1]).permute(0, 3, 1, 2).contiguous()
+
+
+def to_p16(x_nchw, ld=None, off=0):
+    """NCHW cpu fp32 -> P16 device buffer [N,H,W,ld] (zeros elsewhere) holding the tensor at channel word offset off"""
+    B, C, H, W = x_nchw.shape
+    ld = _r16(C) + off if ld is None else ld
+    buf = torch.zeros(B, H, W, ld, device=DEV)
+    buf[..., off:off + _r16(C)] = p16_ref_encode(x_nchw.permute(0, 2, 3, 1).contiguous()).to(DEV)
+    return buf
+
+
+def from_p16(buf, C, off=0):
+    return p16_ref_decode(buf[..., off:off + _r16(C)].cpu(), C).permute(0, 3, 1, 2).contiguous()
+
+
+def test_encode_decode_kernels_match_host_restatement():
+    x = _rand(2, 5, 7, 49, seed=1, scale=3.0)
+    x[0, 0, 0, :4] = torch.tensor([0.0, 1e-7, -65504.0, 6.1e-5])
+    xd = x.to(DEV)
+    y = torch.zeros(2, 5, 7, 80, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.p16_encode(ops.view(xd), ops.view(y, 16, 64), 2 * 5 * 7, flag)
+    ref = p16_ref_encode(x)
+    assert torch.equal(y[..., 16:80].cpu().view(torch.int32), ref.view(torch.int32))
+    assert y[..., :16].abs().max().item() == 0 and int(flag.item()) == 0
+    back = torch.zeros(2, 5, 7, 52, device=DEV)
+    ops.p16_decode(ops.view(y, 16, 64), 49, ops.view(back, 0, 49), 2 * 5 * 7)
+    assert torch.equal(back[..., :49].cpu(), p16_ref_decode(ref, 49))
+    rel = ((back[..., :49].cpu() - x).abs() / x.abs().clamp_min(1e-30)).max().item()
+    assert rel <= 2.0 ** -21
+    # out of range -> flag
+    xd[1, 2, 3, 4] = 7.0e4
+    ops.p16_encode(ops.view(xd), ops.view(y, 16, 64), 2 * 5 * 7, flag)
+    assert int(flag.item()) == 1
+
+
+CONV_CASES = [  # cin, cout, kh, kw, stride, lrelu, H, W, out_fmt
+    (32, 64, 1, 1, 1, True, 16, 24, 0), (32, 128, 1, 1, 1, True, 9, 12, 0), (49, 128, 3, 3, 1, True, 16, 16, 0),
+    (130, 128, 3, 3, 1, True, 40, 12, 0), (132, 128, 3, 3, 1, True, 8, 8, 0), (128, 128, 3, 3, 1, True, 34, 16, 0),
+    (128, 64, 3, 3, 1, True, 16, 16, 0), (64, 64, 3, 3, 1, True, 33, 20, 0), (64, 32, 3, 3, 1, True, 70, 8, 0),
+    (32, 32, 3, 3, 1, True, 16, 16, 0), (32, 49, 7, 1, 1, False, 20, 16, 0), (49, 49, 1, 7, 1, False, 20, 16, 1),
+    (32, 25, 5, 1, 1, False, 12, 12, 0), (25, 25, 1, 5, 1, False, 12, 12, 1), (32, 9, 3, 3, 1, False, 8, 8, 1),
+    (96, 96, 3, 3, 1, True, 12, 12, 0), (128, 96, 3, 3, 1, True, 12, 12, 0), (96, 64, 3, 3, 1, True, 12, 12, 0),
+    (386, 128, 3, 3, 1, True, 8, 8, 0), (258, 128, 3, 3, 1, True, 4, 4, 0), (64, 32, 3, 3, 1, True, 2, 2, 0),
+    (32, 32, 3, 3, 2, True, 32, 48, 0), (32, 64, 3, 3, 2, True, 16, 16, 0), (64, 96, 3, 3, 2, True, 16, 24, 0),
+    (96, 128, 3, 3, 2, True, 8, 8, 0), (128, 96, 3, 3, 2, True, 8, 8, 0), (128, 96, 3, 3, 2, True, 4, 4, 0),
+    (32, 64, 1, 1, 1, True, 16, 24, 1), (64, 64, 3, 3, 1, True, 6, 6, 0), (32, 14, 1, 7, 1, False, 24, 16, 2),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=str)
+def test_conv_p16_vs_torch(case):
+    cin, cout, kh, kw, st, act, H, W, fmt = case
+    w, b = _rand(cout, cin, kh, kw, seed=1, scale=1.0 / math.sqrt(cin * kh * kw)), _rand(cout, seed=2)
+    x = _rand(2, cin, H, W, seed=3)
+    ref = F.conv2d(p16_round(x).double(), w.double(), b.double(), stride=st, padding=(kh // 2, kw // 2))
+    ref = torch.where(ref >= 0, ref, 0.1 * ref) if act else ref
+    cw = pack_conv(w, b, st).to_(DEV)
+    if st == 2:
+        w_img, mode = cw.w_s2, cw.s2_passes
+    elif cw.w_f16s is not None:
+        w_img, mode = cw.w_f16s, 5
+    else:
+        w_img, mode = cw.w_f16, 4
+    xin = to_p16(x, ld=_r16(cin) + 16, off=16)                      # a slice of a wider buffer
+    Ho, Wo = ref.shape[2], ref.shape[3]
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    if fmt == 0:
+        y = torch.full((2, Ho, Wo, _r16(cout) + 32), 7.0, device=DEV)
+        ops.conv_p16(ops.view(xin, 16, _r16(cin)), 2, H, W, cin, w_img, mode, cw.bias, ops.view(y, 16, _r16(cout)), cout, kh, kw, st,
+                     act, ops.OUT_P16, 0, flag)
+        out = from_p16(y, cout, off=16)
+        # neighbours untouched, pad channels of the last group exactly zero
+        assert (y[..., :16] == 7.0).all() and (y[..., 16 + _r16(cout):] == 7.0).all()
+        if cout % 16:
+            pad = p16_ref_decode(y[..., 16:16 + _r16(cout)].cpu(), _r16(cout))[..., cout:]
+            assert pad.abs().max().item() == 0
+    elif fmt == 1:
+        ld = (cout + 3) & ~3
+        y = torch.zeros(2, Ho, Wo, ld, device=DEV)
+        ops.conv_p16(ops.view(xin, 16, _r16(cin)), 2, H, W, cin, w_img, mode, cw.bias, ops.view(y), cout, kh, kw, st, act,
+                     ops.OUT_F32, 0, flag)
+        out = y[..., :cout].permute(0, 3, 1, 2).cpu()
+    else:
+        npl = cout // 2
+        planes = torch.zeros(npl, 2 * Ho * Wo, 2, device=DEV)
+        ops.conv_p16(ops.view(xin, 16, _r16(cin)), 2, H, W, cin, w_img, mode, cw.bias, ops.view(planes.view(1, npl, 2 * Ho * Wo, 2)),
+                     cout, kh, kw, st, act, ops.OUT_PLANES, 2 * 2 * Ho * Wo, flag)
+        out = planes.view(npl, 2, Ho, Wo, 2).permute(1, 0, 4, 2, 3).reshape(2, cout, Ho, Wo).cpu()
+    assert int(flag.item()) == 0
+    err = (out.double() - ref).abs().max().item()
+    tol = 3e-5 if fmt != 0 else 3e-5 + 2.0 ** -21 * ref.abs().max().item()
+    assert err <= tol, err
+
+
+def test_conv_p16_range_flag():
+    w, b = _rand(32, 32, 3, 3, seed=1), _rand(32, seed=2)
+    x = _rand(1, 32, 16, 16, seed=3, scale=3000.0)                   # outputs ~ 3000 * sqrt(288) ~ 5e4 .. 2e5
+    cw = pack_conv(w, b, 1).to_(DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    y = torch.zeros(1, 16, 16, 32, device=DEV)
+    ops.conv_p16(ops.view(to_p16(x)), 1, 16, 16, 32, cw.w_f16, 4, cw.bias, ops.view(y), 32, 3, 3, 1, True, ops.OUT_P16, 0, flag)
+    assert int(flag.item()) == 1
+
+
+def test_conv_stem_p16_vs_torch():
+    w, b = _rand(32, 3, 7, 7, seed=1, scale=1.0 / math.sqrt(147)), _rand(32, seed=2)
+    x = _rand(2, 3, 24, 40, seed=3)
+    ref = F.conv2d(x.double(), w.double(), b.double(), padding=3)
+    ref = torch.where(ref >= 0, ref, 0.1 * ref)
+    cw = pack_stem(w, b).to_(DEV)
+    img_pad = torch.zeros(2, 24, 40 + 8, 4, device=DEV)
+    img_pad[:, :, 4:44, :3] = x.permute(0, 2, 3, 1).to(DEV)
+    y = torch.zeros(2, 24, 40, 32, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.conv_stem_p16(img_pad, 2, 24, 40, cw.w_f16, cw.bias, ops.view(y), True, flag)
+    out = from_p16(y, 32)
+    assert (out.double() - ref).abs().max().item() <= 3e-5 and int(flag.item()) == 0
+
+
+@pytest.mark.parametrize("in_p16", [False, True])
+@pytest.mark.parametrize("C,H,W", [(64, 16, 24), (96, 9, 7), (192, 2, 3)])
+def test_warp_p16_vs_oracle(in_p16, C, H, W):
+    x = _rand(2, C, H, W, seed=5)
+    flow = _rand(2, 2, H, W, seed=6, scale=2.5)
+    scale = 1.25
+    src = p16_round(x) if in_p16 else x
+    ref = O.backwarp(src, flow * scale)
+    xin = to_p16(x) if in_p16 else x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = torch.zeros(2, H, W, 2 * C + 16, device=DEV)
+    fl = flow.permute(0, 2, 3, 1).contiguous().to(DEV)
+    ops.warp_p16(ops.view(xin), in_p16, fl, scale, ops.view(y, C, C), 2, H, W, C)
+    out = from_p16(y, C, off=C)
+    assert (out - ref).abs().max().item() <= 1e-5
+    assert y[..., :C].abs().max().item() == 0 and y[..., 2 * C:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("H,W", [(8, 12), (5, 3)])
+def test_deconv_p16_vs_torch(H, W):
+    x = _rand(2, 49, H, W, seed=7)
+    w = _rand(49, 1, 4, 4, seed=8)
+    ref = F.conv_transpose2d(x, w, stride=2, padding=1, groups=49)
+    xin = torch.zeros(2, H, W, 52, device=DEV)
+    xin[..., :49] = x.permute(0, 2, 3, 1).to(DEV)
+    y = torch.full((2, 2 * H, 2 * W, 64), 3.0, device=DEV)
+    ops.deconv4x4s2_dw_p16(ops.view(xin, 0, 49), 2, H, W, 49, w.reshape(49, 16).contiguous().to(DEV), ops.view(y))
+    out = from_p16(y, 64)
+    assert (out[:, :49] - ref).abs().max().item() <= 1e-5 and out[:, 49:].abs().max().item() == 0
+
+
+def test_reg_input_p16_matches_fp32_kernel():
+    B, H, W = 2, 12, 20
+    img = torch.zeros(2 * B, H, W, 4, device=DEV)
+    img[..., :3] = _rand(2 * B, H, W, 3, seed=9).to(DEV)
+    flow = _rand(B, H, W, 2, seed=10, scale=2.0).to(DEV)
+    partial = torch.zeros(B, ops.flow_mean_parts(), 2, device=DEV)
+    ops.flow_mean(flow, partial)
+    ref = torch.zeros(B, H, W, 4, device=DEV)
+    ops.reg_input(img[:B], img[B:], flow, 2.5, partial, ops.view(ref, 0, 3))
+    y = torch.zeros(B, H, W, 144, device=DEV)
+    ops.reg_input_p16(img[:B], img[B:], flow, 2.5, partial, ops.view(y, 128, 16))
+    out = p16_ref_decode(y[..., 128:144].cpu(), 16)
+    r = ref[..., :3].cpu()
+    assert (out[..., :3] - r).abs().max().item() <= 2.0 ** -21 * r.abs().max().item() + 1e-9
+    assert out[..., 3:].abs().max().item() == 0 and y[..., :128].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("f2_p16,out_p16", [(False, False), (True, False), (True, True), (False, True)])
+@pytest.mark.parametrize("C,s,H,W", [(64, 2, 32, 48), (96, 1, 16, 24), (192, 1, 2, 3)])
+def test_corr_p16_variants(C, s, H, W, f2_p16, out_p16):
+    f1, f2 = _rand(2, C, H, W, seed=1), _rand(2, C, H, W, seed=2)
+    flow = _rand(2, 2, H, W, seed=3, scale=2.0)
+    scale = 1.25
+    f2src = p16_round(f2) if f2_p16 else f2
+    ref = O.lrelu(O.correlation(p16_round(f1), O.backwarp(f2src, flow * scale), s))
+    Ho, Wo = -(-H // s), -(-W // s)
+    a = to_p16(f1, ld=2 * C + 16)                              # the f1 slice of a Subpixel concat buffer
+    b = to_p16(f2) if f2_p16 else f2.permute(0, 2, 3, 1).contiguous().to(DEV)
+    fl = flow.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = torch.zeros(2, Ho, Wo, 64 if out_p16 else 52, device=DEV)
+    ops.corr_p16(ops.view(a, 0, C), True, ops.view(b), f2_p16, fl, scale, ops.view(out) if out_p16 else ops.view(out, 0, 49),
+                 out_p16, 2, H, W, C, s, True)
+    got = from_p16(out, 64) if out_p16 else out[..., :49].permute(0, 3, 1, 2).cpu()
+    assert (got[:, :49] - ref).abs().max().item() <= 3e-5
+    if out_p16:
+        assert got[:, 49:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("K,H,W", [(7, 24, 16), (5, 9, 12), (3, 4, 4), (7, 2, 2)])
+def test_flow_head_rows_vs_torch(K, H, W):
+    """The tensor-core flow head: 1xK convolution to 2K row planes + K-row gather-sum == the KxK 32 -> 2 convolution."""
+    w, b = _rand(2, 32, K, K, seed=1, scale=1.0 / math.sqrt(32 * K * K)), _rand(2, seed=2)
+    x = _rand(2, 32, H, W, seed=3)
+    res = _rand(2, H, W, 2, seed=4)
+    ref = F.conv2d(p16_round(x).double(), w.double(), b.double(), padding=K // 2) + res.permute(0, 3, 1, 2).double()
+    rw = pack_conv(w.permute(2, 0, 1, 3).reshape(2 * K, 32, 1, K), None, 1).to_(DEV)
+    planes = torch.zeros(K, 2 * H * W, 2, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.conv_p16(ops.view(to_p16(x)), 2, H, W, 32, rw.w_f16, 4, None, ops.view(planes.view(1, K, 2 * H * W, 2)), 2 * K, 1, K, 1,
+                 False, ops.OUT_PLANES, 2 * 2 * H * W, flag)
+    out = torch.zeros(2, H, W, 2, device=DEV)
+    sb = torch.zeros(2, H, W, 144, device=DEV)
+    ops.head_rows_sum(planes, K, b.to(DEV), res.to(DEV), out, ops.view(sb, 128, 16), 2, H, W, flag)
+    got = out.permute(0, 3, 1, 2).cpu().double()
+    assert (got - ref).abs().max().item() <= 2e-5 and int(flag.item()) == 0
+    slot = p16_ref_decode(sb[..., 128:144].cpu(), 16)
+    assert (slot[..., :2] - out.cpu()).abs().max().item() <= 2.0 ** -21 * out.abs().max().item()
+    assert slot[..., 2:].abs().max().item() == 0

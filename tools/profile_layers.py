@@ -38,6 +38,19 @@ def conv_hook(self, key, x, n, h, w, y, lrelu=True, res=None):
 
 M.Plan._conv = conv_hook
 
+from pivlfn import plan16 as P16  # noqa: E402
+
+_conv16 = P16.Plan16._conv
+
+
+def conv16_hook(self, key, x, n, h, w, y, lrelu=True, out_fmt=0, cin=None):
+    cur["label"] = key
+    _conv16(self, key, x, n, h, w, y, lrelu, out_fmt, cin)
+    cur["label"] = ""
+
+
+P16.Plan16._conv = conv16_hook
+
 
 def wrap(name, work):
     fn = getattr(ops, name)
@@ -108,6 +121,38 @@ def w_copy(src, dst, npix):
     return 8.0 * npix * src.C, "B", f"copy C={src.C}"
 
 
+def w_conv_p16(x, N, Hh, Ww, cin, w_img, mode, bias, y, cout, KH, KW, stride=1, lrelu=True, out_fmt=0, plane_stride=0, flag=None):
+    return 2.0 * N * (Hh // stride) * (Ww // stride) * cin * cout * KH * KW, "F", \
+        f"{cin}->{cout} {KH}x{KW} s{stride} mode{mode} out{out_fmt} @{Hh}x{Ww}"
+
+
+def w_stem16(img_pad, N, Hh, Ww, w_img, bias, y, lrelu=True, flag=None):
+    return 2.0 * N * Hh * Ww * 3 * 32 * 49, "F", f"stem 3->32 7x7 @{Hh}x{Ww}"
+
+
+def w_corr16(f1, f1_p16, f2, f2_p16, flow, scale, out, out_p16, N, Hh, Ww, C, stride, lrelu=True, flag=None):
+    ho, wo = (Hh + stride - 1) // stride, (Ww + stride - 1) // stride
+    return 4.0 * N * (2 * C * Hh * Ww + (2 * Hh * Ww if flow is not None else 0) + 49 * ho * wo), "B", \
+        f"corr C={C} s{stride} @{Hh}x{Ww}"
+
+
+def w_warp16(x, in_p16, flow, scale, y, N, Hh, Ww, C, flag=None):
+    return 4.0 * N * Hh * Ww * (2 * C + 2), "B", f"warp C={C} @{Hh}x{Ww}"
+
+
+def w_deconv16(x, N, Hh, Ww, C, w, y, flag=None):
+    return 4.0 * N * Hh * Ww * (52 + 4 * 64), "B", f"deconv C={C} @{Hh}x{Ww} (fp32 -> P16)"
+
+
+def w_reginput16(img1, img2, flow, scale, partial, out, flag=None):
+    N, Hh, Ww, _ = flow.shape
+    return 4.0 * N * Hh * Ww * 13, "B", f"reg_input @{Hh}x{Ww}"
+
+
+def w_rows(planes, K, bias, res, out, out_p16, N, Hh, Ww, flag=None):
+    return 4.0 * N * Hh * Ww * (2 * K + 4 + (8 if out_p16 is not None else 0)), "B", f"head_rows_sum K={K} @{Hh}x{Ww}"
+
+
 def w_small(*a, **k):
     return 0.0, "B", ""
 
@@ -115,7 +160,9 @@ def w_small(*a, **k):
 for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_tc", w_stem), ("conv_s2_tc", w_s2), ("conv1x1_pairs_tc", w_pairs),
                ("flow_head_sum", w_headsum), ("flow_head", w_head), ("deconv4x4s2_dw", w_deconv), ("warp", w_warp), ("corr_nhwc", w_corr),
                ("reg_tail", w_regtail), ("reg_input", w_reginput), ("copy", w_copy), ("flow_mean", w_small),
-               ("prep_images", w_small), ("avgpool2", w_small)):
+               ("prep_images", w_small), ("avgpool2", w_small), ("conv_p16", w_conv_p16), ("conv_stem_p16", w_stem16),
+               ("corr_p16", w_corr16), ("warp_p16", w_warp16), ("deconv4x4s2_dw_p16", w_deconv16),
+               ("reg_input_p16", w_reginput16), ("head_rows_sum", w_rows)):
     wrap(nm, wk)
 
 acc = None
