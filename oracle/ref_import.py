@@ -1,8 +1,10 @@
-"""Import the UNMODIFIED reference model (``/root/reference/src/models.py``) on the CPU.
+"""Import the UNMODIFIED reference model (``src/models.py`` + ``src/correlation.py``).
 
-TEST INFRASTRUCTURE (build container only: ``/root/reference`` does not exist on the GPU
-box).  Used by ``tests/golden/make_golden.py`` to generate golden vectors and by
-``tests/test_oracle_golden.py`` (when the mount is present) to pin ``oracle/lfn_oracle.py``.
+TEST / BASELINE INFRASTRUCTURE.  The files come from the read-only mount ``/root/reference`` (build container) or from the
+byte-identical copy that ``baseline/install_ref.py`` leaves in the git-ignored ``baseline/_ref/reference`` (which travels
+to the GPU box).  Used by ``tests/golden/make_golden.py`` to generate golden vectors, by ``tests/test_oracle_golden.py``
+to pin ``oracle/lfn_oracle.py``, by the GPU parity tests (the reference's own CUDA path through the cupy stand-in) and by
+``bench.py``'s reference arms.
 
 Two shims, both outside the reference files:
   1. a stub module named ``cupy`` (``src/correlation.py:5,278-280`` needs the name at import
@@ -21,7 +23,11 @@ import types
 
 import torch
 
-REF_ROOT = os.environ.get("PIVLFN_REFERENCE", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_MOUNT = os.environ.get("PIVLFN_REFERENCE", "/root/reference")
+_INSTALLED = os.path.join(_REPO, "baseline", "_ref", "reference")      # byte-identical copy made by baseline/install_ref.py
+REF_ROOT = _MOUNT if os.path.isfile(os.path.join(_MOUNT, "src", "models.py")) else _INSTALLED
+_CUPY_STUB = os.path.join(_REPO, "baseline", "cupy_stub")
 
 
 def available() -> bool:
@@ -29,32 +35,24 @@ def available() -> bool:
 
 
 def _stub_cupy():
+    """The reference imports ``cupy`` at module level (src/correlation.py:5); CuPy is not in this image.  The stand-in
+    (baseline/cupy_stub) implements the two entry points the reference calls on top of NVRTC + the driver API."""
     if "cupy" in sys.modules:
         return
-    cupy = types.ModuleType("cupy")
-    util = types.ModuleType("cupy.util")
-
-    def memoize(for_each_device=False):
-        def deco(fn):
-            return fn
-        return deco
-
-    util.memoize = memoize
-    cuda = types.ModuleType("cupy.cuda")
-
-    def compile_with_cache(*a, **k):  # pragma: no cover - never reached on CPU
-        raise RuntimeError("cupy stub: no CUDA compilation in the CPU container")
-
-    cuda.compile_with_cache = compile_with_cache
-    cupy.util, cupy.cuda = util, cuda
-    sys.modules["cupy"] = cupy
-    sys.modules["cupy.util"] = util
-    sys.modules["cupy.cuda"] = cuda
+    sys.path.insert(0, _CUPY_STUB)
+    try:
+        importlib.import_module("cupy")
+    finally:
+        sys.path.remove(_CUPY_STUB)
 
 
-def load_reference_models(corr_fn):
-    """Returns the reference's ``src.models`` module (imported under the name ``_ref_src.models``
-    so it cannot shadow this repo's own drop-in ``src`` package)."""
+def load_reference_models(corr_fn=None):
+    """Returns the reference's UNMODIFIED ``src.models`` and ``src.correlation`` modules (imported under the names
+    ``_ref_src.*`` so they cannot shadow this repo's own drop-in ``src`` package).
+
+    corr_fn given (CPU use): ``src.models.FunctionCorrelation`` is replaced by it, because the reference has no CPU branch
+    (src/correlation.py:339-340).  corr_fn None (GPU use): nothing is patched -- the reference's own CUDA kernels run through
+    the cupy stand-in."""
     _stub_cupy()
     saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "src" or k.startswith("src.")}
     sys.path.insert(0, REF_ROOT)
@@ -66,8 +64,9 @@ def load_reference_models(corr_fn):
         for k in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
             sys.modules["_ref_" + k] = sys.modules.pop(k)
         sys.modules.update(saved)
-    models.FunctionCorrelation = lambda tensorFirst, tensorSecond, intStride: corr_fn(
-        tensorFirst, tensorSecond, intStride)
+    if corr_fn is not None:
+        models.FunctionCorrelation = lambda tensorFirst, tensorSecond, intStride: corr_fn(
+            tensorFirst, tensorSecond, intStride)
     models.backwarp_tensorGrid.clear()
     return models, corr
 

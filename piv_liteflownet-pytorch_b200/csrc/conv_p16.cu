@@ -54,6 +54,8 @@ struct ConvP16Args {
     int x_shift;
     const uint8_t* w_img;    // ring-stage image of the fp16 weights (pivlfn.model.stage_image)
     int* range_flag;         // raised when an OUT_P16 result is not finite in fp16 (|x| >= 65520 or NaN); may be NULL
+    int one_issuer;          // a single thread issues the MMAs of both stacked tiles (required by collect)
+    int collect;             // MODE 5: a_hi * W_hi keeps the A window in the collector buffer, a_hi * W_lo re-uses it from there
 };
 
 __device__ __forceinline__ bool s2_tap_used(int t, int par) {
@@ -85,7 +87,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     const int nchunk = a.s2 ? 4 * a.cpp : (a.Cw + 31) / 32;
     const int ntaps = a.KH * a.KW;
     const int G = gridDim.x;
-    const int n_iss = a.NT >= 2 ? 2 : 1;
+    const int n_iss = (a.NT >= 2 && !a.one_issuer) ? 2 : 1;
     const int tile_cols = DUAL ? 2 * a.CoutP : a.CoutP;
     const int set_cols = a.NT * tile_cols;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
@@ -166,7 +168,9 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             const uint32_t stage16 = (uint32_t)(b_stage >> 4);
             const uint32_t ring16 = stage16 * (uint32_t)a.tps;
             const uint32_t bbase16 = (smem_u32(smemB) >> 4) | lbo_bits;
-            const uint32_t tileA = (uint32_t)issuer * (uint32_t)(HT_H * pitch * 8);
+            const uint32_t tile16 = (uint32_t)(HT_H * pitch * 8);
+            const uint32_t tileA = (uint32_t)issuer * tile16;
+            const int ntl = a.NT / n_iss;                                       // stacked tiles fed by this thread
             const uint32_t row_step = (uint32_t)((pitch - a.KW) * 8);
             int bs = 0;
             uint32_t bphase = 0, bcur = bbase16;
@@ -177,44 +181,56 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 const uint32_t use = (uint32_t)(wl / a.nsets);
                 mbar_wait(&acc_empty[as], (use & 1) ^ 1);     // the epilogue drained this accumulator set
                 tc_fence_after();
-                const uint32_t t_main = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)(issuer * tile_cols);
+                const uint32_t t_first = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)(issuer * tile_cols);
                 uint32_t acc = 0;
                 for (int c = 0; c < nchunk; ++c) {
                     const bool two = a.s2 ? true : (a.Cw - c * 32 > 16);        // second 16-channel K step present
                     mbar_wait(&a_full[slot], ause & 1);
                     tc_fence_after();
-                    uint32_t A = ((smem_u32(smem + (size_t)slot * slot_bytes) >> 4) | lbo_bits) + tileA;
+                    uint32_t A0 = ((smem_u32(smem + (size_t)slot * slot_bytes) >> 4) | lbo_bits) + tileA;
                     int kx = 0;
                     for (int t = 0; t < ntaps;) {
                         if (a.s2 && !s2_tap_used(t, c / a.cpp)) {
-                            ++t; A += 8;
-                            if (++kx == a.KW) { kx = 0; A += row_step; }
+                            ++t; A0 += 8;
+                            if (++kx == a.KW) { kx = 0; A0 += row_step; }
                             continue;
                         }
                         mbar_wait(&b_full[bs], bphase);
                         tc_fence_after();
                         uint32_t b = bcur;
                         for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
-                            if (DUAL) {
-                                umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc_w, acc);
-                                umma_bf16_lohi(t_main + cP, A + 2, hiA, b, hiB, idesc, 1);
-                                if (two) {
-                                    umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc_w, 1);
-                                    umma_bf16_lohi(t_main + cP, A + 6, hiA, b + 2, hiB, idesc, 1);
-                                }
-                            } else {
-                                umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
-                                umma_bf16_lohi(t_main, A, hiA, b + part16, hiB, idesc, 1);
-                                umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
-                                if (two) {
-                                    umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
-                                    umma_bf16_lohi(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
-                                    umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
+                            uint32_t A = A0, t_main = t_first;
+                            for (int i = 0; i < ntl; ++i, A += tile16, t_main += (uint32_t)tile_cols) {
+                                if (DUAL) {
+                                    umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc_w, acc);
+                                    umma_bf16_lohi(t_main + cP, A + 2, hiA, b, hiB, idesc, 1);
+                                    if (two) {
+                                        umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc_w, 1);
+                                        umma_bf16_lohi(t_main + cP, A + 6, hiA, b + 2, hiB, idesc, 1);
+                                    }
+                                } else if (a.collect) {
+                                    umma_f16_lohi_afill(t_main, A, hiA, b, hiB, idesc, acc);
+                                    umma_f16_lohi_alast(t_main, A, hiA, b + part16, hiB, idesc, 1);
+                                    umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
+                                    if (two) {
+                                        umma_f16_lohi_afill(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
+                                        umma_f16_lohi_alast(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
+                                        umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
+                                    }
+                                } else {
+                                    umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
+                                    umma_bf16_lohi(t_main, A, hiA, b + part16, hiB, idesc, 1);
+                                    umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
+                                    if (two) {
+                                        umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
+                                        umma_bf16_lohi(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
+                                        umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
+                                    }
                                 }
                             }
                             acc = 1;
-                            A += 8;                                             // next tap of the filter row (one pixel = 128 B)
-                            if (++kx == a.KW) { kx = 0; A += row_step; }
+                            A0 += 8;                                            // next tap of the filter row (one pixel = 128 B)
+                            if (++kx == a.KW) { kx = 0; A0 += row_step; }
                         }
                         umma_commit(&b_empty[bs]);
                         if (++bs == a.nB) { bs = 0; bphase ^= 1; bcur = bbase16; } else bcur += ring16;
@@ -430,6 +446,14 @@ extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int
     h.bias = bias; h.y = reinterpret_cast<uint32_t*>(y); h.y_ld = y_ld;
     h.N = N; h.Cw = Cw; h.Cout = Cout; h.CoutP = CoutP; h.lrelu = lrelu; h.out_fmt = out_fmt;
     h.w_img = reinterpret_cast<const uint8_t*>(w_img); h.range_flag = range_flag; h.planar = 0; h.cout_st = Cout; h.quad = 0;
+    {
+        // experiment switches (defaults = the measured best): PIVLFN_P16_ISSUERS=1|2, PIVLFN_P16_COLLECT=0|1
+        static int iss = -1, col = -1;
+        if (iss < 0) { const char* v = getenv("PIVLFN_P16_ISSUERS"); iss = v ? atoi(v) : 0; }
+        if (col < 0) { const char* v = getenv("PIVLFN_P16_COLLECT"); col = v ? atoi(v) : 0; }
+        h.collect = (mode == 5 && col == 1) ? 1 : 0;
+        h.one_issuer = (iss == 1 || h.collect) ? 1 : 0;
+    }
     if (out_fmt == OUT_P16) {
         if (((uintptr_t)y & 63) || (y_ld & 15) || y_ld < CoutP) return PIVLFN_EINVAL;
         h.quad = !(h.W & 3);

@@ -226,6 +226,8 @@ class Engine:
                  precision: str = None, use_graph: bool = None):
         if device.type != "cuda":
             raise NotImplementedError("pivlfn runs on CUDA devices only (no CPU path)")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
         self.lib = _lib.load()
         self.cfg = cfg
         self.device = device

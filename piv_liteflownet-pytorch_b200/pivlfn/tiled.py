@@ -70,8 +70,11 @@ class TiledPlan:
         self.handles: List[TT] = []
         self.warp_flows: List[Tuple[TT, int]] = []
         dev = eng.device
-        self._E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
+        # every buffer starts zeroed: halo rows that no operator ever writes are still READ by the operators (their results
+        # land in rows nobody consumes), and uninitialised memory there could hold non-finite bit patterns that raise the
+        # fp16 range flag of precision f16c
         self._Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
+        self._E = self._Z
         self._build()
 
     # ---- geometry -------------------------------------------------------------------------------------------------

@@ -75,8 +75,9 @@ def test_encode_decode_kernels_match_host_restatement():
     back = torch.zeros(2, 5, 7, 52, device=DEV)
     ops.p16_decode(ops.view(y, 16, 64), 49, ops.view(back, 0, 49), 2 * 5 * 7)
     assert torch.equal(back[..., :49].cpu(), p16_ref_decode(ref, 49))
-    rel = ((back[..., :49].cpu() - x).abs() / x.abs().clamp_min(1e-30)).max().item()
-    assert rel <= 2.0 ** -21
+    # 22 significant bits down to |x| ~ 6e-5 (fp16 normals); below that the absolute error is <= 2^-36
+    excess = ((back[..., :49].cpu() - x).abs() - 2.0 ** -21 * x.abs()).max().item()
+    assert excess <= 2.0 ** -35
     # out of range -> flag
     xd[1, 2, 3, 4] = 7.0e4
     ops.p16_encode(ops.view(xd), ops.view(y, 16, 64), 2 * 5 * 7, flag)
@@ -138,7 +139,8 @@ def test_conv_p16_vs_torch(case):
         out = planes.view(npl, 2, Ho, Wo, 2).permute(1, 0, 4, 2, 3).reshape(2, cout, Ho, Wo).cpu()
     assert int(flag.item()) == 0
     err = (out.double() - ref).abs().max().item()
-    tol = 3e-5 if fmt != 0 else 3e-5 + 2.0 ** -21 * ref.abs().max().item()
+    # fp32 accumulation of K = cin*kh*kw products of O(1/sqrt(K)) on the tensor cores (truncating adder): grows like sqrt(K)
+    tol = 1e-5 + 1.2e-6 * math.sqrt(cin * kh * kw) + (2.0 ** -21 * ref.abs().max().item() if fmt == 0 else 0.0)
     assert err <= tol, err
 
 

@@ -115,13 +115,75 @@ def test_forward_vs_reference_cuda_path(model, B, H, W, kind, precision):
     assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
 
 
+def _unmodified_reference_forward(sd, a, b, model, version=1):
+    """The reference ITSELF on the GPU: its unmodified src/models.py + src/correlation.py (baseline/_ref/reference, installed by
+    baseline/install_ref.py), its CUDA kernels compiled at run time through the cupy stand-in (baseline/cupy_stub: NVRTC +
+    driver API, the reference's own launch geometry), stock torch ops in true fp32 (TF32 off)."""
+    from collections import OrderedDict
+    from oracle import ref_import as R
+    models, _ = R.load_reference_models()
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        fac = models.piv_liteflownet if model.startswith("piv") else models.hui_liteflownet
+        net = fac(OrderedDict((k, v.clone()) for k, v in sd.items()), version).to(DEV).eval()
+        with torch.no_grad():
+            return net(a.to(DEV).clone(), b.to(DEV).clone())
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _ref_installed():
+    from oracle import ref_import as R
+    return R.available()
+
+
+needs_installed_ref = pytest.mark.skipif(not _ref_installed(), reason="baseline/_ref/reference not installed")
+
+
 @pytest.mark.gpu
-@needs_ref
-def test_cfg2_bench_batch_vs_reference_cuda_path():
+@needs_installed_ref
+@pytest.mark.parametrize("model,version,B,H,W,kind", [("piv", 1, 1, 128, 128, "rankine"), ("piv", 1, 2, 64, 96, "shear"),
+                                                     ("hui", 1, 1, 64, 128, "uniform"), ("piv2", 2, 1, 64, 64, "shear"),
+                                                     ("hui2", 2, 1, 64, 64, "uniform")])
+def test_forward_vs_unmodified_reference_on_gpu(model, version, B, H, W, kind):
+    """This repo's drop-in (default precision) against the UNMODIFIED reference running its own CUDA path on the same B200,
+    same inputs, same weights: north_star tolerance, absolute."""
+    from src.models import hui_liteflownet, piv_liteflownet
+    sd = synth.synthetic_state_dict(model, 5)
+    a, b, _ = synth.particle_batch(B, H, W, 300 + H, kind)
+    ref = _unmodified_reference_forward(sd, a, b, model, version)
+    net = (piv_liteflownet if model.startswith("piv") else hui_liteflownet)(sd, version).to(DEV).eval()
+    with torch.no_grad():
+        out = net(a.to(DEV), b.to(DEV))
+    diff = (out - ref).abs()
+    _report(f"forward vs UNMODIFIED reference on the GPU {model} {B}x{H}x{W} {net.engine().precision}: max {diff.max().item():.3e} "
+            f"mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
+    assert out.shape == ref.shape
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@needs_installed_ref
+def test_unmodified_reference_correlation_matches_cubins_and_oracle():
+    """The cupy stand-in runs the reference's kernels exactly like the ahead-of-time cubins do (same source, same geometry)."""
+    from oracle import ref_import as R
+    _, corr = R.load_reference_models()
+    f1, f2 = _rand((2, 64, 32, 32), 5).to(DEV), _rand((2, 64, 32, 32), 6).to(DEV)
+    out = corr.FunctionCorrelation(tensorFirst=f1, tensorSecond=f2, intStride=2)
+    assert (out.cpu() - O.correlation(f1.cpu(), f2.cpu(), 2)).abs().max().item() <= 1e-5
+    if (2, 64, 32, 32, 2) in SHAPES:
+        assert torch.equal(out, RC.reference_correlation(f1, f2, 2))
+
+
+@pytest.mark.gpu
+@needs_installed_ref
+def test_cfg2_bench_batch_vs_unmodified_reference():
     """BASELINE configs[1] at its own shape: the 64-pair 256x256 batch bench.py times goes through piv_liteflownet in ONE
-    forward (default precision); 8 of its pairs (every 8th: one of each pool image / roll) are checked against the
-    reference's GPU path (stock torch fp32 convolutions, TF32 off, + the reference's correlation cubins).  Absolute
-    north_star tolerance: flow max <= 1e-2 px, mean <= 1e-3 px."""
+    forward (default precision); 8 of its pairs (every 9th: all 8 pool images, several rolls) are checked against the
+    UNMODIFIED reference on the GPU (its own correlation kernels, fp32 convolutions with TF32 off).  Absolute north_star
+    tolerance: flow max <= 1e-2 px, mean <= 1e-3 px."""
     import bench
     from src.models import piv_liteflownet
     sd = synth.synthetic_state_dict("piv", 0)
@@ -130,11 +192,11 @@ def test_cfg2_bench_batch_vs_reference_cuda_path():
     net = piv_liteflownet(sd, 1).to(DEV).eval()
     with torch.no_grad():
         out = net(a.to(DEV), b.to(DEV))
-    idx = list(range(0, 64, 9))                             # 0, 9, ..., 63: all 8 pool images, several rolls
-    ref = _reference_cuda_forward(sd, a[idx], b[idx], "piv")
+    idx = list(range(0, 64, 9))                             # 0, 9, ..., 63
+    ref = _unmodified_reference_forward(sd, a[idx], b[idx], "piv")
     diff = (out[idx] - ref).abs()
-    _report(f"cfg2 (batch 64 of 256x256, {net.engine().precision}) vs reference CUDA path on pairs {idx}: max {diff.max().item():.3e} "
-            f"mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
+    _report(f"cfg2 (batch 64 of 256x256, {net.engine().precision}) vs UNMODIFIED reference on the GPU, pairs {idx}: "
+            f"max {diff.max().item():.3e} mean {diff.mean().item():.3e} (|flow|max {ref.abs().max().item():.2f})")
     assert ref.abs().max().item() > 1.0
     assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
 
