@@ -107,20 +107,42 @@ def synthetic_batch(n, seed0):
     return torch.stack(a), torch.stack(b)
 
 
-def cpu_reference_rate(n_pairs, threads):
-    """Oracle forward on the host: pairs/s over ``n_pairs`` single-pair steps after one warm-up."""
+def _cpu_forward_fn(threads):
+    """One single-pair forward of the reference's algorithm on the host cores.  Preferred: the UNMODIFIED reference
+    (src/models.py from baseline/_ref/reference or the mount) with the two shims it needs to run without a GPU -- a pure-torch
+    correlation in place of its CuPy kernels and Tensor.cuda as a no-op (BASELINE.json: "the reference model's CPU path with
+    its CuPy correlation replaced by a pure-torch unfold-correlation shim") -> kind "reference".  Fallback: the oracle port."""
     from oracle import lfn_oracle as O
+    from oracle import ref_import as R
     from pivlfn import synth
     torch.set_num_threads(threads)
     sd = synth.synthetic_state_dict("piv", 0)
     a, b = synthetic_batch(1, 1000)
-    with torch.no_grad():
-        O.forward(sd, a, b, "piv")
-        t0 = time.perf_counter()
-        for _ in range(n_pairs):
-            O.forward(sd, a, b, "piv")
-        dt = time.perf_counter() - t0
-    return n_pairs / dt, dt
+    if R.available():
+        from collections import OrderedDict
+        models, _ = R.load_reference_models(O.correlation)
+        net = models.piv_liteflownet(OrderedDict((k, v.clone()) for k, v in sd.items()), 1).eval()
+
+        def fwd():
+            with torch.no_grad(), R.cpu_cuda_noop():
+                return net(a.clone(), b.clone())
+        return fwd, "reference", "unmodified reference src/models.py (pure-torch correlation shim), torch fp32 CPU"
+
+    def fwd():
+        with torch.no_grad():
+            return O.forward(sd, a, b, "piv")
+    return fwd, "port", "oracle port of the reference forward, torch fp32 CPU"
+
+
+def cpu_reference_rate(n_pairs, threads):
+    """pairs/s over ``n_pairs`` single-pair steps after one warm-up."""
+    fwd, kind, what = _cpu_forward_fn(threads)
+    fwd()
+    t0 = time.perf_counter()
+    for _ in range(n_pairs):
+        fwd()
+    dt = time.perf_counter() - t0
+    return n_pairs / dt, dt, kind, what
 
 
 def run_reference(args, rank, world):
@@ -128,26 +150,21 @@ def run_reference(args, rank, world):
         return
     threads = os.cpu_count() or 1
     # warm-up steps are single pairs too; every timed step is one 256x256 pair of the 64-pair workload
-    from oracle import lfn_oracle as O
-    from pivlfn import synth
-    torch.set_num_threads(threads)
-    sd = synth.synthetic_state_dict("piv", 0)
-    a, b = synthetic_batch(1, 1000)
-    with torch.no_grad():
-        for _ in range(max(args.warmup, 1)):
-            O.forward(sd, a, b, "piv")
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            O.forward(sd, a, b, "piv")
-        dt = time.perf_counter() - t0
+    fwd, kind, what = _cpu_forward_fn(threads)
+    for _ in range(max(args.warmup, 1)):
+        fwd()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd()
+    dt = time.perf_counter() - t0
     v = args.steps / dt
-    sample = f"{args.steps} steps of 1 pair 256x256 each (of the 64-pair batch), oracle port of the reference forward, torch fp32 CPU"
+    sample = f"{args.steps} steps of 1 pair 256x256 each (of the 64-pair batch), {what}"
     print(json.dumps({
         "impl": "reference", "metric": "PIV pairs/sec", "value": v, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "sample": sample},
-        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -183,7 +200,12 @@ def kernel_rooflines(eng, pk):
     cw = eng.w[key]
     x, y = ops.view(d["t"][128][0]), ops.view(d["t"][128][1])
     flops = 2.0 * B * h * w * 128 * 128 * 9
-    if eng.precision != SIMT and cw.w_hi is not None:
+    if eng.p16:
+        ms = time_kernel(lambda: ops.conv_p16(x, B, h, w, 128, cw.w_f16s, 5, cw.bias, y, 128, 3, 3, 1, True, ops.OUT_P16, 0,
+                                              eng.flag), 10)
+        name = ("conv_p16_kernel<5> (tcgen05 kind::f16 on P16 activations: fp16 (hi, lo') pairs straight from HBM by TMA, "
+                "3 products, one accumulator, 16 epilogue warps)")
+    elif eng.precision != SIMT and cw.w_hi is not None:
         from pivlfn.model import PASSES
         passes = cw.passes_for(PASSES.get(eng.precision, 1))
         ms = time_kernel(lambda: ops.conv_tc(x, B, h, w, cw.w_hi, cw.w_lo, cw.bias, y, 3, 3, True, passes, None,
@@ -201,37 +223,160 @@ def kernel_rooflines(eng, pk):
     tpath = os.path.join(ROOT, "profiles", "conv_tc_ncu_traffic.json")
     if os.path.isfile(tpath):
         try:
-            traffic = json.load(open(tpath)).get(eng.precision, {}).get("dram_bytes_per_launch")
+            traffic = json.load(open(tpath)).get("p16" if eng.p16 else eng.precision, {}).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
     out["roofline"] = {"kernel": name, "layer": key + " 3x3 128->128 @256x256 x64", "bound": "tensor",
                        "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
                        "peak_source": pk["src"] + ", dense bf16 burst (kind::f16 runs at this rate, kind::tf32 at half); the fp32-"
                                       "equivalent modes spend 3 products per useful one (f16c), so their ceiling is 1/3 of it",
+                       "issued_tflops": 3 * ach if eng.precision == "f16c" else ach, "issued_frac": (3 * ach if eng.precision == "f16c" else ach) / pk["bf16"],
                        "ms_per_launch": ms, "traffic": traffic, "flops_per_launch": flops,
                        "algorithmic_bytes_per_launch": 4.0 * B * h * w * (128 + 128)}
     # memory-bound: level-1 cost volume (stride 2, C=64, fused backwarp + LeakyReLU)
     cm = 64
     S_f1 = ops.view(d["Sbuf"], 0, cm)
-    ms = time_kernel(lambda: ops.corr_nhwc(S_f1, ops.view(d["f2"]), d["flowU"], 5.0, ops.view(d["corr"], 0, 49),
-                                           B, h, w, 2, True), 10)
+    if eng.p16:
+        ms = time_kernel(lambda: ops.corr_p16(S_f1, True, ops.view(d["f2"]), False, d["flowU"], 5.0, ops.view(d["corr"], 0, 49),
+                                              False, B, h, w, cm, 2, True, eng.flag), 10)
+    else:
+        ms = time_kernel(lambda: ops.corr_nhwc(S_f1, ops.view(d["f2"]), d["flowU"], 5.0, ops.view(d["corr"], 0, 49),
+                                               B, h, w, 2, True), 10)
     byts = 4.0 * B * (2 * cm * h * w + 2 * h * w + 49 * (h // 2) * (w // 2))
+    # what a stride-2 launch must really move: every second pixel of every second row of f1, the (up to) 2x2 bilinear
+    # footprint of every sampled f2 position, the flow at the sampled positions, the 49-channel result
+    true_b = 4.0 * B * (cm * (h // 2) * (w // 2) + cm * h * w + 2 * (h // 2) * (w // 2) + 49 * (h // 2) * (w // 2))
     ach = byts / (ms * 1e-3) / 1e9
     out["roofline_corr"] = {"kernel": "corr_nhwc_kernel (level 1, s=2, fused backwarp)", "bound": "hbm", "achieved": ach,
-                            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
+                            "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None,
+                            "true_min_bytes": true_b, "frac_of_true_min": true_b / (ms * 1e-3) / 1e9 / pk["hbm"]}
     ms = time_kernel(lambda: ops.reg_tail(ops.view(d["dist"], 0, 49), d["flowS"],
                                           eng.raw["NetE_R.0.moduleScaleX.weight"], eng.raw["NetE_R.0.moduleScaleX.bias"],
                                           eng.raw["NetE_R.0.moduleScaleY.weight"], eng.raw["NetE_R.0.moduleScaleY.bias"],
                                           d["flowR"], None, 5.0, 7), 10)
     byts = 4.0 * B * h * w * (49 + 4)
     ach = byts / (ms * 1e-3) / 1e9
-    out["roofline_reg_tail"] = {"kernel": "reg_tail_kernel<7> (level 1)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+    out["roofline_reg_tail"] = {"kernel": "reg_tail_bulk_kernel<7> (level 1)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
-    ms = time_kernel(lambda: ops.warp(ops.view(d["f2"]), d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w), 10)
+    if eng.p16:
+        ms = time_kernel(lambda: ops.warp_p16(ops.view(d["f2"]), False, d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w, cm,
+                                              eng.flag), 10)
+    else:
+        ms = time_kernel(lambda: ops.warp(ops.view(d["f2"]), d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w), 10)
     byts = 4.0 * B * h * w * (2 * cm + 2)
     ach = byts / (ms * 1e-3) / 1e9
-    out["roofline_warp"] = {"kernel": "warp_nhwc_kernel (level 1, C=64)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
-                            "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
+    out["roofline_warp"] = {"kernel": "warp_p16_kernel (level 1, C=64)" if eng.p16 else "warp_nhwc_kernel (level 1, C=64)",
+                            "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
+                            "ms_per_launch": ms, "traffic": None}
+    return out
+
+
+def _time_forward(fn, reps, warm=1):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def ref_gpu_leg(net, dev, a64, b64, ours_cfg2_ms):
+    """The north_star's ">= 10x the reference's own CuPy/cuDNN GPU path" denominator, measured here: the UNMODIFIED reference
+    (baseline/_ref/reference: src/models.py + src/correlation.py, its CUDA kernels through the cupy stand-in) on this GPU,
+    eager like run.py drives it, CUDA-event timed, in true fp32 (TF32 off) and with torch's TF32-default convolutions,
+    (i) at the bench workload (batch 64 of 256x256) and (ii) on one 1024x1024 pair per step (run.py -n 1000 shape).
+    Outside the timed region of the headline; rank 0, N = 1 only."""
+    from collections import OrderedDict
+    from oracle import ref_import as R
+    from pivlfn import synth
+    if not R.available():
+        return {"unavailable": "baseline/_ref/reference not installed (python baseline/install_ref.py needs /root/reference)"}
+    models, _ = R.load_reference_models()
+    sd = synth.synthetic_state_dict("piv", 0)
+    ref = models.piv_liteflownet(OrderedDict((k, v.clone()) for k, v in sd.items()), 1).to(dev).eval()
+    i1, i2, _ = synth.particle_pair(1024, 1024, 5, "rankine")
+    xa = synth.to_rgb_tensor(i1)[None].to(dev)
+    xb = synth.to_rgb_tensor(i2)[None].to(dev)
+    res = {"impl": "unmodified reference src/models.py + src/correlation.py (CUDA kernels via NVRTC cupy stand-in), eager torch "
+                   + torch.__version__ + " / cuDNN", "cases": {}}
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    try:
+        with torch.no_grad():
+            ours_1024 = _time_forward(lambda: net(xa.clone(), xb.clone()), 5, warm=3)
+            for tag, tf32 in (("fp32", False), ("tf32_default", True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                m64 = _time_forward(lambda: ref(a64.clone(), b64.clone()), 2, warm=1)
+                m1024 = _time_forward(lambda: ref(xa.clone(), xb.clone()), 3, warm=1)
+                res["cases"][tag] = {
+                    "cfg2_batch64_256": {"ref_ms_per_step": m64, "ref_pairs_per_s": BATCH / (m64 * 1e-3),
+                                         "pivlfn_ms_per_step": ours_cfg2_ms, "ratio": m64 / ours_cfg2_ms},
+                    "one_1024_pair": {"ref_ms_per_pair": m1024, "ref_pairs_per_s": 1e3 / m1024,
+                                      "pivlfn_ms_per_pair": ours_1024, "pivlfn_pairs_per_s": 1e3 / ours_1024,
+                                      "ratio": m1024 / ours_1024}}
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+            d = (net(xa.clone(), xb.clone()) - ref(xa.clone(), xb.clone())).abs()
+            res["flow_max_abs_diff_1024"] = d.max().item()
+            res["flow_mean_abs_diff_1024"] = d.mean().item()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    return res
+
+
+def tiled_4096_leg(eng, dev, rank, world, size=4096):
+    """BASELINE configs[4]: ONE size x size PIV pair.  world == 1: the single-GPU forward (device-resident, CUDA events): the
+    baseline the multi-GPU lines are compared with.  world > 1: tiled by rows across the ranks (pivlfn.tiled.DistGroup: NCCL
+    send/recv of halo rows, 2-float all-reduce of the flow mean per level), max over ranks of the device time, and the
+    max |diff| of every rank's rows against its own single-GPU forward of the whole frame."""
+    import torch.distributed as dist
+    from pivlfn import synth
+    i1, i2, _ = synth.particle_pair(512, 512, 7, "shear")
+    reps = (size + 511) // 512
+    a = synth.to_rgb_tensor(np.tile(i1, (reps, reps))[:size, :size])[None].to(dev)
+    b = synth.to_rgb_tensor(np.tile(i2, (reps, reps))[:size, :size])[None].to(dev)
+    out = {"workload": f"PIV-LiteFlowNet-en, one {size}x{size} pair (BASELINE configs[4])", "n_gpus": world}
+    if world == 1:
+        ms = _time_forward(lambda: eng.forward(a.clone(), b.clone()), 5, warm=2)
+        out.update({"mode": "single GPU", "ms_per_frame": ms, "frames_per_s": 1e3 / ms})
+        eng._plans.clear()
+        torch.cuda.empty_cache()
+        return out
+    from pivlfn.tiled import DistGroup, TiledPlan
+    plan = TiledPlan(eng, size, size, rank, world, halo=24, warp_reach=16)
+    group = DistGroup(plan)
+    plan.load_inputs(a, b)
+    group.run()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = 5
+    e0.record()
+    for _ in range(iters):
+        group.run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tiled = plan.owned_output().clone()
+    nex = sum(1 for st in plan.steps if st.kind == "exchange")
+    del plan, group
+    torch.cuda.empty_cache()
+    ref = eng.forward(a.clone(), b.clone())
+    own = size // world
+    dmax = (tiled - ref[:, :, rank * own:(rank + 1) * own]).abs().max().reshape(1)
+    dist.all_reduce(dmax, op=dist.ReduceOp.MAX)
+    single = torch.tensor([_time_forward(lambda: eng.forward(a.clone(), b.clone()), 3, warm=0)], device=dev)
+    dist.all_reduce(single, op=dist.ReduceOp.MAX)
+    eng._plans.clear()
+    torch.cuda.empty_cache()
+    out.update({"mode": "row-tiled, NCCL halo exchange", "ms_per_frame": float(ms.item()), "frames_per_s": 1e3 / float(ms.item()),
+                "halo_exchanges_per_forward": nex, "max_abs_diff_vs_single_gpu_px": float(dmax.item()),
+                "single_gpu_ms_per_frame": float(single.item()), "speedup_vs_single_gpu": float(single.item()) / float(ms.item())})
     return out
 
 
@@ -372,10 +517,26 @@ def main():
             line["pairs_per_s_1024"] = {"error": repr(ex)}
     if rank == 0 and world == 1 and not args.no_extra:
         try:
+            line["ref_gpu"] = ref_gpu_leg(net, dev, a.to(dev), b.to(dev), ms / args.steps)
+        except Exception as ex:
+            line["ref_gpu"] = {"error": repr(ex)}
+    if not args.no_extra:
+        # one 4096x4096 pair: single GPU at N = 1, row-tiled over NCCL at N > 1 (every rank takes part)
+        try:
+            eng._plans.clear()
+            torch.cuda.empty_cache()
+            t4 = tiled_4096_leg(eng, dev, rank, world)
+            if rank == 0:
+                line["tiled_4096"] = t4
+        except Exception as ex:
+            if rank == 0:
+                line["tiled_4096"] = {"error": repr(ex)}
+    if rank == 0 and world == 1 and not args.no_extra:
+        try:
             threads = os.cpu_count() or 1
-            v, dt = cpu_reference_rate(3, threads)
-            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                                    "sample": f"3 single 256x256 pairs of the workload after 1 warm-up ({dt:.1f} s), oracle port, torch fp32"}
+            v, dt, kind, what = cpu_reference_rate(3, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": threads, "kind": kind,
+                                    "sample": f"3 single 256x256 pairs of the workload after 1 warm-up ({dt:.1f} s), {what}"}
         except Exception as ex:
             line["cpu_baseline"] = {"error": repr(ex)}
     if rank == 0:

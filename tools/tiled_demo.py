@@ -28,7 +28,7 @@ rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_S
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-os.environ.setdefault("MASTER_PORT", "29533")
+os.environ.setdefault("MASTER_PORT", "29533")  # (torchrun sets it)
 dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
 sd = {k: v.to(dev) for k, v in synth.synthetic_state_dict("piv", 0).items()}
