@@ -259,13 +259,18 @@ def kernel_rooflines(eng, pk):
     out["roofline_reg_tail"] = {"kernel": "reg_tail_bulk_kernel<7> (level 1)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
     if eng.p16:
-        ms = time_kernel(lambda: ops.warp_p16(ops.view(d["f2"]), False, d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w, cm,
+        # (with PIVLFN_FUSE_WARP=1, the default, the forward does not launch this kernel: the Subpixel backwarp is gathered
+        # inside conv_S.0; it remains the standalone backwarp operator and is timed into a scratch buffer)
+        scratch = torch.zeros(B, h, w, cm, device=d["f2"].device)
+        ms = time_kernel(lambda: ops.warp_p16(ops.view(d["f2"]), False, d["flowM"], 5.0, ops.view(scratch), B, h, w, cm,
                                               eng.flag), 10)
+        del scratch
     else:
         ms = time_kernel(lambda: ops.warp(ops.view(d["f2"]), d["flowM"], 5.0, ops.view(d["Sbuf"], cm, cm), B, h, w), 10)
     byts = 4.0 * B * h * w * (2 * cm + 2)
     ach = byts / (ms * 1e-3) / 1e9
-    out["roofline_warp"] = {"kernel": "warp_p16_kernel (level 1, C=64)" if eng.p16 else "warp_nhwc_kernel (level 1, C=64)",
+    out["roofline_warp"] = {"kernel": ("warp_p16_kernel (level 1, C=64; standalone operator -- the forward fuses the Subpixel backwarp "
+                                       "into conv_S.0's gather warps)") if eng.p16 else "warp_nhwc_kernel (level 1, C=64)",
                             "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"],
                             "ms_per_launch": ms, "traffic": None}
     return out

@@ -207,6 +207,16 @@ int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const
                     const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                     int out_fmt, long long plane_stride, int* range_flag, void* stream);
 
+/* pivlfn_conv_p16 (stride 1, P16 output) with a BACKWARP FUSED INTO ITS INPUT (src/models.py:209-217, the Subpixel consumer):
+ * of the Cin logical input channels, [wc0, wc0 + wn) are backwarp(wsrc, wscale * wflow) (src/models.py:20-35) and do not exist in
+ * memory: the kernel's gather warps sample wsrc (fp32 NHWC with pitch wsrc_ld floats, or P16 with wsrc_p16 = 1), blend, split
+ * into fp16 pairs and write the MMA operand tile directly.  x holds the other Cin - wn channels contiguously ([0, wc0) then
+ * [wc0 + wn, Cin)).  wc0 and wn are multiples of 32; wflow: dense [N,H,W,2]. */
+int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                         const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                         const void* wsrc, int wsrc_ld, int wsrc_p16, const float* wflow, float wscale,
+                         int wc0, int wn, int* range_flag, void* stream);
+
 /* NetC.conv1 (see pivlfn_conv_stem_tc) with the fp16-split arithmetic and a P16 output; w_img: stage image of the
  * passes-4 pack of the [32, 7, 32] stem weights.  W % 4 == 0, W >= 8. */
 int pivlfn_conv_stem_p16(const float* img_pad, int N, int H, int W, const void* w_img, const float* bias,

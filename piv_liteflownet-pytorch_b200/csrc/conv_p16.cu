@@ -54,6 +54,13 @@ struct ConvP16Args {
     int x_shift;
     const uint8_t* w_img;    // ring-stage image of the fp16 weights (pivlfn.model.stage_image)
     int* range_flag;         // raised when an OUT_P16 result is not finite in fp16 (|x| >= 65520 or NaN); may be NULL
+    // fused backwarp (src/models.py:20-35, the Subpixel consumer :209-217): the wnc 32-channel chunks [wc0, wc0 + wnc) of the GEMM K
+    // range are NOT in the input buffer; they are backwarp(wsrc, wscale * wflow), gathered, blended, split into fp16 pairs and
+    // written into the swizzled activation slot by 8 of the 16 epilogue warps.  The warped features never exist in HBM.
+    const uint8_t* wsrc;     // NHWC source of the warp: fp32 (wsrc_p16 = 0) or P16, pixel pitch wsrc_ld words
+    const float2* wflow;     // dense [N,H,W,2]
+    float wscale;
+    int wsrc_ld, wsrc_p16, wc0, wnc;
     int one_issuer;          // a single thread issues the MMAs of both stacked tiles (required by collect)
     int collect;             // MODE 5: a_hi * W_hi keeps the A window in the collector buffer, a_hi * W_lo re-uses it from there
 };
@@ -84,13 +91,14 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     __shared__ __align__(16) float bias_s[128];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunk = a.s2 ? 4 * a.cpp : (a.Cw + 31) / 32;
+    const int nchunk = a.s2 ? 4 * a.cpp : (a.Cw + 31) / 32 + a.wnc;              // GEMM K range in 32-channel chunks
     const int ntaps = a.KH * a.KW;
     const int G = gridDim.x;
     const int n_iss = (a.NT >= 2 && !a.one_issuer) ? 2 : 1;
     const int tile_cols = DUAL ? 2 * a.CoutP : a.CoutP;
     const int set_cols = a.NT * tile_cols;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
+    const int negr = a.wnc ? 2 : 4;                 // epilogue warp groups (of 4 warps); the other 8 warps gather when a warp is fused
 
     if (threadIdx.x >= 128 && threadIdx.x < 256) {
         const int i = threadIdx.x - 128;
@@ -99,7 +107,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], n_iss); }
         for (int i = 0; i < a.nB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], n_iss); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], EPI_WARPS); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], n_iss); mbar_init(&acc_empty[i], 4 * negr); }
         fence_barrier_init();
         tma_prefetch_desc(&tmA);
     }
@@ -121,14 +129,20 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             for (int w = blockIdx.x; w < a.total; w += G) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
                 for (int c = 0; c < nchunk; ++c, ++g) {
-                    mbar_wait(&a_free[slot], (use & 1) ^ 1);  // the MMAs of the slot's previous tenant have retired
-                    mbar_expect_tx(&a_full[slot], halo_bytes);
-                    int c0, c1, c2;
-                    if (a.s2) {
-                        const int par = c / a.cpp, cc = c - par * a.cpp;
-                        c0 = cc * 32; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
-                    } else { c0 = c * 32; c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2; }
-                    tma_load_4d(smem + (size_t)slot * slot_bytes, &tmA, &a_full[slot], c0, c1, c2, n);
+                    const bool gathered = a.wnc && c >= a.wc0 && c < a.wc0 + a.wnc;      // filled by the gather warps
+                    if (!gathered) {
+                        mbar_wait(&a_free[slot], (use & 1) ^ 1);  // the MMAs of the slot's previous tenant have retired
+                        mbar_expect_tx(&a_full[slot], halo_bytes);
+                        int c0, c1, c2;
+                        if (a.s2) {
+                            const int par = c / a.cpp, cc = c - par * a.cpp;
+                            c0 = cc * 32; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
+                        } else {
+                            c0 = ((a.wnc && c >= a.wc0 + a.wnc) ? c - a.wnc : c) * 32;       // chunk index inside the input buffer
+                            c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2;
+                        }
+                        tma_load_4d(smem + (size_t)slot * slot_bytes, &tmA, &a_full[slot], c0, c1, c2, n);
+                    }
                     if (++slot == a.nA) { slot = 0; ++use; }
                 }
             }
@@ -184,7 +198,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 const uint32_t t_first = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)(issuer * tile_cols);
                 uint32_t acc = 0;
                 for (int c = 0; c < nchunk; ++c) {
-                    const bool two = a.s2 ? true : (a.Cw - c * 32 > 16);        // second 16-channel K step present
+                    // second 16-channel K step present?  (only the last chunk of the input buffer can be half empty)
+                    const bool two = (a.s2 || (a.wnc && c < a.wc0 + a.wnc)) ? true : (a.Cw - (c - a.wnc) * 32 > 16);
                     mbar_wait(&a_full[slot], ause & 1);
                     tc_fence_after();
                     uint32_t A0 = ((smem_u32(smem + (size_t)slot * slot_bytes) >> 4) | lbo_bits) + tileA;
@@ -248,6 +263,78 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
         // words of f16x2 hi + 8 of lo' = one P16 group), quad-transposed so that every store instruction writes 64 contiguous
         // bytes per pixel.
         const int eg = (warp - EPI_WARP0) >> 2, q = warp & 3;
+        if (eg >= negr) {
+            // ============================ fused-backwarp gather warps ============================
+            // 256 threads; item = (pixel of the halo tile, 8-channel unit): 4 bilinear taps x 2 x 16 bytes gathered, blended in
+            // fp32, split into (hi, lo') and stored where TMA + the 128B swizzle would have put them (16-byte unit index XOR
+            // the low 3 bits of the 128-byte row index; slots are 1024-byte aligned).
+            const int gt = threadIdx.x - (EPI_WARP0 + 4 * negr) * 32;
+            constexpr int NG = 256;
+            const int npx = halo_rows * pitch;
+            uint32_t bad = 0;
+            int wl = 0;
+            for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+                const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
+                const int xs = tx * HT_W + a.x_shift, ys = ty * HT_H * a.NT - a.KH / 2;
+                const long long img = (long long)n * a.H * a.W;
+                for (int k = 0; k < a.wnc; ++k) {
+                    const int g = wl * nchunk + a.wc0 + k;                   // global chunk counter of this chunk
+                    const int slot = g % a.nA;
+                    const uint32_t use = (uint32_t)(g / a.nA);
+                    mbar_wait(&a_free[slot], (use & 1) ^ 1);
+                    uint8_t* const dst = smem + (size_t)slot * slot_bytes;
+                    for (int item = gt; item < npx * 4; item += NG) {
+                        const int p = item >> 2, u = item & 3;
+                        const int r = p / pitch, cx = p - r * pitch;
+                        const int y = ys + r, x = xs + cx;
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+                        if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                            const float2 fl = __ldg(a.wflow + img + (long long)y * a.W + x);
+                            const BilinearTaps tp = make_taps((float)x + fl.x * a.wscale, (float)y + fl.y * a.wscale, a.H, a.W);
+                            const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+                            const int cu = k * 4 + u;                        // 8-channel unit of the warp source
+                            const int off = a.wsrc_p16 ? p16::unit_off_bytes(cu) : cu * 32;
+                            const int off2 = a.wsrc_p16 ? off + 32 : off + 16;
+                            uint4 va[4], vb[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                va[t] = vb[t] = make_uint4(0u, 0u, 0u, 0u);
+                                if (wgt[t] != 0.f) {                         // taps outside the frame are never dereferenced
+                                    const uint8_t* src = a.wsrc + (img + (long long)(tp.y0 + (t >> 1)) * a.W + (tp.x0 + (t & 1))) * (long long)a.wsrc_ld * 4;
+                                    va[t] = __ldg(reinterpret_cast<const uint4*>(src + off));
+                                    vb[t] = __ldg(reinterpret_cast<const uint4*>(src + off2));
+                                }
+                            }
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                float f[8];
+                                if (a.wsrc_p16) p16::decode8(va[t], vb[t], f);
+                                else {
+                                    f[0] = __uint_as_float(va[t].x); f[1] = __uint_as_float(va[t].y); f[2] = __uint_as_float(va[t].z); f[3] = __uint_as_float(va[t].w);
+                                    f[4] = __uint_as_float(vb[t].x); f[5] = __uint_as_float(vb[t].y); f[6] = __uint_as_float(vb[t].z); f[7] = __uint_as_float(vb[t].w);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = fmaf(wgt[t], f[j], v[j]);
+                            }
+                        }
+                        uint4 h, l;
+                        p16::encode8(v, h, l);
+                        bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
+                        const uint32_t ub = (uint32_t)p16::unit_off_bytes(u) >> 4;          // 16-byte unit of hi inside the 128-byte row
+                        const uint32_t sw = (uint32_t)(p & 7);
+                        uint8_t* rowp = dst + (size_t)p * 128;
+                        *reinterpret_cast<uint4*>(rowp + ((ub ^ sw) << 4)) = h;
+                        *reinterpret_cast<uint4*>(rowp + (((ub + 2) ^ sw) << 4)) = l;
+                    }
+                    fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    if (gt == 0) mbar_arrive(&a_full[slot]);
+                }
+            }
+            if (a.range_flag && p16::any_nonfinite(bad)) *a.range_flag = 1;
+        } else {
         const int row = q * 32 + lane;
         const int ncg = a.CoutP >> 4;
         const int nunits = a.NT * ncg;
@@ -269,7 +356,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 if (DUAL) tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + a.CoutP + cg * 16), u);
             };
             if (eg < nunits) issue(eg);
-            for (int unit = eg; unit < nunits; unit += 4) {
+            for (int unit = eg; unit < nunits; unit += negr) {
                 const int i = unit / ncg, cb = (unit - i * ncg) * 16;
                 tmem_ld_wait();
                 float r[16];
@@ -286,7 +373,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                     }
                 }
                 // v / u are consumed: the TMEM loads of this warp's next unit hide behind the conversion and the stores
-                if (unit + 4 < nunits) issue(unit + 4);
+                if (unit + negr < nunits) issue(unit + negr);
                 const int yy = (ty * a.NT + i) * HT_H + (row >> 3);
                 const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
                 if (a.out_fmt == OUT_PLANES) {
@@ -360,6 +447,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             if (lane == 0) mbar_arrive(&acc_empty[as]);
         }
         if (a.range_flag && p16::any_nonfinite(bad)) *a.range_flag = 1;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -419,21 +507,32 @@ int configure(ConvP16Args& h, int mode) {
     return 0;
 }
 
-}  // namespace
 
-/* see include/pivlfn.h */
-extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
-                               const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
-                               int out_fmt, long long plane_stride, int* range_flag, void* stream) {
+
+struct WarpSrc { const void* src; int ld, p16; const float* flow; float scale; int c0, n; };
+
+int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                  const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
+                  int out_fmt, long long plane_stride, int* range_flag, const WarpSrc* ws, void* stream) {
     if (!x || !w_img || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
     if (mode != 4 && mode != 5) return PIVLFN_EINVAL;
     if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
     if (out_fmt < OUT_P16 || out_fmt > OUT_PLANES) return PIVLFN_EINVAL;
     const int CoutP = (Cout + 15) & ~15;
     if (CoutP > 128 || (mode == 4 && CoutP > 64)) return PIVLFN_EUNSUPPORTED;
-    const int Cw = (Cin + 15) & ~15;                        // the P16 buffer holds whole 16-channel groups
-    if (((uintptr_t)x & 63) || (x_ld & 15) || x_ld < Cw || ((uintptr_t)w_img & 15)) return PIVLFN_EINVAL;
     ConvP16Args h;
+    h.wsrc = nullptr; h.wflow = nullptr; h.wscale = 0.f; h.wsrc_ld = 0; h.wsrc_p16 = 0; h.wc0 = 0; h.wnc = 0;
+    int Cbuf = Cin;                                         // channels that live in the input buffer
+    if (ws) {
+        if (!ws->src || !ws->flow || stride != 1 || (ws->c0 & 31) || (ws->n & 31) || ws->n <= 0 || ws->c0 + ws->n > Cin) return PIVLFN_EINVAL;
+        if (ws->p16 ? (((uintptr_t)ws->src & 63) || (ws->ld & 15)) : (((uintptr_t)ws->src & 15) || (ws->ld & 3))) return PIVLFN_EINVAL;
+        if (ws->ld < ws->n || ((uintptr_t)ws->flow & 7)) return PIVLFN_EINVAL;
+        h.wsrc = reinterpret_cast<const uint8_t*>(ws->src); h.wflow = reinterpret_cast<const float2*>(ws->flow); h.wscale = ws->scale;
+        h.wsrc_ld = ws->ld; h.wsrc_p16 = ws->p16; h.wc0 = ws->c0 / 32; h.wnc = ws->n / 32;
+        Cbuf = Cin - ws->n;
+    }
+    const int Cw = (Cbuf + 15) & ~15;                       // the P16 buffer holds whole 16-channel groups
+    if (((uintptr_t)x & 63) || (x_ld & 15) || x_ld < Cw || ((uintptr_t)w_img & 15)) return PIVLFN_EINVAL;
     h.s2 = 0; h.cpp = 1;
     if (stride == 2) {
         if (KH != 3 || KW != 3 || (H & 1) || (W & 1) || (Cin % 32)) return PIVLFN_EUNSUPPORTED;
@@ -498,4 +597,23 @@ extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int
     }
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
+}
+
+}  // namespace
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                               const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
+                               int out_fmt, long long plane_stride, int* range_flag, void* stream) {
+    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, mode, bias, y, y_ld, Cout, KH, KW, stride, lrelu, out_fmt, plane_stride,
+                         range_flag, nullptr, stream);
+}
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
+                                    const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int lrelu,
+                                    const void* wsrc, int wsrc_ld, int wsrc_p16, const float* wflow, float wscale,
+                                    int wc0, int wn, int* range_flag, void* stream) {
+    WarpSrc ws{wsrc, wsrc_ld, wsrc_p16, wflow, wscale, wc0, wn};
+    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, mode, bias, y, y_ld, Cout, KH, KW, 1, lrelu, OUT_P16, 0, range_flag, &ws, stream);
 }

@@ -241,6 +241,17 @@ def conv_p16(x: View, N, H, W, cin, w_img, mode, bias, y: View, cout, KH, KW, st
                                            _flag(flag), _stream()), "conv_p16")
 
 
+def conv_p16_warp(x: View, N, H, W, cin, w_img, mode, bias, y: View, cout, KH, KW, lrelu, wsrc: View, wsrc_p16: bool,
+                  wflow: torch.Tensor, wscale: float, wc0: int, wn: int, flag: Optional[torch.Tensor] = None):
+    """conv_p16 whose input channels [wc0, wc0 + wn) are backwarp(wsrc, wscale * wflow), gathered inside the kernel; x holds the
+    remaining cin - wn channels contiguously."""
+    _lib.check(_lib.load().pivlfn_conv_p16_warp(x.ptr, x.ld, N, H, W, int(cin), w_img.data_ptr(), int(mode),
+                                                bias.data_ptr() if bias is not None else None, y.ptr, y.ld, int(cout),
+                                                int(KH), int(KW), int(lrelu), wsrc.ptr, wsrc.ld, int(wsrc_p16),
+                                                wflow.data_ptr(), float(wscale), int(wc0), int(wn), _flag(flag), _stream()),
+               "conv_p16_warp")
+
+
 def conv_stem_p16(img_pad: torch.Tensor, N, H, W, w_img, bias, y: View, lrelu=True, flag: Optional[torch.Tensor] = None):
     _lib.check(_lib.load().pivlfn_conv_stem_p16(img_pad.data_ptr(), N, H, W, w_img.data_ptr(),
                                                 bias.data_ptr() if bias is not None else None, y.ptr, y.ld, int(lrelu),

@@ -3,7 +3,8 @@ activation that feeds a convolution kept in HBM as the fp16 (hi, lo') pairs the 
 
 Same reference semantics (src/models.py:319-370 / :660-716), same buffers-as-concats idea as ``Plan``:
 
-    Sbuf[l] = [ f1 (Cm) | backwarp(f2) (Cm) | flow_M (2) + 14 zero ]      P16, input of conv_S   (src/models.py:216)
+    Sbuf[l] = [ f1 (Cm) | flow_M (2) + 14 zero ]                          P16, input of conv_S   (src/models.py:216); the
+              middle Cm channels of the reference's concat, backwarp(f2), exist only inside conv_S.0's shared memory
     Rbuf[l] = [ feat (Cr) | err, rm_u, rm_v + 13 zero ]                   P16, input of conv_R   (src/models.py:280)
 
 Channel slices start at multiples of 16 (one P16 group = 64 bytes per pixel).  What stays fp32 NHWC: the images, the
@@ -13,11 +14,15 @@ half-resolution cost volume in front of upCorr_M, the flow-head row planes and t
 Differences from ``Plan`` besides the format:
   * all convolutions (stride-2 NetC layers, the 192-channel conv6 as two 96-channel halves, tiny levels) run in ONE kernel
     family, ``pivlfn_conv_p16``: no operand split in shared memory, 16 epilogue warps;
+  * the Subpixel backwarp (src/models.py:214) is fused into its consumer: conv_S.0's gather warps sample f2 and write the MMA
+    operand tile directly (``pivlfn_conv_p16_warp``), so the warped features never reach HBM (PIVLFN_FUSE_WARP=0: separate
+    ``pivlfn_warp_p16`` kernel writing a slice of Sbuf);
   * the KxK 32 -> 2 flow heads run on the tensor cores as a 1xK convolution to 2K row planes + a K-row gather-sum
     (``pivlfn_head_rows_sum``), which also writes flow_M's P16 group into Sbuf.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -46,6 +51,7 @@ class Plan16(Plan):
         E = lambda *shape: torch.empty(shape, device=dev, dtype=torch.float32)
         Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
         self.hw = {l: (H >> (l - 1), W >> (l - 1)) for l in range(1, 7)}
+        self.fuse_warp = os.environ.get("PIVLFN_FUSE_WARP", "1") != "0"
         N2 = 2 * B
         self.in1, self.in2 = E(B, 3, H, W), E(B, 3, H, W)
         self.img = {1: E(N2, H, W, 4)}
@@ -71,7 +77,7 @@ class Plan16(Plan):
                 flowU=E(B, h, w, 2) if l != 6 else None,
                 corr=Z(B, (h + s - 1) // s, (w + s - 1) // s, 52) if l < 4 else None,    # fp32, in front of upCorr_M
                 corrU=Z(B, h, w, 64),                                                    # P16: input of conv_M
-                Sbuf=Z(B, h, w, 2 * cm + 16),
+                Sbuf=Z(B, h, w, (cm if self.fuse_warp else 2 * cm) + 16),
                 Rbuf=Z(B, h, w, cr + 16),
                 flowM=E(B, h, w, 2), flowS=E(B, h, w, 2), flowR=E(B, h, w, 2),
                 partial=E(B, ops.flow_mean_parts(), 2),
@@ -106,19 +112,28 @@ class Plan16(Plan):
         ops.conv_p16(x, n, h, w, cin, w_img, mode, cw.bias, y, cw.cout, cw.kh, cw.kw, cw.stride, lrelu, out_fmt, 0, eng.flag)
 
     def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: Optional[torch.Tensor], out: torch.Tensor,
-               out_p16: Optional[View] = None):
-        """conv_M / conv_S: 3x3 conv + LeakyReLU ..., then the KxK 32->2 flow head plus residual flow."""
+               out_p16: Optional[View] = None, warp=None):
+        """conv_M / conv_S: 3x3 conv + LeakyReLU ..., then the KxK 32->2 flow head plus residual flow.
+        warp = (src view, src_p16, flow, scale, c0, n): channels [c0, c0 + n) of the first layer's input are
+        backwarp(src, scale * flow), gathered inside the kernel."""
         eng, B = self.eng, self.B
         h, w = self.hw[l]
         d = self.lv[l]
         t = d["t"]
         used: Dict[int, int] = {}
         for j in idxs[:-1]:
-            c = eng.w[f"{prefix}.{j}"].cout
+            cw = eng.w[f"{prefix}.{j}"]
+            c = cw.cout
             k = used.get(c, 0)
             used[c] = k ^ 1
             y = view(t[c][k])
-            self._conv(f"{prefix}.{j}", x, B, h, w, y)
+            if warp is not None and j == idxs[0]:
+                src, src_p16, flow, scale, c0, n = warp
+                w_img, mode = (cw.w_f16s, 5) if cw.w_f16s is not None else (cw.w_f16, 4)
+                ops.conv_p16_warp(x, B, h, w, cw.cin, w_img, mode, cw.bias, y, cw.cout, cw.kh, cw.kw, True, src, src_p16, flow, scale,
+                                  c0, n, eng.flag)
+            else:
+                self._conv(f"{prefix}.{j}", x, B, h, w, y)
             x = y
         key = f"{prefix}.{idxs[-1]}"
         K = KSIZE[l]
@@ -167,7 +182,8 @@ class Plan16(Plan):
             scale = eng.sf[l]
             feat = self.feat[l]                      # [2B,h,w,Cf] P16
             feat1, feat2 = feat[:B], feat[B:]
-            S_f1, S_f2w, S_fl = view(d["Sbuf"], 0, cm), view(d["Sbuf"], cm, cm), view(d["Sbuf"], 2 * cm, 16)
+            fuse = self.fuse_warp
+            S_f1, S_fl = view(d["Sbuf"], 0, cm), view(d["Sbuf"], cm if fuse else 2 * cm, 16)
             if l <= 2:
                 # NetC_ext (src/models.py:353-355): list index idx = l-1 uses NetC_ext[idx-1] (wraps to [-1])
                 e = (l - 2) % cfg.n_ext
@@ -191,8 +207,12 @@ class Plan16(Plan):
                 ops.corr_p16(S_f1, True, f2, f2_p16, flowU, scale, view(d["corrU"]), True, B, h, w, cm, s, True, fl)
             self._chain(f"NetE_M.{i}.conv_M", head_idx, view(d["corrU"]), l, flowU, d["flowM"], S_fl)
             # ---- Subpixel (src/models.py:209-217) ------------------------------------------------------------
-            ops.warp_p16(f2, f2_p16, d["flowM"], scale, S_f2w, B, h, w, cm, fl)
-            self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"]), l, d["flowM"], d["flowS"])
+            if fuse:
+                self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"]), l, d["flowM"], d["flowS"],
+                            warp=(f2, f2_p16, d["flowM"], scale, cm, cm))
+            else:
+                ops.warp_p16(f2, f2_p16, d["flowM"], scale, view(d["Sbuf"], cm, cm), B, h, w, cm, fl)
+                self._chain(f"NetE_S.{i}.conv_S", head_idx, view(d["Sbuf"]), l, d["flowM"], d["flowS"])
             # ---- Regularization (src/models.py:274-303) ------------------------------------------------------
             ops.flow_mean(d["flowS"], d["partial"])
             ops.reg_input_p16(self.img[l][:B], self.img[l][B:], d["flowS"], scale, d["partial"], view(d["Rbuf"], cr, 16), fl)

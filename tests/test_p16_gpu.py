@@ -257,3 +257,34 @@ def test_flow_head_rows_vs_torch(K, H, W):
     slot = p16_ref_decode(sb[..., 128:144].cpu(), 16)
     assert (slot[..., :2] - out.cpu()).abs().max().item() <= 2.0 ** -21 * out.abs().max().item()
     assert slot[..., 2:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("src_p16", [False, True])
+@pytest.mark.parametrize("cm,H,W", [(64, 40, 24), (96, 16, 16), (192, 4, 4)])
+def test_conv_p16_with_fused_backwarp(cm, H, W, src_p16):
+    """conv_S.0 (src/models.py:209-217): cat[f1, backwarp(f2, scale * flow), flow] -> 3x3 conv, with the middle cm channels
+    gathered inside the kernel instead of being read from memory."""
+    cin = 2 * cm + 2
+    w, b = _rand(128, cin, 3, 3, seed=1, scale=1.0 / math.sqrt(cin * 9)), _rand(128, seed=2)
+    f1, f2 = _rand(2, cm, H, W, seed=3), _rand(2, cm, H, W, seed=4)
+    flow = _rand(2, 2, H, W, seed=5, scale=2.0)
+    scale = 1.25
+    f2src = p16_round(f2) if src_p16 else f2
+    f2w = O.backwarp(f2src, flow * scale)
+    xin = torch.cat([p16_round(f1), p16_round(f2w), p16_round(flow)], 1)
+    ref = F.conv2d(xin.double(), w.double(), b.double(), padding=1)
+    ref = torch.where(ref >= 0, ref, 0.1 * ref)
+    cw = pack_conv(w, b, 1).to_(DEV)
+    sbuf = torch.zeros(2, H, W, cm + 16, device=DEV)
+    sbuf[..., :cm] = p16_ref_encode(f1.permute(0, 2, 3, 1).contiguous()).to(DEV)
+    sbuf[..., cm:] = p16_ref_encode(flow.permute(0, 2, 3, 1).contiguous()).to(DEV)
+    src = to_p16(f2) if src_p16 else f2.permute(0, 2, 3, 1).contiguous().to(DEV)
+    y = torch.zeros(2, H, W, 128, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    ops.conv_p16_warp(ops.view(sbuf), 2, H, W, cin, cw.w_f16s, 5, cw.bias, ops.view(y), 128, 3, 3, True, ops.view(src), src_p16,
+                      flow.permute(0, 2, 3, 1).contiguous().to(DEV), scale, cm, cm, flag)
+    out = from_p16(y, 128)
+    err = (out.double() - ref).abs().max().item()
+    # (the in-kernel warp rounds its result to P16 exactly like the reference chain above)
+    assert err <= 1e-5 + 1.2e-6 * math.sqrt(cin * 9) + 2.0 ** -21 * ref.abs().max().item(), err
+    assert int(flag.item()) == 0
