@@ -49,7 +49,9 @@ struct ConvP16Args {
     int quad;                // rows 16-byte aligned and W % 4 == 0: quad-transposed 64-byte runs
     int cout_st;             // OUT_F32: channels that may be stored (Cout, or Cout rounded up to 4 when the rows are that wide)
     long long planar;        // OUT_PLANES: floats per channel-pair plane
-    int NT, nA, nB, tps, nsets;
+    int NT, nA, nB, tps, nsets;   // nA = nT + nG activation slots
+    int nT, nG;              // slots filled by TMA / by the gather warps (fused backwarp): every slot has ONE producer, so each
+                             // producer sees every phase of the barriers it waits on (mbarrier parity cannot tell 0 from 2)
     int s2, cpp;             // stride-2 restatement over the four input parities (see conv_tc.cu): cpp chunks per parity
     int x_shift;
     const uint8_t* w_img;    // ring-stage image of the fp16 weights (pivlfn.model.stage_image)
@@ -67,6 +69,13 @@ struct ConvP16Args {
 
 __device__ __forceinline__ bool s2_tap_used(int t, int par) {
     return ((t >> 1) >= 1 - (par >> 1)) && ((t & 1) >= 1 - (par & 1));
+}
+
+// Order in which the K chunks are processed when a backwarp is fused in (wc0 == wnc: the concat is [f1 | warp(f2) | rest]): TMA
+// and gathered chunks alternate, so that the single gather slot is refilled while the MMAs of a TMA chunk run.
+__device__ __forceinline__ int chunk_at(int i, int wc0, int wnc) {
+    if (wnc && wc0 == wnc && i < 2 * wnc) return (i & 1) ? wc0 + (i >> 1) : (i >> 1);
+    return i;
 }
 
 __device__ __forceinline__ void st_global_v4(uint32_t* p, const uint4& v) {
@@ -123,27 +132,25 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     if (warp == 0) {
         // ================================ activation tiles ==============================
         if (elect_one()) {
-            int g = 0;                                        // global chunk counter: slot g % nA, use g / nA
-            int slot = 0;
+            int slot = 0;                                     // TMA slots 0 .. nT-1, in the order of the TMA chunks
             uint32_t use = 0;
             for (int w = blockIdx.x; w < a.total; w += G) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
-                for (int c = 0; c < nchunk; ++c, ++g) {
-                    const bool gathered = a.wnc && c >= a.wc0 && c < a.wc0 + a.wnc;      // filled by the gather warps
-                    if (!gathered) {
-                        mbar_wait(&a_free[slot], (use & 1) ^ 1);  // the MMAs of the slot's previous tenant have retired
-                        mbar_expect_tx(&a_full[slot], halo_bytes);
-                        int c0, c1, c2;
-                        if (a.s2) {
-                            const int par = c / a.cpp, cc = c - par * a.cpp;
-                            c0 = cc * 32; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
-                        } else {
-                            c0 = ((a.wnc && c >= a.wc0 + a.wnc) ? c - a.wnc : c) * 32;       // chunk index inside the input buffer
-                            c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2;
-                        }
-                        tma_load_4d(smem + (size_t)slot * slot_bytes, &tmA, &a_full[slot], c0, c1, c2, n);
+                for (int i = 0; i < nchunk; ++i) {
+                    const int c = chunk_at(i, a.wc0, a.wnc);
+                    if (a.wnc && c >= a.wc0 && c < a.wc0 + a.wnc) continue;              // filled by the gather warps
+                    mbar_wait(&a_free[slot], (use & 1) ^ 1);  // the MMAs of the slot's previous tenant have retired
+                    mbar_expect_tx(&a_full[slot], halo_bytes);
+                    int c0, c1, c2;
+                    if (a.s2) {
+                        const int par = c / a.cpp, cc = c - par * a.cpp;
+                        c0 = cc * 32; c1 = 2 * (tx * HT_W - 1) + (par & 1); c2 = 2 * (ty * HT_H * a.NT - 1) + (par >> 1);
+                    } else {
+                        c0 = ((a.wnc && c >= a.wc0 + a.wnc) ? c - a.wnc : c) * 32;       // chunk index inside the input buffer
+                        c1 = tx * HT_W + a.x_shift; c2 = ty * HT_H * a.NT - a.KH / 2;
                     }
-                    if (++slot == a.nA) { slot = 0; ++use; }
+                    tma_load_4d(smem + (size_t)slot * slot_bytes, &tmA, &a_full[slot], c0, c1, c2, n);
+                    if (++slot == a.nT) { slot = 0; ++use; }
                 }
             }
         }
@@ -153,7 +160,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             int bs = 0;
             uint32_t bphase = 0;
             for (int w = blockIdx.x; w < a.total; w += G) {
-                for (int c = 0; c < nchunk; ++c) {
+                for (int i = 0; i < nchunk; ++i) {
+                    const int c = chunk_at(i, a.wc0, a.wnc);
                     for (int t = 0; t < ntaps; t += a.tps) {
                         if (a.s2 && !s2_tap_used(t, c / a.cpp)) continue;
                         mbar_wait(&b_empty[bs], bphase ^ 1);
@@ -188,8 +196,9 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             const uint32_t row_step = (uint32_t)((pitch - a.KW) * 8);
             int bs = 0;
             uint32_t bphase = 0, bcur = bbase16;
-            int slot = 0, wl = 0;
-            uint32_t ause = 0;
+            int wl = 0;
+            int tslot = 0, gslot = 0;                                           // next TMA / gather slot
+            uint32_t tuse = 0, guse = 0;
             for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
                 const int as = wl % a.nsets;
                 const uint32_t use = (uint32_t)(wl / a.nsets);
@@ -197,10 +206,13 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 tc_fence_after();
                 const uint32_t t_first = tmem_base + (uint32_t)(as * set_cols) + (uint32_t)(issuer * tile_cols);
                 uint32_t acc = 0;
-                for (int c = 0; c < nchunk; ++c) {
+                for (int ci = 0; ci < nchunk; ++ci) {
+                    const int c = chunk_at(ci, a.wc0, a.wnc);
                     // second 16-channel K step present?  (only the last chunk of the input buffer can be half empty)
                     const bool two = (a.s2 || (a.wnc && c < a.wc0 + a.wnc)) ? true : (a.Cw - (c - a.wnc) * 32 > 16);
-                    mbar_wait(&a_full[slot], ause & 1);
+                    const bool gathered = a.wnc && c >= a.wc0 && c < a.wc0 + a.wnc;
+                    const int slot = gathered ? a.nT + gslot : tslot;
+                    mbar_wait(&a_full[slot], (gathered ? guse : tuse) & 1);
                     tc_fence_after();
                     uint32_t A0 = ((smem_u32(smem + (size_t)slot * slot_bytes) >> 4) | lbo_bits) + tileA;
                     int kx = 0;
@@ -251,7 +263,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                         if (++bs == a.nB) { bs = 0; bphase ^= 1; bcur = bbase16; } else bcur += ring16;
                     }
                     umma_commit(&a_free[slot]);
-                    if (++slot == a.nA) { slot = 0; ++ause; }
+                    if (gathered) { if (++gslot == a.nG) { gslot = 0; ++guse; } }
+                    else if (++tslot == a.nT) { tslot = 0; ++tuse; }
                 }
                 umma_commit(&acc_full[as]);
             }
@@ -272,16 +285,15 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             constexpr int NG = 256;
             const int npx = halo_rows * pitch;
             uint32_t bad = 0;
-            int wl = 0;
-            for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
+            int gslot = 0;
+            uint32_t guse = 0;
+            for (int w = blockIdx.x; w < a.total; w += G) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
                 const int xs = tx * HT_W + a.x_shift, ys = ty * HT_H * a.NT - a.KH / 2;
                 const long long img = (long long)n * a.H * a.W;
-                for (int k = 0; k < a.wnc; ++k) {
-                    const int g = wl * nchunk + a.wc0 + k;                   // global chunk counter of this chunk
-                    const int slot = g % a.nA;
-                    const uint32_t use = (uint32_t)(g / a.nA);
-                    mbar_wait(&a_free[slot], (use & 1) ^ 1);
+                for (int k = 0; k < a.wnc; ++k) {                            // (the gathered chunks are processed in increasing order)
+                    const int slot = a.nT + gslot;
+                    mbar_wait(&a_free[slot], (guse & 1) ^ 1);
                     uint8_t* const dst = smem + (size_t)slot * slot_bytes;
                     for (int item = gt; item < npx * 4; item += NG) {
                         const int p = item >> 2, u = item & 3;
@@ -331,6 +343,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                     fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
                     asm volatile("bar.sync 2, 256;" ::: "memory");
                     if (gt == 0) mbar_arrive(&a_full[slot]);
+                    if (++gslot == a.nG) { gslot = 0; ++guse; }
                 }
             }
             if (a.range_flag && p16::any_nonfinite(bad)) *a.range_flag = 1;
@@ -497,6 +510,7 @@ int configure(ConvP16Args& h, int mode) {
         if (nB > MAX_B) nB = MAX_B;
         if (nB < 2) continue;
         h.NT = NT; h.nA = nA; h.nB = nB; h.tps = tps;
+        h.nG = h.wnc ? 1 : 0; h.nT = nA - h.nG;
         h.nsets = (2 * NT * tile_cols <= 512) ? 2 : 1;
         h.tiles_x = cdiv(h.W, HT_W); h.tiles_y = cdiv(h.H, HT_H * NT);
         const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
