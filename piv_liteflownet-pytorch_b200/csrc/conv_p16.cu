@@ -58,7 +58,7 @@ struct ConvP16Args {
     int* range_flag;         // raised when an OUT_P16 result is not finite in fp16 (|x| >= 65520 or NaN); may be NULL
     // fused backwarp (src/models.py:20-35, the Subpixel consumer :209-217): the wnc 32-channel chunks [wc0, wc0 + wnc) of the GEMM K
     // range are NOT in the input buffer; they are backwarp(wsrc, wscale * wflow), gathered, blended, split into fp16 pairs and
-    // written into the swizzled activation slot by 8 of the 16 epilogue warps.  The warped features never exist in HBM.
+    // written into the swizzled activation slot by 12 of the 16 epilogue warps.  The warped features never exist in HBM.
     const uint8_t* wsrc;     // NHWC source of the warp: fp32 (wsrc_p16 = 0) or P16, pixel pitch wsrc_ld words
     const float2* wflow;     // dense [N,H,W,2]
     float wscale;
@@ -107,7 +107,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     const int tile_cols = DUAL ? 2 * a.CoutP : a.CoutP;
     const int set_cols = a.NT * tile_cols;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
-    const int negr = a.wnc ? 2 : 4;                 // epilogue warp groups (of 4 warps); the other 8 warps gather when a warp is fused
+    const int negr = a.wnc ? 1 : 4;                 // epilogue warp groups (of 4 warps); the other 12 warps gather when a backwarp is fused
+                                                    // (that layer is MMA-bound: 4 warps drain its accumulators with time to spare)
 
     if (threadIdx.x >= 128 && threadIdx.x < 256) {
         const int i = threadIdx.x - 128;
@@ -278,11 +279,11 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
         const int eg = (warp - EPI_WARP0) >> 2, q = warp & 3;
         if (eg >= negr) {
             // ============================ fused-backwarp gather warps ============================
-            // 256 threads; item = (pixel of the halo tile, 8-channel unit): 4 bilinear taps x 2 x 16 bytes gathered, blended in
+            // 384 threads; item = (pixel of the halo tile, 8-channel unit): 4 bilinear taps x 2 x 16 bytes gathered, blended in
             // fp32, split into (hi, lo') and stored where TMA + the 128B swizzle would have put them (16-byte unit index XOR
             // the low 3 bits of the 128-byte row index; slots are 1024-byte aligned).
             const int gt = threadIdx.x - (EPI_WARP0 + 4 * negr) * 32;
-            constexpr int NG = 256;
+            constexpr int NG = 384;
             const int npx = halo_rows * pitch;
             uint32_t bad = 0;
             int gslot = 0;
@@ -341,7 +342,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                         *reinterpret_cast<uint4*>(rowp + (((ub + 2) ^ sw) << 4)) = l;
                     }
                     fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
-                    asm volatile("bar.sync 2, 256;" ::: "memory");
+                    asm volatile("bar.sync 2, 384;" ::: "memory");
                     if (gt == 0) mbar_arrive(&a_full[slot]);
                     if (++gslot == a.nG) { gslot = 0; ++guse; }
                 }

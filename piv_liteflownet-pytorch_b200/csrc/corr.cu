@@ -424,8 +424,8 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
                                                  nullptr, (cudaStream_t)stream);
 }
 
-// corr_ps.cu: the persistent producer / consumer kernel for (f1 P16, fp32 rows out)
-int pivlfn_corr_ps_launch(const void* f1, int f1_ld, const void* f2, int f2_ld, int f2_p16, const float* flow, float flow_scale,
+// corr_sp.cu: the software-pipelined kernel for (f1 P16, fp32 rows out)
+int pivlfn_corr_sp_launch(const void* f1, int f1_ld, const void* f2, int f2_ld, int f2_p16, const float* flow, float flow_scale,
                           float* out, int out_ld, int N, int H, int W, int C, int stride, int lrelu, cudaStream_t st);
 
 /* see include/pivlfn.h */
@@ -443,11 +443,11 @@ extern "C" int pivlfn_corr_p16(const void* f1, int f1_ld, int f1_p16, const void
     const float* b = reinterpret_cast<const float*>(f2);
     float* o = reinterpret_cast<float*>(out);
     cudaStream_t st = (cudaStream_t)stream;
-    if (f1_p16 && !out_p16 && !(C & 15)) {
-        static int use_ps = -1;
-        if (use_ps < 0) { const char* v = getenv("PIVLFN_CORR_PS"); use_ps = (v && v[0] == '0') ? 0 : 1; }
-        if (use_ps) {
-            const int rc = pivlfn_corr_ps_launch(f1, f1_ld, f2, f2_ld, f2_p16, flow, flow_scale, o, out_ld, N, H, W, C, stride, lrelu, st);
+    if (f1_p16 && !out_p16 && !(C & 7)) {
+        static int use_sp = -1;
+        if (use_sp < 0) { const char* v = getenv("PIVLFN_CORR_SP"); use_sp = (v && v[0] == '0') ? 0 : 1; }
+        if (use_sp) {
+            const int rc = pivlfn_corr_sp_launch(f1, f1_ld, f2, f2_ld, f2_p16, flow, flow_scale, o, out_ld, N, H, W, C, stride, lrelu, st);
             if (rc != PIVLFN_EUNSUPPORTED) return rc;
         }
     }
