@@ -424,10 +424,6 @@ extern "C" int pivlfn_corr_nhwc(const float* f1, int f1_ld, const float* f2, int
                                                  nullptr, (cudaStream_t)stream);
 }
 
-// corr_sp.cu: the software-pipelined kernel for (f1 P16, fp32 rows out)
-int pivlfn_corr_sp_launch(const void* f1, int f1_ld, const void* f2, int f2_ld, int f2_p16, const float* flow, float flow_scale,
-                          float* out, int out_ld, int N, int H, int W, int C, int stride, int lrelu, cudaStream_t st);
-
 /* see include/pivlfn.h */
 extern "C" int pivlfn_corr_p16(const void* f1, int f1_ld, int f1_p16, const void* f2, int f2_ld, int f2_p16,
                                const float* flow, float flow_scale, void* out, int out_ld, int out_p16,
@@ -443,14 +439,6 @@ extern "C" int pivlfn_corr_p16(const void* f1, int f1_ld, int f1_p16, const void
     const float* b = reinterpret_cast<const float*>(f2);
     float* o = reinterpret_cast<float*>(out);
     cudaStream_t st = (cudaStream_t)stream;
-    if (f1_p16 && !out_p16 && !(C & 7)) {
-        static int use_sp = -1;
-        if (use_sp < 0) { const char* v = getenv("PIVLFN_CORR_SP"); use_sp = (v && v[0] == '0') ? 0 : 1; }
-        if (use_sp) {
-            const int rc = pivlfn_corr_sp_launch(f1, f1_ld, f2, f2_ld, f2_p16, flow, flow_scale, o, out_ld, N, H, W, C, stride, lrelu, st);
-            if (rc != PIVLFN_EUNSUPPORTED) return rc;
-        }
-    }
 #define PIVLFN_CORR_CASE(A, B, O) \
     if ((f1_p16 != 0) == A && (f2_p16 != 0) == B && (out_p16 != 0) == O) \
         return launch_corr_nhwc<A, B, O>(a, f1_ld, b, f2_ld, flow, flow_scale, o, out_ld, N, H, W, C, stride, lrelu, range_flag, st);
