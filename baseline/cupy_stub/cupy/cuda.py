@@ -35,7 +35,7 @@ class _Function:
         from cuda.bindings import driver as drv
         if len(args) != len(self._kinds):
             raise TypeError("cupy stub: wrong number of kernel arguments")
-        vals = [np.array([a], dtype=k) for a, k in zip(args, self._kinds)]
+        vals = [np.array([0 if a is None else a], dtype=k) for a, k in zip(args, self._kinds)]     # None -> NULL pointer
         argv = np.array([v.ctypes.data for v in vals], dtype=np.uint64)
         grid = tuple(grid) + (1,) * (3 - len(grid))
         block = tuple(block) + (1,) * (3 - len(block))

@@ -2,7 +2,8 @@
 ``baseline/_ref/reference/`` (git-ignored; it travels to the GPU box with the snapshot, like a pip-installed baseline
 would).  The reference has no setup.py / build system, so "install" is a copy of its source files:
 
-    src/__init__.py, src/models.py, src/correlation.py, LICENSE
+    src/__init__.py, src/models.py, src/correlation.py, LICENSE, the demo pair + its shipped output .flo, and the pretrained
+    state_dict files if the mount has them (it does not: .MISSING_LARGE_BLOBS)
 
 (``inference.py`` / ``run.py`` import cv2, imutils, torchvision and the plotting stack at module level and are not needed:
 ``estimate`` is 12 arithmetic lines around ``net(img1, img2)``.)
@@ -19,7 +20,12 @@ import shutil
 HERE = os.path.dirname(os.path.abspath(__file__))
 DST = os.path.join(HERE, "_ref", "reference")
 SRC = os.environ.get("PIVLFN_REFERENCE", "/root/reference")
-FILES = ["src/__init__.py", "src/models.py", "src/correlation.py", "LICENSE"]
+FILES = ["src/__init__.py", "src/models.py", "src/correlation.py", "LICENSE",
+         # the reference's one golden artefact (needs the pretrained blob, absent from the mount: tests/test_demo_blob.py lights up
+         # when models/pretrain_torch/PIV-LiteFlowNet-en.paramOnly appears) and, if ever present, the weight blobs themselves
+         "images/demo/DNS_turbulence_img1.tif", "images/demo/DNS_turbulence_img2.tif", "images/demo/DNS_turbulence_out.flo",
+         "images/demo/DNS_turbulence_flow.flo",
+         "models/pretrain_torch/PIV-LiteFlowNet-en.paramOnly", "models/pretrain_torch/Hui-LiteFlowNet.paramOnly"]
 
 
 def install() -> str:

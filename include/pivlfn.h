@@ -40,6 +40,12 @@ int pivlfn_corr_nchw(const float* first, const float* second, float* out,
 
 /* ---- model-internal operators (NHWC views) ---------------------------------------------- */
 
+/* Gradients of pivlfn_corr_nchw (src/correlation.py:106-234,348-405; training only): grad_out [B,49,ceil(H/s),ceil(W/s)] contiguous
+ * -> grad_first / grad_second [B,C,H,W] (either may be NULL: not computed).  At stride 2 only the even positions the forward samples
+ * receive a gradient, the others are written as zero (the reference allocates them with new_zeros). */
+int pivlfn_corr_backward_nchw(const float* first, const float* second, const float* grad_out,
+                              float* grad_first, float* grad_second, int B, int C, int H, int W, int stride, void* stream);
+
 /* src/models.py:321-323 (in-place per-channel mean subtraction of BOTH caller tensors) fused with
  * the NCHW->NHWC pack.  img1,img2: [B,3,H,W] NCHW, modified in place.  out: [2B,H,W,4] (images of
  * img1 first, then img2; 4th channel zero).  out_pad (optional): [2B,H,W+8,4] copy with a 4-pixel border left

@@ -50,6 +50,7 @@ struct ConvP16Args {
     int cout_st;             // OUT_F32: channels that may be stored (Cout, or Cout rounded up to 4 when the rows are that wide)
     long long planar;        // OUT_PLANES: floats per channel-pair plane
     int NT, nA, nB, tps, nsets;   // nA = nT + nG activation slots
+    int tap_off;             // fused backwarp: byte offset of the tap table (24 B per halo-tile pixel) in dynamic shared memory
     int nT, nG;              // slots filled by TMA / by the gather warps (fused backwarp): every slot has ONE producer, so each
                              // producer sees every phase of the barriers it waits on (mbarrier parity cannot tell 0 from 2)
     int s2, cpp;             // stride-2 restatement over the four input parities (see conv_tc.cu): cpp chunks per parity
@@ -288,58 +289,92 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             uint32_t bad = 0;
             int gslot = 0;
             uint32_t guse = 0;
+            const int npx4 = npx * 4;
+            float4* const tapw = reinterpret_cast<float4*>(smem + a.tap_off);     // bilinear weights of the halo-tile pixels
+            int2* const tapxy = reinterpret_cast<int2*>(tapw + npx);              // top-left tap (x0, y0)
             for (int w = blockIdx.x; w < a.total; w += G) {
                 const int tx = w % a.tiles_x, ty = (w / a.tiles_x) % a.tiles_y, n = w / (a.tiles_x * a.tiles_y);
                 const int xs = tx * HT_W + a.x_shift, ys = ty * HT_H * a.NT - a.KH / 2;
                 const long long img = (long long)n * a.H * a.W;
+                // taps of the tile's pixels, once per work item (they do not depend on the channel): one flow fetch per pixel here
+                // instead of one per (pixel, 8 channels), and the gathers below no longer wait behind it
+                for (int p = gt; p < npx; p += NG) {
+                    const int r = p / pitch, cx = p - r * pitch;
+                    const int y = ys + r, x = xs + cx;
+                    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    int2 xy = make_int2(0, 0);
+                    if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
+                        const float2 fl = __ldg(a.wflow + img + (long long)y * a.W + x);
+                        const BilinearTaps tp = make_taps((float)x + fl.x * a.wscale, (float)y + fl.y * a.wscale, a.H, a.W);
+                        wv = make_float4(tp.w00, tp.w01, tp.w10, tp.w11);
+                        xy = make_int2(tp.x0, tp.y0);
+                    }
+                    tapw[p] = wv;
+                    tapxy[p] = xy;
+                }
+                asm volatile("bar.sync 2, 384;" ::: "memory");
                 for (int k = 0; k < a.wnc; ++k) {                            // (the gathered chunks are processed in increasing order)
                     const int slot = a.nT + gslot;
-                    mbar_wait(&a_free[slot], (guse & 1) ^ 1);
+                    // ONE warp polls the mbarrier, the other eleven sleep in the named barrier: twelve warps spinning on
+                    // try_wait would compete with the MMA issuers for issue slots and with the operand reads for shared memory
+                    if (gt < 32) mbar_wait(&a_free[slot], (guse & 1) ^ 1);
+                    asm volatile("bar.sync 2, 384;" ::: "memory");
                     uint8_t* const dst = smem + (size_t)slot * slot_bytes;
-                    for (int item = gt; item < npx * 4; item += NG) {
-                        const int p = item >> 2, u = item & 3;
-                        const int r = p / pitch, cx = p - r * pitch;
-                        const int y = ys + r, x = xs + cx;
-                        float v[8];
+                    constexpr int UNR = 2;                                   // two items = 16 x 16-byte gathers in flight per thread
+                    for (int base = gt; base < npx4; base += UNR * NG) {
+                        uint4 va[UNR][4], vb[UNR][4];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = 0.f;
-                        if (y >= 0 && y < a.H && x >= 0 && x < a.W) {
-                            const float2 fl = __ldg(a.wflow + img + (long long)y * a.W + x);
-                            const BilinearTaps tp = make_taps((float)x + fl.x * a.wscale, (float)y + fl.y * a.wscale, a.H, a.W);
-                            const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
+                        for (int e = 0; e < UNR; ++e) {
+                            const int item = base + e * NG;
+                            const bool ok = item < npx4;
+                            const int p = ok ? item >> 2 : 0, u = item & 3;
+                            const float4 wv = tapw[p];
+                            const int2 xy = tapxy[p];
+                            const float wgt[4] = {wv.x, wv.y, wv.z, wv.w};
                             const int cu = k * 4 + u;                        // 8-channel unit of the warp source
                             const int off = a.wsrc_p16 ? p16::unit_off_bytes(cu) : cu * 32;
                             const int off2 = a.wsrc_p16 ? off + 32 : off + 16;
-                            uint4 va[4], vb[4];
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
-                                va[t] = vb[t] = make_uint4(0u, 0u, 0u, 0u);
-                                if (wgt[t] != 0.f) {                         // taps outside the frame are never dereferenced
-                                    const uint8_t* src = a.wsrc + (img + (long long)(tp.y0 + (t >> 1)) * a.W + (tp.x0 + (t & 1))) * (long long)a.wsrc_ld * 4;
-                                    va[t] = __ldg(reinterpret_cast<const uint4*>(src + off));
-                                    vb[t] = __ldg(reinterpret_cast<const uint4*>(src + off2));
+                                va[e][t] = vb[e][t] = make_uint4(0u, 0u, 0u, 0u);
+                                if (ok && wgt[t] != 0.f) {                   // taps outside the frame are never dereferenced
+                                    const uint8_t* src = a.wsrc + (img + (long long)(xy.y + (t >> 1)) * a.W + (xy.x + (t & 1))) * (long long)a.wsrc_ld * 4;
+                                    va[e][t] = __ldg(reinterpret_cast<const uint4*>(src + off));
+                                    vb[e][t] = __ldg(reinterpret_cast<const uint4*>(src + off2));
                                 }
-                            }
-#pragma unroll
-                            for (int t = 0; t < 4; ++t) {
-                                float f[8];
-                                if (a.wsrc_p16) p16::decode8(va[t], vb[t], f);
-                                else {
-                                    f[0] = __uint_as_float(va[t].x); f[1] = __uint_as_float(va[t].y); f[2] = __uint_as_float(va[t].z); f[3] = __uint_as_float(va[t].w);
-                                    f[4] = __uint_as_float(vb[t].x); f[5] = __uint_as_float(vb[t].y); f[6] = __uint_as_float(vb[t].z); f[7] = __uint_as_float(vb[t].w);
-                                }
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) v[j] = fmaf(wgt[t], f[j], v[j]);
                             }
                         }
-                        uint4 h, l;
-                        p16::encode8(v, h, l);
-                        bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
-                        const uint32_t ub = (uint32_t)p16::unit_off_bytes(u) >> 4;          // 16-byte unit of hi inside the 128-byte row
-                        const uint32_t sw = (uint32_t)(p & 7);
-                        uint8_t* rowp = dst + (size_t)p * 128;
-                        *reinterpret_cast<uint4*>(rowp + ((ub ^ sw) << 4)) = h;
-                        *reinterpret_cast<uint4*>(rowp + (((ub + 2) ^ sw) << 4)) = l;
+#pragma unroll
+                        for (int e = 0; e < UNR; ++e) {
+                            const int item = base + e * NG;
+                            if (item < npx4) {
+                                const int p = item >> 2, u = item & 3;
+                                const float4 wv = tapw[p];
+                                const float wgt[4] = {wv.x, wv.y, wv.z, wv.w};
+                                float v[8];
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) v[j] = 0.f;
+#pragma unroll
+                                for (int t = 0; t < 4; ++t) {
+                                    float f[8];
+                                    if (a.wsrc_p16) p16::decode8(va[e][t], vb[e][t], f);
+                                    else {
+                                        f[0] = __uint_as_float(va[e][t].x); f[1] = __uint_as_float(va[e][t].y); f[2] = __uint_as_float(va[e][t].z); f[3] = __uint_as_float(va[e][t].w);
+                                        f[4] = __uint_as_float(vb[e][t].x); f[5] = __uint_as_float(vb[e][t].y); f[6] = __uint_as_float(vb[e][t].z); f[7] = __uint_as_float(vb[e][t].w);
+                                    }
+#pragma unroll
+                                    for (int j = 0; j < 8; ++j) v[j] = fmaf(wgt[t], f[j], v[j]);
+                                }
+                                uint4 h, l;
+                                p16::encode8(v, h, l);
+                                bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
+                                const uint32_t ub = (uint32_t)p16::unit_off_bytes(u) >> 4;      // 16-byte unit of hi inside the 128-byte row
+                                const uint32_t sw = (uint32_t)(p & 7);
+                                uint8_t* rowp = dst + (size_t)p * 128;
+                                *reinterpret_cast<uint4*>(rowp + ((ub ^ sw) << 4)) = h;
+                                *reinterpret_cast<uint4*>(rowp + (((ub + 2) ^ sw) << 4)) = l;
+                            }
+                        }
                     }
                     fence_proxy_async();                      // generic-proxy writes -> visible to the tensor core (async proxy)
                     asm volatile("bar.sync 2, 384;" ::: "memory");
@@ -503,11 +538,13 @@ int configure(ConvP16Args& h, int mode) {
         const int halo_rows = HT_H * NT + h.KH - 1;
         if (halo_rows > 256 || pitch > 256) continue;
         const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
+        const int taps = h.wnc ? ((halo_rows * pitch * 24 + 1023) & ~1023) : 0;      // fused backwarp: tap table
+        const int budget = SMEM_BUDGET - taps;
         int tps = 1;
-        if (!h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 && (SMEM_BUDGET - 2 * slot) / (3 * b_stage) >= 2) tps = 3;
-        // a third activation slot when it still leaves a deep weight ring
-        int nA = ((SMEM_BUDGET - 3 * slot) / (tps * b_stage) >= 4) ? 3 : 2;
-        int nB = (SMEM_BUDGET - nA * slot) / (tps * b_stage);
+        if (!h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 && (budget - 2 * slot) / (3 * b_stage) >= 2) tps = 3;
+        // a third activation slot when it still leaves a deep weight ring (fused backwarp: always, one slot is the gather's)
+        int nA = ((budget - 3 * slot) / (tps * b_stage) >= (h.wnc ? 2 : 4)) ? 3 : 2;
+        int nB = (budget - nA * slot) / (tps * b_stage);
         if (nB > MAX_B) nB = MAX_B;
         if (nB < 2) continue;
         h.NT = NT; h.nA = nA; h.nB = nB; h.tps = tps;
@@ -517,7 +554,8 @@ int configure(ConvP16Args& h, int mode) {
         const long long total = (long long)h.tiles_x * h.tiles_y * h.N;
         if (total > 0x7FFFFFFFLL) return 0;
         h.total = (int)total;
-        return nA * slot + nB * tps * b_stage;
+        h.tap_off = nA * slot + nB * tps * b_stage;
+        return h.tap_off + taps;
     }
     return 0;
 }

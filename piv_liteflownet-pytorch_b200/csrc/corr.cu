@@ -393,6 +393,76 @@ extern "C" int pivlfn_corr_nchw(const float* first, const float* second, float* 
 }
 
 namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Gradients of the public NCHW operator (src/correlation.py:106-234 kernels, :348-405 host side): training only.
+//   gradFirst [b,c,Y,X]  = (1/C) sum_{p,o} gradOut[b, (p+3)*7+(o+3), Y/s, X/s] * second[b,c, Y + s p, X + s o]
+//   gradSecond[b,c,Y,X]  = (1/C) sum_{p,o} gradOut[b, (p+3)*7+(o+3), Y/s - p, X/s - o] * first[b,c, Y - s p, X - s o]
+// at positions with Y % s == 0 and X % s == 0 (the only ones the forward samples; all others get zero), terms whose
+// gradOut / feature index falls outside contribute nothing.  One thread per gradient element, X fastest: gradOut and the
+// feature rows are read coalesced; the (p, o) sum runs in the reference's order (p outer, o inner).
+// ------------------------------------------------------------------------------------------------
+template <bool SECOND>
+__global__ void __launch_bounds__(256)
+corr_grad_nchw_kernel(const float* __restrict__ other, const float* __restrict__ gout, float* __restrict__ grad,
+                      int C, int H, int W, int Ho, int Wo, int s, long long total) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W);
+        long long t = i / W;
+        const int Y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % C);
+        const long long b = t / C;
+        float sum = 0.f;
+        if (Y % s == 0 && X % s == 0) {
+            const int y0 = Y / s, x0 = X / s;
+            const float* ob = other + (b * C + c) * (long long)H * W;
+            const float* gb = gout + b * 49 * (long long)Ho * Wo;
+            for (int p = -3; p <= 3; ++p)
+                for (int o = -3; o <= 3; ++o) {
+                    const int op = (p + 3) * 7 + (o + 3);
+                    if (!SECOND) {
+                        // out[y0, x0] saw second at (Y + s p, X + s o)
+                        const int yy = Y + s * p, xx = X + s * o;
+                        if (y0 < Ho && x0 < Wo && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                            sum += __ldg(gb + ((long long)op * Ho + y0) * Wo + x0) * __ldg(ob + (long long)yy * W + xx);
+                    } else {
+                        // out[y0 - p, x0 - o] saw second at (Y, X) next to first at (Y - s p, X - s o)
+                        const int y = y0 - p, x = x0 - o;
+                        if (y >= 0 && y < Ho && x >= 0 && x < Wo)
+                            sum += __ldg(gb + ((long long)op * Ho + y) * Wo + x) * __ldg(ob + (long long)(y * s) * W + x * s);
+                    }
+                }
+        }
+        grad[i] = sum / (float)C;
+    }
+}
+
+}  // namespace
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_corr_backward_nchw(const float* first, const float* second, const float* grad_out,
+                                         float* grad_first, float* grad_second, int B, int C, int H, int W, int stride, void* stream) {
+    if (!first || !second || !grad_out || B <= 0 || C <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
+    if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
+    const int Ho = cdiv(H, stride), Wo = cdiv(W, stride);
+    const long long total = (long long)B * C * H * W;
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)pivlfn_num_sms() * 32;
+    const int grid = (int)(g < cap ? g : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (grad_first) {
+        corr_grad_nchw_kernel<false><<<grid, 256, 0, st>>>(second, grad_out, grad_first, C, H, W, Ho, Wo, stride, total);
+        PIVLFN_LAUNCHED();
+    }
+    if (grad_second) {
+        corr_grad_nchw_kernel<true><<<grid, 256, 0, st>>>(first, grad_out, grad_second, C, H, W, Ho, Wo, stride, total);
+        PIVLFN_LAUNCHED();
+    }
+    return pivlfn_last_error();
+}
+
+namespace {
 template <bool F1P, bool F2P, bool OUTP>
 int launch_corr_nhwc(const float* f1, int f1_ld, const float* f2, int f2_ld, const float* flow, float flow_scale, float* out,
                      int out_ld, int N, int H, int W, int C, int stride, int lrelu, int* range_flag, cudaStream_t st) {

@@ -15,6 +15,7 @@ PROTOTYPES = {
     "pivlfn_device_is_sm100": (_i, []),
     "pivlfn_launch_count": (_ll, []),
     "pivlfn_corr_nchw": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "pivlfn_corr_backward_nchw": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "pivlfn_prep_images": (_i, [_p, _p, _p, _p, _i, _i, _i, C.POINTER(_f), _p]),
     "pivlfn_avgpool2": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "pivlfn_conv_simt": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _i, _p]),

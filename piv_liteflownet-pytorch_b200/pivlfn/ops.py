@@ -77,6 +77,20 @@ def corr_nchw(first: torch.Tensor, second: torch.Tensor, stride: int) -> torch.T
     return out
 
 
+def corr_backward_nchw(first: torch.Tensor, second: torch.Tensor, grad_out: torch.Tensor, stride: int, need_first: bool,
+                       need_second: bool):
+    lib = _lib.load()
+    _need_cuda(first, second, grad_out)
+    B, Cc, H, W = first.shape
+    g1 = torch.empty_like(first) if need_first else None
+    g2 = torch.empty_like(first) if need_second else None
+    _lib.check(lib.pivlfn_corr_backward_nchw(first.data_ptr(), second.data_ptr(), grad_out.data_ptr(),
+                                             g1.data_ptr() if g1 is not None else None,
+                                             g2.data_ptr() if g2 is not None else None, B, Cc, H, W, int(stride), _stream()),
+               "corr_backward_nchw")
+    return g1, g2
+
+
 def prep_images(img1, img2, out, mean6, out_pad=None):
     lib = _lib.load()
     _need_cuda(img1, img2, out, out_pad)

@@ -1,11 +1,12 @@
-"""Drop-in for the reference's ``src/correlation.py`` (forward only).
+"""Drop-in for the reference's ``src/correlation.py``.
 
 ``FunctionCorrelation(tensorFirst, tensorSecond, intStride)`` (src/correlation.py:411-412) and
 ``ModuleCorrelation`` (:417-424) keep their names, argument meaning and error behaviour
 (:297-298 ``assert`` contiguity, :339-340 ``NotImplementedError`` for CPU tensors), but run ONE
 sm_100a kernel (``pivlfn_corr_nchw`` in libpivlfn.so) instead of CuPy-JIT'd rearrange x2 +
-updateOutput + three memsets.  The backward kernels (:106-234, :348-405) are training-only and out
-of scope: asking for a gradient raises instead of silently returning none.
+updateOutput + three memsets.  ``backward`` (:348-405, kernels :106-234) returns the same gradients from
+``pivlfn_corr_backward_nchw`` (training is outside the accelerated path; the operator stays differentiable so that the
+reference's trainer keeps working against it).
 """
 import os
 import sys
@@ -24,11 +25,17 @@ class _FunctionCorrelation(torch.autograd.Function):
         if first.is_cuda is not True or second.is_cuda is not True:
             raise NotImplementedError()
         assert first.shape == second.shape and first.dim() == 4
+        ctx.save_for_backward(first, second)
+        ctx.intStride = int(intStride)
         return ops.corr_nchw(first, second, int(intStride))
 
     @staticmethod
     def backward(ctx, gradOutput):
-        raise NotImplementedError("pivlfn implements the forward pass only (correlation backward is out of scope)")
+        first, second = ctx.saved_tensors
+        assert gradOutput.is_contiguous() is True
+        gradFirst, gradSecond = ops.corr_backward_nchw(first, second, gradOutput, ctx.intStride, ctx.needs_input_grad[0],
+                                                       ctx.needs_input_grad[1])
+        return gradFirst, gradSecond, None
 
 
 def FunctionCorrelation(tensorFirst, tensorSecond, intStride):

@@ -1,32 +1,34 @@
-"""Drop-in for the two input helpers of the reference's ``src/utils_data.py`` that the batch driver uses:
-``image_files_from_folder`` (:12-33) and ``read_gen`` (:46-56)."""
+"""Drop-in names of the two input helpers of the reference's ``src/utils_data.py`` that the batch driver uses
+(``image_files_from_folder`` :12-33, ``read_gen`` :46-56), over ``pivlfn.io``."""
 import os
-from glob import glob
 from typing import List, Tuple
 
 import numpy as np
 
+from pivlfn import io as _io
+
 
 def image_files_from_folder(folder: str, pair: bool = True, upper: bool = True, n_images: int = -1, start_at: int = 0,
-                            extensions: Tuple[str, ...] = ('jpg', 'jpeg', 'png', 'bmp', 'tif', 'ppm')) -> List[str]:
-    img_files: List[str] = []
-    for ext in extensions:
-        pattern = f'*_img1.{ext}' if pair else f'*.{ext}'
-        img_files += sorted(glob(os.path.join(folder, pattern)))
-        if upper:
-            pattern = f'*_img1.{ext.upper()}' if pair else f'*.{ext.upper()}'
-            img_files += sorted(glob(os.path.join(folder, pattern)))
-    return img_files[start_at:] if n_images < 0 else img_files[start_at:start_at + n_images]
+                            extensions: Tuple[str, ...] = _io.IMAGE_SUFFIXES) -> List[str]:
+    """Image files of ``folder`` (only the ``*_img1.*`` ones when ``pair``), grouped by extension in the given order."""
+    names = sorted(os.listdir(folder))
+    found: List[str] = []
+    for e in extensions:
+        for suffix in ((e, e.upper()) if upper else (e,)):
+            tail = ('_img1.' if pair else '.') + suffix
+            found.extend(os.path.join(folder, n) for n in names if n.endswith(tail))
+    stop = None if n_images < 0 else start_at + n_images
+    return found[start_at:stop]
 
 
-def read_gen(file_name: str, im_extensions: Tuple[str, ...] = ('.jpg', '.jpeg', '.png', '.bmp', '.tif', '.ppm')):
-    ext = os.path.splitext(file_name)[-1]
-    if ext in im_extensions:
+def read_gen(file_name: str, im_extensions: Tuple[str, ...] = tuple('.' + s for s in _io.IMAGE_SUFFIXES)):
+    """A PIL RGB image for image files, an array for ``.bin`` / ``.raw`` / ``.flo``, ``[]`` otherwise."""
+    kind = os.path.splitext(file_name)[-1]
+    if kind in im_extensions:
         import PIL.Image
         return PIL.Image.open(file_name).convert('RGB')
-    if ext in ('.bin', '.raw'):
+    if kind == '.flo':
+        return _io.read_flo(file_name)
+    if kind in ('.bin', '.raw'):
         return np.load(file_name)
-    if ext == '.flo':
-        from .utils_plot import read_flow
-        return read_flow(file_name)
     return []

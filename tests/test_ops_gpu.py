@@ -65,9 +65,25 @@ def test_function_correlation_errors():
         FunctionCorrelation(a.cpu(), a.cpu(), 1)
     with pytest.raises(AssertionError):
         FunctionCorrelation(a, a, 3)
-    g = a.clone().requires_grad_(True)
-    with pytest.raises((NotImplementedError, RuntimeError)):
-        FunctionCorrelation(g, a, 1).sum().backward()
+
+
+@pytest.mark.parametrize("C,s,H,W", [(8, 1, 9, 11), (16, 2, 12, 16), (5, 2, 7, 9)])
+def test_function_correlation_backward_vs_autograd_of_the_oracle(C, s, H, W):
+    """The operator is differentiable like the reference's (src/correlation.py:348-405): gradients against torch autograd through
+    the oracle's pure-torch restatement, fp64."""
+    from src.correlation import FunctionCorrelation
+    f1, f2 = _rand(2, C, H, W, seed=21), _rand(2, C, H, W, seed=22)
+    go = _rand(2, 49, -(-H // s), -(-W // s), seed=23)
+    a, b = f1.double().requires_grad_(True), f2.double().requires_grad_(True)
+    (O.correlation(a, b, s) * go.double()).sum().backward()
+    x, y = f1.to(DEV).requires_grad_(True), f2.to(DEV).requires_grad_(True)
+    (FunctionCorrelation(x, y, s) * go.to(DEV)).sum().backward()
+    assert (x.grad.cpu().double() - a.grad).abs().max().item() <= 1e-5
+    assert (y.grad.cpu().double() - b.grad).abs().max().item() <= 1e-5
+    # only one input needs a gradient
+    x2 = f1.to(DEV).requires_grad_(True)
+    FunctionCorrelation(x2, f2.to(DEV), s).sum().backward()
+    assert x2.grad is not None and torch.isfinite(x2.grad).all()
 
 
 # ---- model-internal correlation: backwarp fused into the tile load + LeakyReLU -----------------------------

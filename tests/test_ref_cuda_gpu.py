@@ -179,6 +179,27 @@ def test_unmodified_reference_correlation_matches_cubins_and_oracle():
 
 @pytest.mark.gpu
 @needs_installed_ref
+@pytest.mark.parametrize("shape", [(2, 16, 12, 16, 2), (1, 8, 9, 11, 1), (1, 64, 32, 32, 2)], ids=str)
+def test_correlation_backward_vs_unmodified_reference(shape):
+    """gradFirst / gradSecond of the drop-in operator against the reference's own backward (its updateGradFirst / updateGradSecond
+    CUDA kernels, compiled at run time through the cupy stand-in)."""
+    from oracle import ref_import as R
+    from src.correlation import FunctionCorrelation
+    _, corr = R.load_reference_models()
+    B, C, H, W, s = shape
+    f1, f2 = _rand((B, C, H, W), 31).to(DEV), _rand((B, C, H, W), 32).to(DEV)
+    go = _rand((B, 49, -(-H // s), -(-W // s)), 33).to(DEV)
+    a, b = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+    corr.FunctionCorrelation(tensorFirst=a, tensorSecond=b, intStride=s).backward(go)
+    x, y = f1.clone().requires_grad_(True), f2.clone().requires_grad_(True)
+    FunctionCorrelation(tensorFirst=x, tensorSecond=y, intStride=s).backward(go)
+    d1, d2 = (x.grad - a.grad).abs().max().item(), (y.grad - b.grad).abs().max().item()
+    _report(f"correlation backward vs UNMODIFIED reference {shape}: max|diff| gradFirst {d1:.3e} gradSecond {d2:.3e}")
+    assert d1 <= 1e-5 and d2 <= 1e-5
+
+
+@pytest.mark.gpu
+@needs_installed_ref
 def test_cfg2_bench_batch_vs_unmodified_reference():
     """BASELINE configs[1] at its own shape: the 64-pair 256x256 batch bench.py times goes through piv_liteflownet in ONE
     forward (default precision); 8 of its pairs (every 9th: all 8 pool images, several rolls) are checked against the
