@@ -665,8 +665,19 @@ class Plan:
                 self.in2.copy_(keep2)
             g = torch.cuda.CUDAGraph()
             c0 = ops.launch_count()
-            with torch.cuda.graph(g):
-                self.launch_all()
+            # thread_local: only THIS thread's calls are checked while the stream is capturing.  The batch driver's reader /
+            # writer threads pin host memory and wait on events at any time (pivlfn.io), which in the default global mode
+            # invalidates a capture that happens to be in progress (cudaErrorStreamCaptureInvalidated); the cyclic garbage
+            # collector is paused for the same reason (it may destroy an old plan's graph and free its pool mid-capture).
+            import gc
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self.launch_all()
+            finally:
+                if gc_was_on:
+                    gc.enable()
             self.graph_launches = ops.launch_count() - c0
             self.graph = g
         self.graph.replay()

@@ -75,15 +75,18 @@ def test_function_correlation_backward_vs_autograd_of_the_oracle(C, s, H, W):
     f1, f2 = _rand(2, C, H, W, seed=21), _rand(2, C, H, W, seed=22)
     go = _rand(2, 49, -(-H // s), -(-W // s), seed=23)
     a, b = f1.double().requires_grad_(True), f2.double().requires_grad_(True)
-    (O.correlation(a, b, s) * go.double()).sum().backward()
+    O.correlation(a, b, s).backward(go.double())
     x, y = f1.to(DEV).requires_grad_(True), f2.to(DEV).requires_grad_(True)
-    (FunctionCorrelation(x, y, s) * go.to(DEV)).sum().backward()
+    FunctionCorrelation(x, y, s).backward(go.to(DEV))
     assert (x.grad.cpu().double() - a.grad).abs().max().item() <= 1e-5
     assert (y.grad.cpu().double() - b.grad).abs().max().item() <= 1e-5
     # only one input needs a gradient
     x2 = f1.to(DEV).requires_grad_(True)
-    FunctionCorrelation(x2, f2.to(DEV), s).sum().backward()
-    assert x2.grad is not None and torch.isfinite(x2.grad).all()
+    FunctionCorrelation(x2, f2.to(DEV), s).backward(go.to(DEV))
+    assert torch.equal(x2.grad, x.grad)
+    # like the reference (src/correlation.py:352), a non-contiguous gradient (here: the stride-0 expansion of a scalar) is refused
+    with pytest.raises(AssertionError):
+        FunctionCorrelation(f1.to(DEV).requires_grad_(True), f2.to(DEV), s).sum().backward()
 
 
 # ---- model-internal correlation: backwarp fused into the tile load + LeakyReLU -----------------------------
