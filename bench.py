@@ -369,7 +369,10 @@ def tiled_4096_leg(eng, dev, rank, world, size=4096):
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     tiled = plan.owned_output().clone()
     nex = sum(1 for st in plan.steps if st.kind == "exchange")
+    plan.steps.clear()                      # the step closures hold every buffer of the tiled workspace (tens of GB)
     del plan, group
+    import gc
+    gc.collect()
     torch.cuda.empty_cache()
     ref = eng.forward(a.clone(), b.clone())
     own = size // world

@@ -532,19 +532,51 @@ class LoopbackGroup:
 class DistGroup:
     """One process per GPU: NCCL send/recv of halo row blocks with the row neighbours, all-reduce, all-gather."""
 
-    def __init__(self, plan: TiledPlan):
+    def __init__(self, plan: TiledPlan, use_graph: Optional[bool] = None):
+        import os
         import torch.distributed as dist
         self.plan, self.dist = plan, dist
+        self.use_graph = (os.environ.get("PIVLFN_TILED_GRAPH", "1") != "0") if use_graph is None else use_graph
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._warm = False
 
     def run(self):
         """One forward; raises TiledBoundsError on all ranks together when any rank saw a displacement beyond the
-        provisioned backwarp reach or an fp16 range overflow (2-float MAX all-reduce)."""
+        provisioned backwarp reach or an fp16 range overflow (2-float MAX all-reduce).
+
+        The whole per-rank step list -- ~170 kernel launches, the NCCL send/recv groups of the halo exchanges, the flow-mean
+        all-reduces and the coarse-level all-gathers -- is captured ONCE into a CUDA graph (NCCL operations are capturable)
+        and replayed: at 8 ranks a rank's share of the GPU work is ~20 ms, against which ~200 eager launches and ~35
+        torch.distributed calls from Python were a third of the wall time."""
         p = self.plan
         p.clear_range_flag()
-        self._steps()
+        if not self.use_graph:
+            self._steps()
+        elif self.graph is not None:
+            self.graph.replay()
+        else:
+            if not self._warm:
+                self._steps()                    # eager once: NCCL communicators / channels are set up outside the capture
+                torch.cuda.current_stream().synchronize()
+                self._warm = True
+            self._capture()
+            self.graph.replay()
         red = p.local_bounds()
         self.dist.all_reduce(red, op=self.dist.ReduceOp.MAX)
         p.check_bounds(red)
+
+    def _capture(self):
+        import gc
+        g = torch.cuda.CUDAGraph()
+        gc_was_on = gc.isenabled()
+        gc.disable()
+        try:
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._steps()
+        finally:
+            if gc_was_on:
+                gc.enable()
+        self.graph = g
 
     def _steps(self):
         dist, p = self.dist, self.plan
