@@ -537,56 +537,88 @@ class DistGroup:
         import torch.distributed as dist
         self.plan, self.dist = plan, dist
         self.use_graph = (os.environ.get("PIVLFN_TILED_GRAPH", "1") != "0") if use_graph is None else use_graph
-        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self._segments = None            # [(kind, payload)]: ("graph", CUDAGraph) for a run of local steps, ("comm", Step)
         self._warm = False
 
     def run(self):
         """One forward; raises TiledBoundsError on all ranks together when any rank saw a displacement beyond the
         provisioned backwarp reach or an fp16 range overflow (2-float MAX all-reduce).
 
-        The whole per-rank step list -- ~170 kernel launches, the NCCL send/recv groups of the halo exchanges, the flow-mean
-        all-reduces and the coarse-level all-gathers -- is captured ONCE into a CUDA graph (NCCL operations are capturable)
-        and replayed: at 8 ranks a rank's share of the GPU work is ~20 ms, against which ~200 eager launches and ~35
-        torch.distributed calls from Python were a third of the wall time."""
+        The ~170 kernel launches of a rank are captured into CUDA graphs, one per run of LOCAL steps between two communication
+        steps (about 40 segments); the NCCL calls themselves stay eager -- capturing the P2P groups into the graphs as well
+        was tried and dead-locked at 2 ranks.  At 8 ranks a rank's share of the GPU work is ~20 ms, against which ~200 eager
+        ctypes launches from Python were a quarter of the wall time."""
         p = self.plan
         p.clear_range_flag()
         if not self.use_graph:
             self._steps()
-        elif self.graph is not None:
-            self.graph.replay()
         else:
             if not self._warm:
-                self._steps()                    # eager once: NCCL communicators / channels are set up outside the capture
+                self._steps()                    # eager once: lazy module loading, NCCL communicator set-up
                 torch.cuda.current_stream().synchronize()
                 self._warm = True
-            self._capture()
-            self.graph.replay()
+            if self._segments is None:
+                self._compile()
+            for kind, payload in self._segments:
+                if kind == "graph":
+                    payload.replay()
+                else:
+                    self._comm(payload)
         red = p.local_bounds()
         self.dist.all_reduce(red, op=self.dist.ReduceOp.MAX)
         p.check_bounds(red)
 
-    def _capture(self):
+    def _compile(self):
+        """Split the step list at the communication steps and capture every local run into its own CUDA graph (each rank
+        captures only its own kernels: no other rank is involved while a capture is in progress)."""
         import gc
-        g = torch.cuda.CUDAGraph()
-        gc_was_on = gc.isenabled()
-        gc.disable()
-        try:
-            with torch.cuda.graph(g, capture_error_mode="thread_local"):
-                self._steps()
-        finally:
-            if gc_was_on:
-                gc.enable()
-        self.graph = g
+        p = self.plan
+        segs, run = [], []
+
+        def flush():
+            if not run:
+                return
+            steps = list(run)
+            run.clear()
+            g = torch.cuda.CUDAGraph()
+            gc_was_on = gc.isenabled()
+            gc.disable()
+            try:
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    for st in steps:
+                        if st.kind == "op":
+                            st.fn()
+                        else:
+                            _zero_outside(st.tt, p)
+            finally:
+                if gc_was_on:
+                    gc.enable()
+            segs.append(("graph", g))
+
+        for st in p.steps:
+            if st.kind in ("op", "zero"):
+                run.append(st)
+            else:
+                flush()
+                segs.append(("comm", st))
+        flush()
+        self._segments = segs
 
     def _steps(self):
-        dist, p = self.dist, self.plan
-        E = p.E
+        p = self.plan
         for st in p.steps:
             if st.kind == "op":
                 st.fn()
             elif st.kind == "zero":
                 _zero_outside(st.tt, p)
-            elif st.kind == "exchange":
+            else:
+                self._comm(st)
+
+    def _comm(self, st):
+        dist, p = self.dist, self.plan
+        E = p.E
+        if True:
+            if st.kind == "exchange":
                 t, own = st.tt.t, p.own[st.tt.level]
                 reqs = []
                 bufs = []
