@@ -351,8 +351,8 @@ def tiled_4096_leg(eng, dev, rank, world, size=4096):
         eng._plans.clear()
         torch.cuda.empty_cache()
         return out
-    from pivlfn.tiled import DistGroup, TiledPlan
-    plan = TiledPlan(eng, size, size, rank, world, halo=24, warp_reach=16)
+    from pivlfn.tiled import DistGroup, make_tiled_plan
+    plan = make_tiled_plan(eng, size, size, rank, world, halo=24, warp_reach=16)
     group = DistGroup(plan)
     plan.load_inputs(a, b)
     group.run()

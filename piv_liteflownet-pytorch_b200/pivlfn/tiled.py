@@ -639,3 +639,294 @@ class DistGroup:
                 for n in range(st.src.shape[0]):
                     piece = st.src[n, 1:1 + o2].contiguous()
                     dist.all_gather_into_tensor(st.dst[n], piece)
+
+
+# =================================================================================================================
+# P16 pipeline (engines with precision f16c, see plan16.py): the same row-slab plan over the P16 kernels
+# =================================================================================================================
+def _r16(c: int) -> int:
+    return (c + 15) & ~15
+
+
+class TiledPlan16(TiledPlan):
+    """TiledPlan for an engine that runs the P16 pipeline: activations that feed convolutions are P16 (channel counts rounded
+    up to 16 words per pixel, csrc/p16.cuh), every convolution is ``pivlfn_conv_p16`` (incl. the stride-2 NetC layers and
+    the 192-channel conv6), the flow heads run as 1xK row planes + ``pivlfn_head_rows_sum``.  Halo validity tracking, exchange
+    and zeroing rules are inherited unchanged: a P16 row block is sent as the 4-byte words it is stored in, and all-zero
+    words are (hi, lo') = (0, 0)."""
+
+    def conv16(self, key: str, x: TT, xo: int, y: TT, yo: int, lrelu: bool = True, out_fmt: int = ops.OUT_P16,
+               cin: Optional[int] = None, yc: Optional[int] = None):
+        """stride-1 convolution x[:, :, :, xo:] -> y[:, :, :, yo:] on the whole local buffer (valid rows shrink by KH // 2)."""
+        eng = self.eng
+        cw = eng.w[key]
+        cin = cw.cin if cin is None else cin
+        r = cw.kh // 2
+        self._need(x, r)
+        N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
+        w_img, mode = (cw.w_f16s, 5) if cw.w_f16s is not None else (cw.w_f16, 4)
+        yc = (_r16(cw.cout) if out_fmt == ops.OUT_P16 else y.t.shape[3] - yo) if yc is None else yc
+
+        def run():
+            for n in range(N):
+                xv = view(self._img(x, n), xo, _r16(cin))
+                yv = view(self._img(y, n), yo, yc)
+                ops.conv_p16(xv, 1, hh, ww, cin, w_img, mode, cw.bias, yv, cw.cout, cw.kh, cw.kw, 1, lrelu, out_fmt, 0, eng.flag)
+        self._op(run, y, x.valid - r)
+
+    def down(self, kind: str, x: TT, y: TT, key: Optional[str] = None, C: int = 4):
+        if kind == "pool":
+            return super().down(kind, x, y, key, C)
+        # 3x3 stride-2 NetC convolution on P16 buffers (conv6: two 96-channel halves)
+        eng, N, E = self.eng, x.t.shape[0], self.E
+        halves = [(key, 0)] if key in eng.w and eng.w[key].w_s2 is not None else [(key + "#a", 0), (key + "#b", 96)]
+
+        def call(a: torch.Tensor, b: torch.Tensor):
+            for k, off in halves:
+                cw = eng.w[k]
+                ops.conv_p16(view(a, 0, _r16(cw.cin)), 1, a.shape[1], a.shape[2], cw.cin, cw.w_s2, cw.s2_passes, cw.bias,
+                             view(b, off, _r16(cw.cout)), cw.cout, 3, 3, 2, True, ops.OUT_P16, 0, eng.flag)
+
+        if x.tiled and not y.tiled:
+            self._need(x, 2)
+            own2 = self.own[y.level]
+            tmp = self._E(N, own2 + 2, self.Wl[y.level], y.t.shape[3])
+
+            def run():
+                for n in range(N):
+                    call(self._img(x, n, E - 2, 2 * own2 + 4), tmp[n:n + 1])
+            self.steps.append(Step("op", fn=run))
+            self.steps.append(Step("allgather", src=tmp, dst=y.t))
+            return
+        self._need(x, 1)
+
+        def run2():
+            for n in range(N):
+                a, b, _ = self._down_views(x, y, n, 1)
+                call(a, b)
+        v = (x.valid - 1) // 2
+        self._op(run2, y, min(v, E // 2) if y.tiled else v)
+
+    def _head(self, key: str, x: TT, l: int, res: Optional[TT], out: TT, out16: Optional[TT], out16_off: int, planes: torch.Tensor):
+        """KxK 32 -> 2 flow head: 1xK convolution to K row planes, then the K-row gather-sum (+ bias + residual flow)."""
+        eng = self.eng
+        K = KSIZE[l]
+        rw = eng.w[key + "#rows"]
+        self._need(x, 0)
+        if res is not None:
+            self._need(res, 0)
+        hh, ww = x.t.shape[1], x.t.shape[2]
+
+        def run():
+            ops.conv_p16(view(self._img(x, 0), 0, _r16(rw.cin)), 1, hh, ww, rw.cin, rw.w_f16, 4, None, view(planes.view(1, K, hh * ww, 2)),
+                         2 * K, 1, K, 1, False, ops.OUT_PLANES, 2 * hh * ww, eng.flag)
+            ops.head_rows_sum(planes, K, eng.w[key].bias, self._img(res, 0) if res is not None else None, self._img(out, 0),
+                              view(self._img(out16, 0), out16_off, 16) if out16 is not None else None, 1, hh, ww, eng.flag)
+        v = x.valid - K // 2
+        if res is not None:
+            v = min(v, res.valid)
+        self._op(run, out, v)
+        if out16 is not None:
+            out16.valid = out.valid
+
+    def _chain16(self, prefix: str, idxs: List[int], x: TT, l: int, res: Optional[TT], out: TT, out16: Optional[TT] = None,
+                 out16_off: int = 0, planes: Optional[torch.Tensor] = None):
+        for j in idxs[:-1]:
+            key = f"{prefix}.{j}"
+            y = self.new(key, l, _r16(self.eng.w[key].cout))
+            self.conv16(key, x, 0, y, 0)
+            x = y
+        self._head(f"{prefix}.{idxs[-1]}", x, l, res, out, out16, out16_off, planes)
+
+    def _build(self):
+        eng, cfg, E = self.eng, self.eng.cfg, self.E
+        fl = eng.flag
+        self.in1 = self._E(1, 3, self.rows(1), self.W)
+        self.in2 = self._E(1, 3, self.rows(1), self.W)
+        img: Dict[int, TT] = {1: self.new("img1", 1, 4, N=2)}
+        img_pad = TT(self._Z(2, self.rows(1), self.W + 8, 4), 1, True, "img_pad")
+        img_pad.valid = E
+
+        def prep():
+            ops.prep_images(self.in1, self.in2, img[1].t, (0.0,) * 6, img_pad.t)
+        self.steps.append(Step("op", fn=prep))
+        img[1].valid = E
+        for l in range(2, 7):
+            img[l] = self.new(f"img{l}", l, 4, N=2)
+            self.down("pool", img[l - 1], img[l])
+        # ---- NetC on both images ------------------------------------------------------------------------------------
+        feats: Dict[int, TT] = {}
+        x, lvl = img[1], 1
+        for i, (seq, idx, cin, cout, k, st) in enumerate(NETC):
+            key = f"NetC.{seq}.{idx}"
+            if st == 2:
+                lvl += 1
+                y = self.new(key, lvl, _r16(cout), N=2)
+                self.down("conv", x, y, key)
+            elif i == 0:
+                y = self.new(key, lvl, 32, N=2)
+                cw = eng.w[key]
+                self._need(img_pad, 3)
+                hh, ww = y.t.shape[1], y.t.shape[2]
+
+                def run_stem(y=y, cw=cw, hh=hh, ww=ww):
+                    for n in range(2):
+                        ops.conv_stem_p16(self._img(img_pad, n), 1, hh, ww, cw.w_f16, cw.bias, view(self._img(y, n)), True, fl)
+                self._op(run_stem, y, img_pad.valid - 3)
+            else:
+                y = self.new(key, lvl, _r16(cout), N=2)
+                self.conv16(key, x, 0, y, 0)
+            x = y
+            if NETC_LEVEL_END[lvl] == i:
+                feats[lvl] = y
+        nh = len(cfg.head)
+        head_idx = [2 * j for j in range(nh + 1)]
+        xflow: Optional[TT] = None
+        self.flows: Dict[int, TT] = {}
+        for i in reversed(range(len(cfg.levels))):
+            l = cfg.levels[i]
+            cm = MATCH_FEAT_CH[l]
+            cr = 128 if l < 5 else LEVEL_FEAT_CH[l]
+            s = 2 if l < 4 else 1
+            scale = eng.sf[l]
+            K = KSIZE[l]
+            feat = feats[l]
+            f1 = TT(feat.t[0:1], l, feat.tiled, f"feat1_{l}"); f1.valid = feat.valid
+            f2r = TT(feat.t[1:2], l, feat.tiled, f"feat2_{l}"); f2r.valid = feat.valid
+            self.handles += [f1, f2r]
+            im1 = TT(img[l].t[0:1], l, img[l].tiled, f"im1_{l}"); im1.valid = img[l].valid
+            im2 = TT(img[l].t[1:2], l, img[l].tiled, f"im2_{l}"); im2.valid = img[l].valid
+            self.handles += [im1, im2]
+            planes = self._E(K, self.rows(l) * self.Wl[l], 2)
+            Sbuf = self.new(f"Sbuf{l}", l, 2 * cm + 16, zero=True)            # [f1 | backwarp(f2) | flow_M group]
+            S_f2w, S_fl = self.alias(Sbuf, f"S_f2w{l}"), self.alias(Sbuf, f"S_fl{l}")
+            if l <= 2:
+                e = (l - 2) % cfg.n_ext
+                self.conv16(f"NetC_ext.{e}.conv_ext.0", f1, 0, Sbuf, 0)
+                f2 = self.new(f"f2e{l}", l, cm)                                # fp32 NHWC: read by the cost volume and the warp only
+                self.conv16(f"NetC_ext.{e}.conv_ext.0", f2r, 0, f2, 0, out_fmt=ops.OUT_F32)
+                f2_p16 = False
+            else:
+                self.copy(f1, 0, cm, Sbuf, 0)
+                f2, f2_p16 = f2r, True
+            # ---- Matching ------------------------------------------------------------------------------------
+            flowU = None
+            if xflow is not None:
+                flowU = self.new(f"flowU{l}", l, 2)
+                self.up(xflow, 2, eng.raw[f"NetE_M.{i}.upConv_M.weight"], flowU)
+            self._need(Sbuf, 0)
+            self._need(f2, 3 * s + (self.wr if flowU is not None else 0))
+            if flowU is not None:
+                self._need(flowU, 3 * s)
+                self._steers_warp(flowU, flowU.valid)
+            vin = min(Sbuf.valid, f2.valid - 3 * s - (self.wr if flowU is not None else 0),
+                      flowU.valid - 3 * s if flowU is not None else 1 << 30)
+            corrU = self.new(f"corrU{l}", l, 64, zero=True)                    # P16: input of conv_M
+            if s == 2:
+                corr_rows = (self.rows(l) + 1) // 2
+                corr = self._Z(1, corr_rows, (self.Wl[l] + 1) // 2, 52)
+
+                def run_corr(Sbuf=Sbuf, f2=f2, f2_p16=f2_p16, flowU=flowU, corr=corr, corrU=corrU, cm=cm, scale=scale, i=i):
+                    a, b = self._img(Sbuf, 0), self._img(f2, 0)
+                    ops.corr_p16(view(a, 0, cm), True, view(b, 0, cm), f2_p16, self._img(flowU, 0) if flowU is not None else None, scale,
+                                 view(corr, 0, 49), False, 1, a.shape[1], a.shape[2], cm, 2, True, fl)
+                    ops.deconv4x4s2_dw_p16(view(corr, 0, 49), 1, corr.shape[1], corr.shape[2], 49,
+                                           eng.raw[f"NetE_M.{i}.upCorr_M.weight"], view(corrU.t), fl)
+                # half-resolution cost volume rows 2 apart: valid rows shrink by 2 through the 4x4 up-convolution
+                self._op(run_corr, corrU, vin - 2)
+            else:
+                def run_corr1(Sbuf=Sbuf, f2=f2, f2_p16=f2_p16, flowU=flowU, corrU=corrU, cm=cm, scale=scale):
+                    a, b = self._img(Sbuf, 0), self._img(f2, 0)
+                    ops.corr_p16(view(a, 0, cm), True, view(b, 0, cm), f2_p16, self._img(flowU, 0) if flowU is not None else None, scale,
+                                 view(corrU.t), True, 1, a.shape[1], a.shape[2], cm, 1, True, fl)
+                self._op(run_corr1, corrU, vin)
+            flowM = self.new(f"flowM{l}", l, 2)
+            self._chain16(f"NetE_M.{i}.conv_M", head_idx, corrU, l, flowU, flowM, S_fl, 2 * cm, planes)
+            # ---- Subpixel ------------------------------------------------------------------------------------
+            self._need(f2, self.wr)
+            self._need(flowM, 0)
+            self._steers_warp(flowM, min(flowM.valid, f2.valid - self.wr))
+
+            def run_warp(f2=f2, f2_p16=f2_p16, flowM=flowM, Sbuf=Sbuf, cm=cm, scale=scale):
+                a, b = self._img(f2, 0), self._img(Sbuf, 0)
+                ops.warp_p16(view(a, 0, cm), f2_p16, self._img(flowM, 0), scale, view(b, cm, cm), 1, a.shape[1], a.shape[2], cm, fl)
+            self._op(run_warp, S_f2w, min(flowM.valid, f2.valid - self.wr))
+            Sall = self.alias(Sbuf, f"Sall{l}")
+            Sall.valid = min(Sbuf.valid, S_f2w.valid, S_fl.valid)
+            flowS = self.new(f"flowS{l}", l, 2)
+            self._chain16(f"NetE_S.{i}.conv_S", head_idx, Sall, l, flowM, flowS, None, 0, planes)
+            # ---- Regularization ------------------------------------------------------------------------------
+            partial = self._E(1, ops.flow_mean_parts(), 2)
+            r0, nr = (E, self.own[l]) if flowS.tiled else (0, self.Hl[l])
+            frac = float(self.rows(l)) / float(self.Hl[l])     # reg_input divides by the LOCAL pixel count
+
+            def run_mean(flowS=flowS, partial=partial, r0=r0, nr=nr):
+                ops.flow_mean(self._img(flowS, 0, r0, nr).contiguous(), partial)
+            self.steps.append(Step("op", fn=run_mean))
+            if flowS.tiled:
+                self.steps.append(Step("allreduce", src=partial))
+                self.steps.append(Step("op", fn=lambda partial=partial, frac=frac: partial.mul_(frac)))
+            Rbuf = self.new(f"Rbuf{l}", l, cr + 16, zero=True)
+            R_in = self.alias(Rbuf, f"R_in{l}")
+            self._need(im2, self.wr)
+            self._need(im1, 0)
+            self._need(flowS, 0)
+
+            def run_ri(im1=im1, im2=im2, flowS=flowS, partial=partial, Rbuf=Rbuf, cr=cr, scale=scale):
+                ops.reg_input_p16(self._img(im1, 0), self._img(im2, 0), self._img(flowS, 0), scale, partial,
+                                  view(self._img(Rbuf, 0), cr, 16), fl)
+            self._steers_warp(flowS, min(im1.valid, flowS.valid, im2.valid - self.wr))
+            self._op(run_ri, R_in, min(im1.valid, flowS.valid, im2.valid - self.wr))
+            if l < 5:
+                self.conv16(f"NetE_R.{i}.moduleFeat.0", f1, 0, Rbuf, 0)
+            else:
+                self.copy(f1, 0, cr, Rbuf, 0)
+            Rall = self.alias(Rbuf, f"Rall{l}")
+            Rall.valid = min(Rbuf.valid, R_in.valid)
+            x = Rall
+            for j in range(len(CONV_R)):
+                key = f"NetE_R.{i}.conv_R.{2 * j}"
+                y = self.new(key, l, _r16(eng.w[key].cout))
+                self.conv16(key, x, 0, y, 0)
+                x = y
+            dc = DIST_CH[l]
+            dist = self.new(f"dist{l}", l, (dc + 3) & ~3)
+            if l < 5:
+                dist0 = self.new(f"dist0{l}", l, _r16(dc), zero=True)
+                self.conv16(f"NetE_R.{i}.conv_dist_R.0", x, 0, dist0, 0, lrelu=False)
+                self.conv16(f"NetE_R.{i}.conv_dist_R.1", dist0, 0, dist, 0, lrelu=False, out_fmt=ops.OUT_F32)
+            else:
+                self.conv16(f"NetE_R.{i}.conv_dist_R.0", x, 0, dist, 0, lrelu=False, out_fmt=ops.OUT_F32)
+            flowR = self.new(f"flowR{l}", l, 2)
+            last = l == cfg.lowest_level
+            if last:
+                self.out_local = self._E(1, 2, self.rows(l), self.Wl[l])
+            self._need(flowS, K // 2)
+            self._need(dist, 0)
+            p = f"NetE_R.{i}"
+
+            def run_tail(dist=dist, flowS=flowS, flowR=flowR, dc=dc, K=K, last=last, p=p):
+                ops.reg_tail(view(self._img(dist, 0), 0, dc), self._img(flowS, 0), eng.raw[p + ".moduleScaleX.weight"],
+                             eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
+                             eng.raw[p + ".moduleScaleY.bias"], self._img(flowR, 0), self.out_local if last else None,
+                             eng.sf[1], K)
+            self._op(run_tail, flowR, min(dist.valid, flowS.valid - K // 2))
+            self.flows[l] = flowS
+            xflow = flowR
+
+    # the engine-owned range flag replaces the library-global one of the fp32-activation kernels
+    def local_bounds(self) -> torch.Tensor:
+        m = torch.zeros((), device=self.eng.device, dtype=torch.float32)
+        for f, v in self.warp_flows:
+            E, own = self.E, self.own[f.level]
+            m = torch.maximum(m, f.t[:, E - v:E + own + v, :, 1].abs().max() * self.eng.sf[f.level] + 1.0)
+        return torch.stack([m, self.eng.flag[0].to(torch.float32)])
+
+    def clear_range_flag(self):
+        self.eng.flag.zero_()
+
+
+def make_tiled_plan(eng: Engine, H: int, W: int, rank: int, world: int, halo: int = 16, warp_reach: int = 8) -> TiledPlan:
+    """The tiled plan that matches the engine's pipeline (P16 for precision f16c, else the fp32-activation kernels)."""
+    cls = TiledPlan16 if getattr(eng, "p16", False) else TiledPlan
+    return cls(eng, H, W, rank, world, halo=halo, warp_reach=warp_reach)

@@ -8,14 +8,15 @@ import torch
 from pivlfn import synth
 from pivlfn.arch import CFGS
 from pivlfn.model import Engine
-from pivlfn.tiled import LoopbackGroup, TiledPlan
+from pivlfn.tiled import LoopbackGroup, TiledPlan, make_tiled_plan
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
 @pytest.mark.parametrize("model,H,W,P,precision", [("piv", 256, 128, 2, "simt"), ("piv", 384, 96, 3, "3xtf32"),
-                                                    ("hui", 256, 64, 2, "tf32c"), ("piv", 512, 64, 4, "f16c")])
+                                                    ("hui", 256, 64, 2, "tf32c"), ("piv", 512, 64, 4, "f16c"),
+                                                    ("hui", 256, 128, 2, "f16c"), ("piv", 384, 64, 3, "f16c")])
 def test_tiled_equals_single_gpu(model, H, W, P, precision):
     sd = {k: v.to(DEV) for k, v in synth.synthetic_state_dict(model, 0).items()}
     eng = Engine(CFGS[model], sd, torch.device(DEV), precision, use_graph=False)
@@ -23,7 +24,7 @@ def test_tiled_equals_single_gpu(model, H, W, P, precision):
     a = synth.to_rgb_tensor(i1)[None].to(DEV)
     b = synth.to_rgb_tensor(i2)[None].to(DEV)
     ref = eng.forward(a.clone(), b.clone())
-    plans = [TiledPlan(eng, H, W, r, P, halo=24, warp_reach=16) for r in range(P)]
+    plans = [make_tiled_plan(eng, H, W, r, P, halo=24, warp_reach=16) for r in range(P)]
     assert 1 <= plans[0].Lt <= 6
     for p in plans:
         p.load_inputs(a, b)
@@ -51,7 +52,7 @@ def test_tiled_raises_when_displacement_exceeds_warp_reach():
     b = synth.to_rgb_tensor(i2)[None].to(DEV)
     ref = eng.forward(a.clone(), b.clone())
     assert ref[:, 1].abs().max().item() > 1.5          # the synthetic weights produce multi-pixel vertical flows
-    plans = [TiledPlan(eng, 256, 64, r, 2, halo=8, warp_reach=1) for r in range(2)]
+    plans = [make_tiled_plan(eng, 256, 64, r, 2, halo=8, warp_reach=1) for r in range(2)]
     assert len(plans[0].warp_flows) >= 3
     for p in plans:
         p.load_inputs(a, b)

@@ -18,7 +18,7 @@ import torch.distributed as dist  # noqa: E402
 from pivlfn import synth  # noqa: E402
 from pivlfn.arch import CFGS  # noqa: E402
 from pivlfn.model import Engine  # noqa: E402
-from pivlfn.tiled import DistGroup, TiledPlan  # noqa: E402
+from pivlfn.tiled import DistGroup, make_tiled_plan  # noqa: E402
 
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 H = int(args[0]) if len(args) > 0 else 4096
@@ -39,7 +39,7 @@ reps = ((H + 511) // 512, (W + 511) // 512)
 a = synth.to_rgb_tensor(np.tile(i1, reps)[:H, :W])[None]
 b = synth.to_rgb_tensor(np.tile(i2, reps)[:H, :W])[None]
 
-plan = TiledPlan(eng, H, W, rank, world, halo=24, warp_reach=16)
+plan = make_tiled_plan(eng, H, W, rank, world, halo=24, warp_reach=16)
 group = DistGroup(plan)
 plan.load_inputs(a, b)
 group.run()                      # warm-up
