@@ -120,7 +120,10 @@ warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restr
 }
 
 // ---- depthwise ConvTranspose 4x4 s2 (upCorr_M, src/models.py:151-152): fp32 NHWC in -> P16 out ---------------------------
-// one thread = one INPUT pixel position x 8 channels -> the 2x2 output block (see deconv4x4s2_dw_block_kernel in misc.cu)
+// one thread = one INPUT pixel position x 4 channels -> the 2x2 output block (see deconv4x4s2_dw_block_kernel in misc.cu): the
+// 3x3 input neighbourhood is read once (9 float4), the 16 taps of the 4 channels come from shared memory, and every output
+// is written as 8 bytes of hi + 8 bytes of lo' -- four consecutive lanes complete a 32-byte sector of each.  (8 channels per
+// thread kept 18 float4 live, 98 registers, 23 % occupancy: 2.2 TB/s; this shape runs at 2.5x the occupancy.)
 constexpr int DC_MAXC = 64;
 __global__ void __launch_bounds__(256)
 deconv4x4s2_dw_p16_kernel(const float* __restrict__ in, int in_ld, int in_c4, const float* __restrict__ w,
@@ -131,62 +134,56 @@ deconv4x4s2_dw_p16_kernel(const float* __restrict__ in, int in_ld, int in_c4, co
         w_s[i] = c < C ? __ldg(w + c * 16 + tap) : 0.f;
     }
     __syncthreads();
-    const int U = ((C + 15) >> 4) * 2;
+    const int Q = ((C + 15) >> 4) * 4;                      // channel quads of the P16 output (whole 16-channel groups)
     const int Wo = 2 * W;
-    const long long total = (long long)N * H * W * U;
+    const long long total = (long long)N * H * W * Q;
     uint32_t bad = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int u = (int)(i % U);
-        const long long p = i / U;
+        const int q = (int)(i % Q);
+        const long long p = i / Q;
         const int ix = (int)(p % W);
         const long long t = p / W;
         const int iy = (int)(t % H);
         const long long n = t / H;
-        const int c = u * 8;
+        const int c = q * 4;
         const float* base = in + (n * H * W) * in_ld + c;
-        const bool has0 = c + 4 <= in_c4, has1 = c + 8 <= in_c4;      // float4 halves that exist in the input rows
-        float4 v0[3][3], v1[3][3];
+        const bool has = c + 4 <= in_c4;                    // this quad exists in the input rows (else: zero pad of the last group)
+        float4 v[3][3];
 #pragma unroll
         for (int a = 0; a < 3; ++a)
 #pragma unroll
             for (int b = 0; b < 3; ++b) {
                 const int yy = iy + a - 1, xx = ix + b - 1;
-                const bool ok = yy >= 0 && yy < H && xx >= 0 && xx < W;
-                const float* s = base + ((long long)yy * W + xx) * in_ld;
-                v0[a][b] = (ok && has0) ? __ldg(reinterpret_cast<const float4*>(s)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                v1[a][b] = (ok && has1) ? __ldg(reinterpret_cast<const float4*>(s + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                v[a][b] = (has && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                              ? __ldg(reinterpret_cast<const float4*>(base + ((long long)yy * W + xx) * in_ld))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 2; ++dx) {
-                float acc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
                     for (int b = 0; b < 2; ++b) {
                         const int ky = dy ? (a ? 0 : 2) : (a ? 1 : 3), kx = dx ? (b ? 0 : 2) : (b ? 1 : 3);
-                        const float4 q0 = v0[dy + a][dx + b], q1 = v1[dy + a][dx + b];
-                        const float4 w0 = *reinterpret_cast<const float4*>(&w_s[(ky * 4 + kx) * DC_MAXC + c]);
-                        const float4 w1 = *reinterpret_cast<const float4*>(&w_s[(ky * 4 + kx) * DC_MAXC + c + 4]);
-                        acc[0] = fmaf(q0.x, w0.x, acc[0]); acc[1] = fmaf(q0.y, w0.y, acc[1]);
-                        acc[2] = fmaf(q0.z, w0.z, acc[2]); acc[3] = fmaf(q0.w, w0.w, acc[3]);
-                        acc[4] = fmaf(q1.x, w1.x, acc[4]); acc[5] = fmaf(q1.y, w1.y, acc[5]);
-                        acc[6] = fmaf(q1.z, w1.z, acc[6]); acc[7] = fmaf(q1.w, w1.w, acc[7]);
+                        const float4 x4 = v[dy + a][dx + b];
+                        const float4 ww = *reinterpret_cast<const float4*>(&w_s[(ky * 4 + kx) * DC_MAXC + c]);
+                        acc.x = fmaf(x4.x, ww.x, acc.x); acc.y = fmaf(x4.y, ww.y, acc.y);
+                        acc.z = fmaf(x4.z, ww.z, acc.z); acc.w = fmaf(x4.w, ww.w, acc.w);
                     }
-                // (pad channels: zero weights -> exact zeros whatever the input pads hold, unless they are non-finite)
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (c + j >= C) acc[j] = 0.f;
-                uint4 h, l;
-                p16::encode8(acc, h, l);
-                bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
+                // pad channels: zero weights -> exact zeros whatever the input pads hold (unless they are non-finite)
+                if (c + 1 >= C) acc.y = 0.f;
+                if (c + 2 >= C) acc.z = 0.f;
+                if (c + 3 >= C) acc.w = 0.f;
+                if (c >= C) acc.x = 0.f;
+                const uint32_t h0 = p16::pack_hi(acc.x, acc.y), h1 = p16::pack_hi(acc.z, acc.w);
+                bad |= p16::nonfinite_bits(h0) | p16::nonfinite_bits(h1);
                 const long long op = (n * 2 * H + 2 * iy + dy) * Wo + 2 * ix + dx;
-                uint8_t* o = out + op * (long long)out_ld * 4 + p16::unit_off_bytes(u);
-                stg_u4(o, h);
-                stg_u4(o + 32, l);
+                uint8_t* o = out + op * (long long)out_ld * 4 + (c >> 4) * 64 + (c & 15) * 2;
+                *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
+                *reinterpret_cast<uint2*>(o + 32) = make_uint2(p16::pack_lo(acc.x, acc.y, h0), p16::pack_lo(acc.z, acc.w, h1));
             }
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;
@@ -316,7 +313,7 @@ extern "C" int pivlfn_deconv4x4s2_dw_p16(const float* in, int in_ld, const float
     const int c4 = (C + 3) & ~3;
     if (((uintptr_t)in & 15) || (in_ld & 3) || in_ld < c4) return PIVLFN_EINVAL;
     if (((uintptr_t)out & 63) || (out_ld & 15) || out_ld < ((C + 15) & ~15)) return PIVLFN_EINVAL;
-    const long long total = (long long)N * H * W * (((C + 15) >> 4) * 2);
+    const long long total = (long long)N * H * W * (((C + 15) >> 4) * 4);
     deconv4x4s2_dw_p16_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
         in, in_ld, in_ld & ~3, w, reinterpret_cast<uint8_t*>(out), out_ld, N, H, W, C, range_flag);
     PIVLFN_LAUNCHED();
