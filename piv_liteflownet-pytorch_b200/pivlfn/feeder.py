@@ -1,0 +1,87 @@
+"""Keep the GPU busy between host batches: uploads of batch k+1 and the download of batch k-1's flow run on two side streams
+while batch k's forward runs on the caller's stream (three-stage software pipeline over double-buffered device inputs and
+pinned host outputs).  Used by ``run.py`` and by the end-to-end leg of ``bench.py``; every step still pays its own
+host-to-device copy of both images and its device-to-host copy of the flow -- they just overlap the neighbours' compute.
+
+    feeder = Feeder(net, device)
+    for a_host, b_host in batches:            # pinned host tensors, [B,3,H,W] float32 (or uint8 [B,H,W,3] with unpack=...)
+        feeder.push(a_host, b_host, tag)      # returns finished (tag, flow_host, event) items, oldest first
+    feeder.drain()
+"""
+from __future__ import annotations
+
+from collections import deque
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+
+class Feeder:
+    def __init__(self, net, device, unpack: Optional[Callable[[torch.Tensor], torch.Tensor]] = None, depth: int = 2,
+                 to_host: Optional[Callable[[torch.Tensor], torch.Tensor]] = None):
+        self.net, self.device, self.unpack, self.depth = net, torch.device(device), unpack, max(2, depth)
+        self.to_host = to_host                       # device flow -> device tensor laid out like the host buffer (default: as is)
+        self.up = torch.cuda.Stream(self.device)
+        self.down = torch.cuda.Stream(self.device)
+        self._dev: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None] * self.depth
+        self._free = [None] * self.depth             # event: the slot's device inputs may be overwritten
+        self._inflight: deque = deque()
+        self._k = 0
+
+    def _slot_tensors(self, s: int, a_host: torch.Tensor, b_host: torch.Tensor):
+        cur = self._dev[s]
+        if cur is None or cur[0].shape != a_host.shape or cur[0].dtype != a_host.dtype:
+            self._dev[s] = (torch.empty(a_host.shape, dtype=a_host.dtype, device=self.device),
+                            torch.empty(b_host.shape, dtype=b_host.dtype, device=self.device))
+        return self._dev[s]
+
+    def push(self, a_host: torch.Tensor, b_host: torch.Tensor, tag=None):
+        """Enqueue one batch; returns the (tag, flow_host, event) items that are older than ``depth`` batches -- wait for ``event``
+        before reading ``flow_host`` (a pinned tensor that now belongs to the caller)."""
+        s = self._k % self.depth
+        cur = torch.cuda.current_stream(self.device)
+        da, db = self._slot_tensors(s, a_host, b_host)
+        with torch.cuda.stream(self.up):
+            if self._free[s] is not None:
+                self.up.wait_event(self._free[s])     # the forward that read (and mean-subtracted) this slot has finished
+            da.copy_(a_host, non_blocking=True)
+            db.copy_(b_host, non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self.up)
+        cur.wait_event(uploaded)
+        with torch.no_grad():
+            x1, x2 = (self.unpack(da), self.unpack(db)) if self.unpack is not None else (da, db)
+            flow = self.net(x1, x2)
+            if self.to_host is not None:
+                flow = self.to_host(flow)
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._free[s] = done
+        # a fresh pinned tensor per batch (torch's caching host allocator recycles the blocks): whoever receives it -- e.g. a
+        # writer thread -- may keep it as long as it likes
+        host = torch.empty(flow.shape, dtype=flow.dtype, pin_memory=True)
+        with torch.cuda.stream(self.down):
+            self.down.wait_event(done)
+            host.copy_(flow, non_blocking=True)
+            flow.record_stream(self.down)
+            landed = torch.cuda.Event()
+            landed.record(self.down)
+        self._inflight.append((tag, host, landed))
+        self._k += 1
+        out = []
+        while len(self._inflight) >= self.depth:       # its host buffer is the next one to be reused: hand it out now
+            out.append(self._inflight.popleft())
+        return out
+
+    def drain(self):
+        out = list(self._inflight)
+        self._inflight.clear()
+        return out
+
+    def join(self):
+        """Make the caller's stream wait for everything enqueued on the side streams."""
+        cur = torch.cuda.current_stream(self.device)
+        for st in (self.up, self.down):
+            ev = torch.cuda.Event()
+            ev.record(st)
+            cur.wait_event(ev)

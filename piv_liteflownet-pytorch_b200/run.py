@@ -19,6 +19,7 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import torch  # noqa: E402
 from inference import estimate  # noqa: E402
 from pivlfn import io as pio  # noqa: E402
+from pivlfn.feeder import Feeder  # noqa: E402
 from pivlfn import shard  # noqa: E402
 from src.models import hui_liteflownet, piv_liteflownet  # noqa: E402
 
@@ -53,24 +54,34 @@ def _run_pairs(net, pairs, lo: int, hi: int, writer: pio.FloWriter, device, batc
                brightness: float = 1.0, contrast: float = 1.0) -> int:
     """pairs[lo:hi] through the network in batches; flows go to ``writer`` under ``stems[i]`` (default: the pair's stem)."""
     reader = pio.BatchReader(pairs, lo, hi, batch, brightness=brightness, contrast=contrast)
+    # uint8 frames are uploaded on a side stream while the previous batch runs, unpacked to [B,3,H,W] fp32 on the device, the
+    # flows come back as [B,H,W,2] (the .flo layout) on a third stream into pinned buffers that the writer threads own
+    feeder = Feeder(lambda x1, x2: estimate(net, x1, x2, tensor=True), device, unpack=pio.unpack_u8,
+                    to_host=lambda f: f.permute(0, 2, 3, 1).contiguous())
     done = lo
+    pending = []                                   # (batch, first index) whose staging buffers are still being uploaded
+
+    def hand_over(items):
+        for (names, _b), host, landed in items:
+            writer.submit(host, names, landed)
+
     try:
         for b in reader:
             n = len(b.stems)
-            a8 = b.first.to(device, non_blocking=True)
-            b8 = b.second.to(device, non_blocking=True)
-            x1, x2 = pio.unpack_u8(a8), pio.unpack_u8(b8)
-            copied = torch.cuda.Event()
-            copied.record()
-            flow = estimate(net, x1, x2, tensor=True)                                    # [n, 2, H, W]
-            host = torch.empty(n, flow.shape[2], flow.shape[3], 2, dtype=torch.float32).pin_memory()
-            host.copy_(flow.permute(0, 2, 3, 1), non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record()
-            writer.submit(host, b.stems if stems is None else [stems[k] for k in range(done, done + n)], ev)
-            copied.synchronize()                    # the staging buffers may be refilled once their upload has finished
-            reader.release(b)
+            names = b.stems if stems is None else [stems[k] for k in range(done, done + n)]
+            hand_over(feeder.push(b.first, b.second, (names, b)))
+            uploaded = torch.cuda.Event()
+            uploaded.record(feeder.up)
+            pending.append((b, uploaded))
+            while pending and (len(pending) > 2 or pending[0][1].query()):
+                pb, ev = pending.pop(0)
+                ev.synchronize()                    # the staging buffers may be refilled once their upload has finished
+                reader.release(pb)
             done += n
+        hand_over(feeder.drain())
+        for pb, ev in pending:
+            ev.synchronize()
+            reader.release(pb)
     finally:
         reader.close()
     return done - lo
