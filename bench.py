@@ -469,10 +469,10 @@ def main():
 
     def run_e2e(n):
         for _ in range(n):
-            for _tag, _host, landed in feeder.push(a_pin, b_pin):
-                pass
-        for _tag, _host, landed in feeder.drain():
-            pass
+            for _tag, host, landed in feeder.push(a_pin, b_pin):
+                feeder.recycle(host)            # (reused two pushes later at the earliest, after its copy has landed)
+        for _tag, host, landed in feeder.drain():
+            feeder.recycle(host)
         feeder.join()
 
     run_e2e(2)

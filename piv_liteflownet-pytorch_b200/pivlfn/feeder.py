@@ -5,11 +5,13 @@ host-to-device copy of both images and its device-to-host copy of the flow -- th
 
     feeder = Feeder(net, device)
     for a_host, b_host in batches:            # pinned host tensors, [B,3,H,W] float32 (or uint8 [B,H,W,3] with unpack=...)
-        feeder.push(a_host, b_host, tag)      # returns finished (tag, flow_host, event) items, oldest first
-    feeder.drain()
+        for tag, flow_host, event in feeder.push(a_host, b_host, tag):     # items older than `depth` batches, oldest first
+            event.synchronize(); consume(flow_host); feeder.recycle(flow_host)
+    ... same for feeder.drain()
 """
 from __future__ import annotations
 
+import threading
 from collections import deque
 from typing import Callable, List, Optional, Tuple
 
@@ -27,6 +29,8 @@ class Feeder:
         self._free = [None] * self.depth             # event: the slot's device inputs may be overwritten
         self._inflight: deque = deque()
         self._k = 0
+        self._pool: List[torch.Tensor] = []
+        self._lock = threading.Lock()
 
     def _slot_tensors(self, s: int, a_host: torch.Tensor, b_host: torch.Tensor):
         cur = self._dev[s]
@@ -57,9 +61,7 @@ class Feeder:
         done = torch.cuda.Event()
         done.record(cur)
         self._free[s] = done
-        # a fresh pinned tensor per batch (torch's caching host allocator recycles the blocks): whoever receives it -- e.g. a
-        # writer thread -- may keep it as long as it likes
-        host = torch.empty(flow.shape, dtype=flow.dtype, pin_memory=True)
+        host = self._take_host(flow)
         with torch.cuda.stream(self.down):
             self.down.wait_event(done)
             host.copy_(flow, non_blocking=True)
@@ -72,6 +74,21 @@ class Feeder:
         while len(self._inflight) >= self.depth:       # its host buffer is the next one to be reused: hand it out now
             out.append(self._inflight.popleft())
         return out
+
+    def _take_host(self, like: torch.Tensor) -> torch.Tensor:
+        """A pinned host tensor for one batch's flow: from the pool of recycled ones if the shape fits, else newly pinned
+        (cudaHostAlloc of tens of MB blocks for milliseconds, so steady state must not allocate)."""
+        with self._lock:
+            for i, t in enumerate(self._pool):
+                if t.shape == like.shape and t.dtype == like.dtype:
+                    return self._pool.pop(i)
+        return torch.empty(like.shape, dtype=like.dtype, pin_memory=True)
+
+    def recycle(self, host: torch.Tensor) -> None:
+        """Hand a flow buffer received from push() / drain() back once it has been consumed (thread-safe)."""
+        with self._lock:
+            if len(self._pool) < 8:
+                self._pool.append(host)
 
     def drain(self):
         out = list(self._inflight)

@@ -249,7 +249,7 @@ class FloWriter:
     def path_for(self, stem: str) -> str:
         return os.path.join(self.folder, stem + self.suffix)
 
-    def _write(self, host: torch.Tensor, stems: List[str], event) -> None:
+    def _write(self, host: torch.Tensor, stems: List[str], event, done) -> None:
         if event is not None:
             event.synchronize()
         arr = host.numpy()
@@ -258,9 +258,11 @@ class FloWriter:
             write_flo(path, arr[k])
             with self._lock:
                 self.written.append(path)
+        if done is not None:
+            done(host)                   # e.g. Feeder.recycle: the pinned buffer may be reused
 
-    def submit(self, host: torch.Tensor, stems: List[str], event=None) -> None:
-        self._pending.append(self._pool.submit(self._write, host, list(stems), event))
+    def submit(self, host: torch.Tensor, stems: List[str], event=None, done=None) -> None:
+        self._pending.append(self._pool.submit(self._write, host, list(stems), event, done))
 
     def drain(self) -> List[str]:
         for f in self._pending:

@@ -63,7 +63,7 @@ def _run_pairs(net, pairs, lo: int, hi: int, writer: pio.FloWriter, device, batc
 
     def hand_over(items):
         for (names, _b), host, landed in items:
-            writer.submit(host, names, landed)
+            writer.submit(host, names, landed, feeder.recycle)
 
     try:
         for b in reader:
