@@ -33,10 +33,17 @@ class Feeder:
         self._lock = threading.Lock()
 
     def _slot_tensors(self, s: int, a_host: torch.Tensor, b_host: torch.Tensor):
-        cur = self._dev[s]
-        if cur is None or cur[0].shape != a_host.shape or cur[0].dtype != a_host.dtype:
+        slot = self._dev[s]
+        if slot is None or slot[0].shape != a_host.shape or slot[0].dtype != a_host.dtype:
+            # The caching allocator hands out memory that is free in the order of the CURRENT stream; the upload stream must not
+            # touch it before everything already queued there (which may still use a recycled block) has finished, and the
+            # allocator must know that the upload stream uses these tensors too.
+            cur = torch.cuda.current_stream(self.device)
             self._dev[s] = (torch.empty(a_host.shape, dtype=a_host.dtype, device=self.device),
                             torch.empty(b_host.shape, dtype=b_host.dtype, device=self.device))
+            self.up.wait_stream(cur)
+            for t in self._dev[s]:
+                t.record_stream(self.up)
         return self._dev[s]
 
     def push(self, a_host: torch.Tensor, b_host: torch.Tensor, tag=None):
