@@ -223,6 +223,16 @@ int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W, int Cin, 
                          const void* wsrc, int wsrc_ld, int wsrc_p16, const float* wflow, float wscale,
                          int wc0, int wn, int* range_flag, void* stream);
 
+/* pivlfn_conv_p16 (mode 4, stride 1, no activation) whose K*K output channels are the Regularization distances, with the rest of the
+ * Regularization block FUSED INTO ITS EPILOGUE (src/models.py:279-300 (PIV) / :620-641 (Hui); replaces conv_dist + pivlfn_reg_tail): per pixel
+ * softmax_k(-d_k^2) over the K*K channels read straight from the accumulators, the weighted K x K unfold of flow_in, the 1x1
+ * moduleScaleX / moduleScaleY convolutions (wx, bx, wy, by: device pointers to K*K weights / 1 bias each) and the division.
+ * flow_in, flow_out: dense [N,H,W,2] (distinct buffers); out_nchw: optional [N,2,H,W] copy times final_scale (the network
+ * output), or NULL.  K = 3, 5, 7; Cout = K*K is implied.  Bit-identical to pivlfn_conv_p16(out_fmt 1) + pivlfn_reg_tail. */
+int pivlfn_conv_p16_tail(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, const float* bias,
+                         int KH, int KW, int K, const float* flow_in, const float* wx, const float* bx, const float* wy,
+                         const float* by, float* flow_out, float* out_nchw, float final_scale, void* stream);
+
 /* NetC.conv1 (see pivlfn_conv_stem_tc) with the fp16-split arithmetic and a P16 output; w_img: stage image of the
  * passes-4 pack of the [32, 7, 32] stem weights.  W % 4 == 0, W >= 8. */
 int pivlfn_conv_stem_p16(const float* img_pad, int N, int H, int W, const void* w_img, const float* bias,

@@ -34,7 +34,20 @@ constexpr int P16_THREADS = 640;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
 constexpr int SMEM_BUDGET = 226 * 1024;  // 227 KB opt-in minus the static part (padded to 1 KB by the 1024-byte alignment)
 
-enum { OUT_P16 = 0, OUT_F32 = 1, OUT_PLANES = 2 };
+enum { OUT_P16 = 0, OUT_F32 = 1, OUT_PLANES = 2, OUT_TAIL = 3 };
+
+// OUT_TAIL: the K*K output channels are the Regularization distances (src/models.py:279-300); the epilogue turns them into the
+// regularised flow while they are still in TMEM (negative square, softmax over the K*K neighbours, weighted unfold of the flow,
+// the two 1x1 ScaleX / ScaleY convolutions and the division) -- the distance tensor never exists in HBM.
+struct TailArgs {
+    const float2* flow;      // dense [N,H,W,2] flow that is unfolded (the Subpixel output)
+    const float *wx, *wy;    // moduleScaleX / moduleScaleY weights [K*K]
+    const float *bx, *by;    // their biases [1]
+    float2* out;             // dense [N,H,W,2] regularised flow
+    float* nchw;             // optional [N,2,H,W] copy scaled by `scale` (the network output), or NULL
+    float scale;
+    int K;
+};
 
 struct ConvP16Args {
     const float* bias;
@@ -66,7 +79,76 @@ struct ConvP16Args {
     int wsrc_ld, wsrc_p16, wc0, wnc;
     int one_issuer;          // a single thread issues the MMAs of both stacked tiles (required by collect)
     int collect;             // MODE 5: a_hi * W_hi keeps the A window in the collector buffer, a_hi * W_lo re-uses it from there
+    TailArgs tl;             // OUT_TAIL only
 };
+
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// OUT_TAIL epilogue of one output pixel (same arithmetic, in the same order, as reg_tail_pixel in misc.cu, so the fused and the
+// two-kernel forms give identical bits): pass 1 finds min_k d_k^2 over the K*K accumulator columns, pass 2 re-reads them from
+// TMEM (cheaper than 49 live registers next to the 32 staging ones) and accumulates the softmax-weighted neighbour flows.
+// tcol = TMEM address of this thread's accumulator row ([main CoutP | corr CoutP] columns).
+__device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, const float* bias_s, int n, int x, int y) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int K = a.tl.K, KK = K * K, P = K >> 1;
+    const int ncg = a.CoutP >> 4;
+    uint32_t v[16], u[16];
+    float mn = INFINITY;
+    for (int cg = 0; cg < ncg; ++cg) {
+        tmem_ld16_nowait(tcol + (uint32_t)(cg * 16), v);
+        tmem_ld16_nowait(tcol + (uint32_t)(a.CoutP + cg * 16), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float d = fmaf(__uint_as_float(u[j]), p16::LO_INV, __uint_as_float(v[j])) + bias_s[cg * 16 + j];
+            if (cg * 16 + j < KK) mn = fminf(mn, d * d);
+        }
+    }
+    unsigned cm = 0, rm = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+        cm |= (unsigned)(j < K && x + j - P >= 0 && x + j - P < a.W) << j;
+        rm |= (unsigned)(j < K && y + j - P >= 0 && y + j - P < a.H) << j;
+    }
+    const float2* ptr = a.tl.flow + ((long long)n * a.H + (y - P)) * a.W + (x - P);
+    int kx = 0;
+    unsigned m = (rm & 1u) ? cm : 0u;
+    float sum = 0.f, au = 0.f, av = 0.f;
+    for (int cg = 0; cg < ncg; ++cg) {
+        tmem_ld16_nowait(tcol + (uint32_t)(cg * 16), v);
+        tmem_ld16_nowait(tcol + (uint32_t)(a.CoutP + cg * 16), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int k = cg * 16 + j;
+            if (k < KK) {
+                const float d = fmaf(__uint_as_float(u[j]), p16::LO_INV, __uint_as_float(v[j])) + bias_s[k];
+                const float e = ex2_ftz((mn - d * d) * LOG2E);
+                sum += e;
+                float2 f = make_float2(0.f, 0.f);
+                if ((m >> kx) & 1u) f = __ldg(ptr);
+                au = fmaf(__ldg(a.tl.wx + k), e * f.x, au);
+                av = fmaf(__ldg(a.tl.wy + k), e * f.y, av);
+                ++ptr;
+                if (++kx == K) { kx = 0; rm >>= 1; m = (rm & 1u) ? cm : 0u; ptr += a.W - K; }
+            }
+        }
+    }
+    if (x < a.W && y < a.H) {
+        const float r = 1.f / sum;
+        const float fu = (au + __ldg(a.tl.bx)) * r, fv = (av + __ldg(a.tl.by)) * r;
+        const long long HW = (long long)a.H * a.W, q = (long long)y * a.W + x;
+        a.tl.out[n * HW + q] = make_float2(fu, fv);
+        if (a.tl.nchw) {
+            a.tl.nchw[(n * 2LL + 0) * HW + q] = fu * a.tl.scale;
+            a.tl.nchw[(n * 2LL + 1) * HW + q] = fv * a.tl.scale;
+        }
+    }
+}
 
 __device__ __forceinline__ bool s2_tap_used(int t, int par) {
     return ((t >> 1) >= 1 - (par >> 1)) && ((t & 1) >= 1 - (par & 1));
@@ -398,6 +480,16 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             mbar_wait(&acc_full[as], use & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
+            if (a.out_fmt == OUT_TAIL) {
+                if constexpr (DUAL) {
+                    for (int i = eg; i < a.NT; i += negr)
+                        tail_pixel(a, trow + (uint32_t)(i * tile_cols), bias_s, n, x, (ty * a.NT + i) * HT_H + (row >> 3));
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[as]);
+                continue;
+            }
             uint32_t v[16], u[16];
             auto issue = [&](int unit) {
                 const int i = unit / ncg, cg = unit - i * ncg;
@@ -566,11 +658,11 @@ struct WarpSrc { const void* src; int ld, p16; const float* flow; float scale; i
 
 int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
                   const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
-                  int out_fmt, long long plane_stride, int* range_flag, const WarpSrc* ws, void* stream) {
-    if (!x || !w_img || !y || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
+                  int out_fmt, long long plane_stride, int* range_flag, const WarpSrc* ws, const TailArgs* tail, void* stream) {
+    if (!x || !w_img || (!y && out_fmt != OUT_TAIL) || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
     if (mode != 4 && mode != 5) return PIVLFN_EINVAL;
     if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
-    if (out_fmt < OUT_P16 || out_fmt > OUT_PLANES) return PIVLFN_EINVAL;
+    if (out_fmt < OUT_P16 || out_fmt > OUT_TAIL || (out_fmt == OUT_TAIL) != (tail != nullptr)) return PIVLFN_EINVAL;
     const int CoutP = (Cout + 15) & ~15;
     if (CoutP > 128 || (mode == 4 && CoutP > 64)) return PIVLFN_EUNSUPPORTED;
     ConvP16Args h;
@@ -613,10 +705,16 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
         if (((uintptr_t)y & 3) || y_ld < Cout) return PIVLFN_EINVAL;
         h.cout_st = (y_ld == ((Cout + 3) & ~3)) ? y_ld : Cout;
         h.quad = !(h.W & 3) && !((uintptr_t)y & 15) && !(y_ld & 3);
-    } else {
+    } else if (out_fmt == OUT_PLANES) {
         if (((uintptr_t)y & 7) || plane_stride < 2LL * N * h.H * h.W) return PIVLFN_EINVAL;
         h.planar = plane_stride;
+    } else {
+        if (mode != 4 || stride != 1 || ws) return PIVLFN_EUNSUPPORTED;
+        if (tail->K != 3 && tail->K != 5 && tail->K != 7) return PIVLFN_EUNSUPPORTED;
+        if (Cout != tail->K * tail->K || !tail->flow || !tail->wx || !tail->wy || !tail->bx || !tail->by || !tail->out) return PIVLFN_EINVAL;
+        if (((uintptr_t)tail->flow & 7) || ((uintptr_t)tail->out & 7) || tail->flow == tail->out) return PIVLFN_EINVAL;
     }
+    h.tl = tail ? *tail : TailArgs{};
     EncodeTiledFn enc = get_encode();
     if (!enc) return PIVLFN_EDRIVER;
     const int smem = configure(h, mode);
@@ -659,7 +757,7 @@ extern "C" int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int
                                const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                                int out_fmt, long long plane_stride, int* range_flag, void* stream) {
     return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, mode, bias, y, y_ld, Cout, KH, KW, stride, lrelu, out_fmt, plane_stride,
-                         range_flag, nullptr, stream);
+                         range_flag, nullptr, nullptr, stream);
 }
 
 /* see include/pivlfn.h */
@@ -668,5 +766,13 @@ extern "C" int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W
                                     const void* wsrc, int wsrc_ld, int wsrc_p16, const float* wflow, float wscale,
                                     int wc0, int wn, int* range_flag, void* stream) {
     WarpSrc ws{wsrc, wsrc_ld, wsrc_p16, wflow, wscale, wc0, wn};
-    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, mode, bias, y, y_ld, Cout, KH, KW, 1, lrelu, OUT_P16, 0, range_flag, &ws, stream);
+    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, mode, bias, y, y_ld, Cout, KH, KW, 1, lrelu, OUT_P16, 0, range_flag, &ws, nullptr, stream);
+}
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_conv_p16_tail(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, const float* bias,
+                                    int KH, int KW, int K, const float* flow_in, const float* wx, const float* bx, const float* wy,
+                                    const float* by, float* flow_out, float* out_nchw, float final_scale, void* stream) {
+    TailArgs t{reinterpret_cast<const float2*>(flow_in), wx, wy, bx, by, reinterpret_cast<float2*>(flow_out), out_nchw, final_scale, K};
+    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, 4, bias, nullptr, 0, K * K, KH, KW, 1, 0, OUT_TAIL, 0, nullptr, nullptr, &t, stream);
 }

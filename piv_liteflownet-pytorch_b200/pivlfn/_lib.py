@@ -38,6 +38,7 @@ PROTOTYPES = {
     "pivlfn_p16_encode": (_i, [_p, _i, _i, _p, _i, _ll, _p, _p]),
     "pivlfn_p16_decode": (_i, [_p, _i, _i, _p, _i, _ll, _p]),
     "pivlfn_conv_p16": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _ll, _p, _p]),
+    "pivlfn_conv_p16_tail": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _f, _p]),
     "pivlfn_conv_p16_warp": (_i, [_p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _i, _i, _p, _f, _i, _i, _p, _p]),
     "pivlfn_conv_stem_p16": (_i, [_p, _i, _i, _i, _p, _p, _p, _i, _i, _p, _p]),
     "pivlfn_corr_p16": (_i, [_p, _i, _i, _p, _i, _i, _p, _f, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),

@@ -266,6 +266,15 @@ def conv_p16_warp(x: View, N, H, W, cin, w_img, mode, bias, y: View, cout, KH, K
                "conv_p16_warp")
 
 
+def conv_p16_tail(x: View, N, H, W, cin, w_img, bias, KH, KW, K, flow_in, wx, bx, wy, by, flow_out, out_nchw, final_scale):
+    """conv_dist (mode 4, cout = K*K, no activation) + the Regularization tail (see reg_tail) in one launch."""
+    _lib.check(_lib.load().pivlfn_conv_p16_tail(x.ptr, x.ld, N, H, W, int(cin), w_img.data_ptr(),
+                                                bias.data_ptr() if bias is not None else None, int(KH), int(KW), int(K),
+                                                flow_in.data_ptr(), wx.data_ptr(), bx.data_ptr(), wy.data_ptr(), by.data_ptr(),
+                                                flow_out.data_ptr(), out_nchw.data_ptr() if out_nchw is not None else None,
+                                                float(final_scale), _stream()), "conv_p16_tail")
+
+
 def conv_stem_p16(img_pad: torch.Tensor, N, H, W, w_img, bias, y: View, lrelu=True, flag: Optional[torch.Tensor] = None):
     _lib.check(_lib.load().pivlfn_conv_stem_p16(img_pad.data_ptr(), N, H, W, w_img.data_ptr(),
                                                 bias.data_ptr() if bias is not None else None, y.ptr, y.ld, int(lrelu),

@@ -52,6 +52,7 @@ class Plan16(Plan):
         Z = lambda *shape: torch.zeros(shape, device=dev, dtype=torch.float32)
         self.hw = {l: (H >> (l - 1), W >> (l - 1)) for l in range(1, 7)}
         self.fuse_warp = os.environ.get("PIVLFN_FUSE_WARP", "1") != "0"
+        self.fuse_tail = os.environ.get("PIVLFN_FUSE_TAIL", "1") != "0"
         N2 = 2 * B
         self.in1, self.in2 = E(B, 3, H, W), E(B, 3, H, W)
         self.img = {1: E(N2, H, W, 4)}
@@ -231,14 +232,20 @@ class Plan16(Plan):
                 self._conv(f"NetE_R.{i}.conv_R.{j}", x, B, h, w, y)
                 x = y
             dc = DIST_CH[l]
-            if l < 5:
-                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist0"]), lrelu=False)
-                self._conv(f"NetE_R.{i}.conv_dist_R.1", view(d["dist0"]), B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
-            else:
-                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
             p = f"NetE_R.{i}"
             last = (l == cfg.lowest_level)
-            ops.reg_tail(view(d["dist"], 0, dc), d["flowS"], eng.raw[p + ".moduleScaleX.weight"],
-                         eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
-                         eng.raw[p + ".moduleScaleY.bias"], d["flowR"], self.out if last else None, eng.sf[1], KSIZE[l])
+            tail = (d["flowS"], eng.raw[p + ".moduleScaleX.weight"], eng.raw[p + ".moduleScaleX.bias"], eng.raw[p + ".moduleScaleY.weight"],
+                    eng.raw[p + ".moduleScaleY.bias"], d["flowR"], self.out if last else None, eng.sf[1])
+            if l < 5:
+                self._conv(f"NetE_R.{i}.conv_dist_R.0", x, B, h, w, view(d["dist0"]), lrelu=False)
+                dkey, dx = f"NetE_R.{i}.conv_dist_R.1", view(d["dist0"])
+            else:
+                dkey, dx = f"NetE_R.{i}.conv_dist_R.0", x
+            cw = eng.w[dkey]
+            if self.fuse_tail and cw.w_f16s is None:
+                # the distances never leave TMEM: softmax(-d^2), unfold, ScaleX / ScaleY and the division run in the conv's epilogue
+                ops.conv_p16_tail(dx, B, h, w, cw.cin, cw.w_f16, cw.bias, cw.kh, cw.kw, KSIZE[l], *tail)
+            else:
+                self._conv(dkey, dx, B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
+                ops.reg_tail(view(d["dist"], 0, dc), *tail, KSIZE[l])
             xflow = d["flowR"]

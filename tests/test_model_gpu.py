@@ -194,3 +194,23 @@ def test_f16c_range_flag_falls_back_to_tf32c():
         net3 = _net("piv", sd3, "f16c")
         assert net3.engine().precision == "tf32c"
     assert any("fp16 range" in str(w.message) for w in wlist)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_model_on_second_device_while_first_is_current():
+    """Per-device state (shared-memory opt-ins, SM count, range flag, current stream): a model on cuda:1 driven while cuda:0 is
+    the current device gives the same flow as on cuda:0, and a second engine on the other device is unaffected."""
+    sd = synth.synthetic_state_dict("piv", 0)
+    a, b, _ = synth.particle_batch(2, 64, 96, 17, "rankine")
+    from src.models import piv_liteflownet
+    torch.cuda.set_device(0)
+    n0 = piv_liteflownet(sd, 1).to("cuda:0").eval()
+    n1 = piv_liteflownet(sd, 1).to("cuda:1").eval()
+    with torch.no_grad():
+        o1 = n1(a.to("cuda:1"), b.to("cuda:1"))          # current device is 0
+        o0 = n0(a.to("cuda:0"), b.to("cuda:0"))
+        o1b = n1(a.to("cuda:1"), b.to("cuda:1"))
+    assert o1.device == torch.device("cuda", 1) and o0.device == torch.device("cuda", 0)
+    assert torch.equal(o1.cpu(), o0.cpu()) and torch.equal(o1b.cpu(), o0.cpu())
+    with pytest.raises(RuntimeError):
+        n1(a.to("cuda:0"), b.to("cuda:0"))

@@ -288,3 +288,41 @@ def test_conv_p16_with_fused_backwarp(cm, H, W, src_p16):
     # (the in-kernel warp rounds its result to P16 exactly like the reference chain above)
     assert err <= 1e-5 + 1.2e-6 * math.sqrt(cin * 9) + 2.0 ** -21 * ref.abs().max().item(), err
     assert int(flag.item()) == 0
+
+
+@pytest.mark.parametrize("K,cin,kh,kw,B,H,W", [(7, 49, 1, 7, 2, 40, 24), (7, 49, 1, 7, 1, 13, 9), (5, 25, 1, 5, 3, 9, 12), (3, 32, 3, 3, 2, 4, 4),
+                                               (7, 49, 1, 7, 5, 64, 64)])
+def test_conv_p16_tail_is_conv_plus_reg_tail(K, cin, kh, kw, B, H, W):
+    """The Regularization tail fused into the conv_dist epilogue (OUT_TAIL) against the two launches it replaces
+    (conv_p16 with fp32 output + reg_tail): same accumulators, same arithmetic in the same order -> identical bits; and against
+    the fp64 restatement of src/models.py:279-300 on the same distances."""
+    KK = K * K
+    x = to_p16(_rand(B, cin, H, W, seed=1))
+    w = _rand(KK, cin, kh, kw, seed=2) / math.sqrt(cin * kh * kw)
+    cw = pack_conv(w, _rand(KK, seed=3), 1).to_(DEV)
+    assert cw.w_f16s is None
+    flow = _rand(B, H, W, 2, seed=4, scale=2.0).to(DEV)
+    wx, wy = _rand(KK, seed=5).to(DEV), _rand(KK, seed=6).to(DEV)
+    bx, by = _rand(1, seed=7).to(DEV), _rand(1, seed=8).to(DEV)
+    dist = torch.zeros(B, H, W, (KK + 3) & ~3, device=DEV)
+    ops.conv_p16(ops.view(x), B, H, W, cin, cw.w_f16, 4, cw.bias, ops.view(dist), KK, kh, kw, 1, False, ops.OUT_F32, 0, None)
+    ref_flow, ref_out = torch.empty_like(flow), torch.empty(B, 2, H, W, device=DEV)
+    ops.reg_tail(ops.view(dist, 0, KK), flow, wx, bx, wy, by, ref_flow, ref_out, 2.5, K)
+    got_flow, got_out = torch.full_like(flow, float("nan")), torch.full((B, 2, H, W), float("nan"), device=DEV)
+    ops.conv_p16_tail(ops.view(x), B, H, W, cin, cw.w_f16, cw.bias, kh, kw, K, flow, wx, bx, wy, by, got_flow, got_out, 2.5)
+    torch.cuda.synchronize()
+    assert torch.equal(got_flow, ref_flow)
+    assert torch.equal(got_out, ref_out)
+    # fp64 restatement on the kernel's own distances
+    d = dist[..., :KK].double().permute(0, 3, 1, 2)
+    neg = -d * d
+    e = (neg - neg.max(1, True)[0]).exp()                   # the bias of ScaleX / ScaleY is divided by the sum as well (:288-300)
+    fl = flow.double().permute(0, 3, 1, 2)
+    un = [F.unfold(fl[:, c:c + 1], K, padding=K // 2).view(B, KK, H, W) for c in range(2)]
+    u = (((e * un[0]) * wx.double().view(1, KK, 1, 1)).sum(1) + bx.double()) / e.sum(1)
+    v = (((e * un[1]) * wy.double().view(1, KK, 1, 1)).sum(1) + by.double()) / e.sum(1)
+    want = torch.stack([u, v], dim=-1)
+    assert (got_flow.double() - want).abs().max().item() < 2e-4 * max(1.0, want.abs().max().item())
+    got_only = torch.empty_like(flow)
+    ops.conv_p16_tail(ops.view(x), B, H, W, cin, cw.w_f16, cw.bias, kh, kw, K, flow, wx, bx, wy, by, got_only, None, 1.0)
+    assert torch.equal(got_only, ref_flow)

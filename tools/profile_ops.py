@@ -67,3 +67,19 @@ y = torch.empty(B, H, H, 128, device=dev)
 timeit(lambda: ops.conv_p16_warp(ops.view(Sbuf), B, H, H, cin, cw.w_f16s, 5, cw.bias, ops.view(y), 128, 3, 3, True, ops.view(f2), False, flow,
                                  5.0, cm, cm, flag),
        "conv_S.0 130->128 3x3 + fused backwarp (TFLOP/s in the rate column / 1000)", 2.0 * B * H * H * cin * 128 * 9, unit="GFLOP/s")
+# conv_dist_R.1 (1x7, 49 -> 49) + Regularization tail: two launches against the fused epilogue
+d0 = torch.zeros(B, H, H, 64, device=dev)
+ops.p16_encode(ops.view(torch.randn(B, H, H, 49, generator=g).to(dev)), ops.view(d0), B * H * H, flag)
+wd = torch.randn(49, 49, 1, 7, generator=g) / math.sqrt(49 * 7)
+cd = pack_conv(wd, torch.randn(49, generator=g), 1).to_(dev)
+dist2 = torch.zeros(B, H, H, 52, device=dev)
+
+
+def two():
+    ops.conv_p16(ops.view(d0), B, H, H, 49, cd.w_f16, 4, cd.bias, ops.view(dist2), 49, 1, 7, 1, False, ops.OUT_F32, 0, None)
+    ops.reg_tail(ops.view(dist2, 0, 49), flow, wx, bx, wy, by, flow_out, None, 5.0, 7)
+
+
+timeit(two, "conv_dist_R.1 + reg_tail (2 launches)", 2.0 * B * H * H * 49 * 49 * 7, unit="GFLOP/s")
+timeit(lambda: ops.conv_p16_tail(ops.view(d0), B, H, H, 49, cd.w_f16, cd.bias, 1, 7, 7, flow, wx, bx, wy, by, flow_out, None, 5.0),
+       "conv_dist_R.1 with the tail in its epilogue", 2.0 * B * H * H * 49 * 49 * 7, unit="GFLOP/s")
