@@ -201,7 +201,7 @@ def kernel_rooflines(eng, pk):
     x, y = ops.view(d["t"][128][0]), ops.view(d["t"][128][1])
     flops = 2.0 * B * h * w * 128 * 128 * 9
     if eng.p16:
-        ms = time_kernel(lambda: ops.conv_p16(x, B, h, w, 128, cw.w_f16s, 5, cw.bias, y, 128, 3, 3, 1, True, ops.OUT_P16, 0,
+        ms = time_kernel(lambda: ops.conv_p16(x, B, h, w, 128, cw.w_f8, 6, cw.bias, y, 128, 3, 3, 1, True, ops.OUT_P16, 0,
                                               eng.flag), 10)
         name = ("conv_p16_kernel<5> (tcgen05 kind::f16 on P16 activations: fp16 (hi, lo') pairs straight from HBM by TMA, "
                 "3 products, one accumulator, 16 epilogue warps)")

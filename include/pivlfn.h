@@ -228,7 +228,7 @@ int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W, int Cin, 
  * softmax_k(-d_k^2) over the K*K channels read straight from the accumulators, the weighted K x K unfold of flow_in, the 1x1
  * moduleScaleX / moduleScaleY convolutions (wx, bx, wy, by: device pointers to K*K weights / 1 bias each) and the division.
  * flow_in, flow_out: dense [N,H,W,2] (distinct buffers); out_nchw: optional [N,2,H,W] copy times final_scale (the network
- * output), or NULL.  K = 3, 5, 7; Cout = K*K is implied.  Bit-identical to pivlfn_conv_p16(out_fmt 1) + pivlfn_reg_tail. */
+ * output), or NULL.  K = 3, 5, 7; Cout = K*K is implied.  Same arithmetic in the same order as pivlfn_conv_p16(out_fmt 1) + pivlfn_reg_tail (agrees to rounding). */
 int pivlfn_conv_p16_tail(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, const float* bias,
                          int KH, int KW, int K, const float* flow_in, const float* wx, const float* bx, const float* wy,
                          const float* by, float* flow_out, float* out_nchw, float final_scale, void* stream);

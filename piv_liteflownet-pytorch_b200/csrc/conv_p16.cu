@@ -32,6 +32,8 @@ constexpr int HT_W = 8, HT_H = 16;       // accumulator tile: 16 rows of 8 pixel
 constexpr int MAX_A = 3, MAX_B = 8;
 constexpr int P16_THREADS = 640;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
+// weights are packed times W_SCALE (pivlfn.model._pack_f8: keeps W_hi 2^-11 and W_lo inside the normal range of e5m2)
+constexpr float W_SCALE_INV = 1.f / 1024.f;
 constexpr int SMEM_BUDGET = 226 * 1024;  // 227 KB opt-in minus the static part (padded to 1 KB by the 1024-byte alignment)
 
 enum { OUT_P16 = 0, OUT_F32 = 1, OUT_PLANES = 2, OUT_TAIL = 3 };
@@ -77,8 +79,7 @@ struct ConvP16Args {
     const float2* wflow;     // dense [N,H,W,2]
     float wscale;
     int wsrc_ld, wsrc_p16, wc0, wnc;
-    int one_issuer;          // a single thread issues the MMAs of both stacked tiles (required by collect)
-    int collect;             // MODE 5: a_hi * W_hi keeps the A window in the collector buffer, a_hi * W_lo re-uses it from there
+    int one_issuer;          // a single thread issues the MMAs of both stacked tiles (experiment switch)
     TailArgs tl;             // OUT_TAIL only
 };
 
@@ -88,53 +89,64 @@ __device__ __forceinline__ float ex2_ftz(float x) {
     return y;
 }
 
-// OUT_TAIL epilogue of one output pixel (same arithmetic, in the same order, as reg_tail_pixel in misc.cu, so the fused and the
-// two-kernel forms give identical bits): pass 1 finds min_k d_k^2 over the K*K accumulator columns, pass 2 re-reads them from
+// OUT_TAIL epilogue of one output pixel (same arithmetic, in the same order, as reg_tail_pixel in misc.cu: the fused and the
+// two-kernel forms agree to rounding): pass 1 finds min_k d_k^2 over the K*K accumulator columns, pass 2 re-reads them from
 // TMEM (cheaper than 49 live registers next to the 32 staging ones) and accumulates the softmax-weighted neighbour flows.
-// tcol = TMEM address of this thread's accumulator row ([main CoutP | corr CoutP] columns).
-__device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, const float* bias_s, int n, int x, int y) {
+// Fully unrolled over the K*K neighbours so that the K*K flow loads are independent of each other.
+// tcol = TMEM address of this thread's accumulator row (CoutP columns, scaled by W_SCALE); sw = [wx 64 | wy 64] in shared memory.
+template <int K>
+__device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, const float* bias_s, const float* sw, int n, int x, int y) {
     constexpr float LOG2E = 1.4426950408889634f;
-    const int K = a.tl.K, KK = K * K, P = K >> 1;
-    const int ncg = a.CoutP >> 4;
-    uint32_t v[16], u[16];
+    constexpr int KK = K * K, P = K / 2, NCG = (KK + 15) / 16;
+    uint32_t v[16];
     float mn = INFINITY;
-    for (int cg = 0; cg < ncg; ++cg) {
+#pragma unroll
+    for (int cg = 0; cg < NCG; ++cg) {
         tmem_ld16_nowait(tcol + (uint32_t)(cg * 16), v);
-        tmem_ld16_nowait(tcol + (uint32_t)(a.CoutP + cg * 16), u);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-            const float d = fmaf(__uint_as_float(u[j]), p16::LO_INV, __uint_as_float(v[j])) + bias_s[cg * 16 + j];
-            if (cg * 16 + j < KK) mn = fminf(mn, d * d);
+            if (cg * 16 + j < KK) {
+                const float d = fmaf(__uint_as_float(v[j]), W_SCALE_INV, bias_s[cg * 16 + j]);
+                mn = fminf(mn, __fmul_rn(d, d));
+            }
         }
     }
     unsigned cm = 0, rm = 0;
 #pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        cm |= (unsigned)(j < K && x + j - P >= 0 && x + j - P < a.W) << j;
-        rm |= (unsigned)(j < K && y + j - P >= 0 && y + j - P < a.H) << j;
+    for (int j = 0; j < K; ++j) {
+        cm |= (unsigned)(x + j - P >= 0 && x + j - P < a.W) << j;
+        rm |= (unsigned)(y + j - P >= 0 && y + j - P < a.H) << j;
     }
-    const float2* ptr = a.tl.flow + ((long long)n * a.H + (y - P)) * a.W + (x - P);
-    int kx = 0;
-    unsigned m = (rm & 1u) ? cm : 0u;
+    const float2* c0 = a.tl.flow + ((long long)n * a.H + (y - P)) * a.W + (x - P);
     float sum = 0.f, au = 0.f, av = 0.f;
-    for (int cg = 0; cg < ncg; ++cg) {
-        tmem_ld16_nowait(tcol + (uint32_t)(cg * 16), v);
-        tmem_ld16_nowait(tcol + (uint32_t)(a.CoutP + cg * 16), u);
-        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-            const int k = cg * 16 + j;
-            if (k < KK) {
-                const float d = fmaf(__uint_as_float(u[j]), p16::LO_INV, __uint_as_float(v[j])) + bias_s[k];
-                const float e = ex2_ftz((mn - d * d) * LOG2E);
-                sum += e;
-                float2 f = make_float2(0.f, 0.f);
-                if ((m >> kx) & 1u) f = __ldg(ptr);
-                au = fmaf(__ldg(a.tl.wx + k), e * f.x, au);
-                av = fmaf(__ldg(a.tl.wy + k), e * f.y, av);
-                ++ptr;
-                if (++kx == K) { kx = 0; rm >>= 1; m = (rm & 1u) ? cm : 0u; ptr += a.W - K; }
+    for (int cg = 0; cg < NCG; ++cg) {
+        tmem_ld16_nowait(tcol + (uint32_t)(cg * 16), v);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+            // the neighbour flows of this half column group: 8 independent loads in flight (the first batch ahead of the TMEM wait)
+            float2 f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = cg * 16 + hh * 8 + j;
+                f[j] = make_float2(0.f, 0.f);
+                if (k < KK) {
+                    const int ky = k / K, kx = k - ky * K;
+                    if (((rm >> ky) & 1u) && ((cm >> kx) & 1u)) f[j] = __ldg(c0 + (long long)ky * a.W + kx);
+                }
+            }
+            if (hh == 0) tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = cg * 16 + hh * 8 + j;
+                if (k < KK) {
+                    const float d = fmaf(__uint_as_float(v[hh * 8 + j]), W_SCALE_INV, bias_s[k]);
+                    const float e = ex2_ftz((mn - __fmul_rn(d, d)) * LOG2E);   // d*d rounded on its own, as in pass 1
+                    sum += e;
+                    au = fmaf(sw[k], e * f[j].x, au);
+                    av = fmaf(sw[64 + k], e * f[j].y, av);
+                }
             }
         }
     }
@@ -168,7 +180,7 @@ __device__ __forceinline__ void st_global_v4(uint32_t* p, const uint4& v) {
 template <int MODE>
 __global__ void __launch_bounds__(P16_THREADS, 1)
 conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
-    constexpr bool DUAL = MODE == 4;
+    static_assert(MODE == 6, "one product scheme: f16 main + fp8 corrections, single accumulator");
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int pitch = HT_W + a.KW - 1;
@@ -176,7 +188,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     const int halo_bytes = halo_rows * pitch * 128;
     const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int part_bytes = a.CoutP * 64;                        // one fp16 weight tile: CoutP rows of 32 channels
-    const int b_stage = (DUAL ? 2 : 3) * part_bytes;            // per tap
+    const int b_stage = 2 * part_bytes;                         // per tap: [W_hi f16 | (W_hi 2^-11 ; W_lo) e5m2]
     uint8_t* smemB = smem + (size_t)a.nA * slot_bytes;
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_free[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -187,7 +199,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     const int ntaps = a.KH * a.KW;
     const int G = gridDim.x;
     const int n_iss = (a.NT >= 2 && !a.one_issuer) ? 2 : 1;
-    const int tile_cols = DUAL ? 2 * a.CoutP : a.CoutP;
+    const int tile_cols = a.CoutP;
     const int set_cols = a.NT * tile_cols;
     const uint32_t ncols = tmem_cols_for(a.nsets * set_cols);
     const int negr = a.wnc ? 1 : 4;                 // epilogue warp groups (of 4 warps); the other 12 warps gather when a backwarp is fused
@@ -196,6 +208,10 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     if (threadIdx.x >= 128 && threadIdx.x < 256) {
         const int i = threadIdx.x - 128;
         bias_s[i] = (a.bias && i < a.Cout) ? a.bias[i] : 0.f;
+    }
+    if (a.out_fmt == OUT_TAIL && threadIdx.x >= 256 && threadIdx.x < 384) {
+        const int i = threadIdx.x - 256, k = i & 63;
+        reinterpret_cast<float*>(smem + a.tap_off)[i] = k < a.Cout ? __ldg((i < 64 ? a.tl.wx : a.tl.wy) + k) : 0.f;
     }
     if (threadIdx.x == 0) {
         for (int i = 0; i < a.nA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_free[i], n_iss); }
@@ -268,8 +284,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             const uint32_t hiA = (uint32_t)((((uint64_t)((pitch * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32);
             const uint32_t hiB = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
             const uint32_t idesc = make_idesc_f16(a.CoutP);
-            const uint32_t idesc_w = make_idesc_f16(2 * a.CoutP);
-            const uint32_t cP = (uint32_t)a.CoutP;
+            const uint32_t idesc8 = make_idesc_e5m2(a.CoutP);
             const uint32_t part16 = (uint32_t)(part_bytes >> 4);
             const uint32_t stage16 = (uint32_t)(b_stage >> 4);
             const uint32_t ring16 = stage16 * (uint32_t)a.tps;
@@ -312,31 +327,12 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                         for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
                             uint32_t A = A0, t_main = t_first;
                             for (int i = 0; i < ntl; ++i, A += tile16, t_main += (uint32_t)tile_cols) {
-                                if (DUAL) {
-                                    umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc_w, acc);
-                                    umma_bf16_lohi(t_main + cP, A + 2, hiA, b, hiB, idesc, 1);
-                                    if (two) {
-                                        umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc_w, 1);
-                                        umma_bf16_lohi(t_main + cP, A + 6, hiA, b + 2, hiB, idesc, 1);
-                                    }
-                                } else if (a.collect) {
-                                    umma_f16_lohi_afill(t_main, A, hiA, b, hiB, idesc, acc);
-                                    umma_f16_lohi_alast(t_main, A, hiA, b + part16, hiB, idesc, 1);
-                                    umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
-                                    if (two) {
-                                        umma_f16_lohi_afill(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
-                                        umma_f16_lohi_alast(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
-                                        umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
-                                    }
-                                } else {
-                                    umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
-                                    umma_bf16_lohi(t_main, A, hiA, b + part16, hiB, idesc, 1);
-                                    umma_bf16_lohi(t_main, A + 2, hiA, b + 2 * part16, hiB, idesc, 1);
-                                    if (two) {
-                                        umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
-                                        umma_bf16_lohi(t_main, A + 4, hiA, b + part16 + 2, hiB, idesc, 1);
-                                        umma_bf16_lohi(t_main, A + 6, hiA, b + 2 * part16 + 2, hiB, idesc, 1);
-                                    }
+                                // per 16-channel K step: a_hi * W_hi (f16, K = 16) and [a_lo8 | a_hi8] * [W_hi 2^-11 ; W_lo] (e5m2, K = 32)
+                                umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
+                                umma_f8_lohi(t_main, A + 2, hiA, b + part16, hiB, idesc8, 1);
+                                if (two) {
+                                    umma_bf16_lohi(t_main, A + 4, hiA, b + 2, hiB, idesc, 1);
+                                    umma_f8_lohi(t_main, A + 6, hiA, b + part16 + 2, hiB, idesc8, 1);
                                 }
                             }
                             acc = 1;
@@ -415,14 +411,19 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                             const float wgt[4] = {wv.x, wv.y, wv.z, wv.w};
                             const int cu = k * 4 + u;                        // 8-channel unit of the warp source
                             const int off = a.wsrc_p16 ? p16::unit_off_bytes(cu) : cu * 32;
-                            const int off2 = a.wsrc_p16 ? off + 32 : off + 16;
+                            const int off2 = a.wsrc_p16 ? p16::unit_lo8_bytes(cu) : off + 16;
 #pragma unroll
                             for (int t = 0; t < 4; ++t) {
                                 va[e][t] = vb[e][t] = make_uint4(0u, 0u, 0u, 0u);
                                 if (ok && wgt[t] != 0.f) {                   // taps outside the frame are never dereferenced
                                     const uint8_t* src = a.wsrc + (img + (long long)(xy.y + (t >> 1)) * a.W + (xy.x + (t & 1))) * (long long)a.wsrc_ld * 4;
                                     va[e][t] = __ldg(reinterpret_cast<const uint4*>(src + off));
-                                    vb[e][t] = __ldg(reinterpret_cast<const uint4*>(src + off2));
+                                    if (a.wsrc_p16) {                        // 8 lo8 bytes
+                                        const uint2 l8 = __ldg(reinterpret_cast<const uint2*>(src + off2));
+                                        vb[e][t].x = l8.x; vb[e][t].y = l8.y;
+                                    } else {
+                                        vb[e][t] = __ldg(reinterpret_cast<const uint4*>(src + off2));
+                                    }
                                 }
                             }
                         }
@@ -439,7 +440,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
 #pragma unroll
                                 for (int t = 0; t < 4; ++t) {
                                     float f[8];
-                                    if (a.wsrc_p16) p16::decode8(va[e][t], vb[e][t], f);
+                                    if (a.wsrc_p16) p16::decode8(va[e][t], make_uint2(vb[e][t].x, vb[e][t].y), f);
                                     else {
                                         f[0] = __uint_as_float(va[e][t].x); f[1] = __uint_as_float(va[e][t].y); f[2] = __uint_as_float(va[e][t].z); f[3] = __uint_as_float(va[e][t].w);
                                         f[4] = __uint_as_float(vb[e][t].x); f[5] = __uint_as_float(vb[e][t].y); f[6] = __uint_as_float(vb[e][t].z); f[7] = __uint_as_float(vb[e][t].w);
@@ -447,14 +448,18 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
 #pragma unroll
                                     for (int j = 0; j < 8; ++j) v[j] = fmaf(wgt[t], f[j], v[j]);
                                 }
-                                uint4 h, l;
-                                p16::encode8(v, h, l);
-                                bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
-                                const uint32_t ub = (uint32_t)p16::unit_off_bytes(u) >> 4;      // 16-byte unit of hi inside the 128-byte row
+                                uint4 h;
+                                uint2 l, g;
+                                p16::encode8(v, h, l, g);
+                                bad |= p16::nonfinite_bits(h);
+                                // 16-byte units of the 128-byte row: group base gb = 4 * (u / 2); hi of this half group at gb + (u & 1),
+                                // the lo8 bytes in unit gb + 2 and the hi8 bytes in unit gb + 3, each at byte 8 * (u & 1)
+                                const uint32_t gb = (uint32_t)(u >> 1) * 4u, hf = (uint32_t)(u & 1);
                                 const uint32_t sw = (uint32_t)(p & 7);
                                 uint8_t* rowp = dst + (size_t)p * 128;
-                                *reinterpret_cast<uint4*>(rowp + ((ub ^ sw) << 4)) = h;
-                                *reinterpret_cast<uint4*>(rowp + (((ub + 2) ^ sw) << 4)) = l;
+                                *reinterpret_cast<uint4*>(rowp + (((gb + hf) ^ sw) << 4)) = h;
+                                *reinterpret_cast<uint2*>(rowp + (((gb + 2) ^ sw) << 4) + hf * 8) = l;
+                                *reinterpret_cast<uint2*>(rowp + (((gb + 3) ^ sw) << 4) + hf * 8) = g;
                             }
                         }
                     }
@@ -469,7 +474,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
         const int row = q * 32 + lane;
         const int ncg = a.CoutP >> 4;
         const int nunits = a.NT * ncg;
-        const float osc = DUAL ? 1.f : (1.f / 256.f);
+        const float osc = W_SCALE_INV;
         uint32_t bad = 0;
         int wl = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
@@ -481,20 +486,25 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             tc_fence_after();
             const uint32_t trow = tmem_base + (uint32_t)(as * set_cols) + ((uint32_t)(q * 32) << 16);
             if (a.out_fmt == OUT_TAIL) {
-                if constexpr (DUAL) {
-                    for (int i = eg; i < a.NT; i += negr)
-                        tail_pixel(a, trow + (uint32_t)(i * tile_cols), bias_s, n, x, (ty * a.NT + i) * HT_H + (row >> 3));
+                {
+                    const float* sw = reinterpret_cast<const float*>(smem + a.tap_off);
+                    for (int i = eg; i < a.NT; i += negr) {
+                        const uint32_t tc = trow + (uint32_t)(i * tile_cols);
+                        const int yy = (ty * a.NT + i) * HT_H + (row >> 3);
+                        if (a.tl.K == 7) tail_pixel<7>(a, tc, bias_s, sw, n, x, yy);
+                        else if (a.tl.K == 5) tail_pixel<5>(a, tc, bias_s, sw, n, x, yy);
+                        else tail_pixel<3>(a, tc, bias_s, sw, n, x, yy);
+                    }
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&acc_empty[as]);
                 continue;
             }
-            uint32_t v[16], u[16];
+            uint32_t v[16];
             auto issue = [&](int unit) {
                 const int i = unit / ncg, cg = unit - i * ncg;
                 tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + cg * 16), v);
-                if (DUAL) tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + a.CoutP + cg * 16), u);
             };
             if (eg < nunits) issue(eg);
             for (int unit = eg; unit < nunits; unit += negr) {
@@ -507,9 +517,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                     const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        float t;
-                        if (DUAL) t = fmaf(__uint_as_float(u[4 * j + k]), p16::LO_INV, __uint_as_float(v[4 * j + k])) + bb[k];
-                        else t = fmaf(__uint_as_float(v[4 * j + k]), osc, bb[k]);
+                        const float t = fmaf(__uint_as_float(v[4 * j + k]), osc, bb[k]);
                         r[4 * j + k] = a.lrelu ? lrelu_f(t) : t;
                     }
                 }
@@ -529,15 +537,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 }
                 uint4 t4[4];
                 if (a.out_fmt == OUT_P16) {
-                    uint32_t h[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) { h[j] = p16::pack_hi(r[2 * j], r[2 * j + 1]); bad |= p16::nonfinite_bits(h[j]); }
-                    t4[0] = make_uint4(h[0], h[1], h[2], h[3]);
-                    t4[1] = make_uint4(h[4], h[5], h[6], h[7]);
-                    t4[2] = make_uint4(p16::pack_lo(r[0], r[1], h[0]), p16::pack_lo(r[2], r[3], h[1]),
-                                       p16::pack_lo(r[4], r[5], h[2]), p16::pack_lo(r[6], r[7], h[3]));
-                    t4[3] = make_uint4(p16::pack_lo(r[8], r[9], h[4]), p16::pack_lo(r[10], r[11], h[5]),
-                                       p16::pack_lo(r[12], r[13], h[6]), p16::pack_lo(r[14], r[15], h[7]));
+                    p16::encode16(r, t4[0], t4[1], t4[2], t4[3]);
+                    bad |= p16::nonfinite_bits(t4[0]) | p16::nonfinite_bits(t4[1]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
@@ -619,8 +620,8 @@ EncodeTiledFn get_encode() {
 // NT / slots / ring depth; returns the dynamic shared memory size or 0
 int configure(ConvP16Args& h, int mode) {
     const int pitch = HT_W + h.KW - 1;
-    const int b_stage = (mode == 4 ? 2 : 3) * h.CoutP * 64;
-    const int tile_cols = mode == 4 ? 2 * h.CoutP : h.CoutP;
+    const int b_stage = 2 * h.CoutP * 64;
+    const int tile_cols = h.CoutP;
     int NT = 2;
     static int nt_env = -1;
     if (nt_env < 0) { const char* v = getenv("PIVLFN_P16_NT"); nt_env = v ? atoi(v) : 0; }
@@ -630,7 +631,8 @@ int configure(ConvP16Args& h, int mode) {
         const int halo_rows = HT_H * NT + h.KH - 1;
         if (halo_rows > 256 || pitch > 256) continue;
         const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;
-        const int taps = h.wnc ? ((halo_rows * pitch * 24 + 1023) & ~1023) : 0;      // fused backwarp: tap table
+        // fused backwarp: tap table; OUT_TAIL: the ScaleX / ScaleY weights
+        const int taps = h.wnc ? ((halo_rows * pitch * 24 + 1023) & ~1023) : (h.out_fmt == OUT_TAIL ? 1024 : 0);
         const int budget = SMEM_BUDGET - taps;
         int tps = 1;
         if (!h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 && (budget - 2 * slot) / (3 * b_stage) >= 2) tps = 3;
@@ -660,11 +662,11 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
                   const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int stride, int lrelu,
                   int out_fmt, long long plane_stride, int* range_flag, const WarpSrc* ws, const TailArgs* tail, void* stream) {
     if (!x || !w_img || (!y && out_fmt != OUT_TAIL) || N <= 0 || H <= 0 || W <= 0 || Cin <= 0 || Cout <= 0) return PIVLFN_EINVAL;
-    if (mode != 4 && mode != 5) return PIVLFN_EINVAL;
+    if (mode != 6) return PIVLFN_EINVAL;                  // 6 = f16 main product + e5m2 corrections (pivlfn.model._pack_f8)
     if (stride != 1 && stride != 2) return PIVLFN_EINVAL;
     if (out_fmt < OUT_P16 || out_fmt > OUT_TAIL || (out_fmt == OUT_TAIL) != (tail != nullptr)) return PIVLFN_EINVAL;
     const int CoutP = (Cout + 15) & ~15;
-    if (CoutP > 128 || (mode == 4 && CoutP > 64)) return PIVLFN_EUNSUPPORTED;
+    if (CoutP > 128) return PIVLFN_EUNSUPPORTED;
     ConvP16Args h;
     h.wsrc = nullptr; h.wflow = nullptr; h.wscale = 0.f; h.wsrc_ld = 0; h.wsrc_p16 = 0; h.wc0 = 0; h.wnc = 0;
     int Cbuf = Cin;                                         // channels that live in the input buffer
@@ -691,12 +693,10 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
     h.N = N; h.Cw = Cw; h.Cout = Cout; h.CoutP = CoutP; h.lrelu = lrelu; h.out_fmt = out_fmt;
     h.w_img = reinterpret_cast<const uint8_t*>(w_img); h.range_flag = range_flag; h.planar = 0; h.cout_st = Cout; h.quad = 0;
     {
-        // experiment switches (defaults = the measured best): PIVLFN_P16_ISSUERS=1|2, PIVLFN_P16_COLLECT=0|1
-        static int iss = -1, col = -1;
+        // experiment switch (default = the measured best): PIVLFN_P16_ISSUERS=1|2
+        static int iss = -1;
         if (iss < 0) { const char* v = getenv("PIVLFN_P16_ISSUERS"); iss = v ? atoi(v) : 0; }
-        if (col < 0) { const char* v = getenv("PIVLFN_P16_COLLECT"); col = v ? atoi(v) : 0; }
-        h.collect = (mode == 5 && col == 1) ? 1 : 0;
-        h.one_issuer = (iss == 1 || h.collect) ? 1 : 0;
+        h.one_issuer = iss == 1 ? 1 : 0;
     }
     if (out_fmt == OUT_P16) {
         if (((uintptr_t)y & 63) || (y_ld & 15) || y_ld < CoutP) return PIVLFN_EINVAL;
@@ -709,7 +709,7 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
         if (((uintptr_t)y & 7) || plane_stride < 2LL * N * h.H * h.W) return PIVLFN_EINVAL;
         h.planar = plane_stride;
     } else {
-        if (mode != 4 || stride != 1 || ws) return PIVLFN_EUNSUPPORTED;
+        if (stride != 1 || ws || CoutP > 64) return PIVLFN_EUNSUPPORTED;
         if (tail->K != 3 && tail->K != 5 && tail->K != 7) return PIVLFN_EUNSUPPORTED;
         if (Cout != tail->K * tail->K || !tail->flow || !tail->wx || !tail->wy || !tail->bx || !tail->by || !tail->out) return PIVLFN_EINVAL;
         if (((uintptr_t)tail->flow & 7) || ((uintptr_t)tail->out & 7) || tail->flow == tail->out) return PIVLFN_EINVAL;
@@ -735,17 +735,10 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
     const int nsm = pivlfn_num_sms();
     const int grid = h.total < nsm ? h.total : nsm;
     cudaStream_t st = (cudaStream_t)stream;
-    static unsigned long long cfg4 = 0, cfg5 = 0;
-    cudaError_t e;
-    if (mode == 4) {
-        e = pivlfn_optin_smem(conv_p16_kernel<4>, SMEM_BUDGET, cfg4);
-        if (e != cudaSuccess) return (int)e;
-        conv_p16_kernel<4><<<grid, P16_THREADS, smem, st>>>(tmA, h);
-    } else {
-        e = pivlfn_optin_smem(conv_p16_kernel<5>, SMEM_BUDGET, cfg5);
-        if (e != cudaSuccess) return (int)e;
-        conv_p16_kernel<5><<<grid, P16_THREADS, smem, st>>>(tmA, h);
-    }
+    static unsigned long long cfg6 = 0;
+    cudaError_t e = pivlfn_optin_smem(conv_p16_kernel<6>, SMEM_BUDGET, cfg6);
+    if (e != cudaSuccess) return (int)e;
+    conv_p16_kernel<6><<<grid, P16_THREADS, smem, st>>>(tmA, h);
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
@@ -774,5 +767,5 @@ extern "C" int pivlfn_conv_p16_tail(const void* x, int x_ld, int N, int H, int W
                                     int KH, int KW, int K, const float* flow_in, const float* wx, const float* bx, const float* wy,
                                     const float* by, float* flow_out, float* out_nchw, float final_scale, void* stream) {
     TailArgs t{reinterpret_cast<const float2*>(flow_in), wx, wy, bx, by, reinterpret_cast<float2*>(flow_out), out_nchw, final_scale, K};
-    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, 4, bias, nullptr, 0, K * K, KH, KW, 1, 0, OUT_TAIL, 0, nullptr, nullptr, &t, stream);
+    return conv_p16_impl(x, x_ld, N, H, W, Cin, w_img, 6, bias, nullptr, 0, K * K, KH, KW, 1, 0, OUT_TAIL, 0, nullptr, nullptr, &t, stream);
 }

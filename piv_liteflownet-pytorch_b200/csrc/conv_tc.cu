@@ -904,17 +904,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                             if (a.out_p16) {
                                 const float r[16] = {t4[0].x, t4[0].y, t4[0].z, t4[0].w, t4[1].x, t4[1].y, t4[1].z, t4[1].w,
                                                      t4[2].x, t4[2].y, t4[2].z, t4[2].w, t4[3].x, t4[3].y, t4[3].z, t4[3].w};
-                                uint32_t hh[8], ll[8];
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    hh[j] = p16::pack_hi(r[2 * j], r[2 * j + 1]);
-                                    ll[j] = p16::pack_lo(r[2 * j], r[2 * j + 1], hh[j]);
-                                    p16_bad |= p16::nonfinite_bits(hh[j]);
-                                }
-                                t4[0] = make_float4(__uint_as_float(hh[0]), __uint_as_float(hh[1]), __uint_as_float(hh[2]), __uint_as_float(hh[3]));
-                                t4[1] = make_float4(__uint_as_float(hh[4]), __uint_as_float(hh[5]), __uint_as_float(hh[6]), __uint_as_float(hh[7]));
-                                t4[2] = make_float4(__uint_as_float(ll[0]), __uint_as_float(ll[1]), __uint_as_float(ll[2]), __uint_as_float(ll[3]));
-                                t4[3] = make_float4(__uint_as_float(ll[4]), __uint_as_float(ll[5]), __uint_as_float(ll[6]), __uint_as_float(ll[7]));
+                                uint4 e0, e1, e2, e3;
+                                p16::encode16(r, e0, e1, e2, e3);
+                                p16_bad |= p16::nonfinite_bits(e0) | p16::nonfinite_bits(e1);
+                                t4[0] = make_float4(__uint_as_float(e0.x), __uint_as_float(e0.y), __uint_as_float(e0.z), __uint_as_float(e0.w));
+                                t4[1] = make_float4(__uint_as_float(e1.x), __uint_as_float(e1.y), __uint_as_float(e1.z), __uint_as_float(e1.w));
+                                t4[2] = make_float4(__uint_as_float(e2.x), __uint_as_float(e2.y), __uint_as_float(e2.z), __uint_as_float(e2.w));
+                                t4[3] = make_float4(__uint_as_float(e3.x), __uint_as_float(e3.y), __uint_as_float(e3.z), __uint_as_float(e3.w));
                             }
                             if (dual) {
                                 // v / u are consumed: start the TMEM loads of the next 16-column group (next stacked tile

@@ -181,13 +181,12 @@ __device__ __forceinline__ float4 ld_quad(const float* src, int c, int C) {
 // channels c .. c+3 of a P16 pixel row (p16.cuh): 8 bytes of hi + 8 bytes of lo' -> 4 floats (pad channels of the last group are
 // stored as zeros, so no channel-count test is needed)
 __device__ __forceinline__ float4 ld_quad_p16(const float* pixel_row, int c) {
-    const uint8_t* p = reinterpret_cast<const uint8_t*>(pixel_row) + (c >> 4) * 64 + (c & 15) * 2;
-    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p));
-    const uint2 l = __ldg(reinterpret_cast<const uint2*>(p + 32));
-    float4 v;
-    p16::decode2(h.x, l.x, v.x, v.y);
-    p16::decode2(h.y, l.y, v.z, v.w);
-    return v;
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(pixel_row) + (c >> 4) * 64;
+    const uint2 h = __ldg(reinterpret_cast<const uint2*>(p + (c & 15) * 2));
+    const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(p + 32 + (c & 15)));
+    float v[4];
+    p16::decode4(h.x, h.y, l, v);
+    return make_float4(v[0], v[1], v[2], v[3]);
 }
 
 // F1P / F2P: the feature maps are P16 (f*_ld = pixel pitch in words either way); OUTP: the result is written as P16 groups
@@ -346,12 +345,14 @@ corr_nhwc_kernel(const float* __restrict__ f1, int f1_ld, const float* __restric
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = (un * 8 + j < 49) ? so[p * NH_OLD + un * 8 + j] : 0.f;
-                uint4 h, l;
-                p16::encode8(v, h, l);
-                bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
-                uint8_t* o = reinterpret_cast<uint8_t*>(out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld) + p16::unit_off_bytes(un);
-                *reinterpret_cast<uint4*>(o) = h;
-                *reinterpret_cast<uint4*>(o + 32) = l;
+                uint4 h;
+                uint2 l, g;
+                p16::encode8(v, h, l, g);
+                bad |= p16::nonfinite_bits(h);
+                uint8_t* o = reinterpret_cast<uint8_t*>(out + ((size_t)n * Ho * Wo + (size_t)oy * Wo + ox) * out_ld);
+                *reinterpret_cast<uint4*>(o + p16::unit_off_bytes(un)) = h;
+                *reinterpret_cast<uint2*>(o + p16::unit_lo8_bytes(un)) = l;
+                *reinterpret_cast<uint2*>(o + p16::unit_hi8_bytes(un)) = g;
             }
         }
         if (range_flag && p16::any_nonfinite(bad)) *range_flag = 1;

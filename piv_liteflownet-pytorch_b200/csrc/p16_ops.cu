@@ -1,4 +1,4 @@
-// Memory-bound glue kernels of the P16 pipeline (p16.cuh): the producers that hand MMA-ready (hi, lo') pair rows to the
+// Memory-bound glue kernels of the P16 pipeline (p16.cuh): the producers that hand MMA-ready (hi | lo8 | hi8) rows to the
 // tensor-core convolutions of conv_p16.cu, and the converters between P16 and fp32 NHWC.
 #include "common.cuh"
 #include "p16.cuh"
@@ -13,6 +13,8 @@ inline int grid_for(long long total, int block) {
 
 __device__ __forceinline__ uint4 ldg_u4(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ void stg_u4(void* p, const uint4& v) { *reinterpret_cast<uint4*>(p) = v; }
+__device__ __forceinline__ uint2 ldg_u2(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+__device__ __forceinline__ void stg_u2(void* p, const uint2& v) { *reinterpret_cast<uint2*>(p) = v; }
 
 // ---- fp32 NHWC <-> P16 -----------------------------------------------------------------------------------------------
 // one thread = one pixel x 8 channels
@@ -27,12 +29,14 @@ __global__ void p16_encode_kernel(const float* __restrict__ x, int x_ld, int C, 
         float v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = (8 * u + j < C) ? __ldg(x + p * x_ld + 8 * u + j) : 0.f;
-        uint4 h, l;
-        p16::encode8(v, h, l);
-        bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
-        uint8_t* o = y + p * (long long)y_ld * 4 + p16::unit_off_bytes(u);
-        stg_u4(o, h);
-        stg_u4(o + 32, l);
+        uint4 h;
+        uint2 l, g;
+        p16::encode8(v, h, l, g);
+        bad |= p16::nonfinite_bits(h);
+        uint8_t* o = y + p * (long long)y_ld * 4;
+        stg_u4(o + p16::unit_off_bytes(u), h);
+        stg_u2(o + p16::unit_lo8_bytes(u), l);
+        stg_u2(o + p16::unit_hi8_bytes(u), g);
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;
 }
@@ -43,9 +47,9 @@ __global__ void p16_decode_kernel(const uint8_t* __restrict__ x, int x_ld, int C
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const long long p = i / U;
         const int u = (int)(i - p * U);
-        const uint8_t* s = x + p * (long long)x_ld * 4 + p16::unit_off_bytes(u);
+        const uint8_t* s = x + p * (long long)x_ld * 4;
         float v[8];
-        p16::decode8(ldg_u4(s), ldg_u4(s + 32), v);
+        p16::decode8(ldg_u4(s + p16::unit_off_bytes(u)), ldg_u2(s + p16::unit_lo8_bytes(u)), v);
 #pragma unroll
         for (int j = 0; j < 8; ++j)
             if (8 * u + j < C) y[p * y_ld + 8 * u + j] = v[j];
@@ -55,7 +59,7 @@ __global__ void p16_decode_kernel(const uint8_t* __restrict__ x, int x_ld, int C
 // ---- backwarp (src/models.py:20-35) -> P16 slice of the Subpixel concat buffer ----------------------------------------
 // 8x8 pixel patch per block, 4 lanes per pixel walking the 8-channel units (see warp_nhwc_kernel in misc.cu); the input is
 // fp32 NHWC (NetC_ext output for the second image: consumed only by the cost volume and this kernel) or P16 (NetC features
-// of the coarse levels).  The output unit is encoded and written as two 16-byte vectors.
+// of the coarse levels).  The output unit is encoded and written as one 16-byte and two 8-byte vectors.
 template <bool IN_P16>
 __global__ void __launch_bounds__(256, 4)
 warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restrict__ flow, float scale,
@@ -86,13 +90,18 @@ warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restr
         }
         uint8_t* o = out + p * (long long)out_ld * 4;
         for (int u = lq; u < U; u += 4) {
-            uint4 a[4], b[4];
+            uint4 a[4], b[4];                                  // IN_P16: b.x, b.y = the 8 lo8 bytes
             const int off = IN_P16 ? p16::unit_off_bytes(u) : u * 32;
-            const int off2 = IN_P16 ? off + 32 : off + 16;
+            const int off2 = IN_P16 ? p16::unit_lo8_bytes(u) : off + 16;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 a[k] = on[k] ? ldg_u4(src[k] + off) : make_uint4(0, 0, 0, 0);
-                b[k] = on[k] ? ldg_u4(src[k] + off2) : make_uint4(0, 0, 0, 0);
+                if (IN_P16) {
+                    const uint2 l = on[k] ? ldg_u2(src[k] + off2) : make_uint2(0, 0);
+                    b[k] = make_uint4(l.x, l.y, 0, 0);
+                } else {
+                    b[k] = on[k] ? ldg_u4(src[k] + off2) : make_uint4(0, 0, 0, 0);
+                }
             }
             float v[8];
 #pragma unroll
@@ -100,7 +109,7 @@ warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restr
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 float t[8];
-                if (IN_P16) p16::decode8(a[k], b[k], t);
+                if (IN_P16) p16::decode8(a[k], make_uint2(b[k].x, b[k].y), t);
                 else {
                     t[0] = __uint_as_float(a[k].x); t[1] = __uint_as_float(a[k].y); t[2] = __uint_as_float(a[k].z); t[3] = __uint_as_float(a[k].w);
                     t[4] = __uint_as_float(b[k].x); t[5] = __uint_as_float(b[k].y); t[6] = __uint_as_float(b[k].z); t[7] = __uint_as_float(b[k].w);
@@ -108,12 +117,13 @@ warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restr
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = fmaf(wgt[k], t[j], v[j]);
             }
-            uint4 h, l;
-            p16::encode8(v, h, l);
-            bad |= p16::nonfinite_bits(h.x) | p16::nonfinite_bits(h.y) | p16::nonfinite_bits(h.z) | p16::nonfinite_bits(h.w);
-            const int oo = p16::unit_off_bytes(u);
-            stg_u4(o + oo, h);
-            stg_u4(o + oo + 32, l);
+            uint4 h;
+            uint2 l, g;
+            p16::encode8(v, h, l, g);
+            bad |= p16::nonfinite_bits(h);
+            stg_u4(o + p16::unit_off_bytes(u), h);
+            stg_u2(o + p16::unit_lo8_bytes(u), l);
+            stg_u2(o + p16::unit_hi8_bytes(u), g);
         }
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;
@@ -122,7 +132,7 @@ warp_p16_kernel(const uint8_t* __restrict__ in, int in_ld, const float2* __restr
 // ---- depthwise ConvTranspose 4x4 s2 (upCorr_M, src/models.py:151-152): fp32 NHWC in -> P16 out ---------------------------
 // one thread = one INPUT pixel position x 4 channels -> the 2x2 output block (see deconv4x4s2_dw_block_kernel in misc.cu): the
 // 3x3 input neighbourhood is read once (9 float4), the 16 taps of the 4 channels come from shared memory, and every output
-// is written as 8 bytes of hi + 8 bytes of lo' -- four consecutive lanes complete a 32-byte sector of each.  (8 channels per
+// is written as 8 bytes of hi + 4 bytes of lo8 + 4 bytes of hi8 -- four consecutive lanes complete the 64-byte group.  (8 channels per
 // thread kept 18 float4 live, 98 registers, 23 % occupancy: 2.2 TB/s; this shape runs at 2.5x the occupancy.)
 constexpr int DC_MAXC = 64;
 __global__ void __launch_bounds__(256)
@@ -181,9 +191,10 @@ deconv4x4s2_dw_p16_kernel(const float* __restrict__ in, int in_ld, int in_c4, co
                 const uint32_t h0 = p16::pack_hi(acc.x, acc.y), h1 = p16::pack_hi(acc.z, acc.w);
                 bad |= p16::nonfinite_bits(h0) | p16::nonfinite_bits(h1);
                 const long long op = (n * 2 * H + 2 * iy + dy) * Wo + 2 * ix + dx;
-                uint8_t* o = out + op * (long long)out_ld * 4 + (c >> 4) * 64 + (c & 15) * 2;
-                *reinterpret_cast<uint2*>(o) = make_uint2(h0, h1);
-                *reinterpret_cast<uint2*>(o + 32) = make_uint2(p16::pack_lo(acc.x, acc.y, h0), p16::pack_lo(acc.z, acc.w, h1));
+                uint8_t* o = out + op * (long long)out_ld * 4 + (c >> 4) * 64;
+                *reinterpret_cast<uint2*>(o + (c & 15) * 2) = make_uint2(h0, h1);
+                *reinterpret_cast<uint32_t*>(o + 32 + (c & 15)) = p16::pack_lo4(acc.x, acc.y, acc.z, acc.w, h0, h1);
+                *reinterpret_cast<uint32_t*>(o + 48 + (c & 15)) = p16::pack_e5m2x4(acc.x, acc.y, acc.z, acc.w);
             }
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;
@@ -226,7 +237,8 @@ __global__ void reg_input_p16_kernel(const float4* __restrict__ img1, const floa
         uint8_t* o = out + p * (long long)out_ld * 4;
         // channels 3..15 of the group stay zero (the buffer is zero-initialised once and nobody else writes them)
         stg_u4(o, make_uint4(h0, h1, 0u, 0u));
-        stg_u4(o + 32, make_uint4(p16::pack_lo(e, ru, h0), p16::pack_lo(rv, 0.f, h1), 0u, 0u));
+        stg_u4(o + 32, make_uint4(p16::pack_lo4(e, ru, rv, 0.f, h0, h1), 0u, 0u, 0u));
+        stg_u4(o + 48, make_uint4(p16::pack_e5m2x4(e, ru, rv, 0.f), 0u, 0u, 0u));
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;
 }
@@ -264,7 +276,8 @@ head_rows_sum_kernel(const float2* __restrict__ planes, long long plane_pix, con
             bad |= p16::nonfinite_bits(h0);
             uint8_t* o = out_p16 + p * (long long)p16_ld * 4;
             stg_u4(o, make_uint4(h0, 0u, 0u, 0u));
-            stg_u4(o + 32, make_uint4(p16::pack_lo(su, sv, h0), 0u, 0u, 0u));
+            stg_u4(o + 32, make_uint4(p16::pack_lo4(su, sv, 0.f, 0.f, h0, 0u), 0u, 0u, 0u));
+            stg_u4(o + 48, make_uint4(p16::pack_e5m2x4(su, sv, 0.f, 0.f), 0u, 0u, 0u));
         }
     }
     if (flag && p16::any_nonfinite(bad)) *flag = 1;

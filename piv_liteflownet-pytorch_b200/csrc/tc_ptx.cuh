@@ -126,6 +126,19 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
         "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// kind::f8f6f4 with e5m2 operands (K = 32 per instruction), fp32 accumulate: twice the f16 rate
+__device__ __forceinline__ void umma_f8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 // the same with the A-operand collector: FILL keeps the A tile read from shared memory in the tensor core's collector buffer,
 // LASTUSE takes A from that buffer (no shared-memory read) -- for consecutive MMAs of ONE issuing thread that share A
 __device__ __forceinline__ void umma_f16_lohi_afill(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
@@ -158,6 +171,10 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
 // kind::f16 with fp16 operands (mode PASSES == 4): A and B format F16
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+}
+// kind::f8f6f4 with e5m2 operands: A and B format E5M2 (= 1), D fp32
+__device__ __forceinline__ uint32_t make_idesc_e5m2(int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 // two fp32 -> packed f16x2 (round to nearest even), low half = first value
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {

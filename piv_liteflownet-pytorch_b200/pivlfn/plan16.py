@@ -29,7 +29,7 @@ import torch
 
 from . import ops
 from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
-from .model import Plan
+from .model import P16_MODE, Plan
 from .ops import OUT_F32, OUT_P16, OUT_PLANES, View, view
 
 
@@ -98,19 +98,13 @@ class Plan16(Plan):
     # ---------------------------------------------------------------------------------------------
     def _conv(self, key: str, x: View, n: int, h: int, w: int, y: View, lrelu: bool = True, out_fmt: int = OUT_P16,
               cin: Optional[int] = None):
-        """h, w: INPUT size.  The weight pack decides the kernel mode: one accumulator (5) for Cout > 64, else [main | corr] (4)."""
+        """h, w: INPUT size."""
         eng = self.eng
         cw = eng.w[key]
         cin = cw.cin if cin is None else cin
         assert x.C >= _r16(cin) or x.C == cin, (key, x.C, cin)
-        if cw.stride == 2:
-            assert cw.w_s2 is not None, key
-            w_img, mode = cw.w_s2, cw.s2_passes
-        elif cw.w_f16s is not None:
-            w_img, mode = cw.w_f16s, 5
-        else:
-            w_img, mode = cw.w_f16, 4
-        ops.conv_p16(x, n, h, w, cin, w_img, mode, cw.bias, y, cw.cout, cw.kh, cw.kw, cw.stride, lrelu, out_fmt, 0, eng.flag)
+        assert cw.w_f8 is not None, key
+        ops.conv_p16(x, n, h, w, cin, cw.w_f8, P16_MODE, cw.bias, y, cw.cout, cw.kh, cw.kw, cw.stride, lrelu, out_fmt, 0, eng.flag)
 
     def _chain(self, prefix: str, idxs: List[int], x: View, l: int, res: Optional[torch.Tensor], out: torch.Tensor,
                out_p16: Optional[View] = None, warp=None):
@@ -130,7 +124,7 @@ class Plan16(Plan):
             y = view(t[c][k])
             if warp is not None and j == idxs[0]:
                 src, src_p16, flow, scale, c0, n = warp
-                w_img, mode = (cw.w_f16s, 5) if cw.w_f16s is not None else (cw.w_f16, 4)
+                w_img, mode = cw.w_f8, P16_MODE
                 ops.conv_p16_warp(x, B, h, w, cw.cin, w_img, mode, cw.bias, y, cw.cout, cw.kh, cw.kw, True, src, src_p16, flow, scale,
                                   c0, n, eng.flag)
             else:
@@ -139,7 +133,7 @@ class Plan16(Plan):
         key = f"{prefix}.{idxs[-1]}"
         K = KSIZE[l]
         rw = eng.w[key + "#rows"]                       # 1xK convolution to the 2K row channels (ky*2 + co)
-        ops.conv_p16(x, B, h, w, rw.cin, rw.w_f16, 4, None, view(d["planes"].view(1, K, B * h * w, 2)), 2 * K, 1, K, 1, False,
+        ops.conv_p16(x, B, h, w, rw.cin, rw.w_f8, P16_MODE, None, view(d["planes"].view(1, K, B * h * w, 2)), 2 * K, 1, K, 1, False,
                      OUT_PLANES, 2 * B * h * w, eng.flag)
         ops.head_rows_sum(d["planes"], K, eng.w[key].bias, res, out, out_p16, B, h, w, eng.flag)
 
@@ -242,9 +236,9 @@ class Plan16(Plan):
             else:
                 dkey, dx = f"NetE_R.{i}.conv_dist_R.0", x
             cw = eng.w[dkey]
-            if self.fuse_tail and cw.w_f16s is None:
+            if self.fuse_tail:
                 # the distances never leave TMEM: softmax(-d^2), unfold, ScaleX / ScaleY and the division run in the conv's epilogue
-                ops.conv_p16_tail(dx, B, h, w, cw.cin, cw.w_f16, cw.bias, cw.kh, cw.kw, KSIZE[l], *tail)
+                ops.conv_p16_tail(dx, B, h, w, cw.cin, cw.w_f8, cw.bias, cw.kh, cw.kw, KSIZE[l], *tail)
             else:
                 self._conv(dkey, dx, B, h, w, view(d["dist"]), lrelu=False, out_fmt=OUT_F32)
                 ops.reg_tail(view(d["dist"], 0, dc), *tail, KSIZE[l])

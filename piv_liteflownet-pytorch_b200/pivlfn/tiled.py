@@ -27,7 +27,7 @@ import torch
 
 from . import ops
 from .arch import CONV_R, DIST_CH, KSIZE, LEVEL_FEAT_CH, MATCH_FEAT_CH, NETC, NETC_LEVEL_END
-from .model import PASSES, SIMT, Engine, _r8
+from .model import P16_MODE, PASSES, SIMT, Engine, _r8
 from .ops import View, view
 
 
@@ -664,7 +664,7 @@ class TiledPlan16(TiledPlan):
         r = cw.kh // 2
         self._need(x, r)
         N, hh, ww = x.t.shape[0], x.t.shape[1], x.t.shape[2]
-        w_img, mode = (cw.w_f16s, 5) if cw.w_f16s is not None else (cw.w_f16, 4)
+        w_img, mode = cw.w_f8, P16_MODE
         yc = (_r16(cw.cout) if out_fmt == ops.OUT_P16 else y.t.shape[3] - yo) if yc is None else yc
 
         def run():
@@ -679,12 +679,12 @@ class TiledPlan16(TiledPlan):
             return super().down(kind, x, y, key, C)
         # 3x3 stride-2 NetC convolution on P16 buffers (conv6: two 96-channel halves)
         eng, N, E = self.eng, x.t.shape[0], self.E
-        halves = [(key, 0)] if key in eng.w and eng.w[key].w_s2 is not None else [(key + "#a", 0), (key + "#b", 96)]
+        halves = [(key, 0)] if key in eng.w and eng.w[key].w_f8 is not None else [(key + "#a", 0), (key + "#b", 96)]
 
         def call(a: torch.Tensor, b: torch.Tensor):
             for k, off in halves:
                 cw = eng.w[k]
-                ops.conv_p16(view(a, 0, _r16(cw.cin)), 1, a.shape[1], a.shape[2], cw.cin, cw.w_s2, cw.s2_passes, cw.bias,
+                ops.conv_p16(view(a, 0, _r16(cw.cin)), 1, a.shape[1], a.shape[2], cw.cin, cw.w_f8, P16_MODE, cw.bias,
                              view(b, off, _r16(cw.cout)), cw.cout, 3, 3, 2, True, ops.OUT_P16, 0, eng.flag)
 
         if x.tiled and not y.tiled:
@@ -718,7 +718,7 @@ class TiledPlan16(TiledPlan):
         hh, ww = x.t.shape[1], x.t.shape[2]
 
         def run():
-            ops.conv_p16(view(self._img(x, 0), 0, _r16(rw.cin)), 1, hh, ww, rw.cin, rw.w_f16, 4, None, view(planes.view(1, K, hh * ww, 2)),
+            ops.conv_p16(view(self._img(x, 0), 0, _r16(rw.cin)), 1, hh, ww, rw.cin, rw.w_f8, P16_MODE, None, view(planes.view(1, K, hh * ww, 2)),
                          2 * K, 1, K, 1, False, ops.OUT_PLANES, 2 * hh * ww, eng.flag)
             ops.head_rows_sum(planes, K, eng.w[key].bias, self._img(res, 0) if res is not None else None, self._img(out, 0),
                               view(self._img(out16, 0), out16_off, 16) if out16 is not None else None, 1, hh, ww, eng.flag)

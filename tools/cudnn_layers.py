@@ -1,7 +1,7 @@
 """Per-layer comparison with cuDNN (VERDICT r1 item 6 / SURVEY.md section 2.2: "the kernel to beat"): every level-1 convolution of
 PIV-LiteFlowNet-en at batch 64 of 256 x 256, torch.nn.functional.conv2d + bias + LeakyReLU(0.1) as the reference runs it
 (NCHW, and channels_last for cuDNN's preferred tensor-core layout) in true fp32 (TF32 off) and with torch's TF32-default
-convolutions, next to this repo's pivlfn_conv_p16 (fp32-equivalent: 3 fp16 products on split operands).  CUDA events, best of 3
+convolutions, next to this repo's pivlfn_conv_p16 (split operands: one fp16 product + one fp8 product of corrections, flow error ~4e-4 px).  CUDA events, best of 3
 x 3 launches, inputs >> L2.
     python tools/cudnn_layers.py [B] [H] > profiles/r2_cudnn_layers_b64_256.txt"""
 import math
@@ -77,17 +77,12 @@ for cin, cout, kh, kw, st, act, name in LAYERS:
         out = torch.empty(B, H, H, 2, device=dev)
 
         def ours():
-            ops.conv_p16(ops.view(xin), B, H, H, cin, rw.w_f16, 4, None, ops.view(planes.view(1, K, B * H * H, 2)), 2 * K, 1, K, 1, False,
+            ops.conv_p16(ops.view(xin), B, H, H, cin, rw.w_f8, 6, None, ops.view(planes.view(1, K, B * H * H, 2)), 2 * K, 1, K, 1, False,
                          ops.OUT_PLANES, 2 * B * H * H, flag)
             ops.head_rows_sum(planes, K, b, None, out, None, B, H, H, flag)
     else:
         cw = pack_conv(w.cpu(), b.cpu(), st).to_(dev)
-        if st == 2:
-            w_img, mode = cw.w_s2, cw.s2_passes
-        elif cw.w_f16s is not None:
-            w_img, mode = cw.w_f16s, 5
-        else:
-            w_img, mode = cw.w_f16, 4
+        w_img, mode = cw.w_f8, 6
         xin = torch.zeros(B, H, H, (cin + 15) & ~15, device=dev)
         ops.p16_encode(ops.view(x.permute(0, 2, 3, 1).contiguous()), ops.view(xin), B * H * H, flag)
         y = torch.empty(B, H // st, H // st, (cout + 15) & ~15, device=dev)
@@ -104,5 +99,5 @@ for cin, cout, kh, kw, st, act, name in LAYERS:
     del x, xcl, xin
 print(f"# sum over these layers (best layout each): cuDNN fp32 {tot['fp32']:.2f} ms, cuDNN TF32 {tot['tf32']:.2f} ms, pivlfn {tot['ours']:.2f} ms "
       f"-> {tot['fp32'] / tot['ours']:.2f}x / {tot['tf32'] / tot['ours']:.2f}x")
-print("# pivlfn is fp32-equivalent (flow max |diff| ~1e-4 px vs the fp32 reference); cuDNN TF32 rounds both operands to 10 mantissa bits")
+print("# pivlfn: flow max |diff| ~5e-4 px vs the fp32 reference; cuDNN TF32 rounds both operands to 10 mantissa bits")
 print("# (flow max |diff| 2.4e-2 px for the single-pass tf32 mode of this repo, outside the 1e-2 px north_star tolerance)")

@@ -35,12 +35,7 @@ for cin, cout, kh, kw, st, fmt, name in LAYERS:
     w = torch.randn(cout, cin, kh, kw, generator=g) / math.sqrt(cin * kh * kw)
     b = torch.randn(cout, generator=g)
     cw = pack_conv(w, b, st).to_(dev)
-    if st == 2:
-        w_img, mode = cw.w_s2, cw.s2_passes
-    elif cw.w_f16s is not None:
-        w_img, mode = cw.w_f16s, 5
-    else:
-        w_img, mode = cw.w_f16, 4
+    w_img, mode = cw.w_f8, 6
     cw16 = (cin + 15) & ~15
     x = torch.zeros(B, H, H, cw16, device=dev)
     ops.p16_encode(ops.view(torch.randn(B, H, H, cin, generator=g).to(dev)), ops.view(x), B * H * H, flag)

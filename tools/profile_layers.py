@@ -130,6 +130,10 @@ def w_conv_p16_warp(x, N, Hh, Ww, cin, w_img, mode, bias, y, cout, KH, KW, lrelu
     return 2.0 * N * Hh * Ww * cin * cout * KH * KW, "F", f"{cin}->{cout} {KH}x{KW} s1 mode{mode} + fused backwarp of {wn} ch @{Hh}x{Ww}"
 
 
+def w_conv_p16_tail(x, N, Hh, Ww, cin, w_img, bias, KH, KW, K, *rest):
+    return 2.0 * N * Hh * Ww * cin * K * K * KH * KW, "F", f"{cin}->{K * K} {KH}x{KW} s1 + Regularization tail in the epilogue @{Hh}x{Ww}"
+
+
 def w_stem16(img_pad, N, Hh, Ww, w_img, bias, y, lrelu=True, flag=None):
     return 2.0 * N * Hh * Ww * 3 * 32 * 49, "F", f"stem 3->32 7x7 @{Hh}x{Ww}"
 
@@ -164,7 +168,7 @@ def w_small(*a, **k):
 for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_tc", w_stem), ("conv_s2_tc", w_s2), ("conv1x1_pairs_tc", w_pairs),
                ("flow_head_sum", w_headsum), ("flow_head", w_head), ("deconv4x4s2_dw", w_deconv), ("warp", w_warp), ("corr_nhwc", w_corr),
                ("reg_tail", w_regtail), ("reg_input", w_reginput), ("copy", w_copy), ("flow_mean", w_small),
-               ("prep_images", w_small), ("avgpool2", w_small), ("conv_p16", w_conv_p16), ("conv_p16_warp", w_conv_p16_warp), ("conv_stem_p16", w_stem16),
+               ("prep_images", w_small), ("avgpool2", w_small), ("conv_p16", w_conv_p16), ("conv_p16_warp", w_conv_p16_warp), ("conv_p16_tail", w_conv_p16_tail), ("conv_stem_p16", w_stem16),
                ("corr_p16", w_corr16), ("warp_p16", w_warp16), ("deconv4x4s2_dw_p16", w_deconv16),
                ("reg_input_p16", w_reginput16), ("head_rows_sum", w_rows)):
     wrap(nm, wk)

@@ -64,7 +64,7 @@ cin = 2 * cm + 2
 w = torch.randn(128, cin, 3, 3, generator=g) / math.sqrt(cin * 9)
 cw = pack_conv(w, torch.randn(128, generator=g), 1).to_(dev)
 y = torch.empty(B, H, H, 128, device=dev)
-timeit(lambda: ops.conv_p16_warp(ops.view(Sbuf), B, H, H, cin, cw.w_f16s, 5, cw.bias, ops.view(y), 128, 3, 3, True, ops.view(f2), False, flow,
+timeit(lambda: ops.conv_p16_warp(ops.view(Sbuf), B, H, H, cin, cw.w_f8, 6, cw.bias, ops.view(y), 128, 3, 3, True, ops.view(f2), False, flow,
                                  5.0, cm, cm, flag),
        "conv_S.0 130->128 3x3 + fused backwarp (TFLOP/s in the rate column / 1000)", 2.0 * B * H * H * cin * 128 * 9, unit="GFLOP/s")
 # conv_dist_R.1 (1x7, 49 -> 49) + Regularization tail: two launches against the fused epilogue
@@ -76,10 +76,10 @@ dist2 = torch.zeros(B, H, H, 52, device=dev)
 
 
 def two():
-    ops.conv_p16(ops.view(d0), B, H, H, 49, cd.w_f16, 4, cd.bias, ops.view(dist2), 49, 1, 7, 1, False, ops.OUT_F32, 0, None)
+    ops.conv_p16(ops.view(d0), B, H, H, 49, cd.w_f8, 6, cd.bias, ops.view(dist2), 49, 1, 7, 1, False, ops.OUT_F32, 0, None)
     ops.reg_tail(ops.view(dist2, 0, 49), flow, wx, bx, wy, by, flow_out, None, 5.0, 7)
 
 
 timeit(two, "conv_dist_R.1 + reg_tail (2 launches)", 2.0 * B * H * H * 49 * 49 * 7, unit="GFLOP/s")
-timeit(lambda: ops.conv_p16_tail(ops.view(d0), B, H, H, 49, cd.w_f16, cd.bias, 1, 7, 7, flow, wx, bx, wy, by, flow_out, None, 5.0),
+timeit(lambda: ops.conv_p16_tail(ops.view(d0), B, H, H, 49, cd.w_f8, cd.bias, 1, 7, 7, flow, wx, bx, wy, by, flow_out, None, 5.0),
        "conv_dist_R.1 with the tail in its epilogue", 2.0 * B * H * H * 49 * 49 * 7, unit="GFLOP/s")
