@@ -32,8 +32,6 @@ constexpr int HT_W = 8, HT_H = 16;       // accumulator tile: 16 rows of 8 pixel
 constexpr int MAX_A = 3, MAX_B = 8;
 constexpr int P16_THREADS = 640;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
-// weights are packed times W_SCALE (pivlfn.model._pack_f8: keeps W_hi 2^-11 and W_lo inside the normal range of e5m2)
-constexpr float W_SCALE_INV = 1.f / 1024.f;
 constexpr int SMEM_BUDGET = 226 * 1024;  // 227 KB opt-in minus the static part (padded to 1 KB by the 1024-byte alignment)
 
 enum { OUT_P16 = 0, OUT_F32 = 1, OUT_PLANES = 2, OUT_TAIL = 3 };
@@ -93,9 +91,9 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // two-kernel forms agree to rounding): pass 1 finds min_k d_k^2 over the K*K accumulator columns, pass 2 re-reads them from
 // TMEM (cheaper than 49 live registers next to the 32 staging ones) and accumulates the softmax-weighted neighbour flows.
 // Fully unrolled over the K*K neighbours so that the K*K flow loads are independent of each other.
-// tcol = TMEM address of this thread's accumulator row (CoutP columns, scaled by W_SCALE); sw = [wx 64 | wy 64] in shared memory.
+// tcol = TMEM address of this thread's accumulator row (CoutP columns, scaled by the layer's weight scale 1 / osc); sw = [wx 64 | wy 64] in shared memory.
 template <int K>
-__device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, const float* bias_s, const float* sw, int n, int x, int y) {
+__device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, float osc, const float* bias_s, const float* sw, int n, int x, int y) {
     constexpr float LOG2E = 1.4426950408889634f;
     constexpr int KK = K * K, P = K / 2, NCG = (KK + 15) / 16;
     uint32_t v[16];
@@ -107,7 +105,7 @@ __device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, 
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
             if (cg * 16 + j < KK) {
-                const float d = fmaf(__uint_as_float(v[j]), W_SCALE_INV, bias_s[cg * 16 + j]);
+                const float d = fmaf(__uint_as_float(v[j]), osc, bias_s[cg * 16 + j]);
                 mn = fminf(mn, __fmul_rn(d, d));
             }
         }
@@ -141,7 +139,7 @@ __device__ __forceinline__ void tail_pixel(const ConvP16Args& a, uint32_t tcol, 
             for (int j = 0; j < 8; ++j) {
                 const int k = cg * 16 + hh * 8 + j;
                 if (k < KK) {
-                    const float d = fmaf(__uint_as_float(v[hh * 8 + j]), W_SCALE_INV, bias_s[k]);
+                    const float d = fmaf(__uint_as_float(v[hh * 8 + j]), osc, bias_s[k]);
                     const float e = ex2_ftz((mn - __fmul_rn(d, d)) * LOG2E);   // d*d rounded on its own, as in pass 1
                     sum += e;
                     au = fmaf(sw[k], e * f[j].x, au);
@@ -474,7 +472,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
         const int row = q * 32 + lane;
         const int ncg = a.CoutP >> 4;
         const int nunits = a.NT * ncg;
-        const float osc = W_SCALE_INV;
+        // the weights are packed times a per-layer power of two S (pivlfn.model._pack_f8); the image ends with [1 / S, S, 0, 0]
+        const float osc = __ldg(reinterpret_cast<const float*>(a.w_img + (size_t)nchunk * ntaps * b_stage));
         uint32_t bad = 0;
         int wl = 0;
         for (int w = blockIdx.x; w < a.total; w += G, ++wl) {
@@ -491,9 +490,9 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                     for (int i = eg; i < a.NT; i += negr) {
                         const uint32_t tc = trow + (uint32_t)(i * tile_cols);
                         const int yy = (ty * a.NT + i) * HT_H + (row >> 3);
-                        if (a.tl.K == 7) tail_pixel<7>(a, tc, bias_s, sw, n, x, yy);
-                        else if (a.tl.K == 5) tail_pixel<5>(a, tc, bias_s, sw, n, x, yy);
-                        else tail_pixel<3>(a, tc, bias_s, sw, n, x, yy);
+                        if (a.tl.K == 7) tail_pixel<7>(a, tc, osc, bias_s, sw, n, x, yy);
+                        else if (a.tl.K == 5) tail_pixel<5>(a, tc, osc, bias_s, sw, n, x, yy);
+                        else tail_pixel<3>(a, tc, osc, bias_s, sw, n, x, yy);
                     }
                 }
                 tc_fence_before();

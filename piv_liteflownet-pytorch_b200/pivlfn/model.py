@@ -83,8 +83,8 @@ class ConvW:
     s2_passes: int = 0                      # of [CoutP16, 4, 4*Cin] for pivlfn_conv_s2_tc, and its kernel mode (4 or 5)
     w_f16s: Optional[torch.Tensor] = None   # stage_image of [3, CoutP16, KH*KW, CinP32] fp16, W = 256 w: f16(W), f16(W - f16(W)), f16(f16(W) / 2048)
                                             # (single-accumulator variant of f16c, packed for Cout > 64 only)
-    w_f8: Optional[torch.Tensor] = None     # the P16 pipeline's pack (see _pack_f8): stage_image of [2, CoutP16, KH*KW, CinP32], W = 1024 w:
-                                            # f16(W) and the e5m2 correction tile; for a 3x3 stride-2 layer: of the parity restatement
+    w_f8: Optional[torch.Tensor] = None     # the P16 pipeline's weight image (see _pack_f8; bytes): f16(S w) and the e5m2 correction tile
+                                            # + a trailer with 1 / S; for a 3x3 stride-2 layer: of the parity restatement
 
     def to_(self, dev) -> "ConvW":
         for f in ("w_simt", "bias", "w_hi", "w_lo", "w_c16", "w_f16", "w_s2", "w_f16s", "w_f8"):
@@ -129,7 +129,7 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
         if coutp > 64 and stride == 1 and cw.w_f16 is not None and os.environ.get("PIVLFN_F16_SINGLE", "1") != "0":
             cw.w_f16s = stage_image(_pack_f16_single(wt))
         if stride == 1 and coutp <= 128:
-            cw.w_f8 = stage_image(_pack_f8(wt))
+            cw.w_f8 = _pack_f8(wt)
         if stride == 2 and kh == 3 and kw == 3 and cin % 32 == 0 and os.environ.get("PIVLFN_S2_HALO", "1") != "0":
             w2 = _restate_s2(w)                                      # [cout, 4, 4*cin]
             w2 = torch.nn.functional.pad(w2, (0, 0, 0, 0, 0, coutp - cout))
@@ -138,7 +138,7 @@ def pack_conv(w: torch.Tensor, b: Optional[torch.Tensor], stride: int = 1, cin_p
             else:
                 cw.w_s2, cw.s2_passes = stage_image(_pack_f16(w2)), 4
             if coutp <= 128:
-                cw.w_f8 = stage_image(_pack_f8(w2))
+                cw.w_f8 = _pack_f8(w2)
     return cw
 
 
@@ -201,26 +201,38 @@ def _pack_f16_single(wt: torch.Tensor) -> Optional[torch.Tensor]:
 
 
 P16_MODE = 6            # pivlfn_conv_p16's product scheme: f16 main product + e5m2 corrections (csrc/p16.cuh)
-W_SCALE = 1024.0        # == 1 / W_SCALE_INV in csrc/conv_p16.cu
+
+
+def f8_scale(wt: torch.Tensor) -> float:
+    """The power of two S that puts the largest |w| S of a layer into [8192, 16384): W_hi = f16(w S) is finite whatever the
+    weights' magnitude, and the two correction tiles (w S / 2048 and w S - W_hi, about 2^-11 and 2^-12 of W) stay inside the normal
+    range of e5m2 (>= 2^-14) for every weight down to 2^-16 of the layer's largest."""
+    m = float(wt.abs().max())
+    if not math.isfinite(m) or m == 0.0:
+        return 1.0
+    return 2.0 ** max(-40, min(40, math.floor(math.log2(16384.0 / m))))
 
 
 def _pack_f8(wt: torch.Tensor) -> Optional[torch.Tensor]:
-    """[CoutP, ntaps, CinP] fp32 -> the two operand tiles of the P16 convolution, both viewed as fp16 [CoutP, ntaps, CinP] so that
-    stage_image treats them alike (64-byte rows per 32-channel chunk).  With W = 1024 w (keeps both correction tiles inside
-    e5m2's normal range for |w| >= 2.4e-4; smaller weights lose correction bits whose absolute weight is below 2^-27):
+    """[CoutP, ntaps, CinP] fp32 -> the weight image of pivlfn_conv_p16: stage_image of two operand tiles, both viewed as fp16
+    [CoutP, ntaps, CinP] (64-byte rows per 32-channel chunk), plus a 16-byte trailer [1 / S, S, 0, 0] (fp32) that the kernel's
+    epilogue reads.  With W = S w (S = f8_scale, a power of two per layer):
       tile 0: W_hi = f16(W), the B operand of a_hi * W_hi (kind::f16, K = 16: the row's bytes [0,32) and [32,64));
       tile 1: per 16-channel K step 32 e5m2 bytes [e5m2(W / 2048) x 16 | e5m2(W - W_hi) x 16], the B operand of the single
               fp8 MMA (K = 32) whose A operand is the activation's [lo8 x 16 | hi8 x 16] block (csrc/p16.cuh):
               sum lo8 * W 2^-11 + hi8 * W_lo  =  the two correction products of the split."""
     coutp, ntaps, cinp = wt.shape
-    W = wt * W_SCALE
+    if not torch.isfinite(wt).all():
+        return None
+    S = f8_scale(wt)
+    W = wt * S
     hi = W.to(torch.float16)
-    if not torch.isfinite(hi).all():
-        return None                      # a weight outside the fp16 range: the engine falls back to tf32c
     c_lo = (W / 2048.0).to(torch.float8_e5m2).view(torch.uint8).reshape(coutp, ntaps, cinp // 16, 16)
     c_hi = (W - hi.to(torch.float32)).to(torch.float8_e5m2).view(torch.uint8).reshape(coutp, ntaps, cinp // 16, 16)
     corr = torch.cat([c_lo, c_hi], dim=-1).reshape(coutp, ntaps, cinp * 2).contiguous().view(torch.float16)
-    return torch.stack([hi, corr]).contiguous()
+    img = stage_image(torch.stack([hi, corr]).contiguous())
+    trailer = torch.tensor([1.0 / S, S, 0.0, 0.0], dtype=torch.float32).view(torch.uint8)
+    return torch.cat([img.reshape(-1).view(torch.uint8), trailer])
 
 
 def pack_stem(w: torch.Tensor, b: torch.Tensor) -> ConvW:
@@ -290,7 +302,7 @@ class Engine:
         def unpacked(cw):          # a tensor-core layer whose fp16 operand tiles could not be built (weights outside the fp16 range)
             if cw.w_hi is None:
                 return False
-            return cw.w_f16 is None or (self.p16 and cw.w_f8 is None and cw.cout <= 128 and (cw.stride == 1 or cw.w_s2 is not None))
+            return cw.w_f16 is None or (self.p16 and cw.w_f8 is None and not cw.stem and cw.cout <= 128 and (cw.stride == 1 or cw.w_s2 is not None))
         if self.precision == TC_F16C and any(unpacked(cw) for cw in self.w.values()):
             import warnings
             warnings.warn("pivlfn: a weight lies outside the fp16 range; precision 'f16c' replaced by 'tf32c'")

@@ -12,7 +12,7 @@ import torch.nn.functional as F
 
 from oracle import lfn_oracle as O
 from pivlfn import ops
-from pivlfn.model import P16_MODE, W_SCALE, pack_conv, pack_stem
+from pivlfn.model import P16_MODE, f8_scale, pack_conv, pack_stem
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
@@ -79,11 +79,12 @@ def p16_round(x_nchw):
 def conv_emul(x_nchw, w, b, stride=1, padding=0):
     """fp64 value of what pivlfn_conv_p16 computes from the P16 encoding of x and the _pack_f8 tiles of w (before the activation)."""
     hi, lo8, hi8 = (t.permute(0, 3, 1, 2).double() for t in p16_parts(x_nchw.permute(0, 2, 3, 1).contiguous()))
-    W = w.float() * W_SCALE
+    S = f8_scale(w)
+    W = w.float() * S
     Wh = W.to(torch.float16).float()
     c_lo, c_hi = (W / 2048.0).to(E5).double(), (W - Wh).to(E5).double()
     kw = dict(stride=stride, padding=padding)
-    y = (F.conv2d(hi, Wh.double(), None, **kw) + F.conv2d(lo8, c_lo, None, **kw) + F.conv2d(hi8, c_hi, None, **kw)) / W_SCALE
+    y = (F.conv2d(hi, Wh.double(), None, **kw) + F.conv2d(lo8, c_lo, None, **kw) + F.conv2d(hi8, c_hi, None, **kw)) / S
     return y if b is None else y + b.double().view(1, -1, 1, 1)
 
 
