@@ -231,7 +231,7 @@ def _pack_f8(wt: torch.Tensor) -> Optional[torch.Tensor]:
     c_hi = (W - hi.to(torch.float32)).to(torch.float8_e5m2).view(torch.uint8).reshape(coutp, ntaps, cinp // 16, 16)
     corr = torch.cat([c_lo, c_hi], dim=-1).reshape(coutp, ntaps, cinp * 2).contiguous().view(torch.float16)
     img = stage_image(torch.stack([hi, corr]).contiguous())
-    trailer = torch.tensor([1.0 / S, S, 0.0, 0.0], dtype=torch.float32).view(torch.uint8)
+    trailer = torch.tensor([1.0 / S, S, 0.0, 0.0], dtype=torch.float32, device=img.device).view(torch.uint8)
     return torch.cat([img.reshape(-1).view(torch.uint8), trailer])
 
 
