@@ -263,6 +263,11 @@ int pivlfn_reg_input_p16(const float* img1, const float* img2, const float* flow
 int pivlfn_head_rows_sum(const float* planes, int K, const float* bias, const float* res, float* out,
                          void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream);
 
+/* The transposed split of the same head: a Kx1 convolution to 2K channels (column kx*2 + co), whose K planes are added at their
+ * HORIZONTAL offsets (the Kx1 halo tile is 8 pixels wide instead of 8 + K - 1: the convolution runs 1.6x faster). */
+int pivlfn_head_cols_sum(const float* planes, int K, const float* bias, const float* res, float* out,
+                         void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream);
+
 /* ---- stereo-PIV post-processing (stereo_run.py:104-163) ------------------------------------------------------------------
  * stereo/dewarp.py:255-270 nl_trans: new_x = P(A[0:6]) / P(A[6:12]), new_y = P(A[12:18]) / P(A[18:24]) with
  * P(a) = a0 x + a1 y + a2 + a3 x^2 + a4 y^2 + a5 x y, evaluated in float32 in the reference's operation order.

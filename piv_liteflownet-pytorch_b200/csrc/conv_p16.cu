@@ -289,7 +289,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             const uint32_t bbase16 = (smem_u32(smemB) >> 4) | lbo_bits;
             const uint32_t tile16 = (uint32_t)(HT_H * pitch * 8);
             const uint32_t tileA = (uint32_t)issuer * tile16;
-            const int ntl = a.NT / n_iss;                                       // stacked tiles fed by this thread
+            const int ntl = a.NT / n_iss;                                       // stacked tiles fed by this thread: issuer, issuer + n_iss, ..
             const uint32_t row_step = (uint32_t)((pitch - a.KW) * 8);
             int bs = 0;
             uint32_t bphase = 0, bcur = bbase16;
@@ -324,7 +324,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                         uint32_t b = bcur;
                         for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
                             uint32_t A = A0, t_main = t_first;
-                            for (int i = 0; i < ntl; ++i, A += tile16, t_main += (uint32_t)tile_cols) {
+                            for (int i = 0; i < ntl; ++i, A += tile16 * (uint32_t)n_iss, t_main += (uint32_t)(tile_cols * n_iss)) {
                                 // per 16-channel K step: a_hi * W_hi (f16, K = 16) and [a_lo8 | a_hi8] * [W_hi 2^-11 ; W_lo] (e5m2, K = 32)
                                 umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
                                 umma_f8_lohi(t_main, A + 2, hiA, b + part16, hiB, idesc8, 1);
@@ -621,12 +621,15 @@ int configure(ConvP16Args& h, int mode) {
     const int pitch = HT_W + h.KW - 1;
     const int b_stage = 2 * h.CoutP * 64;
     const int tile_cols = h.CoutP;
-    int NT = 2;
+    // stacked tiles per work item: the whole weight tensor streams from L2 once per item, so NT sets the L2 -> SM traffic per
+    // pixel (Cout = 128: 590 KB per item); PIVLFN_P16_NT = 1 | 2 | 4 overrides the choice (experiments)
+    int NT = h.CoutP <= 64 ? 4 : 2;       // Cout <= 64: four tiles still leave two accumulator sets (epilogue overlapped with the next item)
     static int nt_env = -1;
     if (nt_env < 0) { const char* v = getenv("PIVLFN_P16_NT"); nt_env = v ? atoi(v) : 0; }
-    if (nt_env == 1) NT = 1;
-    while (NT > 1 && (NT * tile_cols > 512 || HT_H * (NT - 1) >= h.H)) --NT;
-    for (; NT >= 1; --NT) {
+    if (nt_env == 1 || nt_env == 2 || nt_env == 4) NT = nt_env;
+    if (h.wnc && NT > 2) NT = 2;
+    while (NT > 1 && (NT * tile_cols > 512 || HT_H * (NT - 1) >= h.H)) NT >>= 1;
+    for (; NT >= 1; NT >>= 1) {
         const int halo_rows = HT_H * NT + h.KH - 1;
         if (halo_rows > 256 || pitch > 256) continue;
         const int slot = (halo_rows * pitch * 128 + 1023) & ~1023;

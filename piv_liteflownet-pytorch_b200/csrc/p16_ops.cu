@@ -248,7 +248,9 @@ __global__ void reg_input_p16_kernel(const float4* __restrict__ img1, const floa
 // sum_{kx,c} x[p + kx - P, c] w[co, c, ky, kx]; conv_p16.cu, OUT_PLANES: plane ky = [pixel][2]); this kernel adds the K row
 // planes at their vertical offsets (zero outside the frame), the bias and the residual flow, and writes the dense fp32 flow
 // plus (optionally) its P16 group in the Subpixel concat buffer (the torch.cat of src/models.py:216).
-template <int K>
+// HORIZ: the transposed split -- a Kx1 convolution to 2K column channels (kx*2 + co), summed over kx at horizontal offsets (the
+// Kx1 halo tile is 8 pixels wide instead of 8 + K - 1: conv_p16 runs it 1.6x faster than the 1xK form).
+template <int K, bool HORIZ>
 __global__ void __launch_bounds__(256)
 head_rows_sum_kernel(const float2* __restrict__ planes, long long plane_pix, const float* __restrict__ bias,
                      const float2* __restrict__ res, float2* __restrict__ out, uint8_t* __restrict__ out_p16, int p16_ld,
@@ -258,13 +260,13 @@ head_rows_sum_kernel(const float2* __restrict__ planes, long long plane_pix, con
     const float b0 = bias ? __ldg(bias) : 0.f, b1 = bias ? __ldg(bias + 1) : 0.f;
     uint32_t bad = 0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-        const int y = (int)((p / W) % H);
+        const int y = (int)((p / W) % H), x = (int)(p % W);
         float su = 0.f, sv = 0.f;
 #pragma unroll
-        for (int ky = 0; ky < K; ++ky) {
-            const int yy = y + ky - P;
-            if (yy >= 0 && yy < H) {
-                const float2 d = __ldg(planes + (long long)ky * plane_pix + p + (long long)(ky - P) * W);
+        for (int k = 0; k < K; ++k) {
+            const int q = (HORIZ ? x : y) + k - P;
+            if (q >= 0 && q < (HORIZ ? W : H)) {
+                const float2 d = __ldg(planes + (long long)k * plane_pix + p + (long long)(k - P) * (HORIZ ? 1 : W));
                 su += d.x; sv += d.y;
             }
         }
@@ -346,8 +348,9 @@ extern "C" int pivlfn_reg_input_p16(const float* img1, const float* img2, const 
     return pivlfn_last_error();
 }
 
-extern "C" int pivlfn_head_rows_sum(const float* planes, int K, const float* bias, const float* res, float* out,
-                                    void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream) {
+namespace {
+int head_sum_impl(bool horiz, const float* planes, int K, const float* bias, const float* res, float* out,
+                  void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream) {
     if (!planes || !out || N <= 0 || H <= 0 || W <= 0) return PIVLFN_EINVAL;
     if (((uintptr_t)planes & 7) || ((uintptr_t)out & 7) || (res && ((uintptr_t)res & 7))) return PIVLFN_EINVAL;
     if (out_p16 && (((uintptr_t)out_p16 & 63) || (p16_ld & 15) || p16_ld < 16)) return PIVLFN_EINVAL;
@@ -358,12 +361,29 @@ extern "C" int pivlfn_head_rows_sum(const float* planes, int K, const float* bia
     uint8_t* o16 = reinterpret_cast<uint8_t*>(out_p16);
     cudaStream_t st = (cudaStream_t)stream;
     const int g = grid_for(total, 256);
+#define PIVLFN_HEAD_SUM(KK)                                                                                                   \
+    if (horiz) head_rows_sum_kernel<KK, true><<<g, 256, 0, st>>>(pl, total, bias, rs, o, o16, p16_ld, N, H, W, range_flag);  \
+    else head_rows_sum_kernel<KK, false><<<g, 256, 0, st>>>(pl, total, bias, rs, o, o16, p16_ld, N, H, W, range_flag)
     switch (K) {
-        case 3: head_rows_sum_kernel<3><<<g, 256, 0, st>>>(pl, total, bias, rs, o, o16, p16_ld, N, H, W, range_flag); break;
-        case 5: head_rows_sum_kernel<5><<<g, 256, 0, st>>>(pl, total, bias, rs, o, o16, p16_ld, N, H, W, range_flag); break;
-        case 7: head_rows_sum_kernel<7><<<g, 256, 0, st>>>(pl, total, bias, rs, o, o16, p16_ld, N, H, W, range_flag); break;
+        case 3: PIVLFN_HEAD_SUM(3); break;
+        case 5: PIVLFN_HEAD_SUM(5); break;
+        case 7: PIVLFN_HEAD_SUM(7); break;
         default: return PIVLFN_EINVAL;
     }
+#undef PIVLFN_HEAD_SUM
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
+}
+}  // namespace
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_head_rows_sum(const float* planes, int K, const float* bias, const float* res, float* out,
+                                    void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream) {
+    return head_sum_impl(false, planes, K, bias, res, out, out_p16, p16_ld, N, H, W, range_flag, stream);
+}
+
+/* see include/pivlfn.h */
+extern "C" int pivlfn_head_cols_sum(const float* planes, int K, const float* bias, const float* res, float* out,
+                                    void* out_p16, int p16_ld, int N, int H, int W, int* range_flag, void* stream) {
+    return head_sum_impl(true, planes, K, bias, res, out, out_p16, p16_ld, N, H, W, range_flag, stream);
 }

@@ -46,6 +46,7 @@ PROTOTYPES = {
     "pivlfn_deconv4x4s2_dw_p16": (_i, [_p, _i, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pivlfn_reg_input_p16": (_i, [_p, _p, _p, _f, _p, _p, _i, _i, _i, _i, _p, _p]),
     "pivlfn_head_rows_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
+    "pivlfn_head_cols_sum": (_i, [_p, _i, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "pivlfn_nl_trans": (_i, [_p, _p, C.POINTER(_f), _p, _p, _ll, _p]),
     "pivlfn_stereo_2d3c": (_i, [_p, _p, C.POINTER(_f), C.POINTER(_f), _i, _f, _f, _d, _d, _d, _d, _p, _i, _i, _i, _p]),
     "pivlfn_resize_bilinear_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _f, _f, _p]),

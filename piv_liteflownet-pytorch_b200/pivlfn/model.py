@@ -353,6 +353,9 @@ class Engine:
                     # pivlfn_head_rows_sum (plan16.py)
                     K = w.shape[2]
                     self.w[key + "#rows"] = pack_conv(w.permute(2, 0, 1, 3).reshape(2 * K, w.shape[1], 1, K), None, 1, tc=True)
+                    # the transposed split (Kx1 convolution to the column channels kx*2 + co + pivlfn_head_cols_sum): narrower
+                    # halo tiles, used by the untiled plan; the row form keeps the tiled plan's vertical halo bookkeeping simple
+                    self.w[key + "#cols"] = pack_conv(w.permute(3, 0, 1, 2).reshape(2 * K, w.shape[1], K, 1), None, 1, tc=True)
                 if self.head_mode == "simt" and w.shape[1] == 32:
                     # exact-fp32 CUDA-core flow head (pivlfn_flow_head): weights as [K*K][32][2]
                     self.raw[key + "#head"] = w.permute(2, 3, 1, 0).reshape(-1, 32, 2).contiguous()

@@ -315,6 +315,16 @@ def head_rows_sum(planes: torch.Tensor, K: int, bias, res: Optional[torch.Tensor
                "head_rows_sum")
 
 
+def head_cols_sum(planes: torch.Tensor, K: int, bias, res: Optional[torch.Tensor], out: torch.Tensor,
+                  out_p16: Optional[View], N, H, W, flag: Optional[torch.Tensor] = None):
+    """head_rows_sum for the transposed split: planes kx = Kx1 convolution outputs, summed at horizontal offsets."""
+    _lib.check(_lib.load().pivlfn_head_cols_sum(planes.data_ptr(), int(K), bias.data_ptr() if bias is not None else None,
+                                                res.data_ptr() if res is not None else None, out.data_ptr(),
+                                                out_p16.ptr if out_p16 is not None else None,
+                                                out_p16.ld if out_p16 is not None else 0, N, H, W, _flag(flag), _stream()),
+               "head_cols_sum")
+
+
 def resize_bilinear(x: torch.Tensor, Ho: int, Wo: int, mul_even: float = 1.0, mul_odd: float = 1.0) -> torch.Tensor:
     """[B,C,H,W] -> [B,C,Ho,Wo], bilinear, align_corners=False (inference.py:46-49,57-61)."""
     lib = _lib.load()

@@ -132,10 +132,10 @@ class Plan16(Plan):
             x = y
         key = f"{prefix}.{idxs[-1]}"
         K = KSIZE[l]
-        rw = eng.w[key + "#rows"]                       # 1xK convolution to the 2K row channels (ky*2 + co)
-        ops.conv_p16(x, B, h, w, rw.cin, rw.w_f8, P16_MODE, None, view(d["planes"].view(1, K, B * h * w, 2)), 2 * K, 1, K, 1, False,
+        rw = eng.w[key + "#cols"]                       # Kx1 convolution to the 2K column channels (kx*2 + co)
+        ops.conv_p16(x, B, h, w, rw.cin, rw.w_f8, P16_MODE, None, view(d["planes"].view(1, K, B * h * w, 2)), 2 * K, K, 1, 1, False,
                      OUT_PLANES, 2 * B * h * w, eng.flag)
-        ops.head_rows_sum(d["planes"], K, eng.w[key].bias, res, out, out_p16, B, h, w, eng.flag)
+        ops.head_cols_sum(d["planes"], K, eng.w[key].bias, res, out, out_p16, B, h, w, eng.flag)
 
     def launch_all(self):
         """Enqueue the whole forward on the current stream (inputs already in self.in1 / self.in2)."""

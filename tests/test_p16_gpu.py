@@ -284,21 +284,26 @@ def test_corr_p16_variants(C, s, H, W, f2_p16, out_p16):
         assert got[:, 49:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("K,H,W", [(7, 24, 16), (5, 9, 12), (3, 4, 4), (7, 2, 2)])
-def test_flow_head_rows_vs_torch(K, H, W):
-    """The tensor-core flow head: 1xK convolution to 2K row planes + K-row gather-sum == the KxK 32 -> 2 convolution."""
+@pytest.mark.parametrize("cols", [False, True])
+@pytest.mark.parametrize("K,H,W", [(7, 24, 16), (5, 9, 12), (3, 4, 4), (7, 2, 2), (7, 70, 9)])
+def test_flow_head_rows_vs_torch(K, H, W, cols):
+    """The tensor-core flow head: 1xK convolution to 2K row planes + K-row gather-sum (or the transposed Kx1 / column form)
+    == the KxK 32 -> 2 convolution."""
     w, b = _rand(2, 32, K, K, seed=1, scale=1.0 / math.sqrt(32 * K * K)), _rand(2, seed=2)
     x = _rand(2, 32, H, W, seed=3)
     res = _rand(2, H, W, 2, seed=4)
     ref = conv_emul(x, w, b, 1, K // 2) + res.permute(0, 3, 1, 2).double()
-    rw = pack_conv(w.permute(2, 0, 1, 3).reshape(2 * K, 32, 1, K), None, 1).to_(DEV)
+    if cols:
+        rw = pack_conv(w.permute(3, 0, 1, 2).reshape(2 * K, 32, K, 1), None, 1).to_(DEV)
+    else:
+        rw = pack_conv(w.permute(2, 0, 1, 3).reshape(2 * K, 32, 1, K), None, 1).to_(DEV)
     planes = torch.zeros(K, 2 * H * W, 2, device=DEV)
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
-    ops.conv_p16(ops.view(to_p16(x)), 2, H, W, 32, rw.w_f8, P16_MODE, None, ops.view(planes.view(1, K, 2 * H * W, 2)), 2 * K, 1, K, 1,
-                 False, ops.OUT_PLANES, 2 * 2 * H * W, flag)
+    ops.conv_p16(ops.view(to_p16(x)), 2, H, W, 32, rw.w_f8, P16_MODE, None, ops.view(planes.view(1, K, 2 * H * W, 2)), 2 * K,
+                 K if cols else 1, 1 if cols else K, 1, False, ops.OUT_PLANES, 2 * 2 * H * W, flag)
     out = torch.zeros(2, H, W, 2, device=DEV)
     sb = torch.zeros(2, H, W, 144, device=DEV)
-    ops.head_rows_sum(planes, K, b.to(DEV), res.to(DEV), out, ops.view(sb, 128, 16), 2, H, W, flag)
+    (ops.head_cols_sum if cols else ops.head_rows_sum)(planes, K, b.to(DEV), res.to(DEV), out, ops.view(sb, 128, 16), 2, H, W, flag)
     got = out.permute(0, 3, 1, 2).cpu().double()
     assert (got - ref).abs().max().item() <= 2e-5 and int(flag.item()) == 0
     slot = p16_ref_decode(sb[..., 128:144].cpu(), 16)

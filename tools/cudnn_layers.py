@@ -24,7 +24,7 @@ LAYERS = [  # cin, cout, kh, kw, stride, lrelu, name
     (49, 128, 3, 3, 1, True, "conv_M.0"), (128, 64, 3, 3, 1, True, "conv_M.2 / conv_S.2 / conv_R.4"), (64, 32, 3, 3, 1, True, "conv_M.4 / conv_S.4 / conv_R.8"),
     (130, 128, 3, 3, 1, True, "conv_S.0"), (131, 128, 3, 3, 1, True, "conv_R.0"), (128, 128, 3, 3, 1, True, "conv_R.2"),
     (64, 64, 3, 3, 1, True, "conv_R.6"), (32, 32, 3, 3, 1, True, "conv_R.10"), (32, 49, 7, 1, 1, False, "conv_dist_R.0"),
-    (49, 49, 1, 7, 1, False, "conv_dist_R.1"), (32, 2, 7, 7, 1, False, "flow head 7x7 (ours: 1x7 rows + row sum)"),
+    (49, 49, 1, 7, 1, False, "conv_dist_R.1"), (32, 2, 7, 7, 1, False, "flow head 7x7 (ours: 7x1 columns + column sum)"),
 ]
 
 
@@ -70,16 +70,16 @@ for cin, cout, kh, kw, st, act, name in LAYERS:
     # ours
     if cout == 2:
         K = kh
-        rw = pack_conv(w.cpu().permute(2, 0, 1, 3).reshape(2 * K, cin, 1, K), None, 1).to_(dev)
+        rw = pack_conv(w.cpu().permute(3, 0, 1, 2).reshape(2 * K, cin, K, 1), None, 1).to_(dev)
         xin = torch.zeros(B, H, H, (cin + 15) & ~15, device=dev)
         ops.p16_encode(ops.view(x.permute(0, 2, 3, 1).contiguous()), ops.view(xin), B * H * H, flag)
         planes = torch.empty(K, B * H * H, 2, device=dev)
         out = torch.empty(B, H, H, 2, device=dev)
 
         def ours():
-            ops.conv_p16(ops.view(xin), B, H, H, cin, rw.w_f8, 6, None, ops.view(planes.view(1, K, B * H * H, 2)), 2 * K, 1, K, 1, False,
+            ops.conv_p16(ops.view(xin), B, H, H, cin, rw.w_f8, 6, None, ops.view(planes.view(1, K, B * H * H, 2)), 2 * K, K, 1, 1, False,
                          ops.OUT_PLANES, 2 * B * H * H, flag)
-            ops.head_rows_sum(planes, K, b, None, out, None, B, H, H, flag)
+            ops.head_cols_sum(planes, K, b, None, out, None, B, H, H, flag)
     else:
         cw = pack_conv(w.cpu(), b.cpu(), st).to_(dev)
         w_img, mode = cw.w_f8, 6

@@ -158,7 +158,7 @@ def w_reginput16(img1, img2, flow, scale, partial, out, flag=None):
 
 
 def w_rows(planes, K, bias, res, out, out_p16, N, Hh, Ww, flag=None):
-    return 4.0 * N * Hh * Ww * (2 * K + 4 + (8 if out_p16 is not None else 0)), "B", f"head_rows_sum K={K} @{Hh}x{Ww}"
+    return 4.0 * N * Hh * Ww * (2 * K + 4 + (8 if out_p16 is not None else 0)), "B", f"head_rows/cols_sum K={K} @{Hh}x{Ww}"
 
 
 def w_small(*a, **k):
@@ -170,7 +170,7 @@ for nm, wk in (("conv_tc", w_conv_tc), ("conv_simt", w_conv_simt), ("conv_stem_t
                ("reg_tail", w_regtail), ("reg_input", w_reginput), ("copy", w_copy), ("flow_mean", w_small),
                ("prep_images", w_small), ("avgpool2", w_small), ("conv_p16", w_conv_p16), ("conv_p16_warp", w_conv_p16_warp), ("conv_p16_tail", w_conv_p16_tail), ("conv_stem_p16", w_stem16),
                ("corr_p16", w_corr16), ("warp_p16", w_warp16), ("deconv4x4s2_dw_p16", w_deconv16),
-               ("reg_input_p16", w_reginput16), ("head_rows_sum", w_rows)):
+               ("reg_input_p16", w_reginput16), ("head_rows_sum", w_rows), ("head_cols_sum", w_rows)):
     wrap(nm, wk)
 
 acc = None
