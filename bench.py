@@ -10,8 +10,10 @@ collective -> weak scaling), and the only collective is the max-over-ranks of th
   value      pairs/s, inputs already resident in HBM, timed with CUDA events on the launching stream
   e2e        pairs/s through the drop-in API (src.models net(img1, img2)) with PINNED HOST inputs:
              H2D of both image batches and D2H of the flow are inside the timed region
-  precision  f16c (default): fp32-equivalent -- operands split into fp16 pairs, the three significant products on the
-             tensor cores in kind::f16 (activations outside the fp16 range are detected and re-run in tf32c);
+  precision  f16c (default): split operands -- a = f16(a) + 2^-11 lo, w likewise; the main product runs in kind::f16 and both
+             correction products (a_lo*w_hi + a_hi*w_lo, rounded to e5m2) in ONE fp8 MMA: flow within 1.5e-3 px max /
+             2e-4 px mean of the fp32 reference at this config (north_star tolerance 1e-2 / 1e-3; single-pass TF32, what
+             cuDNN's default does, is 15x further off).  Activations outside the fp16 range are detected and re-run in tf32c;
              tf32c: tf32 main product + bf16 low-order products; 3xtf32: all three products in tf32;
              tf32: one pass (NOT fp32-equivalent, reported separately); simt: fp32 FFMA on the CUDA cores
   roofline   the dominant kernel (tcgen05 3x3 implicit-GEMM convolution, the level-1 128->128 layer of conv_R)
@@ -203,8 +205,8 @@ def kernel_rooflines(eng, pk):
     if eng.p16:
         ms = time_kernel(lambda: ops.conv_p16(x, B, h, w, 128, cw.w_f8, 6, cw.bias, y, 128, 3, 3, 1, True, ops.OUT_P16, 0,
                                               eng.flag), 10)
-        name = ("conv_p16_kernel<5> (tcgen05 kind::f16 on P16 activations: fp16 (hi, lo') pairs straight from HBM by TMA, "
-                "3 products, one accumulator, 16 epilogue warps)")
+        name = ("conv_p16_kernel<6> (tcgen05 on P16 activations straight from HBM by TMA: kind::f16 main product a_hi*W_hi + ONE "
+                "kind::f8f6f4 e5m2 MMA for both correction products, one accumulator, 16 epilogue warps)")
     elif eng.precision != SIMT and cw.w_hi is not None:
         from pivlfn.model import PASSES
         passes = cw.passes_for(PASSES.get(eng.precision, 1))
@@ -218,6 +220,7 @@ def kernel_rooflines(eng, pk):
         ms = time_kernel(lambda: ops.conv_simt(x, B, h, w, cw.w_simt, cw.bias, y, 3, 3, 1, True), 5)
         name = "conv_simt_kernel (fp32 FFMA)"
     ach = flops / (ms * 1e-3) / 1e12
+    mma_slots = 2 if eng.p16 else (3 if eng.precision == "f16c" else 1)       # tensor-pipe time per useful product, in f16-MMA units
     # DRAM traffic of this exact launch from the committed `ncu --set full` capture (profiles/), if there is one
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "conv_tc_ncu_traffic.json")
@@ -228,9 +231,11 @@ def kernel_rooflines(eng, pk):
             traffic = None
     out["roofline"] = {"kernel": name, "layer": key + " 3x3 128->128 @256x256 x64", "bound": "tensor",
                        "achieved": ach, "peak": pk["bf16"], "unit": "TFLOP/s", "frac": ach / pk["bf16"],
-                       "peak_source": pk["src"] + ", dense bf16 burst (kind::f16 runs at this rate, kind::tf32 at half); the fp32-"
-                                      "equivalent modes spend 3 products per useful one (f16c), so their ceiling is 1/3 of it",
-                       "issued_tflops": 3 * ach if eng.precision == "f16c" else ach, "issued_frac": (3 * ach if eng.precision == "f16c" else ach) / pk["bf16"],
+                       "peak_source": pk["src"] + ", dense bf16 burst (kind::f16 runs at this rate, kind::tf32 at half, kind::f8f6f4 at "
+                                      "twice); the P16 scheme spends one f16 MMA (K=16) and one fp8 MMA (K=32: both correction terms) per "
+                                      "16 input channels = 2 f16-MMA times per useful product: its ceiling is 1/2 of the peak; the legacy "
+                                      "fp32-activation f16c plan (PIVLFN_P16=0) spends 3",
+                       "issued_tflops": mma_slots * ach, "issued_frac": mma_slots * ach / pk["bf16"],
                        "ms_per_launch": ms, "traffic": traffic, "flops_per_launch": flops,
                        "algorithmic_bytes_per_launch": 4.0 * B * h * w * (128 + 128)}
     # memory-bound: level-1 cost volume (stride 2, C=64, fused backwarp + LeakyReLU)
@@ -256,7 +261,10 @@ def kernel_rooflines(eng, pk):
                                           d["flowR"], None, 5.0, 7), 10)
     byts = 4.0 * B * h * w * (49 + 4)
     ach = byts / (ms * 1e-3) / 1e9
-    out["roofline_reg_tail"] = {"kernel": "reg_tail_bulk_kernel<7> (level 1)", "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
+    out["roofline_reg_tail"] = {"kernel": "reg_tail_bulk_kernel<7> (level 1)" + (
+                                    "; the P16 forward does not launch it (PIVLFN_FUSE_TAIL=1: the tail runs in conv_dist_R's epilogue, "
+                                    "the distances never leave TMEM) -- timed here as the stand-alone kernel" if eng.p16 else ""),
+                                "bound": "hbm", "achieved": ach, "peak": pk["hbm"],
                                 "unit": "GB/s", "frac": ach / pk["hbm"], "ms_per_launch": ms, "traffic": None}
     if eng.p16:
         # (with PIVLFN_FUSE_WARP=1, the default, the forward does not launch this kernel: the Subpixel backwarp is gathered
@@ -491,7 +499,11 @@ def main():
         "metric": "PIV pairs/sec", "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32" if args.precision != "tf32" else "tf32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "precision": args.precision, "global_batch": BATCH * world,
+        "config": {"workload": WORKLOAD, "precision": args.precision,
+                   "arithmetic": {"f16c": "fp32 in / out and fp32 accumulation; operands split as f16 + e5m2 corrections (2 MMAs per product), "
+                                          "flow within the north_star tolerance of the fp32 reference (tests/test_ref_cuda_gpu.py: cfg2 max 1.5e-3 / "
+                                          "mean 1.7e-4 px against 1e-2 / 1e-3)"}.get(args.precision, args.precision),
+                   "global_batch": BATCH * world,
                    "parallelism": f"pair-sharded x{world}, no data-path collective",
                    "l2": "inputs larger than L2 (multi-GB working set per step)",
                    "weights": "deterministic synthetic (pretrained blobs absent from the reference mount)"},
