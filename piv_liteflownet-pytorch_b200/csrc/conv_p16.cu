@@ -29,7 +29,7 @@ namespace {
 using namespace tcptx;
 
 constexpr int HT_W = 8, HT_H = 16;       // accumulator tile: 16 rows of 8 pixels = 128 GEMM rows
-constexpr int MAX_A = 3, MAX_B = 8;
+constexpr int MAX_A = 3, MAX_B = 12;
 constexpr int P16_THREADS = 640;
 constexpr int EPI_WARP0 = 4, EPI_WARPS = 16;
 constexpr int SMEM_BUDGET = 226 * 1024;  // 227 KB opt-in minus the static part (padded to 1 KB by the 1024-byte alignment)
@@ -640,6 +640,11 @@ int configure(ConvP16Args& h, int mode) {
         if (!h.s2 && h.CoutP <= 64 && (h.KH * h.KW) % 3 == 0 && (budget - 2 * slot) / (3 * b_stage) >= 2) tps = 3;
         // a third activation slot when it still leaves a deep weight ring (fused backwarp: always, one slot is the gather's)
         int nA = ((budget - 3 * slot) / (tps * b_stage) >= (h.wnc ? 2 : 4)) ? 3 : 2;
+        {
+            static int na_env = -1;                       // experiment switch: PIVLFN_P16_NA = 2 | 3
+            if (na_env < 0) { const char* v = getenv("PIVLFN_P16_NA"); na_env = v ? atoi(v) : 0; }
+            if (!h.wnc && (na_env == 2 || (na_env == 3 && 3 * slot + 2 * tps * b_stage <= budget))) nA = na_env;
+        }
         int nB = (budget - nA * slot) / (tps * b_stage);
         if (nB > MAX_B) nB = MAX_B;
         if (nB < 2) continue;
