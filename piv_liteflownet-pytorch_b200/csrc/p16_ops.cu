@@ -206,18 +206,33 @@ __global__ void reg_input_p16_kernel(const float4* __restrict__ img1, const floa
                                      const float2* __restrict__ flow, float scale, const float* __restrict__ partial,
                                      uint8_t* __restrict__ out, int out_ld, int N, int H, int W, int* __restrict__ flag) {
     const long long HW = (long long)H * W, total = (long long)N * HW;
+    const int lane = threadIdx.x & 31;
+    const float inv = 1.f / (float)HW;
     uint32_t bad = 0;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-        const long long n = p / HW;
-        const int x = (int)(p % W), y = (int)((p / W) % H);
-        float mu = 0.f, mv = 0.f;
-#pragma unroll 8
-        for (int i = 0; i < MEAN_PARTS; ++i) {
-            mu += __ldg(partial + (n * MEAN_PARTS + i) * 2);
-            mv += __ldg(partial + (n * MEAN_PARTS + i) * 2 + 1);
+    // warp-uniform loop (whole warps enter; lanes past the end idle): the flow mean of the warp's image is the sum of its
+    // MEAN_PARTS == 32 partials, one per lane, reduced by shuffles (64 loads per pixel otherwise: the kernel was issue-bound)
+    for (long long pb = (long long)blockIdx.x * blockDim.x + (threadIdx.x & ~31); pb < total; pb += (long long)gridDim.x * blockDim.x) {
+        const long long p = pb + lane;
+        const bool act = p < total;
+        const long long n = (act ? p : total - 1) / HW;
+        const long long n0 = __shfl_sync(0xffffffffu, n, 0);
+        const float2 part = __ldg(reinterpret_cast<const float2*>(partial) + n0 * MEAN_PARTS + lane);
+        float mu = part.x, mv = part.y;
+#pragma unroll
+        for (int o = 16; o >= 1; o >>= 1) {
+            mu += __shfl_xor_sync(0xffffffffu, mu, o);
+            mv += __shfl_xor_sync(0xffffffffu, mv, o);
         }
-        const float inv = 1.f / (float)HW;
+        if (!act) continue;
+        if (n != n0) {                                  // the warp straddles two images
+            mu = 0.f; mv = 0.f;
+            for (int i = 0; i < MEAN_PARTS; ++i) {
+                mu += __ldg(partial + (n * MEAN_PARTS + i) * 2);
+                mv += __ldg(partial + (n * MEAN_PARTS + i) * 2 + 1);
+            }
+        }
         mu *= inv; mv *= inv;
+        const int x = (int)(p % W), y = (int)((p / W) % H);
         const float2 fl = __ldg(flow + p);
         const BilinearTaps tp = make_taps((float)x + fl.x * scale, (float)y + fl.y * scale, H, W);
         const float wgt[4] = {tp.w00, tp.w01, tp.w10, tp.w11};
@@ -235,8 +250,9 @@ __global__ void reg_input_p16_kernel(const float4* __restrict__ img1, const floa
         const uint32_t h0 = p16::pack_hi(e, ru), h1 = p16::pack_hi(rv, 0.f);
         bad |= p16::nonfinite_bits(h0) | p16::nonfinite_bits(h1);
         uint8_t* o = out + p * (long long)out_ld * 4;
-        // channels 3..15 of the group stay zero (the buffer is zero-initialised once and nobody else writes them)
+        // the whole 64-byte group (channels 3..15 are zeros): two full 32-byte sectors, no partial-sector writes
         stg_u4(o, make_uint4(h0, h1, 0u, 0u));
+        stg_u4(o + 16, make_uint4(0u, 0u, 0u, 0u));
         stg_u4(o + 32, make_uint4(p16::pack_lo4(e, ru, rv, 0.f, h0, h1), 0u, 0u, 0u));
         stg_u4(o + 48, make_uint4(p16::pack_e5m2x4(e, ru, rv, 0.f), 0u, 0u, 0u));
     }
@@ -277,7 +293,8 @@ head_rows_sum_kernel(const float2* __restrict__ planes, long long plane_pix, con
             const uint32_t h0 = p16::pack_hi(su, sv);
             bad |= p16::nonfinite_bits(h0);
             uint8_t* o = out_p16 + p * (long long)p16_ld * 4;
-            stg_u4(o, make_uint4(h0, 0u, 0u, 0u));
+            stg_u4(o, make_uint4(h0, 0u, 0u, 0u));        // the whole 64-byte group: full sectors
+            stg_u4(o + 16, make_uint4(0u, 0u, 0u, 0u));
             stg_u4(o + 32, make_uint4(p16::pack_lo4(su, sv, 0.f, 0.f, h0, 0u), 0u, 0u, 0u));
             stg_u4(o + 48, make_uint4(p16::pack_e5m2x4(su, sv, 0.f, 0.f), 0u, 0u, 0u));
         }
