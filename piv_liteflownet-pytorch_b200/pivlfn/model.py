@@ -721,7 +721,10 @@ class Plan:
             gc_was_on = gc.isenabled()
             gc.disable()
             try:
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                # an explicit capture stream on THIS engine's device: torch's default capture stream is created once per process
+                # on whatever device captured first, and entering it switches the current device -- a second engine on another
+                # GPU would record its kernels (with its own device's pointers) on the first GPU's stream
+                with torch.cuda.graph(g, stream=torch.cuda.Stream(device=eng.device), capture_error_mode="thread_local"):
                     self.launch_all()
             finally:
                 if gc_was_on:

@@ -584,7 +584,7 @@ class DistGroup:
             gc_was_on = gc.isenabled()
             gc.disable()
             try:
-                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                with torch.cuda.graph(g, stream=torch.cuda.Stream(device=p.eng.device), capture_error_mode="thread_local"):
                     for st in steps:
                         if st.kind == "op":
                             st.fn()
