@@ -472,6 +472,8 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
         const int row = q * 32 + lane;
         const int ncg = a.CoutP >> 4;
         const int nunits = a.NT * ncg;
+        const int u_i0 = eg / ncg, u_c0 = eg - u_i0 * ncg, u_di = negr / ncg, u_dc = negr - u_di * ncg;
+        const float slope = a.lrelu ? PIVLFN_LRELU_SLOPE : 1.f;
         // the weights are packed times a per-layer power of two S (pivlfn.model._pack_f8); the image ends with [1 / S, S, 0, 0]
         const float osc = __ldg(reinterpret_cast<const float*>(a.w_img + (size_t)nchunk * ntaps * b_stage));
         uint32_t bad = 0;
@@ -501,13 +503,15 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                 continue;
             }
             uint32_t v[16];
-            auto issue = [&](int unit) {
-                const int i = unit / ncg, cg = unit - i * ncg;
-                tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + cg * 16), v);
-            };
-            if (eg < nunits) issue(eg);
+            // unit = (stacked tile i, 16-column group cg), walked with two counters (a division per unit cost ~40 instructions of
+            // the ~400 this loop body takes)
+            int i = u_i0, cg = u_c0;
+            if (eg < nunits) tmem_ld16_nowait(trow + (uint32_t)(i * tile_cols + cg * 16), v);
             for (int unit = eg; unit < nunits; unit += negr) {
-                const int i = unit / ncg, cb = (unit - i * ncg) * 16;
+                const int cb = cg * 16;
+                int ni = i + u_di, ncg2 = cg + u_dc;                       // the next unit of this warp
+                if (ncg2 >= ncg) { ncg2 -= ncg; ++ni; }
+                const int i_cur = i;
                 tmem_ld_wait();
                 float r[16];
 #pragma unroll
@@ -517,12 +521,13 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
                         const float t = fmaf(__uint_as_float(v[4 * j + k]), osc, bb[k]);
-                        r[4 * j + k] = a.lrelu ? lrelu_f(t) : t;
+                        r[4 * j + k] = fmaxf(t, t * slope);                 // LeakyReLU(0.1) = max(t, 0.1 t); slope 1: identity
                     }
                 }
                 // v / u are consumed: the TMEM loads of this warp's next unit hide behind the conversion and the stores
-                if (unit + negr < nunits) issue(unit + negr);
-                const int yy = (ty * a.NT + i) * HT_H + (row >> 3);
+                if (unit + negr < nunits) tmem_ld16_nowait(trow + (uint32_t)(ni * tile_cols + ncg2 * 16), v);
+                i = ni; cg = ncg2;
+                const int yy = (ty * a.NT + i_cur) * HT_H + (row >> 3);
                 const size_t pix = ((size_t)n * a.H + yy) * a.W + x;
                 if (a.out_fmt == OUT_PLANES) {
                     if (x < a.W && yy < a.H) {
