@@ -1,6 +1,7 @@
 """Host-side logic on the CPU: architecture tables vs the reference's state_dict contract, weight packing,
 drop-in API surface and error behaviour, sharding arithmetic, synthetic input generator."""
 import json
+import math
 import os
 
 import numpy as np
@@ -225,3 +226,43 @@ def test_weight_stage_image_is_the_swizzled_shared_memory_layout():
     # a stage of tps taps is a contiguous range of tps * parts * CoutP * 64 bytes
     assert img[1, 3:6].reshape(-1).data_ptr() - img[1, 3].data_ptr() == 0
     assert stage_image(None) is None
+
+
+def test_f8_weight_image_layout_scale_and_reconstruction():
+    """pivlfn.model._pack_f8 (the weight image of pivlfn_conv_p16): per-layer power-of-two scale S with max|w| S in [8192, 16384),
+    tile 0 = f16(S w), tile 1 = per 16 channels [e5m2(S w / 2048) x 16 | e5m2(S w - f16(S w)) x 16], both at the byte offsets of
+    the swizzled ring image, and a 16-byte trailer [1 / S, S, 0, 0]; W_hi + W_lo reconstructs the weight to 2^-13 relative (the
+    correction tile has 3 significant bits), whatever the magnitude of the layer (no fp16 overflow: 1e5 packs fine)."""
+    from pivlfn.model import _pack_f8, f8_scale
+    g = torch.Generator().manual_seed(11)
+    for mag in (1e-3, 1.0, 1e5):
+        coutp, ntaps, cinp = 48, 9, 64
+        w = torch.randn(coutp, ntaps, cinp, generator=g) * mag * torch.logspace(-2, 0, cinp)[None, None, :]
+        img = _pack_f8(w)
+        S = f8_scale(w)
+        assert math.log2(S) == round(math.log2(S)) and 8192.0 <= float(w.abs().max()) * S < 16384.0
+        body = (cinp // 32) * ntaps * 2 * coutp * 64
+        assert img.dtype == torch.uint8 and img.numel() == body + 16
+        tr = img[body:].view(torch.float32)
+        assert float(tr[0]) == 1.0 / S and float(tr[1]) == S and float(tr[2]) == 0.0
+        W = w * S
+        hi = W.to(torch.float16)
+        rng = np.random.default_rng(1)
+        for _ in range(300):
+            r, t, k = (int(rng.integers(n)) for n in (coutp, ntaps, cinp))
+            c, kk = divmod(k, 32)
+            row0 = (((c * ntaps + t) * 2 + 0) * coutp + r) * 64            # tile 0: 32 fp16 channels per 64-byte row
+            row1 = (((c * ntaps + t) * 2 + 1) * coutp + r) * 64            # tile 1: [lo x 16 | hi x 16] per 16 channels
+            sw = (r >> 1) & 3
+            b0 = row0 + (((kk // 8) ^ sw) * 16) + (kk % 8) * 2
+            assert img[b0:b0 + 2].view(torch.float16)[0] == hi[r, t, k]
+            grp, j = divmod(kk, 16)                                         # 32 bytes per group: 16-byte unit 2*grp (+1 for W_lo)
+            b_lo = row1 + (((2 * grp) ^ sw) * 16) + j
+            b_hi = row1 + (((2 * grp + 1) ^ sw) * 16) + j
+            assert img[b_lo:b_lo + 1].view(torch.float8_e5m2)[0].float() == (W[r, t, k] / 2048.0).to(torch.float8_e5m2).float()
+            assert img[b_hi:b_hi + 1].view(torch.float8_e5m2)[0].float() == (W[r, t, k] - hi[r, t, k].float()).to(torch.float8_e5m2).float()
+        rec = (hi.double() + (W - hi.float()).to(torch.float8_e5m2).double()) / S
+        assert ((rec - w.double()).abs() <= w.abs().double() * 2.0 ** -13 + float(w.abs().max()) * 2.0 ** -30).all()
+    bad = torch.randn(16, 1, 32, generator=g)
+    bad[0, 0, 0] = float("inf")
+    assert _pack_f8(bad) is None
