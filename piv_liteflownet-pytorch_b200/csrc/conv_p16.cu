@@ -226,6 +226,13 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_s;
+    // Programmatic dependent launch (the launch carries cudaLaunchAttributeProgrammaticStreamSerialization): everything above --
+    // barrier init, TMEM allocation, bias / tail weights (model parameters, never written by a kernel of the forward) -- ran
+    // while the previous kernel of the stream was still draining.  launch_dependents lets the NEXT kernel do the same as soon
+    // as this CTA's SM frees up; wait blocks until the previous kernel has completed and its writes are visible.  Every thread
+    // waits: every role reads activations (TMA, gathers, the tail's flow loads) or writes buffers the predecessor may read.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     if (warp == 0) {
         // ================================ activation tiles ==============================
@@ -750,7 +757,16 @@ int conv_p16_impl(const void* x, int x_ld, int N, int H, int W, int Cin, const v
     static unsigned long long cfg6 = 0;
     cudaError_t e = pivlfn_optin_smem(conv_p16_kernel<6>, SMEM_BUDGET, cfg6);
     if (e != cudaSuccess) return (int)e;
-    conv_p16_kernel<6><<<grid, P16_THREADS, smem, st>>>(tmA, h);
+    static int pdl = -1;                     // PIVLFN_P16_PDL=0: plain stream-ordered launches
+    if (pdl < 0) { const char* v = getenv("PIVLFN_P16_PDL"); pdl = v ? atoi(v) : 1; }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(P16_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    e = cudaLaunchKernelEx(&cfg, conv_p16_kernel<6>, tmA, h);
+    if (e != cudaSuccess) return (int)e;
     PIVLFN_LAUNCHED();
     return pivlfn_last_error();
 }
