@@ -187,9 +187,10 @@ int pivlfn_resize_bilinear_nchw(const float* in, float* out, int NC, int H, int 
                                 float mul_even, float mul_odd, void* stream);
 
 /* ---- the P16 pipeline (default for precision f16c) -----------------------------------------------------------------------
- * P16 is the activation format of the fp16-split arithmetic: an fp32 value x is stored as the pair the tensor cores
- * consume, hi = f16(x) and lo = f16((x - hi) * 2^11) (x = hi + lo / 2048, 22 significant bits, |x| < 65504), 4 bytes per
- * element.  Channels are grouped by 16; one group of one pixel is 64 contiguous bytes [16 x hi | 16 x lo], so that a view
+ * P16 is the activation format of the split-operand arithmetic: an fp32 value x is stored as the operands the tensor cores
+ * consume, hi = f16(x), lo8 = e5m2((x - hi) * 2^11), hi8 = e5m2(x) (x = hi + lo8 / 2048 up to 2^-14 |x|, |x| < 65504), 4 bytes
+ * per element (csrc/p16.cuh).  Channels are grouped by 16; one group of one pixel is 64 contiguous bytes
+ * [16 x hi (f16) | 16 x lo8 | 16 x hi8], so that a view
  * (pointer, pixel pitch in 4-byte words, channel count rounded up to 16) addresses a P16 tensor like an fp32 NHWC one,
  * channel slices start at multiples of 16 and a 32-channel chunk of a pixel is one 128-byte MMA-ready row.  Pad channels
  * of the last group are zero.  P16 pointers are 64-byte aligned, pitches multiples of 16 words.
@@ -201,11 +202,14 @@ int pivlfn_p16_encode(const float* x, int x_ld, int C, void* y, int y_ld, long l
 int pivlfn_p16_decode(const void* x, int x_ld, int C, float* y, int y_ld, long long npix, void* stream);
 
 /* Convolution + bias + LeakyReLU on a P16 input (src/models.py:77-106,124,154-163,197-207,229-272): implicit GEMM on
- * tcgen05 with the three fp16 products of pivlfn_conv_tc's passes 4 / 5, but with NO operand split inside the kernel: TMA
- * delivers MMA-ready halo tiles.  Odd KH, KW <= 7 at stride 1; 3x3 at stride 2 (H, W = INPUT size, even; Cin % 32 == 0;
+ * tcgen05 with NO operand split inside the kernel: TMA delivers MMA-ready halo tiles.  Per 16 input channels the kernel issues
+ * a_hi * W_hi as one kind::f16 MMA (K = 16) and both correction products, [lo8 | hi8] * [W 2^-11 ; W - W_hi], as ONE
+ * kind::f8f6f4 e5m2 MMA (K = 32) into the same fp32 accumulator.  Odd KH, KW <= 7 at stride 1; 3x3 at stride 2 (H, W = INPUT size, even; Cin % 32 == 0;
  * w_img = pack of the parity-restated weights, see pivlfn_conv_s2_tc).  Cin: logical input channels (the buffer holds
- * ceil16(Cin) words per pixel).  w_img: ring-stage image of the fp16 weights (see pivlfn_conv_tc: passes-4 pack for mode 4,
- * Cout <= 64; passes-5 pack for mode 5, Cout <= 128).
+ * ceil16(Cin) words per pixel).  mode: 6 (the only product scheme).  w_img: the weight image built by pivlfn.model._pack_f8 --
+ * per 32-channel chunk and tap [f16(S w) tile | e5m2 correction tile], CoutP rows of 64 bytes each with the 64B swizzle applied
+ * (one ring stage = one contiguous bulk copy), then a 16-byte trailer {1 / S, S, 0, 0} (fp32; S = the layer's power-of-two
+ * weight scale, applied by the epilogue).  Cout <= 128.
  * out_fmt 0: P16 view (pitch y_ld words, >= ceil16(Cout); pad channels written as zeros);
  *         1: fp32 NHWC view (pitch y_ld floats);
  *         2: fp32 channel-PAIR planes, plane p = channels (2p, 2p+1) as [pixel][2], plane_stride floats apart. */
@@ -216,14 +220,14 @@ int pivlfn_conv_p16(const void* x, int x_ld, int N, int H, int W, int Cin, const
 /* pivlfn_conv_p16 (stride 1, P16 output) with a BACKWARP FUSED INTO ITS INPUT (src/models.py:209-217, the Subpixel consumer):
  * of the Cin logical input channels, [wc0, wc0 + wn) are backwarp(wsrc, wscale * wflow) (src/models.py:20-35) and do not exist in
  * memory: the kernel's gather warps sample wsrc (fp32 NHWC with pitch wsrc_ld floats, or P16 with wsrc_p16 = 1), blend, split
- * into fp16 pairs and write the MMA operand tile directly.  x holds the other Cin - wn channels contiguously ([0, wc0) then
+ * into the P16 operands and write the MMA operand tile directly.  x holds the other Cin - wn channels contiguously ([0, wc0) then
  * [wc0 + wn, Cin)).  wc0 and wn are multiples of 32; wflow: dense [N,H,W,2]. */
 int pivlfn_conv_p16_warp(const void* x, int x_ld, int N, int H, int W, int Cin, const void* w_img, int mode,
                          const float* bias, void* y, int y_ld, int Cout, int KH, int KW, int lrelu,
                          const void* wsrc, int wsrc_ld, int wsrc_p16, const float* wflow, float wscale,
                          int wc0, int wn, int* range_flag, void* stream);
 
-/* pivlfn_conv_p16 (mode 4, stride 1, no activation) whose K*K output channels are the Regularization distances, with the rest of the
+/* pivlfn_conv_p16 (stride 1, no activation) whose K*K output channels are the Regularization distances, with the rest of the
  * Regularization block FUSED INTO ITS EPILOGUE (src/models.py:279-300 (PIV) / :620-641 (Hui); replaces conv_dist + pivlfn_reg_tail): per pixel
  * softmax_k(-d_k^2) over the K*K channels read straight from the accumulators, the weighted K x K unfold of flow_in, the 1x1
  * moduleScaleX / moduleScaleY convolutions (wx, bx, wy, by: device pointers to K*K weights / 1 bias each) and the division.
