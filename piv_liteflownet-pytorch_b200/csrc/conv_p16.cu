@@ -1,22 +1,20 @@
 // Convolution (+ bias + LeakyReLU) on P16 activations: implicit GEMM on the 5th-generation tensor cores with NO operand
 // preparation inside the kernel.
 //
-// The fp32-equivalent arithmetic is the three-product fp16 split of conv_tc.cu (modes 4 / 5),
-//     D = a_hi*w_hi + 2^-11 * (a_lo'*w_hi + a_hi*w_lo'),
-// but the activations arrive from HBM already as (hi, lo') pairs (p16.cuh): per 32-channel chunk ONE 4-D TMA box
-//     [16*NT + KH - 1 rows][8 + KW - 1 pixels][128 bytes = hi0 | lo0 | hi1 | lo1]       (128B swizzle, zero fill outside)
+// Split-operand arithmetic (p16.cuh): a = a_hi + 2^-11 a_lo, w = W_hi + W_lo (weights pre-scaled by a per-layer power of two),
+//     D = a_hi*W_hi                               one kind::f16 MMA, K = 16
+//       + [a_lo8 | a_hi8] * [W 2^-11 ; W_lo]      ONE kind::f8f6f4 (e5m2) MMA, K = 32: both correction products
+// into one fp32 accumulator in TMEM: two MMA slots per 16 input channels (three for an fp16 split of the corrections).
+// The activations arrive from HBM already in operand form: per 32-channel chunk ONE 4-D TMA box
+//     [16*NT + KH - 1 rows][8 + KW - 1 pixels][128 bytes = hi0 | c0 | hi1 | c1]         (128B swizzle, zero fill outside)
 // lands in shared memory as the MMA-ready K-major halo tile; every filter tap's A operand is a shifted window into it and
-// the four K = 16 steps of a tap are 32-byte advances of the descriptor start address.  Compared with conv_tc.cu's modes
-// 4 / 5 the 8 operand-split warps, the raw-tile slot and ~15-23 % of the shared-memory traffic are gone, and the freed
+// the four K steps of a tap are 32-byte advances of the descriptor start address.  Compared with conv_tc.cu's f16c modes
+// the 8 operand-split warps, the raw-tile slot and ~15-23 % of the shared-memory traffic are gone, and the freed
 // warps double the epilogue: 16 warps (4 per TMEM lane quarter) turn accumulators into P16 (or fp32) rows.
 //
 //   warp 0        TMA producer of the activation tiles          warp 3   producer of the weight ring (one bulk copy / stage)
-//   warps 1, 2    MMA issuers (stacked tile 0 / 1)              warps 4..19   epilogue
+//   warps 1, 2    MMA issuers (every second stacked tile each)  warps 4..19   epilogue (12 of them gather when a backwarp is fused)
 //
-// MODE 4 (Cout <= 64): a_hi * [w_hi | w_lo'] is ONE MMA of N = 2*Cout filling [main | corr], then a_lo' * w_hi -> corr
-//                      (the A window is read from shared memory twice per tap instead of three times).
-// MODE 5 (Cout > 64):  weights pre-scaled by 2^8 as [W_hi | W_lo | W_hi * 2^-11]: all three products carry the same scale
-//                      and add up in ONE accumulator, which leaves room for two TMEM sets (epilogue overlaps the MMAs).
 // Replaces torch.nn.Conv2d (+LeakyReLU(0.1)) of src/models.py:77-106 (NetC), :124 (NetC_ext), :154-163 (conv_M),
 // :197-207 (conv_S), :229-272 (moduleFeat, conv_R, conv_dist_R).
 #include <cuda.h>

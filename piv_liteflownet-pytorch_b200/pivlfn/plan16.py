@@ -1,5 +1,6 @@
 """Launch plan of the P16 pipeline (the default for precision ``f16c``): the forward of ``pivlfn.model.Plan`` with every
-activation that feeds a convolution kept in HBM as the fp16 (hi, lo') pairs the tensor cores consume (csrc/p16.cuh).
+activation that feeds a convolution kept in HBM as the operands the tensor cores consume (fp16 value, e5m2 residual, e5m2
+value: csrc/p16.cuh).
 
 Same reference semantics (src/models.py:319-370 / :660-716), same buffers-as-concats idea as ``Plan``:
 
@@ -9,7 +10,7 @@ Same reference semantics (src/models.py:319-370 / :660-716), same buffers-as-con
 
 Channel slices start at multiples of 16 (one P16 group = 64 bytes per pixel).  What stays fp32 NHWC: the images, the
 flows, the second image's NetC_ext features at levels 1-2 (read only by the cost volume and the backwarp), the
-half-resolution cost volume in front of upCorr_M, the flow-head row planes and the distance maps of the regularisation tail.
+half-resolution cost volume in front of upCorr_M and the flow-head planes (the distance maps of the regularisation stay in TMEM).
 
 Differences from ``Plan`` besides the format:
   * all convolutions (stride-2 NetC layers, the 192-channel conv6 as two 96-channel halves, tiny levels) run in ONE kernel
@@ -17,8 +18,10 @@ Differences from ``Plan`` besides the format:
   * the Subpixel backwarp (src/models.py:214) is fused into its consumer: conv_S.0's gather warps sample f2 and write the MMA
     operand tile directly (``pivlfn_conv_p16_warp``), so the warped features never reach HBM (PIVLFN_FUSE_WARP=0: separate
     ``pivlfn_warp_p16`` kernel writing a slice of Sbuf);
-  * the KxK 32 -> 2 flow heads run on the tensor cores as a 1xK convolution to 2K row planes + a K-row gather-sum
-    (``pivlfn_head_rows_sum``), which also writes flow_M's P16 group into Sbuf.
+  * the KxK 32 -> 2 flow heads run on the tensor cores as a Kx1 convolution to 2K column planes + a K-column gather-sum
+    (``pivlfn_head_cols_sum``), which also writes flow_M's P16 group into Sbuf;
+  * the Regularization tail (src/models.py:279-300) runs in the epilogue of the last conv_dist_R layer
+    (``pivlfn_conv_p16_tail``; PIVLFN_FUSE_TAIL=0: fp32 distance maps + ``pivlfn_reg_tail``).
 """
 from __future__ import annotations
 
