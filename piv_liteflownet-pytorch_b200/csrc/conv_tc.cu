@@ -1104,16 +1104,18 @@ const HaloEnv& halo_env() {
     if (e.use_halo < 0) {
         const char* v = getenv("PIVLFN_TC_HALO");
         e.use_halo = (v && v[0] == '0') ? 0 : 1;
+#ifdef PIVLFN_DEBUG      // timing experiments (build with -DPIVLFN_DEBUG): not available in the product library
         v = getenv("PIVLFN_TC_BO");
         e.bo_mode = (v && v[0] == '1') ? 1 : 0;
+        v = getenv("PIVLFN_TC_STAGGER");          // percent of one estimated work-item period; 0 = off
+        e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
+#endif
         v = getenv("PIVLFN_TC_NT");
         e.nt_limit = v ? atoi(v) : 0;
         v = getenv("PIVLFN_TC_CORR");
         e.corr_mode = (v && v[0] == '0') ? 0 : 1;
         v = getenv("PIVLFN_TC_SPLIT_TRUNC");
         e.split_trunc = (v && v[0] == '0') ? 0 : 1;
-        v = getenv("PIVLFN_TC_STAGGER");          // percent of one estimated work-item period; 0 = off
-        e.stagger = v ? atoi(v) : 0;              // measured: no effect (the stores are not HBM-bound), off by default
         v = getenv("PIVLFN_TC_QUADSTORE");
         e.quad_store = (v && v[0] == '0') ? 0 : 1;
         v = getenv("PIVLFN_TC_TPS3");
@@ -1186,7 +1188,9 @@ int halo_launch(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensor
                 const CUtensorMap* tmYp = nullptr) {
     const CUtensorMap& tmY = tmYp ? *tmYp : tmA;
     int grid = h.total < num_sms() ? h.total : num_sms();
+#ifdef PIVLFN_DEBUG
     { static int cap = -1; if (cap < 0) { const char* v = getenv("PIVLFN_TC_GRID"); cap = v ? atoi(v) : 0; } if (cap > 0 && cap < grid) grid = cap; }
+#endif
     static unsigned long long cfg1 = 0, cfg2 = 0, cfg3 = 0, cfg4 = 0, cfg5 = 0;
     cudaError_t e = cudaSuccess;
     if (passes == 5) {
@@ -1282,7 +1286,9 @@ extern "C" int pivlfn_conv_tc(const float* x, int x_ld, int N, int H, int W, int
         // TMA tile stores: rows 16-byte aligned, at least one full 16-channel group, no residual to add
         const bool tma_ok = vec_store >= 1 && !res && cout_st >= 16 && halo_env().tma_store;
         if (tma_ok) h.vec_store = 5;
+#ifdef PIVLFN_DEBUG
         if (getenv("PIVLFN_TC_NOSTORE")) h.vec_store = 3;      // timing experiment only: results are not written
+#endif
         int halo_rows = 0;
         int smem = halo_configure(h, passes, &halo_rows);
         if (smem <= 0 && h.vec_store == 5) {                   // no room for the staging area: direct stores
