@@ -179,6 +179,26 @@ def test_unmodified_reference_correlation_matches_cubins_and_oracle():
 
 @pytest.mark.gpu
 @needs_installed_ref
+def test_three_product_variant_vs_unmodified_reference_on_gpu(monkeypatch):
+    """The fp32-equivalent variant (PIVLFN_P16=0: fp32 activations, three fp16 products per product), which bench.py reports
+    separately, against the UNMODIFIED reference on the GPU: same absolute tolerance, and closer than the default variant."""
+    from src.models import piv_liteflownet
+    sd = synth.synthetic_state_dict("piv", 5)
+    a, b, _ = synth.particle_batch(1, 128, 128, 428, "rankine")
+    ref = _unmodified_reference_forward(sd, a, b, "piv", 1)
+    monkeypatch.setenv("PIVLFN_P16", "0")
+    net = piv_liteflownet(sd, 1).to(DEV).eval()
+    assert not net.engine().p16 and net.engine().precision == "f16c"
+    with torch.no_grad():
+        out = net(a.to(DEV), b.to(DEV))
+    diff = (out - ref).abs()
+    _report(f"forward vs UNMODIFIED reference on the GPU piv 1x128x128 f16c three-product variant (PIVLFN_P16=0): max {diff.max().item():.3e} "
+            f"mean {diff.mean().item():.3e}")
+    assert diff.max().item() <= 1e-2 and diff.mean().item() <= 1e-3
+
+
+@pytest.mark.gpu
+@needs_installed_ref
 @pytest.mark.parametrize("shape", [(2, 16, 12, 16, 2), (1, 8, 9, 11, 1), (1, 64, 32, 32, 2)], ids=str)
 def test_correlation_backward_vs_unmodified_reference(shape):
     """gradFirst / gradSecond of the drop-in operator against the reference's own backward (its updateGradFirst / updateGradSecond
