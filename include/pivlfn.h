@@ -204,10 +204,10 @@ int pivlfn_p16_decode(const void* x, int x_ld, int C, float* y, int y_ld, long l
 /* Convolution + bias + LeakyReLU on a P16 input (src/models.py:77-106,124,154-163,197-207,229-272): implicit GEMM on
  * tcgen05 with NO operand split inside the kernel: TMA delivers MMA-ready halo tiles.  Per 16 input channels the kernel issues
  * a_hi * W_hi as one kind::f16 MMA (K = 16) and both correction products, [lo8 | hi8] * [W 2^-11 ; W - W_hi], as ONE
- * kind::f8f6f4 e5m2 MMA (K = 32) into the same fp32 accumulator.  Odd KH, KW <= 7 at stride 1; 3x3 at stride 2 (H, W = INPUT size, even; Cin % 32 == 0;
+ * kind::f8f6f4 MMA (K = 32; activations e5m2, weights e4m3) into the same fp32 accumulator.  Odd KH, KW <= 7 at stride 1; 3x3 at stride 2 (H, W = INPUT size, even; Cin % 32 == 0;
  * w_img = pack of the parity-restated weights, see pivlfn_conv_s2_tc).  Cin: logical input channels (the buffer holds
  * ceil16(Cin) words per pixel).  mode: 6 (the only product scheme).  w_img: the weight image built by pivlfn.model._pack_f8 --
- * per 32-channel chunk and tap [f16(S w) tile | e5m2 correction tile], CoutP rows of 64 bytes each with the 64B swizzle applied
+ * per 32-channel chunk and tap [f16(S w) tile | e4m3 correction tile], CoutP rows of 64 bytes each with the 64B swizzle applied
  * (one ring stage = one contiguous bulk copy), then a 16-byte trailer {1 / S, S, 0, 0} (fp32; S = the layer's power-of-two
  * weight scale, applied by the epilogue).  Cout <= 128.
  * out_fmt 0: P16 view (pitch y_ld words, >= ceil16(Cout); pad channels written as zeros);

@@ -3,7 +3,7 @@
 //
 // Split-operand arithmetic (p16.cuh): a = a_hi + 2^-11 a_lo, w = W_hi + W_lo (weights pre-scaled by a per-layer power of two),
 //     D = a_hi*W_hi                               one kind::f16 MMA, K = 16
-//       + [a_lo8 | a_hi8] * [W 2^-11 ; W_lo]      ONE kind::f8f6f4 (e5m2) MMA, K = 32: both correction products
+//       + [a_lo8 | a_hi8] * [W 2^-11 ; W_lo]      ONE kind::f8f6f4 MMA (A e5m2, B e4m3), K = 32: both correction products
 // into one fp32 accumulator in TMEM: two MMA slots per 16 input channels (three for an fp16 split of the corrections).
 // The activations arrive from HBM already in operand form: per 32-channel chunk ONE 4-D TMA box
 //     [16*NT + KH - 1 rows][8 + KW - 1 pixels][128 bytes = hi0 | c0 | hi1 | c1]         (128B swizzle, zero fill outside)
@@ -184,7 +184,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
     const int halo_bytes = halo_rows * pitch * 128;
     const int slot_bytes = (halo_bytes + 1023) & ~1023;
     const int part_bytes = a.CoutP * 64;                        // one fp16 weight tile: CoutP rows of 32 channels
-    const int b_stage = 2 * part_bytes;                         // per tap: [W_hi f16 | (W_hi 2^-11 ; W_lo) e5m2]
+    const int b_stage = 2 * part_bytes;                         // per tap: [W_hi f16 | (W 2^-11 ; W_lo) e4m3]
     uint8_t* smemB = smem + (size_t)a.nA * slot_bytes;
     __shared__ __align__(8) uint64_t a_full[MAX_A], a_free[MAX_A], b_full[MAX_B], b_empty[MAX_B], acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
@@ -287,7 +287,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
             const uint32_t hiA = (uint32_t)((((uint64_t)((pitch * 128) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61)) >> 32);
             const uint32_t hiB = (uint32_t)((((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61)) >> 32);
             const uint32_t idesc = make_idesc_f16(a.CoutP);
-            const uint32_t idesc8 = make_idesc_e5m2(a.CoutP);
+            const uint32_t idesc8 = make_idesc_f8(a.CoutP);
             const uint32_t part16 = (uint32_t)(part_bytes >> 4);
             const uint32_t stage16 = (uint32_t)(b_stage >> 4);
             const uint32_t ring16 = stage16 * (uint32_t)a.tps;
@@ -330,7 +330,7 @@ conv_p16_kernel(const __grid_constant__ CUtensorMap tmA, const ConvP16Args a) {
                         for (int sub = 0; sub < a.tps; ++sub, ++t, b += stage16) {
                             uint32_t A = A0, t_main = t_first;
                             for (int i = 0; i < ntl; ++i, A += tile16 * (uint32_t)n_iss, t_main += (uint32_t)(tile_cols * n_iss)) {
-                                // per 16-channel K step: a_hi * W_hi (f16, K = 16) and [a_lo8 | a_hi8] * [W_hi 2^-11 ; W_lo] (e5m2, K = 32)
+                                // per 16-channel K step: a_hi * W_hi (f16, K = 16) and [a_lo8 | a_hi8] * [W 2^-11 ; W_lo] (fp8, K = 32)
                                 umma_bf16_lohi(t_main, A, hiA, b, hiB, idesc, acc);
                                 umma_f8_lohi(t_main, A + 2, hiA, b + part16, hiB, idesc8, 1);
                                 if (two) {

@@ -3,9 +3,10 @@
 // An fp32 activation x is kept in HBM as the operands the tensor cores consume, 4 bytes per element like fp32:
 //     hi  = f16(x)                         2 bytes   the main product's operand (kind::f16, K = 16)
 //     lo8 = e5m2((x - hi) * 2^11)          1 byte    } the two correction products a_lo * W_hi + a_hi * W_lo run as ONE fp8 MMA
-//     hi8 = e5m2(x)                        1 byte    } (kind::f8f6f4, K = 32 = [16 x lo8 | 16 x hi8]) at twice the f16 rate
+//     hi8 = e5m2(x)                        1 byte    } (kind::f8f6f4, K = 32 = [16 x lo8 | 16 x hi8]) at twice the f16 rate;
+//                                                       the weight side of that MMA is e4m3 (per-layer scale: pivlfn.model._pack_f8)
 // x = hi + 2^-11 * lo8 up to 2^-14 |x| (the correction terms carry 3 significant bits: tools/sim_precision.py measures the
-// flow error of the whole network at 4e-4 px max against 7e-3 px for single-pass TF32; the 3-product fp16 split it replaces
+// flow error of the whole network at 3e-4 px max against 7e-3 px for single-pass TF32; the 3-product fp16 split it replaces
 // spent three full-rate MMAs per product for 1e-6 px).  e5m2 has the exponent range of fp16, so the range check stays the
 // fp16 one (|x| < 65504; hi8 saturates at 57344, which only touches a correction term).
 // Channels are grouped by 16: one group of one pixel is 64 contiguous bytes,

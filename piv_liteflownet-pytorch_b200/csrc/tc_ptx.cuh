@@ -129,7 +129,7 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
         "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
-// kind::f8f6f4 with e5m2 operands (K = 32 per instruction), fp32 accumulate: twice the f16 rate
+// kind::f8f6f4 with 8-bit operands (K = 32 per instruction), fp32 accumulate: twice the f16 rate
 __device__ __forceinline__ void umma_f8_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
                                              uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -175,9 +175,10 @@ __device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
 __device__ __forceinline__ uint32_t make_idesc_f16(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
-// kind::f8f6f4 with e5m2 operands: A and B format E5M2 (= 1), D fp32
-__device__ __forceinline__ uint32_t make_idesc_e5m2(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
+// kind::f8f6f4: A (activations) in E5M2 (format 1: fp16's exponent range), B (weights, scaled per layer) in E4M3 (format 0: one
+// more mantissa bit), D fp32
+__device__ __forceinline__ uint32_t make_idesc_f8(int n) {
+    return (1u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TILE_M >> 4) << 24);
 }
 // two fp32 -> packed f16x2 (round to nearest even), low half = first value
 __device__ __forceinline__ uint32_t pack_f16(float a, float b) {

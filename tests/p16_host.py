@@ -3,7 +3,7 @@
 import torch
 import torch.nn.functional as F
 
-from pivlfn.model import f8_scale
+from pivlfn.model import W8, f8_scale
 
 E5 = torch.float8_e5m2
 STORE_REL = 2.0 ** -13          # |x - decode(encode(x))| <= 2^-14 |x|; one lo8 step of slack for a 1-ulp different fp32 input
@@ -63,7 +63,7 @@ def conv_emul(x_nchw, w, b, stride=1, padding=0):
     S = f8_scale(w)
     W = w.float() * S
     Wh = W.to(torch.float16).float()
-    c_lo, c_hi = (W / 2048.0).to(E5).double(), (W - Wh).to(E5).double()
+    c_lo, c_hi = (W / 2048.0).to(W8).double(), (W - Wh).to(W8).double()
     kw = dict(stride=stride, padding=padding)
     y = (F.conv2d(hi, Wh.double(), None, **kw) + F.conv2d(lo8, c_lo, None, **kw) + F.conv2d(hi8, c_hi, None, **kw)) / S
     return y if b is None else y + b.double().view(1, -1, 1, 1)

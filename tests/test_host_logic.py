@@ -230,10 +230,10 @@ def test_weight_stage_image_is_the_swizzled_shared_memory_layout():
 
 def test_f8_weight_image_layout_scale_and_reconstruction():
     """pivlfn.model._pack_f8 (the weight image of pivlfn_conv_p16): per-layer power-of-two scale S with max|w| S in [8192, 16384),
-    tile 0 = f16(S w), tile 1 = per 16 channels [e5m2(S w / 2048) x 16 | e5m2(S w - f16(S w)) x 16], both at the byte offsets of
-    the swizzled ring image, and a 16-byte trailer [1 / S, S, 0, 0]; W_hi + W_lo reconstructs the weight to 2^-13 relative (the
-    correction tile has 3 significant bits), whatever the magnitude of the layer (no fp16 overflow: 1e5 packs fine)."""
-    from pivlfn.model import _pack_f8, f8_scale
+    tile 0 = f16(S w), tile 1 = per 16 channels [e4m3(S w / 2048) x 16 | e4m3(S w - f16(S w)) x 16], both at the byte offsets of
+    the swizzled ring image, and a 16-byte trailer [1 / S, S, 0, 0]; W_hi + W_lo reconstructs the weight to 2^-14 relative (the
+    correction tile has 4 significant bits), whatever the magnitude of the layer (no fp16 overflow: 1e5 packs fine)."""
+    from pivlfn.model import W8, _pack_f8, f8_scale
     g = torch.Generator().manual_seed(11)
     for mag in (1e-3, 1.0, 1e5):
         coutp, ntaps, cinp = 48, 9, 64
@@ -259,10 +259,11 @@ def test_f8_weight_image_layout_scale_and_reconstruction():
             grp, j = divmod(kk, 16)                                         # 32 bytes per group: 16-byte unit 2*grp (+1 for W_lo)
             b_lo = row1 + (((2 * grp) ^ sw) * 16) + j
             b_hi = row1 + (((2 * grp + 1) ^ sw) * 16) + j
-            assert img[b_lo:b_lo + 1].view(torch.float8_e5m2)[0].float() == (W[r, t, k] / 2048.0).to(torch.float8_e5m2).float()
-            assert img[b_hi:b_hi + 1].view(torch.float8_e5m2)[0].float() == (W[r, t, k] - hi[r, t, k].float()).to(torch.float8_e5m2).float()
-        rec = (hi.double() + (W - hi.float()).to(torch.float8_e5m2).double()) / S
-        assert ((rec - w.double()).abs() <= w.abs().double() * 2.0 ** -13 + float(w.abs().max()) * 2.0 ** -30).all()
+            assert img[b_lo:b_lo + 1].view(W8)[0].float() == (W[r, t, k] / 2048.0).to(W8).float()
+            assert img[b_hi:b_hi + 1].view(W8)[0].float() == (W[r, t, k] - hi[r, t, k].float()).to(W8).float()
+        rec = (hi.double() + (W - hi.float()).to(W8).double()) / S
+        # e4m3 residual: 4 significant bits of a term <= 2^-11 |w|; absolute floor = its subnormal step, 2^-23 of the layer's largest weight
+        assert ((rec - w.double()).abs() <= w.abs().double() * 2.0 ** -14 + float(w.abs().max()) * 2.0 ** -22).all()
     bad = torch.randn(16, 1, 32, generator=g)
     bad[0, 0, 0] = float("inf")
     assert _pack_f8(bad) is None

@@ -9,6 +9,7 @@ schemes:
   f16+e5  a = hi(fp16) + lo8*2^-11 with lo8 in e5m2; corrections a_lo8*w_hi8 + a_hi8*w_lo8 in e5m2 (an fp8 MMA at twice the rate)
   f16+e4  the same with e4m3 corrections
 This is analysis tooling (it imports oracle/): not part of the product."""
+import math
 import os
 import sys
 
@@ -54,6 +55,11 @@ def make_conv(scheme):
             if scheme == "f16x3":
                 xl, wl = f16(xl), f16(wl)
                 corr = F.conv2d(xl, wh, None, **kw) + F.conv2d(xh, wl, None, **kw)
+            elif scheme == "f16+mix":
+                sw = 2.0 ** math.floor(math.log2(16384.0 / float(w.abs().max())))          # per-layer weight scale (f8_scale)
+                e5, e4 = torch.float8_e5m2, torch.float8_e4m3fn
+                corr = (F.conv2d(q8(xl, e5), q8(wh * sw / 2048.0, e4), None, **kw) * 2048.0
+                        + F.conv2d(q8(xh, e5), q8((w * sw - f16(w * sw)), e4), None, **kw) * 2048.0) / sw
             else:
                 dt = torch.float8_e5m2 if scheme == "f16+e5" else torch.float8_e4m3fn
                 s = 1.0 if scheme == "f16+e5" else 64.0          # e4m3: keep small weights out of the subnormals
@@ -62,9 +68,9 @@ def make_conv(scheme):
         if b is not None:
             y = y + b.view(1, -1, 1, 1)
         y = O.lrelu(y) if act else y
-        if scheme in ("f16+e5", "f16+e4") and act:
+        if scheme in ("f16+e5", "f16+e4", "f16+mix") and act:
             # the stored activation is hi + lo8 * 2^-11
-            dt = torch.float8_e5m2 if scheme == "f16+e5" else torch.float8_e4m3fn
+            dt = torch.float8_e4m3fn if scheme == "f16+e4" else torch.float8_e5m2
             yh = f16(y)
             y = yh + q8((y - yh) * 2048.0, dt) / 2048.0
         elif scheme == "f16x3" and act:
@@ -80,7 +86,7 @@ def main():
     a, b = a.double(), b.double()
     orig = O._conv
     outs = {}
-    for scheme in ("fp64", "f16x3", "f16+e5", "f16+e4", "tf32"):
+    for scheme in ("fp64", "f16x3", "f16+e5", "f16+mix", "f16+e4", "tf32"):
         O._conv = make_conv(scheme)
         with torch.no_grad():
             outs[scheme] = O.forward(sd, a.clone(), b.clone(), "piv")
