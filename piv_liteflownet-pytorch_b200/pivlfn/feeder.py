@@ -1,6 +1,6 @@
 """Keep the GPU busy between host batches: uploads of batch k+1 and the download of batch k-1's flow run on two side streams
 while batch k's forward runs on the caller's stream (three-stage software pipeline over double-buffered device inputs and
-pinned host outputs).  Used by ``run.py`` and by the end-to-end leg of ``bench.py``; every step still pays its own
+pinned host outputs; push(k) enqueues upload k and then runs forward k-1).  Used by ``run.py`` and by the end-to-end leg of ``bench.py``; every step still pays its own
 host-to-device copy of both images and its device-to-host copy of the flow -- they just overlap the neighbours' compute.
 
     feeder = Feeder(net, device)
@@ -28,6 +28,7 @@ class Feeder:
         self._dev: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None] * self.depth
         self._free = [None] * self.depth             # event: the slot's device inputs may be overwritten
         self._inflight: deque = deque()
+        self._pending = None                         # the batch whose upload is enqueued and whose forward has not run yet
         self._k = 0
         self._pool: List[torch.Tensor] = []
         self._lock = threading.Lock()
@@ -48,9 +49,12 @@ class Feeder:
 
     def push(self, a_host: torch.Tensor, b_host: torch.Tensor, tag=None):
         """Enqueue one batch; returns the (tag, flow_host, event) items that are older than ``depth`` batches -- wait for ``event``
-        before reading ``flow_host`` (a pinned tensor that now belongs to the caller)."""
+        before reading ``flow_host`` (a pinned tensor that now belongs to the caller).
+
+        The upload of THIS batch is enqueued first, then the forward of the PREVIOUS one runs: the model's forward may block the
+        host (the synchronous fp16 range check of large batches reads a device flag), and an upload that is only enqueued after
+        that returns cannot overlap the forward it was meant to hide behind."""
         s = self._k % self.depth
-        cur = torch.cuda.current_stream(self.device)
         da, db = self._slot_tensors(s, a_host, b_host)
         with torch.cuda.stream(self.up):
             if self._free[s] is not None:
@@ -59,6 +63,18 @@ class Feeder:
             db.copy_(b_host, non_blocking=True)
             uploaded = torch.cuda.Event()
             uploaded.record(self.up)
+        prev, self._pending = self._pending, (s, da, db, uploaded, tag)
+        self._k += 1
+        if prev is not None:
+            self._forward(prev)
+        out = []
+        while len(self._inflight) >= self.depth:       # its host buffer is the next one to be reused: hand it out now
+            out.append(self._inflight.popleft())
+        return out
+
+    def _forward(self, item) -> None:
+        s, da, db, uploaded, tag = item
+        cur = torch.cuda.current_stream(self.device)
         cur.wait_event(uploaded)
         with torch.no_grad():
             x1, x2 = (self.unpack(da), self.unpack(db)) if self.unpack is not None else (da, db)
@@ -76,11 +92,6 @@ class Feeder:
             landed = torch.cuda.Event()
             landed.record(self.down)
         self._inflight.append((tag, host, landed))
-        self._k += 1
-        out = []
-        while len(self._inflight) >= self.depth:       # its host buffer is the next one to be reused: hand it out now
-            out.append(self._inflight.popleft())
-        return out
 
     def _take_host(self, like: torch.Tensor) -> torch.Tensor:
         """A pinned host tensor for one batch's flow: from the pool of recycled ones if the shape fits, else newly pinned
@@ -98,6 +109,9 @@ class Feeder:
                 self._pool.append(host)
 
     def drain(self):
+        if self._pending is not None:
+            prev, self._pending = self._pending, None
+            self._forward(prev)
         out = list(self._inflight)
         self._inflight.clear()
         return out
